@@ -1,0 +1,196 @@
+/*
+ * tss.h -- C ABI of libtss.so: the B200-native scoring / top-k / prefix-mask
+ * path of trie-semantic-search.
+ *
+ * Every entry point is extern "C", takes plain pointers and sizes, never
+ * throws or unwinds (the reference's release profile is panic = "abort",
+ * Cargo.toml:77), and returns an int status (TSS_OK == 0).  A thread-local
+ * message for the last failure is available from tss_last_error(); the Rust
+ * shim maps it to SearchError::HnswSearchError{details} /
+ * VectorIndexFailed{reason} (src/errors.rs:149-153).
+ *
+ * The reference has no FFI of its own.  The seam this library sits behind is
+ * the private struct HnswIndex in src/vector.rs:184-208 (new / add_vector /
+ * search / size) and, on the trie side, TrieIndex::{insert_*,search}
+ * (src/trie.rs:97-130).  Each declaration below cites what it replaces.
+ * There is NO CPU fallback: without a CUDA device every call that would
+ * touch one returns TSS_ERR_CUDA.
+ *
+ * Threading: a handle is externally synchronised (the reference serialises
+ * vector searches behind a tokio write lock, src/search.rs:249-252).  Distinct
+ * handles may be used from distinct threads.
+ */
+#ifndef TSS_H
+#define TSS_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* libtss is built with -fvisibility=hidden */
+#endif
+
+#define TSS_ABI_VERSION 1
+
+/* ---- status codes ------------------------------------------------------ */
+enum {
+  TSS_OK = 0,
+  TSS_ERR_INVALID_ARG = 1, /* -> SearchError::InvalidSearchQuery / VectorIndexFailed */
+  TSS_ERR_CUDA = 2,        /* -> SearchError::HnswSearchError{details} */
+  TSS_ERR_NCCL = 3,
+  TSS_ERR_OOM = 4,
+  TSS_ERR_STATE = 5 /* call order violated (e.g. search before finalize) */
+};
+
+/* storage type of the embedding matrix in HBM */
+enum { TSS_F32 = 0, TSS_BF16 = 1 };
+
+/* polarity of a row mask handed to a search (SURVEY.md section 8a "semantic gap"):
+ * EXCLUDE is the reference's seen_cases de-dup (src/search.rs:187,214),
+ * INCLUDE is the prefix filter of BASELINE.json config 4. */
+enum { TSS_MASK_NONE = 0, TSS_MASK_INCLUDE = 1, TSS_MASK_EXCLUDE = 2 };
+
+/* how a prefix is matched against the flattened term array */
+enum {
+  TSS_PREFIX_TOKEN = 0, /* token-level, exactly TrieNode::search's walk (src/trie.rs:223-238) */
+  TSS_PREFIX_CHAR = 1   /* byte prefix of the joined term (README.md:41-44 behaviour) */
+};
+
+#define TSS_MAX_K 1024u         /* largest k any search accepts */
+#define TSS_MAX_FUSED_K 128u    /* k <= this runs the fused in-scan top-k */
+#define TSS_ROW_NONE 0xFFFFFFFFu /* row id of an unused output slot */
+
+typedef struct tss_index tss_index; /* replaces HnswIndex, src/vector.rs:40-44 */
+typedef struct tss_mask tss_mask;   /* device bitmask over the rows of one shard */
+typedef struct tss_terms tss_terms; /* flattened, byte-sorted term array + CSR postings */
+typedef struct tss_comm tss_comm;   /* one rank of a row-sharded index (NCCL) */
+
+/* ---- library --------------------------------------------------------------*/
+int tss_abi_version(void);
+const char* tss_last_error(void);
+/* number of CUDA devices visible; 0 (not an error) when there is none. */
+int tss_device_count(void);
+
+/* ---- index lifecycle -------------------------------------------------------
+ * tss_index_create  <- HnswIndex::new(HnswConfig)            src/vector.rs:185-188
+ * tss_index_add     <- HnswIndex::add_vector(DocRef,Vec<f32>) src/vector.rs:190-193
+ *                      (rows are copied before return; the DocRef stays with
+ *                       the caller: row i of the index is the i-th row added)
+ * tss_index_size    <- HnswIndex::size()                      src/vector.rs:204-207
+ * tss_index_destroy <- Drop
+ */
+int tss_index_create(tss_index** out, uint32_t dim, int storage, int device);
+/* optional: size the HBM allocation once (HnswConfig.max_elements, src/config.rs:568). */
+int tss_index_reserve(tss_index* ix, uint64_t nrows);
+/* nrows x dim fp32, row-major, host memory.  NaN / Inf anywhere -> TSS_ERR_INVALID_ARG
+ * and the index is unchanged. */
+int tss_index_add(tss_index* ix, const float* rows, uint64_t nrows);
+/* test / bench utility: append rows [row_begin,row_begin+nrows) of the seeded
+ * synthetic corpus, generated on the device (same integer hash as
+ * oracle/oracle.cpp:gen_row). */
+int tss_index_add_synthetic(tss_index* ix, uint64_t row_begin, uint64_t nrows, uint64_t seed);
+/* completes pending uploads; searches are legal only after this.  More rows may
+ * be added afterwards (finalize again before the next search). */
+int tss_index_finalize(tss_index* ix);
+uint64_t tss_index_size(const tss_index* ix);
+uint32_t tss_index_dim(const tss_index* ix);
+void tss_index_destroy(tss_index* ix);
+/* copy stored rows back (fp32; bf16 storage is widened). Test utility. */
+int tss_index_get_rows(tss_index* ix, uint64_t row_begin, uint64_t nrows, float* out);
+
+/* ---- search ------------------------------------------------------------------
+ * tss_index_search <- HnswIndex::search(&[f32], top_k) -> Vec<(DocRef, f32)>
+ *                     src/vector.rs:195-202, batched over nq queries.
+ * queries: nq x dim fp32 host memory.  Outputs (host, caller-allocated, nq*k
+ * each): rows best-first under (score desc, row asc); scores are cosine
+ * SIMILARITY (the shim returns 1 - s as "distance" to keep the reference
+ * signature, src/vector.rs:144); out_counts[q] <= k valid slots, the rest are
+ * TSS_ROW_NONE / 0.0.  mask may be NULL (mode TSS_MASK_NONE).  For a sharded
+ * index (tss_index_set_shard) the call is collective over the comm and every
+ * rank receives the merged global result; row ids are global.
+ * A zero-norm query or row scores 0.0 (the reference's stub embeds every text
+ * as zeros, src/vector.rs:173, so this is reachable).
+ */
+int tss_index_search(tss_index* ix, const float* queries, uint32_t nq, uint32_t k,
+                     const tss_mask* mask, int mask_mode, uint32_t* out_rows,
+                     float* out_scores, uint32_t* out_counts);
+
+/* Same work with every buffer already in HBM and no host synchronisation:
+ * d_queries nq x dim fp32, d_out_keys nq x k packed keys
+ * ((orderable(score) << 32) | ~row, 0 = unused slot), enqueued on the index
+ * stream.  This is what `value` in bench.py times. */
+int tss_index_search_device(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
+                            const tss_mask* mask, int mask_mode, uint64_t* d_out_keys);
+/* unpack keys produced by tss_index_search_device (host side, pure function). */
+void tss_unpack_keys(const uint64_t* keys, uint64_t n, uint32_t* out_rows, float* out_scores);
+
+/* ---- sharding (BASELINE.json config 5; no reference analogue) ---------------
+ * One process per GPU.  Rank r owns global rows [row_base, row_base + size).
+ * The only exchange on the path is an all-gather of nq*k packed keys per rank
+ * followed by a k-way merge kernel. */
+int tss_comm_unique_id(uint8_t out_id[128]);
+int tss_comm_create(tss_comm** out, const uint8_t id[128], int rank, int nranks, int device);
+void tss_comm_destroy(tss_comm* c);
+int tss_index_set_shard(tss_index* ix, uint64_t row_base, tss_comm* comm /* nullable */);
+
+/* ---- masks ------------------------------------------------------------------*/
+/* nbits rows of ONE shard; bit i <-> local row i (global row row_base + i). */
+int tss_mask_create(tss_mask** out, uint64_t nbits, int device);
+int tss_mask_clear(tss_mask* m);
+/* set the bits of the listed GLOBAL rows that fall inside [row_base,row_base+nbits);
+ * this is how the shim turns seen_cases (src/search.rs:187-206) into an
+ * EXCLUDE mask. */
+int tss_mask_set_rows(tss_mask* m, const uint32_t* rows, uint64_t n, uint64_t row_base);
+int tss_mask_upload(tss_mask* m, const uint32_t* words /* ceil(nbits/32) */);
+int tss_mask_download(const tss_mask* m, uint32_t* words /* ceil(nbits/32) */);
+int tss_mask_popcount(const tss_mask* m, uint64_t* out);
+uint64_t tss_mask_nbits(const tss_mask* m);
+void tss_mask_destroy(tss_mask* m);
+
+/* ---- flattened trie ---------------------------------------------------------
+ * tss_terms_create <- the populated TrieNode tree (src/trie.rs:51-57,211-221),
+ *   exported as T unique terms (tokens joined by one ' '), byte-sorted,
+ *   pool + offsets[T+1]; postings CSR post_off[T+1] / post_rows (global rows,
+ *   insertion order, duplicates kept as in document_refs.push, src/trie.rs:219).
+ * tss_prefix_mask  <- TrieNode::search's walk (src/trie.rs:223-238) + the subtree
+ *   that collect_completions enumerates (src/trie.rs:257-278), without its
+ *   limit-10 and including the matched node itself: sets bit (row - row_base)
+ *   for every posting of every matching term.  The mask is NOT cleared first.
+ */
+typedef struct tss_prefix_stats {
+  uint64_t exact_lo, exact_hi; /* [lo,hi) term range equal to the prefix (0 or 1 term) */
+  uint64_t sub_lo, sub_hi;     /* [lo,hi) term range strictly below it */
+  uint64_t npostings;          /* postings visited (before the shard filter) */
+} tss_prefix_stats;
+
+int tss_terms_create(tss_terms** out, const char* pool, const uint64_t* term_off,
+                     const uint64_t* post_off, const uint32_t* post_rows, uint64_t nterms,
+                     int device);
+uint64_t tss_terms_size(const tss_terms* t);
+void tss_terms_destroy(tss_terms* t);
+int tss_prefix_mask(tss_terms* t, const char* prefix, uint32_t len, int kind, tss_mask* out,
+                    uint64_t row_base, tss_prefix_stats* stats /* nullable: no host sync */);
+
+/* ---- plumbing for callers that time or pipeline the device path ------------ */
+void* tss_index_stream(tss_index* ix); /* cudaStream_t the index enqueues on */
+int tss_index_sync(tss_index* ix);
+int tss_dev_alloc(int device, uint64_t bytes, void** out);
+int tss_dev_free(int device, void* p);
+int tss_dev_h2d(int device, void* dst, const void* src, uint64_t bytes);
+int tss_dev_d2h(int device, void* dst, const void* src, uint64_t bytes);
+int tss_event_create(int device, void** out);
+int tss_event_record(tss_index* ix, void* ev);
+int tss_event_elapsed_ms(void* ev_a, void* ev_b, float* out_ms); /* synchronises on ev_b */
+int tss_event_destroy(void* ev);
+/* kernels launched by this library in this process so far (bench's gpu_launches). */
+uint64_t tss_launch_count(void);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* TSS_H */

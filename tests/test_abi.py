@@ -1,0 +1,81 @@
+"""The C-ABI library loads on a CPU box and exports exactly what include/tss.h declares.
+No compute call is made here (there is no GPU); the product path must fail loudly."""
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "tss.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(tss_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_all_exported(tss):
+    declared = _declared()
+    assert len(declared) >= 40
+    out = subprocess.run(["nm", "-D", "--defined-only", tss.LIB_PATH], capture_output=True,
+                         text=True, check=True).stdout
+    exported = {line.split()[-1] for line in out.splitlines() if " T " in line}
+    missing = [s for s in declared if s not in exported]
+    assert not missing, f"declared in tss.h but not exported: {missing}"
+    # nothing but the ABI leaks out of the library
+    extra = [s for s in exported if not s.startswith("tss_")]
+    assert not extra, f"non-ABI symbols exported: {extra[:5]}"
+    assert sorted(tss.ABI_SYMBOLS) == declared
+
+
+def test_library_loads_and_reports_version(tss):
+    L = tss.lib()
+    assert L.tss_abi_version() == 1
+    assert tss.launch_count() >= 0
+
+
+def test_no_cpu_fallback(tss):
+    if tss.device_count() > 0:
+        pytest.skip("GPU present")
+    with pytest.raises(tss.TssError) as ei:
+        tss.FlatIndex(384)
+    assert ei.value.code == tss.TSS_ERR_CUDA and "no CPU path" in str(ei.value)
+    with pytest.raises(tss.TssError):
+        tss.Mask(100)
+
+
+def test_argument_validation_without_device(tss):
+    import ctypes as C
+    L = tss.lib()
+    p = C.c_void_p()
+    assert L.tss_index_create(C.byref(p), 0, tss.TSS_F32, 0) == tss.TSS_ERR_INVALID_ARG
+    assert L.tss_index_create(C.byref(p), 2048, tss.TSS_F32, 0) == tss.TSS_ERR_INVALID_ARG
+    assert L.tss_index_create(C.byref(p), 384, 7, 0) == tss.TSS_ERR_INVALID_ARG
+    assert b"storage" in L.tss_last_error()
+    assert L.tss_index_size(None) == 0
+    L.tss_index_destroy(None)  # no-op
+    L.tss_mask_destroy(None)
+    L.tss_terms_destroy(None)
+
+
+def test_unpack_keys_is_pure_host(tss, orc):
+    import numpy as np
+    keys = np.array([orc.pack_key(0.75, 12), orc.pack_key(-0.5, 7), 0], dtype=np.uint64)
+    rows, scores = tss.unpack_keys(keys)
+    assert list(rows) == [12, 7, tss.TSS_ROW_NONE]
+    assert list(scores) == [0.75, -0.5, 0.0]
+
+
+def test_terms_validation_runs_before_any_device_call(tss):
+    import numpy as np
+    import ctypes as C
+    L = tss.lib()
+    p = C.c_void_p()
+    pool = np.frombuffer(b"bbaa", dtype=np.uint8)
+    toff = np.array([0, 2, 4], dtype=np.uint64)
+    poff = np.array([0, 0, 0], dtype=np.uint64)
+    rows = np.zeros(1, dtype=np.uint32)
+    rc = L.tss_terms_create(C.byref(p), pool.ctypes.data, toff.ctypes.data, poff.ctypes.data,
+                            rows.ctypes.data, 2, 0)
+    assert rc == tss.TSS_ERR_INVALID_ARG and b"byte-sorted" in L.tss_last_error()

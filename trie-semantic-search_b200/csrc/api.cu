@@ -1,0 +1,875 @@
+// api.cu -- the extern "C" surface declared in include/tss.h.
+//
+// Host-side plumbing only: handles, HBM allocation, staging copies, launch
+// dispatch, NCCL (loaded lazily with dlopen so a single-GPU user needs no
+// NCCL at all).  No CPU fallback anywhere: every data-path call ends in a
+// kernel launch or an error.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/tss.h"
+#include "aux_kernels.cuh"
+#include "scan.cuh"
+#include "scan_launch.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<uint64_t> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+  int code = (e == cudaErrorMemoryAllocation) ? TSS_ERR_OOM : TSS_ERR_CUDA;
+  return fail(code, "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+}
+#define CU(call)                                        \
+  do {                                                  \
+    cudaError_t e__ = (call);                           \
+    if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+  } while (0)
+
+// ---- NCCL, resolved at first use -----------------------------------------------
+typedef struct ncclComm* ncclComm_t;
+typedef struct {
+  char internal[128];
+} ncclUniqueId;
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool ok = false;
+};
+NcclApi g_nccl;
+int load_nccl() {
+  if (g_nccl.ok) return TSS_OK;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) {
+    g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (g_nccl.lib) break;
+  }
+  if (!g_nccl.lib) return fail(TSS_ERR_NCCL, "dlopen(libnccl.so.2) failed: %s", dlerror());
+#define SYM(field, name)                                                          \
+  g_nccl.field = reinterpret_cast<decltype(g_nccl.field)>(dlsym(g_nccl.lib, name)); \
+  if (!g_nccl.field) return fail(TSS_ERR_NCCL, "NCCL symbol %s missing", name);
+  SYM(GetUniqueId, "ncclGetUniqueId")
+  SYM(CommInitRank, "ncclCommInitRank")
+  SYM(CommDestroy, "ncclCommDestroy")
+  SYM(AllGather, "ncclAllGather")
+  SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+  g_nccl.ok = true;
+  return TSS_OK;
+}
+constexpr int kNcclUint64 = 5;
+
+constexpr uint32_t kMaxBq = 4;           // queries per scan launch
+constexpr uint32_t kWsQueries = 1024;    // device query/result workspace, in queries
+constexpr size_t kStageBytes = 64u << 20;  // upload staging buffer
+
+}  // namespace
+
+struct tss_comm {
+  ncclComm_t comm = nullptr;
+  int rank = 0, nranks = 1, device = 0;
+};
+
+struct tss_mask {
+  int device = 0;
+  uint64_t nbits = 0, nwords = 0;
+  uint32_t* d_words = nullptr;
+  unsigned long long* d_scratch = nullptr;
+};
+
+struct tss_terms {
+  int device = 0;
+  uint64_t nterms = 0, pool_bytes = 0, nposts = 0;
+  char* d_pool = nullptr;
+  uint64_t* d_term_off = nullptr;
+  uint64_t* d_post_off = nullptr;
+  uint32_t* d_post_rows = nullptr;
+  char* d_keys = nullptr;     // probe key bytes
+  char* h_keys = nullptr;     // pinned
+  uint64_t* d_bounds = nullptr;  // 4 bounds + npostings
+  uint32_t key_cap = 0;
+  cudaStream_t stream = nullptr;
+};
+
+struct tss_index {
+  int device = 0;
+  uint32_t dim = 0;
+  int storage = TSS_F32;
+  int ns = 0;                 // storage stripes of 128 elements
+  uint32_t stride_elems = 0;  // ns * 128
+  size_t row_bytes = 0;
+  uint8_t* d_rows = nullptr;
+  uint64_t capacity = 0, n_rows = 0;
+  bool finalized = false;
+  cudaStream_t stream = nullptr;
+  int num_sms = 0;
+  uint64_t row_base = 0;
+  tss_comm* comm = nullptr;
+  // workspaces
+  float* d_stage = nullptr;  // kStageBytes upload staging (lazy)
+  int* d_flag = nullptr;
+  float* d_queries = nullptr;      // kWsQueries x dim
+  uint64_t* d_keys = nullptr;      // kWsQueries x TSS_MAX_FUSED_K local results
+  uint64_t* d_gather = nullptr;    // nranks x kWsQueries x k (lazy)
+  uint64_t* d_merged = nullptr;    // kWsQueries x k (lazy)
+  uint64_t* d_partials = nullptr;  // kMaxBq x num_sms x 128
+  unsigned int* d_counter = nullptr;
+  float* h_queries = nullptr;  // pinned
+  uint64_t* h_keys = nullptr;  // pinned
+};
+
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+int ensure_capacity(tss_index* ix, uint64_t need) {
+  if (need <= ix->capacity) return TSS_OK;
+  uint64_t cap = ix->capacity ? ix->capacity + ix->capacity / 2 : 0;
+  if (cap < need) cap = need;
+  // one R-row tile of slack so the last bulk copy never leaves the allocation
+  size_t bytes = (size_t)(cap + 16) * ix->row_bytes;
+  uint8_t* nd = nullptr;
+  cudaError_t e = cudaMalloc(&nd, bytes);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(TSS_ERR_OOM, "cudaMalloc(%zu bytes for %llu rows) failed: %s", bytes,
+                (unsigned long long)cap, cudaGetErrorString(e));
+  }
+  if (ix->n_rows) {
+    CU(cudaMemcpyAsync(nd, ix->d_rows, (size_t)ix->n_rows * ix->row_bytes, cudaMemcpyDeviceToDevice,
+                       ix->stream));
+    CU(cudaStreamSynchronize(ix->stream));
+  }
+  if (ix->d_rows) cudaFree(ix->d_rows);
+  ix->d_rows = nd;
+  ix->capacity = cap;
+  return TSS_OK;
+}
+
+int check_mask(const tss_index* ix, const tss_mask* mask, int mode) {
+  if (mode != TSS_MASK_NONE && mode != TSS_MASK_INCLUDE && mode != TSS_MASK_EXCLUDE)
+    return fail(TSS_ERR_INVALID_ARG, "mask_mode %d is not a TSS_MASK_* value", mode);
+  if (mode != TSS_MASK_NONE) {
+    if (!mask) return fail(TSS_ERR_INVALID_ARG, "mask_mode set but mask is NULL");
+    if (mask->device != ix->device) return fail(TSS_ERR_INVALID_ARG, "mask lives on another device");
+    if (mask->nbits < ix->n_rows)
+      return fail(TSS_ERR_INVALID_ARG, "mask has %llu bits, shard has %llu rows",
+                  (unsigned long long)mask->nbits, (unsigned long long)ix->n_rows);
+  }
+  return TSS_OK;
+}
+
+// enqueue the scan for nq device-resident queries -> d_out (nq x k local keys)
+int enqueue_scan(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
+                 const tss_mask* mask, int mode, uint64_t* d_out) {
+  const uint32_t kp = tss::kp_for_k(k), cap = tss::cap_for_k(k);
+  const uint32_t bq_max = (uint32_t)tss::max_bq_for_k(k);
+  for (uint32_t q0 = 0; q0 < nq;) {
+    uint32_t left = nq - q0;
+    uint32_t take = left < bq_max ? left : bq_max;
+    int bq = take >= 3 ? 4 : (int)take;  // kernel instances: 1, 2, 4
+    tss::ScanParams p{};
+    p.rows = ix->d_rows;
+    p.n_rows = ix->n_rows;
+    p.row_base = (uint32_t)ix->row_base;
+    p.dim = ix->dim;
+    p.queries = d_queries + (size_t)q0 * ix->dim;
+    p.nq_valid = take;
+    p.k = k;
+    p.kp = kp;
+    p.cap = cap;
+    p.mask = mode != TSS_MASK_NONE ? mask->d_words : nullptr;
+    p.mask_mode = mode;
+    p.partials = ix->d_partials;
+    p.done_counter = ix->d_counter;
+    p.out_keys = d_out + (size_t)q0 * k;
+    cudaError_t e = tss::launch_scan(ix->ns, p, bq, ix->storage == TSS_BF16, mode != TSS_MASK_NONE,
+                                     ix->num_sms, ix->device, ix->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "scan_topk_kernel launch");
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    q0 += take;
+  }
+  return TSS_OK;
+}
+
+// sharded tail: all-gather local keys, merge.  d_local: nq x k.  result in d_merged.
+int enqueue_gather_merge(tss_index* ix, const uint64_t* d_local, uint32_t nq, uint32_t k,
+                         uint64_t* d_merged_out) {
+  tss_comm* c = ix->comm;
+  size_t per_rank = (size_t)nq * k;
+  int rc = g_nccl.AllGather(d_local, ix->d_gather, per_rank, kNcclUint64, c->comm, ix->stream);
+  if (rc != 0) return fail(TSS_ERR_NCCL, "ncclAllGather: %s", g_nccl.GetErrorString(rc));
+  cudaError_t e = tss::launch_merge_gathered(ix->d_gather, d_merged_out, (uint32_t)c->nranks, nq, k,
+                                             ix->stream);
+  if (e != cudaSuccess) return cuda_fail(e, "merge_gathered_kernel launch");
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return TSS_OK;
+}
+
+int ensure_gather_ws(tss_index* ix) {
+  if (!ix->comm || ix->d_gather) return TSS_OK;
+  CU(cudaMalloc(&ix->d_gather,
+                (size_t)ix->comm->nranks * kWsQueries * TSS_MAX_FUSED_K * sizeof(uint64_t)));
+  CU(cudaMalloc(&ix->d_merged, (size_t)kWsQueries * TSS_MAX_FUSED_K * sizeof(uint64_t)));
+  return TSS_OK;
+}
+
+int validate_search(const tss_index* ix, const void* queries, uint32_t nq, uint32_t k) {
+  if (!ix) return fail(TSS_ERR_INVALID_ARG, "index is NULL");
+  if (!queries && nq) return fail(TSS_ERR_INVALID_ARG, "queries is NULL");
+  if (k == 0 || k > TSS_MAX_K) return fail(TSS_ERR_INVALID_ARG, "k=%u outside [1,%u]", k, TSS_MAX_K);
+  if (k > TSS_MAX_FUSED_K)
+    return fail(TSS_ERR_INVALID_ARG, "k=%u > %u is not implemented yet", k, TSS_MAX_FUSED_K);
+  if (!ix->finalized) return fail(TSS_ERR_STATE, "search before tss_index_finalize");
+  return TSS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int tss_abi_version(void) { return TSS_ABI_VERSION; }
+const char* tss_last_error(void) { return g_err; }
+uint64_t tss_launch_count(void) { return g_launches.load(); }
+
+int tss_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+// ---- index ---------------------------------------------------------------------------
+int tss_index_create(tss_index** out, uint32_t dim, int storage, int device) {
+  if (!out) return fail(TSS_ERR_INVALID_ARG, "out is NULL");
+  *out = nullptr;
+  if (dim == 0) return fail(TSS_ERR_INVALID_ARG, "dim must be > 0");
+  int ns = tss::storage_stripes_for_dim(dim);
+  if (!ns) return fail(TSS_ERR_INVALID_ARG, "dim=%u > 1024 is not supported", dim);
+  if (storage != TSS_F32 && storage != TSS_BF16)
+    return fail(TSS_ERR_INVALID_ARG, "storage %d is not TSS_F32/TSS_BF16", storage);
+  int ndev = tss_device_count();
+  if (ndev == 0) return fail(TSS_ERR_CUDA, "no CUDA device visible (libtss has no CPU path)");
+  if (device < 0 || device >= ndev) return fail(TSS_ERR_INVALID_ARG, "device %d of %d", device, ndev);
+  DeviceGuard g(device);
+  if (!g.ok) return fail(TSS_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(TSS_ERR_CUDA, "device %d is sm_%d%d; libtss is built for sm_100a only", device,
+                prop.major, prop.minor);
+  tss_index* ix = new (std::nothrow) tss_index();
+  if (!ix) return fail(TSS_ERR_OOM, "host allocation failed");
+  ix->device = device;
+  ix->dim = dim;
+  ix->storage = storage;
+  ix->ns = ns;
+  ix->stride_elems = (uint32_t)ns * 128u;
+  ix->row_bytes = (size_t)ix->stride_elems * (storage == TSS_BF16 ? 2 : 4);
+  ix->num_sms = prop.multiProcessorCount;
+  cudaError_t e;
+#define ALLOC(expr)                    \
+  if ((e = (expr)) != cudaSuccess) {   \
+    tss_index_destroy(ix);             \
+    return cuda_fail(e, #expr);        \
+  }
+  ALLOC(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking))
+  ALLOC(cudaMalloc(&ix->d_flag, sizeof(int)))
+  ALLOC(cudaMalloc(&ix->d_queries, (size_t)kWsQueries * dim * sizeof(float)))
+  ALLOC(cudaMalloc(&ix->d_keys, (size_t)kWsQueries * TSS_MAX_FUSED_K * sizeof(uint64_t)))
+  ALLOC(cudaMalloc(&ix->d_partials, (size_t)kMaxBq * ix->num_sms * 128 * sizeof(uint64_t)))
+  ALLOC(cudaMalloc(&ix->d_counter, sizeof(unsigned int)))
+  ALLOC(cudaMemset(ix->d_counter, 0, sizeof(unsigned int)))
+  ALLOC(cudaMallocHost(&ix->h_queries, (size_t)kWsQueries * dim * sizeof(float)))
+  ALLOC(cudaMallocHost(&ix->h_keys, (size_t)kWsQueries * TSS_MAX_FUSED_K * sizeof(uint64_t)))
+#undef ALLOC
+  *out = ix;
+  return TSS_OK;
+}
+
+void tss_index_destroy(tss_index* ix) {
+  if (!ix) return;
+  DeviceGuard g(ix->device);
+  if (ix->stream) cudaStreamSynchronize(ix->stream);
+  cudaFree(ix->d_rows);
+  cudaFree(ix->d_stage);
+  cudaFree(ix->d_flag);
+  cudaFree(ix->d_queries);
+  cudaFree(ix->d_keys);
+  cudaFree(ix->d_gather);
+  cudaFree(ix->d_merged);
+  cudaFree(ix->d_partials);
+  cudaFree(ix->d_counter);
+  if (ix->h_queries) cudaFreeHost(ix->h_queries);
+  if (ix->h_keys) cudaFreeHost(ix->h_keys);
+  if (ix->stream) cudaStreamDestroy(ix->stream);
+  delete ix;
+}
+
+int tss_index_reserve(tss_index* ix, uint64_t nrows) {
+  if (!ix) return fail(TSS_ERR_INVALID_ARG, "index is NULL");
+  if (nrows >= 0xFFFFFFFFull) return fail(TSS_ERR_INVALID_ARG, "row ids are 32-bit");
+  DeviceGuard g(ix->device);
+  return ensure_capacity(ix, nrows);
+}
+
+int tss_index_add(tss_index* ix, const float* rows, uint64_t nrows) {
+  if (!ix) return fail(TSS_ERR_INVALID_ARG, "index is NULL");
+  if (!nrows) return TSS_OK;
+  if (!rows) return fail(TSS_ERR_INVALID_ARG, "rows is NULL");
+  if (ix->row_base + ix->n_rows + nrows >= 0xFFFFFFFFull)
+    return fail(TSS_ERR_INVALID_ARG, "row ids are 32-bit");
+  DeviceGuard g(ix->device);
+  int rc = ensure_capacity(ix, ix->n_rows + nrows);
+  if (rc) return rc;
+  if (!ix->d_stage) CU(cudaMalloc(&ix->d_stage, kStageBytes));
+  CU(cudaMemsetAsync(ix->d_flag, 0, sizeof(int), ix->stream));
+  const uint64_t chunk_rows = kStageBytes / ((size_t)ix->dim * sizeof(float));
+  if (!chunk_rows) return fail(TSS_ERR_INVALID_ARG, "dim too large for the staging buffer");
+  for (uint64_t r0 = 0; r0 < nrows; r0 += chunk_rows) {
+    uint64_t n = nrows - r0 < chunk_rows ? nrows - r0 : chunk_rows;
+    CU(cudaMemcpyAsync(ix->d_stage, rows + (size_t)r0 * ix->dim, (size_t)n * ix->dim * sizeof(float),
+                       cudaMemcpyHostToDevice, ix->stream));
+    cudaError_t e = tss::launch_check_finite(ix->d_stage, n * ix->dim, ix->d_flag, ix->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "check_finite launch");
+    e = tss::launch_pack_rows(ix->d_stage, ix->d_rows + (size_t)(ix->n_rows + r0) * ix->row_bytes, n,
+                              ix->dim, ix->stride_elems, ix->storage == TSS_BF16, ix->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "pack_rows launch");
+    g_launches.fetch_add(2, std::memory_order_relaxed);
+    // the staging buffer is reused by the next chunk
+    CU(cudaStreamSynchronize(ix->stream));
+  }
+  int flag = 0;
+  CU(cudaMemcpyAsync(&flag, ix->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ix->stream));
+  CU(cudaStreamSynchronize(ix->stream));
+  if (flag)
+    return fail(TSS_ERR_INVALID_ARG, "rows contain NaN or Inf; index unchanged (%llu rows)",
+                (unsigned long long)ix->n_rows);
+  ix->n_rows += nrows;
+  ix->finalized = false;
+  return TSS_OK;
+}
+
+int tss_index_add_synthetic(tss_index* ix, uint64_t row_begin, uint64_t nrows, uint64_t seed) {
+  if (!ix) return fail(TSS_ERR_INVALID_ARG, "index is NULL");
+  if (!nrows) return TSS_OK;
+  if (ix->row_base + ix->n_rows + nrows >= 0xFFFFFFFFull)
+    return fail(TSS_ERR_INVALID_ARG, "row ids are 32-bit");
+  DeviceGuard g(ix->device);
+  int rc = ensure_capacity(ix, ix->n_rows + nrows);
+  if (rc) return rc;
+  cudaError_t e = tss::launch_synth_fill(ix->d_rows + (size_t)ix->n_rows * ix->row_bytes, row_begin,
+                                         nrows, ix->dim, ix->stride_elems, ix->storage == TSS_BF16,
+                                         seed, ix->stream);
+  if (e != cudaSuccess) return cuda_fail(e, "synth_fill launch");
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  ix->n_rows += nrows;
+  ix->finalized = false;
+  return TSS_OK;
+}
+
+int tss_index_finalize(tss_index* ix) {
+  if (!ix) return fail(TSS_ERR_INVALID_ARG, "index is NULL");
+  DeviceGuard g(ix->device);
+  if (!ix->d_rows) {
+    int rc = ensure_capacity(ix, 1);  // an empty index still scans (and finds nothing)
+    if (rc) return rc;
+  }
+  CU(cudaStreamSynchronize(ix->stream));
+  if (ix->d_stage) {
+    cudaFree(ix->d_stage);
+    ix->d_stage = nullptr;
+  }
+  ix->finalized = true;
+  return TSS_OK;
+}
+
+uint64_t tss_index_size(const tss_index* ix) { return ix ? ix->n_rows : 0; }
+uint32_t tss_index_dim(const tss_index* ix) { return ix ? ix->dim : 0; }
+
+int tss_index_get_rows(tss_index* ix, uint64_t row_begin, uint64_t nrows, float* out) {
+  if (!ix || !out) return fail(TSS_ERR_INVALID_ARG, "NULL argument");
+  if (row_begin + nrows > ix->n_rows) return fail(TSS_ERR_INVALID_ARG, "row range out of bounds");
+  if (!nrows) return TSS_OK;
+  DeviceGuard g(ix->device);
+  float* d_tmp = nullptr;
+  CU(cudaMalloc(&d_tmp, (size_t)nrows * ix->dim * sizeof(float)));
+  cudaError_t e = tss::launch_unpack_rows(ix->d_rows + (size_t)row_begin * ix->row_bytes, d_tmp,
+                                          nrows, ix->dim, ix->stride_elems,
+                                          ix->storage == TSS_BF16, ix->stream);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(out, d_tmp, (size_t)nrows * ix->dim * sizeof(float), cudaMemcpyDeviceToHost,
+                        ix->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ix->stream);
+  cudaFree(d_tmp);
+  if (e != cudaSuccess) return cuda_fail(e, "get_rows");
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return TSS_OK;
+}
+
+// ---- search ---------------------------------------------------------------------------
+int tss_index_search_device(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
+                            const tss_mask* mask, int mask_mode, uint64_t* d_out_keys) {
+  int rc = validate_search(ix, d_queries, nq, k);
+  if (rc) return rc;
+  if (!d_out_keys) return fail(TSS_ERR_INVALID_ARG, "d_out_keys is NULL");
+  if ((rc = check_mask(ix, mask, mask_mode))) return rc;
+  if (!nq) return TSS_OK;
+  DeviceGuard g(ix->device);
+  if (!ix->comm) return enqueue_scan(ix, d_queries, nq, k, mask, mask_mode, d_out_keys);
+  if ((rc = ensure_gather_ws(ix))) return rc;
+  for (uint32_t q0 = 0; q0 < nq; q0 += kWsQueries) {
+    uint32_t n = nq - q0 < kWsQueries ? nq - q0 : kWsQueries;
+    if ((rc = enqueue_scan(ix, d_queries + (size_t)q0 * ix->dim, n, k, mask, mask_mode, ix->d_keys)))
+      return rc;
+    if ((rc = enqueue_gather_merge(ix, ix->d_keys, n, k, d_out_keys + (size_t)q0 * k))) return rc;
+  }
+  return TSS_OK;
+}
+
+void tss_unpack_keys(const uint64_t* keys, uint64_t n, uint32_t* out_rows, float* out_scores) {
+  for (uint64_t i = 0; i < n; ++i) {
+    uint64_t key = keys[i];
+    if (key == 0) {
+      if (out_rows) out_rows[i] = TSS_ROW_NONE;
+      if (out_scores) out_scores[i] = 0.0f;
+      continue;
+    }
+    uint32_t o = (uint32_t)(key >> 32);
+    uint32_t u = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
+    float s;
+    memcpy(&s, &u, 4);
+    if (out_rows) out_rows[i] = 0xFFFFFFFFu - (uint32_t)key;
+    if (out_scores) out_scores[i] = s;
+  }
+}
+
+int tss_index_search(tss_index* ix, const float* queries, uint32_t nq, uint32_t k,
+                     const tss_mask* mask, int mask_mode, uint32_t* out_rows, float* out_scores,
+                     uint32_t* out_counts) {
+  int rc = validate_search(ix, queries, nq, k);
+  if (rc) return rc;
+  if (!out_rows || !out_scores || !out_counts)
+    return fail(TSS_ERR_INVALID_ARG, "output pointer is NULL");
+  if ((rc = check_mask(ix, mask, mask_mode))) return rc;
+  if (!nq) return TSS_OK;
+  for (uint64_t i = 0; i < (uint64_t)nq * ix->dim; ++i)
+    if (!std::isfinite(queries[i]))
+      return fail(TSS_ERR_INVALID_ARG, "query %llu contains NaN or Inf",
+                  (unsigned long long)(i / ix->dim));
+  DeviceGuard g(ix->device);
+  if ((rc = ensure_gather_ws(ix))) return rc;
+  for (uint32_t q0 = 0; q0 < nq; q0 += kWsQueries) {
+    uint32_t n = nq - q0 < kWsQueries ? nq - q0 : kWsQueries;
+    size_t qbytes = (size_t)n * ix->dim * sizeof(float);
+    memcpy(ix->h_queries, queries + (size_t)q0 * ix->dim, qbytes);
+    CU(cudaMemcpyAsync(ix->d_queries, ix->h_queries, qbytes, cudaMemcpyHostToDevice, ix->stream));
+    if ((rc = enqueue_scan(ix, ix->d_queries, n, k, mask, mask_mode, ix->d_keys))) return rc;
+    const uint64_t* d_res = ix->d_keys;
+    if (ix->comm) {
+      if ((rc = enqueue_gather_merge(ix, ix->d_keys, n, k, ix->d_merged))) return rc;
+      d_res = ix->d_merged;
+    }
+    CU(cudaMemcpyAsync(ix->h_keys, d_res, (size_t)n * k * sizeof(uint64_t), cudaMemcpyDeviceToHost,
+                       ix->stream));
+    CU(cudaStreamSynchronize(ix->stream));
+    tss_unpack_keys(ix->h_keys, (uint64_t)n * k, out_rows + (size_t)q0 * k,
+                    out_scores + (size_t)q0 * k);
+    for (uint32_t qi = 0; qi < n; ++qi) {
+      uint32_t c = 0;
+      while (c < k && ix->h_keys[(size_t)qi * k + c] != 0) ++c;
+      out_counts[q0 + qi] = c;
+    }
+  }
+  return TSS_OK;
+}
+
+// ---- sharding ---------------------------------------------------------------------------
+int tss_comm_unique_id(uint8_t out_id[128]) {
+  if (!out_id) return fail(TSS_ERR_INVALID_ARG, "out_id is NULL");
+  int rc = load_nccl();
+  if (rc) return rc;
+  ncclUniqueId id;
+  int r = g_nccl.GetUniqueId(&id);
+  if (r != 0) return fail(TSS_ERR_NCCL, "ncclGetUniqueId: %s", g_nccl.GetErrorString(r));
+  memcpy(out_id, id.internal, 128);
+  return TSS_OK;
+}
+
+int tss_comm_create(tss_comm** out, const uint8_t id[128], int rank, int nranks, int device) {
+  if (!out || !id) return fail(TSS_ERR_INVALID_ARG, "NULL argument");
+  *out = nullptr;
+  if (nranks < 1 || rank < 0 || rank >= nranks)
+    return fail(TSS_ERR_INVALID_ARG, "rank %d of %d", rank, nranks);
+  int rc = load_nccl();
+  if (rc) return rc;
+  DeviceGuard g(device);
+  if (!g.ok) return fail(TSS_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+  ncclUniqueId uid;
+  memcpy(uid.internal, id, 128);
+  ncclComm_t comm = nullptr;
+  int r = g_nccl.CommInitRank(&comm, nranks, uid, rank);
+  if (r != 0) return fail(TSS_ERR_NCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString(r));
+  tss_comm* c = new (std::nothrow) tss_comm();
+  if (!c) return fail(TSS_ERR_OOM, "host allocation failed");
+  c->comm = comm;
+  c->rank = rank;
+  c->nranks = nranks;
+  c->device = device;
+  *out = c;
+  return TSS_OK;
+}
+
+void tss_comm_destroy(tss_comm* c) {
+  if (!c) return;
+  DeviceGuard g(c->device);
+  if (c->comm && g_nccl.ok) g_nccl.CommDestroy(c->comm);
+  delete c;
+}
+
+int tss_index_set_shard(tss_index* ix, uint64_t row_base, tss_comm* comm) {
+  if (!ix) return fail(TSS_ERR_INVALID_ARG, "index is NULL");
+  if (row_base + ix->n_rows >= 0xFFFFFFFFull)
+    return fail(TSS_ERR_INVALID_ARG, "row ids are 32-bit");
+  if (comm && comm->device != ix->device)
+    return fail(TSS_ERR_INVALID_ARG, "comm and index live on different devices");
+  if (comm && (uint64_t)comm->nranks * TSS_MAX_FUSED_K * 8 > 48 * 1024)
+    return fail(TSS_ERR_INVALID_ARG, "at most %d ranks", 48 * 1024 / (TSS_MAX_FUSED_K * 8));
+  ix->row_base = row_base;
+  ix->comm = comm;
+  return TSS_OK;
+}
+
+// ---- masks ---------------------------------------------------------------------------------
+int tss_mask_create(tss_mask** out, uint64_t nbits, int device) {
+  if (!out) return fail(TSS_ERR_INVALID_ARG, "out is NULL");
+  *out = nullptr;
+  int ndev = tss_device_count();
+  if (ndev == 0) return fail(TSS_ERR_CUDA, "no CUDA device visible (libtss has no CPU path)");
+  if (device < 0 || device >= ndev) return fail(TSS_ERR_INVALID_ARG, "device %d of %d", device, ndev);
+  DeviceGuard g(device);
+  tss_mask* m = new (std::nothrow) tss_mask();
+  if (!m) return fail(TSS_ERR_OOM, "host allocation failed");
+  m->device = device;
+  m->nbits = nbits;
+  m->nwords = (nbits + 31) / 32;
+  // the scan reads whole words for the last (partial) tile: pad by one word
+  cudaError_t e = cudaMalloc(&m->d_words, (size_t)(m->nwords + 1) * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMemset(m->d_words, 0, (size_t)(m->nwords + 1) * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&m->d_scratch, sizeof(unsigned long long));
+  if (e != cudaSuccess) {
+    tss_mask_destroy(m);
+    return cuda_fail(e, "mask allocation");
+  }
+  *out = m;
+  return TSS_OK;
+}
+
+void tss_mask_destroy(tss_mask* m) {
+  if (!m) return;
+  DeviceGuard g(m->device);
+  cudaFree(m->d_words);
+  cudaFree(m->d_scratch);
+  delete m;
+}
+
+uint64_t tss_mask_nbits(const tss_mask* m) { return m ? m->nbits : 0; }
+
+int tss_mask_clear(tss_mask* m) {
+  if (!m) return fail(TSS_ERR_INVALID_ARG, "mask is NULL");
+  DeviceGuard g(m->device);
+  CU(cudaMemset(m->d_words, 0, (size_t)(m->nwords + 1) * sizeof(uint32_t)));
+  return TSS_OK;
+}
+
+int tss_mask_set_rows(tss_mask* m, const uint32_t* rows, uint64_t n, uint64_t row_base) {
+  if (!m) return fail(TSS_ERR_INVALID_ARG, "mask is NULL");
+  if (!n) return TSS_OK;
+  if (!rows) return fail(TSS_ERR_INVALID_ARG, "rows is NULL");
+  DeviceGuard g(m->device);
+  uint32_t* d_rows = nullptr;
+  CU(cudaMalloc(&d_rows, (size_t)n * sizeof(uint32_t)));
+  cudaError_t e = cudaMemcpy(d_rows, rows, (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = tss::launch_mask_set_rows(m->d_words, m->nbits, d_rows, n, row_base, 0);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  cudaFree(d_rows);
+  if (e != cudaSuccess) return cuda_fail(e, "mask_set_rows");
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return TSS_OK;
+}
+
+int tss_mask_upload(tss_mask* m, const uint32_t* words) {
+  if (!m || !words) return fail(TSS_ERR_INVALID_ARG, "NULL argument");
+  DeviceGuard g(m->device);
+  CU(cudaMemcpy(m->d_words, words, (size_t)m->nwords * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  return TSS_OK;
+}
+
+int tss_mask_download(const tss_mask* m, uint32_t* words) {
+  if (!m || !words) return fail(TSS_ERR_INVALID_ARG, "NULL argument");
+  DeviceGuard g(m->device);
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpy(words, m->d_words, (size_t)m->nwords * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  return TSS_OK;
+}
+
+int tss_mask_popcount(const tss_mask* m, uint64_t* out) {
+  if (!m || !out) return fail(TSS_ERR_INVALID_ARG, "NULL argument");
+  DeviceGuard g(m->device);
+  CU(cudaDeviceSynchronize());
+  cudaError_t e = tss::launch_mask_popcount(m->d_words, m->nwords, m->d_scratch, 0);
+  if (e != cudaSuccess) return cuda_fail(e, "mask_popcount launch");
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  unsigned long long v = 0;
+  CU(cudaMemcpy(&v, m->d_scratch, sizeof(v), cudaMemcpyDeviceToHost));
+  *out = v;
+  return TSS_OK;
+}
+
+// ---- flattened trie ---------------------------------------------------------------------------
+int tss_terms_create(tss_terms** out, const char* pool, const uint64_t* term_off,
+                     const uint64_t* post_off, const uint32_t* post_rows, uint64_t nterms,
+                     int device) {
+  if (!out) return fail(TSS_ERR_INVALID_ARG, "out is NULL");
+  *out = nullptr;
+  if (!term_off || !post_off) return fail(TSS_ERR_INVALID_ARG, "offset arrays are NULL");
+  if (term_off[0] != 0 || post_off[0] != 0)
+    return fail(TSS_ERR_INVALID_ARG, "offset arrays must start at 0");
+  const uint64_t pool_bytes = term_off[nterms], nposts = post_off[nterms];
+  if ((pool_bytes && !pool) || (nposts && !post_rows))
+    return fail(TSS_ERR_INVALID_ARG, "pool / post_rows is NULL");
+  // byte-sorted, strictly increasing (unique) terms: the kernel's binary search relies on it
+  for (uint64_t i = 0; i < nterms; ++i) {
+    if (term_off[i + 1] < term_off[i] || post_off[i + 1] < post_off[i])
+      return fail(TSS_ERR_INVALID_ARG, "offsets not monotone at term %llu", (unsigned long long)i);
+    if (i) {
+      uint64_t la = term_off[i] - term_off[i - 1], lb = term_off[i + 1] - term_off[i];
+      int c = memcmp(pool + term_off[i - 1], pool + term_off[i], la < lb ? la : lb);
+      if (c > 0 || (c == 0 && la >= lb))
+        return fail(TSS_ERR_INVALID_ARG, "terms not strictly byte-sorted at term %llu",
+                    (unsigned long long)i);
+    }
+  }
+  int ndev = tss_device_count();
+  if (ndev == 0) return fail(TSS_ERR_CUDA, "no CUDA device visible (libtss has no CPU path)");
+  if (device < 0 || device >= ndev) return fail(TSS_ERR_INVALID_ARG, "device %d of %d", device, ndev);
+  DeviceGuard g(device);
+  tss_terms* t = new (std::nothrow) tss_terms();
+  if (!t) return fail(TSS_ERR_OOM, "host allocation failed");
+  t->device = device;
+  t->nterms = nterms;
+  t->pool_bytes = pool_bytes;
+  t->nposts = nposts;
+  t->key_cap = 4096;
+  cudaError_t e = cudaSuccess;
+#define TRY(expr) \
+  if (e == cudaSuccess) e = (expr);
+  TRY(cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking))
+  TRY(cudaMalloc(&t->d_pool, pool_bytes + 16))
+  TRY(cudaMalloc(&t->d_term_off, (nterms + 1) * sizeof(uint64_t)))
+  TRY(cudaMalloc(&t->d_post_off, (nterms + 1) * sizeof(uint64_t)))
+  TRY(cudaMalloc(&t->d_post_rows, (nposts + 1) * sizeof(uint32_t)))
+  TRY(cudaMalloc(&t->d_keys, t->key_cap))
+  TRY(cudaMallocHost(&t->h_keys, t->key_cap))
+  TRY(cudaMalloc(&t->d_bounds, 8 * sizeof(uint64_t)))
+  if (pool_bytes) TRY(cudaMemcpy(t->d_pool, pool, pool_bytes, cudaMemcpyHostToDevice))
+  TRY(cudaMemcpy(t->d_term_off, term_off, (nterms + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice))
+  TRY(cudaMemcpy(t->d_post_off, post_off, (nterms + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice))
+  if (nposts) TRY(cudaMemcpy(t->d_post_rows, post_rows, nposts * sizeof(uint32_t), cudaMemcpyHostToDevice))
+#undef TRY
+  if (e != cudaSuccess) {
+    tss_terms_destroy(t);
+    return cuda_fail(e, "terms upload");
+  }
+  *out = t;
+  return TSS_OK;
+}
+
+uint64_t tss_terms_size(const tss_terms* t) { return t ? t->nterms : 0; }
+
+void tss_terms_destroy(tss_terms* t) {
+  if (!t) return;
+  DeviceGuard g(t->device);
+  if (t->stream) cudaStreamSynchronize(t->stream);
+  cudaFree(t->d_pool);
+  cudaFree(t->d_term_off);
+  cudaFree(t->d_post_off);
+  cudaFree(t->d_post_rows);
+  cudaFree(t->d_keys);
+  cudaFree(t->d_bounds);
+  if (t->h_keys) cudaFreeHost(t->h_keys);
+  if (t->stream) cudaStreamDestroy(t->stream);
+  delete t;
+}
+
+int tss_prefix_mask(tss_terms* t, const char* prefix, uint32_t len, int kind, tss_mask* out,
+                    uint64_t row_base, tss_prefix_stats* stats) {
+  if (!t || !out) return fail(TSS_ERR_INVALID_ARG, "NULL argument");
+  if (len && !prefix) return fail(TSS_ERR_INVALID_ARG, "prefix is NULL");
+  if (kind != TSS_PREFIX_TOKEN && kind != TSS_PREFIX_CHAR)
+    return fail(TSS_ERR_INVALID_ARG, "kind %d is not a TSS_PREFIX_* value", kind);
+  if (t->device != out->device) return fail(TSS_ERR_INVALID_ARG, "terms and mask on different devices");
+  if (4 * (len + 1) > t->key_cap) return fail(TSS_ERR_INVALID_ARG, "prefix longer than %u bytes", t->key_cap / 4 - 1);
+  DeviceGuard g(t->device);
+  // probes: bounds[0..1) = exact range, bounds[2..3) = subtree range
+  tss::PrefixKeys keys{};
+  std::string kb;
+  auto push = [&](int i, const std::string& s) {
+    keys.off[i] = (uint32_t)kb.size();
+    kb += s;
+    keys.off[i + 1] = (uint32_t)kb.size();
+    keys.fixed[i] = -1;
+  };
+  auto fixed = [&](int i, int32_t v) {
+    keys.off[i] = (uint32_t)kb.size();
+    keys.off[i + 1] = (uint32_t)kb.size();
+    keys.fixed[i] = v;
+  };
+  const std::string p(prefix ? prefix : "", len);
+  if (kind == TSS_PREFIX_TOKEN) {
+    if (len == 0) {  // zero tokens: node = root (never terminal), subtree = everything
+      fixed(0, 0);
+      fixed(1, 0);
+      fixed(2, 0);
+      fixed(3, -2);
+    } else {
+      push(0, p);                      // first term >= P
+      push(1, p + std::string(1, '\0'));  // first term > P
+      push(2, p + " ");                // first term with a further token
+      push(3, p + "!");                // ' ' + 1
+    }
+  } else {
+    fixed(0, 0);
+    fixed(1, 0);
+    if (len == 0) {
+      fixed(2, 0);
+      fixed(3, -2);
+    } else {
+      push(2, p);
+      std::string succ = p;  // smallest string greater than every string prefixed by P
+      while (!succ.empty() && (unsigned char)succ.back() == 0xFF) succ.pop_back();
+      if (succ.empty()) {
+        fixed(3, -2);
+      } else {
+        succ.back() = (char)((unsigned char)succ.back() + 1);
+        push(3, succ);
+      }
+    }
+  }
+  CU(cudaStreamSynchronize(t->stream));  // h_keys is reused
+  memcpy(t->h_keys, kb.data(), kb.size());
+  if (!kb.empty())
+    CU(cudaMemcpyAsync(t->d_keys, t->h_keys, kb.size(), cudaMemcpyHostToDevice, t->stream));
+  tss::TermsDev td{t->d_pool, t->d_term_off, t->d_post_off, t->d_post_rows, t->nterms};
+  cudaError_t e = tss::launch_prefix_search(td, t->d_keys, keys, t->d_bounds, t->stream);
+  if (e != cudaSuccess) return cuda_fail(e, "prefix_search launch");
+  e = tss::launch_prefix_scatter(td, t->d_bounds, out->d_words, out->nbits, row_base,
+                                 reinterpret_cast<unsigned long long*>(t->d_bounds + 4), 148 * 4,
+                                 t->stream);
+  if (e != cudaSuccess) return cuda_fail(e, "prefix_scatter launch");
+  g_launches.fetch_add(2, std::memory_order_relaxed);
+  // the mask is consumed on other streams: make it visible before returning
+  uint64_t h[5];
+  CU(cudaMemcpyAsync(h, t->d_bounds, sizeof(h), cudaMemcpyDeviceToHost, t->stream));
+  CU(cudaStreamSynchronize(t->stream));
+  if (stats) {
+    stats->exact_lo = h[0];
+    stats->exact_hi = h[1] > h[0] ? h[1] : h[0];
+    stats->sub_lo = h[2];
+    stats->sub_hi = h[3] > h[2] ? h[3] : h[2];
+    stats->npostings = h[4];
+  }
+  return TSS_OK;
+}
+
+// ---- plumbing --------------------------------------------------------------------------------
+void* tss_index_stream(tss_index* ix) { return ix ? (void*)ix->stream : nullptr; }
+
+int tss_index_sync(tss_index* ix) {
+  if (!ix) return fail(TSS_ERR_INVALID_ARG, "index is NULL");
+  DeviceGuard g(ix->device);
+  CU(cudaStreamSynchronize(ix->stream));
+  return TSS_OK;
+}
+
+int tss_dev_alloc(int device, uint64_t bytes, void** out) {
+  if (!out) return fail(TSS_ERR_INVALID_ARG, "out is NULL");
+  DeviceGuard g(device);
+  if (!g.ok) return fail(TSS_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+  CU(cudaMalloc(out, bytes ? bytes : 1));
+  return TSS_OK;
+}
+int tss_dev_free(int device, void* p) {
+  DeviceGuard g(device);
+  CU(cudaFree(p));
+  return TSS_OK;
+}
+int tss_dev_h2d(int device, void* dst, const void* src, uint64_t bytes) {
+  DeviceGuard g(device);
+  CU(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+  return TSS_OK;
+}
+int tss_dev_d2h(int device, void* dst, const void* src, uint64_t bytes) {
+  DeviceGuard g(device);
+  CU(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+  return TSS_OK;
+}
+int tss_event_create(int device, void** out) {
+  if (!out) return fail(TSS_ERR_INVALID_ARG, "out is NULL");
+  DeviceGuard g(device);
+  cudaEvent_t ev;
+  CU(cudaEventCreate(&ev));
+  *out = ev;
+  return TSS_OK;
+}
+int tss_event_record(tss_index* ix, void* ev) {
+  if (!ix || !ev) return fail(TSS_ERR_INVALID_ARG, "NULL argument");
+  DeviceGuard g(ix->device);
+  CU(cudaEventRecord((cudaEvent_t)ev, ix->stream));
+  return TSS_OK;
+}
+int tss_event_elapsed_ms(void* a, void* b, float* out_ms) {
+  if (!a || !b || !out_ms) return fail(TSS_ERR_INVALID_ARG, "NULL argument");
+  CU(cudaEventSynchronize((cudaEvent_t)b));
+  CU(cudaEventElapsedTime(out_ms, (cudaEvent_t)a, (cudaEvent_t)b));
+  return TSS_OK;
+}
+int tss_event_destroy(void* ev) {
+  if (ev) CU(cudaEventDestroy((cudaEvent_t)ev));
+  return TSS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,270 @@
+// aux_kernels.cu -- the small kernels around the scan: synthetic fill, finite
+// check, row packing, mask ops, K4 prefix search + scatter, K5 gathered merge.
+#include "aux_kernels.cuh"
+#include "common.cuh"
+
+namespace tss {
+
+// ---- synthetic corpus (bit-identical to oracle/oracle.cpp:gen_row) ------------------
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__device__ __forceinline__ float synth_from_u32(uint32_t h) {
+  int v = (int)(h & 0xFFFFu) + (int)(h >> 16) - 65535;
+  return (float)v * (1.0f / 65536.0f);
+}
+__device__ __forceinline__ uint16_t f32_to_bf16_rne(float x) {
+  uint32_t u = __float_as_uint(x);
+  if ((u & 0x7F800000u) != 0x7F800000u) u += 0x7FFFu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+
+__global__ void synth_fill_kernel(void* dst, uint64_t row_begin, uint64_t nrows, uint32_t dim,
+                                  uint32_t stride_elems, int bf16, uint64_t seed) {
+  const uint32_t pairs = stride_elems >> 1;
+  const uint64_t total = nrows * pairs;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t r = i / pairs;
+    uint32_t pr = (uint32_t)(i - r * pairs);
+    uint32_t j = pr * 2;
+    float a = 0.f, b = 0.f;
+    if (j < dim) {
+      uint64_t h = mix64((((row_begin + r) << 16) | (uint64_t)pr) + seed * 0x9E3779B97F4A7C15ull);
+      a = synth_from_u32((uint32_t)h);
+      if (j + 1 < dim) b = synth_from_u32((uint32_t)(h >> 32));
+    }
+    if (bf16) {
+      uint32_t packed = (uint32_t)f32_to_bf16_rne(a) | ((uint32_t)f32_to_bf16_rne(b) << 16);
+      reinterpret_cast<uint32_t*>(dst)[r * pairs + pr] = packed;
+    } else {
+      reinterpret_cast<float2*>(dst)[r * pairs + pr] = make_float2(a, b);
+    }
+  }
+}
+
+cudaError_t launch_synth_fill(void* dst, uint64_t row_begin, uint64_t nrows, uint32_t dim,
+                              uint32_t stride_elems, bool bf16, uint64_t seed, cudaStream_t st) {
+  if (!nrows) return cudaSuccess;
+  synth_fill_kernel<<<148 * 8, 256, 0, st>>>(dst, row_begin, nrows, dim, stride_elems, bf16 ? 1 : 0,
+                                             seed);
+  return cudaGetLastError();
+}
+
+__global__ void check_finite_kernel(const float* src, uint64_t count, int* flag) {
+  int bad = 0;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < count;
+       i += (uint64_t)gridDim.x * blockDim.x)
+    bad |= !isfinite(src[i]);
+  if (__any_sync(FULL_MASK, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+}
+cudaError_t launch_check_finite(const float* src, uint64_t count, int* flag, cudaStream_t st) {
+  if (!count) return cudaSuccess;
+  check_finite_kernel<<<148 * 4, 256, 0, st>>>(src, count, flag);
+  return cudaGetLastError();
+}
+
+__global__ void pack_rows_kernel(const float* src, void* dst, uint64_t nrows, uint32_t dim,
+                                 uint32_t stride_elems, int bf16) {
+  const uint64_t total = nrows * stride_elems;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t r = i / stride_elems;
+    uint32_t j = (uint32_t)(i - r * stride_elems);
+    float v = j < dim ? src[r * dim + j] : 0.f;
+    if (bf16)
+      reinterpret_cast<uint16_t*>(dst)[i] = f32_to_bf16_rne(v);
+    else
+      reinterpret_cast<float*>(dst)[i] = v;
+  }
+}
+cudaError_t launch_pack_rows(const float* src, void* dst, uint64_t nrows, uint32_t dim,
+                             uint32_t stride_elems, bool bf16, cudaStream_t st) {
+  if (!nrows) return cudaSuccess;
+  pack_rows_kernel<<<148 * 8, 256, 0, st>>>(src, dst, nrows, dim, stride_elems, bf16 ? 1 : 0);
+  return cudaGetLastError();
+}
+
+__global__ void unpack_rows_kernel(const void* src, float* dst, uint64_t nrows, uint32_t dim,
+                                   uint32_t stride_elems, int bf16) {
+  const uint64_t total = nrows * dim;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t r = i / dim;
+    uint32_t j = (uint32_t)(i - r * dim);
+    uint64_t si = r * stride_elems + j;
+    dst[i] = bf16 ? __uint_as_float((uint32_t)reinterpret_cast<const uint16_t*>(src)[si] << 16)
+                  : reinterpret_cast<const float*>(src)[si];
+  }
+}
+cudaError_t launch_unpack_rows(const void* src, float* dst, uint64_t nrows, uint32_t dim,
+                               uint32_t stride_elems, bool bf16, cudaStream_t st) {
+  if (!nrows) return cudaSuccess;
+  unpack_rows_kernel<<<148 * 8, 256, 0, st>>>(src, dst, nrows, dim, stride_elems, bf16 ? 1 : 0);
+  return cudaGetLastError();
+}
+
+// ---- masks -----------------------------------------------------------------------------
+__global__ void mask_set_rows_kernel(uint32_t* words, uint64_t nbits, const uint32_t* rows,
+                                     uint64_t n, uint64_t row_base) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t r = (uint64_t)rows[i] - row_base;  // wraps to huge if below the shard
+    if (r < nbits) atomicOr(words + (r >> 5), 1u << (uint32_t)(r & 31));
+  }
+}
+cudaError_t launch_mask_set_rows(uint32_t* words, uint64_t nbits, const uint32_t* rows, uint64_t n,
+                                 uint64_t row_base, cudaStream_t st) {
+  if (!n) return cudaSuccess;
+  int grid = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
+  mask_set_rows_kernel<<<grid, 256, 0, st>>>(words, nbits, rows, n, row_base);
+  return cudaGetLastError();
+}
+
+__global__ void mask_popcount_kernel(const uint32_t* words, uint64_t nwords,
+                                     unsigned long long* out) {
+  unsigned long long c = 0;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < nwords;
+       i += (uint64_t)gridDim.x * blockDim.x)
+    c += __popc(words[i]);
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) c += __shfl_xor_sync(FULL_MASK, c, m);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+cudaError_t launch_mask_popcount(const uint32_t* words, uint64_t nwords, unsigned long long* out,
+                                 cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(out, 0, sizeof(unsigned long long), st);
+  if (e != cudaSuccess || !nwords) return e;
+  mask_popcount_kernel<<<148 * 2, 256, 0, st>>>(words, nwords, out);
+  return cudaGetLastError();
+}
+
+// ---- K4: prefix search ------------------------------------------------------------------
+// term i (bytes pool[term_off[i], term_off[i+1])) < key ?  (unsigned byte order;
+// a proper prefix sorts first)
+__device__ __forceinline__ bool term_less(const TermsDev& t, uint64_t i, const char* key,
+                                          uint32_t klen) {
+  uint64_t b = t.term_off[i], e = t.term_off[i + 1];
+  uint32_t tlen = (uint32_t)(e - b);
+  uint32_t n = tlen < klen ? tlen : klen;
+  const unsigned char* tp = reinterpret_cast<const unsigned char*>(t.pool) + b;
+  const unsigned char* kp = reinterpret_cast<const unsigned char*>(key);
+  for (uint32_t j = 0; j < n; ++j) {
+    unsigned char a = tp[j], c = kp[j];
+    if (a != c) return a < c;
+  }
+  return tlen < klen;
+}
+
+// warp-cooperative 32-ary lower bound: first i in [0,T) with term[i] >= key.
+// Invariant: every term < lo is < key, every term >= hi is >= key.
+__device__ uint64_t warp_lower_bound(const TermsDev& t, const char* key, uint32_t klen, int lane) {
+  uint64_t lo = 0, hi = t.nterms;
+  while (hi - lo > 32) {
+    uint64_t step = (hi - lo + 31) / 32;
+    uint64_t pv = lo + (uint64_t)lane * step;
+    bool less = pv < hi && term_less(t, pv, key, klen);
+    unsigned m = __ballot_sync(FULL_MASK, less);
+    int c = __popc(m);  // sorted terms -> the predicate is monotone over lanes
+    if (c == 0) return lo;
+    uint64_t nlo = lo + (uint64_t)(c - 1) * step + 1;
+    uint64_t nhi = lo + (uint64_t)c * step;
+    if (nhi > hi) nhi = hi;
+    lo = nlo;
+    hi = nhi;
+  }
+  uint64_t pv = lo + lane;
+  bool less = pv < hi && term_less(t, pv, key, klen);
+  return lo + __popc(__ballot_sync(FULL_MASK, less));
+}
+
+__global__ void prefix_search_kernel(TermsDev t, const char* keybytes, PrefixKeys keys,
+                                     uint64_t* bounds) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;  // 4 warps, one bound each
+  uint64_t r;
+  if (keys.fixed[warp] >= 0)
+    r = (uint64_t)keys.fixed[warp];
+  else if (keys.fixed[warp] == -2)
+    r = t.nterms;
+  else
+    r = warp_lower_bound(t, keybytes + keys.off[warp], keys.off[warp + 1] - keys.off[warp], lane);
+  if (lane == 0) bounds[warp] = r;
+}
+cudaError_t launch_prefix_search(const TermsDev& t, const char* d_keybytes, PrefixKeys keys,
+                                 uint64_t* d_bounds, cudaStream_t st) {
+  prefix_search_kernel<<<1, 128, 0, st>>>(t, d_keybytes, keys, d_bounds);
+  return cudaGetLastError();
+}
+
+__global__ void prefix_scatter_kernel(TermsDev t, const uint64_t* bounds, uint32_t* words,
+                                      uint64_t nbits, uint64_t row_base,
+                                      unsigned long long* npost) {
+  const uint64_t tid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  const uint64_t nth = (uint64_t)gridDim.x * blockDim.x;
+  uint64_t visited = 0;
+#pragma unroll
+  for (int rng = 0; rng < 2; ++rng) {
+    uint64_t tlo = bounds[2 * rng], thi = bounds[2 * rng + 1];
+    if (thi <= tlo) continue;
+    uint64_t pb = t.post_off[tlo], pe = t.post_off[thi];
+    for (uint64_t i = pb + tid; i < pe; i += nth) {
+      uint64_t r = (uint64_t)t.post_rows[i] - row_base;
+      if (r < nbits) atomicOr(words + (r >> 5), 1u << (uint32_t)(r & 31));
+    }
+    if (tid == 0) visited += pe - pb;
+  }
+  if (tid == 0 && npost) *npost = visited;
+}
+cudaError_t launch_prefix_scatter(const TermsDev& t, const uint64_t* d_bounds, uint32_t* words,
+                                  uint64_t nbits, uint64_t row_base, unsigned long long* d_npost,
+                                  int grid, cudaStream_t st) {
+  prefix_scatter_kernel<<<grid, 256, 0, st>>>(t, d_bounds, words, nbits, row_base, d_npost);
+  return cudaGetLastError();
+}
+
+// ---- K5: merge of all-gathered per-rank top-k lists ---------------------------------------
+// one CTA per query: bitonic sort of P*k keys (padded to a power of two) in smem.
+__global__ void merge_gathered_kernel(const uint64_t* in, uint64_t* out, uint32_t P, uint32_t nq,
+                                      uint32_t k, uint32_t npad) {
+  extern __shared__ uint64_t sk[];
+  const uint32_t qi = blockIdx.x;
+  const uint32_t n = P * k;
+  for (uint32_t i = threadIdx.x; i < npad; i += blockDim.x) {
+    uint64_t v = 0;
+    if (i < n) {
+      uint32_t r = i / k, e = i - r * k;
+      v = in[((size_t)r * nq + qi) * k + e];
+    }
+    sk[i] = v;
+  }
+  __syncthreads();
+  for (uint32_t size = 2; size <= npad; size <<= 1) {
+    for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+      for (uint32_t i = threadIdx.x; i < (npad >> 1); i += blockDim.x) {
+        uint32_t lo = ((i & ~(stride - 1)) << 1) | (i & (stride - 1));
+        uint32_t hi = lo | stride;
+        bool desc = (lo & size) == 0;
+        uint64_t a = sk[lo], b = sk[hi];
+        if ((a < b) == desc) {
+          sk[lo] = b;
+          sk[hi] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (uint32_t e = threadIdx.x; e < k; e += blockDim.x) out[(size_t)qi * k + e] = sk[e];
+}
+cudaError_t launch_merge_gathered(const uint64_t* in, uint64_t* out, uint32_t P, uint32_t nq,
+                                  uint32_t k, cudaStream_t st) {
+  if (!nq) return cudaSuccess;
+  uint32_t n = P * k, npad = 2;
+  while (npad < n) npad <<= 1;
+  if ((size_t)npad * 8 > 48 * 1024) return cudaErrorInvalidConfiguration;
+  merge_gathered_kernel<<<nq, 256, (size_t)npad * 8, st>>>(in, out, P, nq, k, npad);
+  return cudaGetLastError();
+}
+
+}  // namespace tss

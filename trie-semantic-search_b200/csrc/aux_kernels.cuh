@@ -1,0 +1,50 @@
+// aux_kernels.cuh -- host-callable wrappers of the small kernels around the scan.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tss {
+
+// rows [row_begin,row_begin+nrows) of the seeded synthetic corpus written into
+// padded storage (stride_elems elements per row, fp32 or bf16).
+cudaError_t launch_synth_fill(void* dst, uint64_t row_begin, uint64_t nrows, uint32_t dim,
+                              uint32_t stride_elems, bool bf16, uint64_t seed, cudaStream_t st);
+// *flag |= 1 if any of count floats is NaN/Inf
+cudaError_t launch_check_finite(const float* src, uint64_t count, int* flag, cudaStream_t st);
+// unpadded fp32 [nrows][dim] -> padded storage rows (fp32 or bf16 RNE)
+cudaError_t launch_pack_rows(const float* src, void* dst, uint64_t nrows, uint32_t dim,
+                             uint32_t stride_elems, bool bf16, cudaStream_t st);
+// padded storage -> unpadded fp32
+cudaError_t launch_unpack_rows(const void* src, float* dst, uint64_t nrows, uint32_t dim,
+                               uint32_t stride_elems, bool bf16, cudaStream_t st);
+
+// masks
+cudaError_t launch_mask_set_rows(uint32_t* words, uint64_t nbits, const uint32_t* rows, uint64_t n,
+                                 uint64_t row_base, cudaStream_t st);
+cudaError_t launch_mask_popcount(const uint32_t* words, uint64_t nwords, unsigned long long* out,
+                                 cudaStream_t st);
+
+// K4: prefix search over the flattened term array + posting scatter
+struct TermsDev {
+  const char* pool;
+  const uint64_t* term_off;  // T+1
+  const uint64_t* post_off;  // T+1
+  const uint32_t* post_rows;
+  uint64_t nterms;
+};
+struct PrefixKeys {  // up to 4 lower-bound probes, keys concatenated in `bytes`
+  uint32_t off[5];
+  int32_t fixed[4];  // >= 0: bound is this constant (no search); -1: search; -2: nterms
+};
+// bounds[4] <- lower bounds; then ranges [b0,b1) and [b2,b3) are scattered.
+cudaError_t launch_prefix_search(const TermsDev& t, const char* d_keybytes, PrefixKeys keys,
+                                 uint64_t* d_bounds, cudaStream_t st);
+cudaError_t launch_prefix_scatter(const TermsDev& t, const uint64_t* d_bounds, uint32_t* words,
+                                  uint64_t nbits, uint64_t row_base, unsigned long long* d_npost,
+                                  int grid, cudaStream_t st);
+
+// K5: merge P gathered lists of k keys per query: in [P][nq][k] -> out [nq][k]
+cudaError_t launch_merge_gathered(const uint64_t* in, uint64_t* out, uint32_t P, uint32_t nq,
+                                  uint32_t k, cudaStream_t st);
+
+}  // namespace tss

@@ -1,0 +1,375 @@
+// scan.cuh -- K1: HBM-bound exact cosine scan with fused norms and fused top-k.
+//
+// Replaces the body of HnswIndex::search (reference src/vector.rs:195-202,
+// a stub) for single / small query batches.
+//
+// One persistent CTA per SM.  Every warp owns a private shared-memory tile
+// (R rows, contiguous in HBM because the matrix is row-major) and feeds it
+// with its own 1-D TMA bulk copy (cp.async.bulk -> UBLKCP) signalled on its own
+// mbarrier: no producer warp, no CTA-wide barrier in the steady state.  While
+// a warp's tile is in flight the SM's other warps compute, so up to
+// WARPS x TILE_BYTES (192 KB) per SM are outstanding against HBM.
+//
+// Arithmetic is DESIGN.md section 3's canonical order (lane l owns elements 4l..4l+3
+// of every 128-element stripe, 4 sub-accumulators, xor butterfly), so scores
+// are bit-identical to oracle/oracle.cpp:canon_dot_norm.
+//
+// Top-k: each warp keeps an unsorted candidate list in shared memory guarded
+// by a running threshold (its current k-th best key); the list is pruned with
+// a warp bitonic sort when full.  Lists are merged per CTA, written as
+// per-CTA partials, and the last CTA to finish (atomic ticket) merges the
+// partials into the final k keys -- one launch per query batch.
+#pragma once
+
+#include "common.cuh"
+
+namespace tss {
+
+struct ScanParams {
+  const void* rows;        // device matrix, rows padded to NS*128 elements
+  uint64_t n_rows;         // rows in this shard
+  uint32_t row_base;       // global id of local row 0
+  uint32_t dim;            // logical dimension (<= NS*128)
+  const float* queries;    // nq_valid x dim, device
+  uint32_t nq_valid;       // <= BQ
+  uint32_t k, kp, cap;     // k, pow2 >= k (>= 8), per-warp list capacity (pow2, >= 2*max(kp,32))
+  const uint32_t* mask;    // bit (r&31) of word r>>5 <-> local row r; may be null
+  int mask_mode;           // TSS_MASK_*
+  uint64_t* partials;      // [BQ][gridDim.x][kp]
+  unsigned int* done_counter;
+  uint64_t* out_keys;      // [nq_valid][k]
+  uint32_t smem_bytes;     // dynamic shared memory size of this launch
+};
+
+// ---- warp-level candidate list ----------------------------------------------------
+__device__ __forceinline__ void warp_bitonic_sort_desc(uint64_t* list, uint32_t cap, int lane) {
+  for (uint32_t size = 2; size <= cap; size <<= 1) {
+    for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+      for (uint32_t i = lane; i < (cap >> 1); i += 32) {
+        uint32_t lo = ((i & ~(stride - 1)) << 1) | (i & (stride - 1));
+        uint32_t hi = lo | stride;
+        bool desc = (lo & size) == 0;
+        uint64_t a = list[lo], b = list[hi];
+        if ((a < b) == desc) {
+          list[lo] = b;
+          list[hi] = a;
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// sort the list, keep the best k, refresh the threshold
+__device__ __forceinline__ void warp_prune(uint64_t* list, uint32_t& n, uint32_t k, uint32_t cap,
+                                           uint64_t& thresh, int lane) {
+  for (uint32_t i = n + lane; i < cap; i += 32) list[i] = 0;
+  __syncwarp();
+  warp_bitonic_sort_desc(list, cap, lane);
+  if (n >= k) {
+    n = k;
+    thresh = list[k - 1];
+  }
+}
+
+__device__ __forceinline__ void warp_offer(uint64_t key, bool valid, uint64_t* list, uint32_t& n,
+                                           uint32_t k, uint32_t cap, uint64_t& thresh, int lane) {
+  bool c = valid && key > thresh;
+  unsigned m = __ballot_sync(FULL_MASK, c);
+  if (m == 0) return;  // warp-uniform
+  if (n + __popc(m) > cap) {
+    warp_prune(list, n, k, cap, thresh, lane);
+    c = valid && key > thresh;
+    m = __ballot_sync(FULL_MASK, c);
+  }
+  if (c) list[n + __popc(m & ((1u << lane) - 1u))] = key;
+  n += __popc(m);
+  __syncwarp();
+}
+
+// ---- block-level merge of L descending-sorted lists of kp keys -------------------
+// list i lives at base + i*stride; the merged top-kp ends up in list 0.
+__device__ __forceinline__ void block_merge_lists(uint64_t* base, uint32_t stride, uint32_t L,
+                                                  uint32_t kp, int tid, int nthreads) {
+  for (uint32_t step = 1; step < L; step <<= 1) {
+    // pairs (a = i*2*step, b = a + step) with b < L
+    uint32_t npairs = (L - step + 2 * step - 1) / (2 * step);
+    for (uint32_t idx = tid; idx < npairs * kp; idx += nthreads) {
+      uint32_t pi = idx / kp, e = idx - pi * kp;
+      uint64_t* A = base + (size_t)(pi * 2 * step) * stride;
+      uint64_t* B = A + (size_t)step * stride;
+      uint64_t a = A[e], b = B[kp - 1 - e];
+      A[e] = a > b ? a : b;  // bitonic sequence holding the top kp of A u B
+    }
+    __syncthreads();
+    for (uint32_t s = kp >> 1; s > 0; s >>= 1) {
+      uint32_t half = kp >> 1;
+      for (uint32_t idx = tid; idx < npairs * half; idx += nthreads) {
+        uint32_t pi = idx / half, i = idx - pi * half;
+        uint64_t* A = base + (size_t)(pi * 2 * step) * stride;
+        uint32_t lo = ((i & ~(s - 1)) << 1) | (i & (s - 1));
+        uint32_t hi = lo | s;
+        uint64_t a = A[lo], b = A[hi];
+        if (a < b) {
+          A[lo] = b;
+          A[hi] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// ---- tile geometry -------------------------------------------------------------------
+template <int NS, bool BF16>
+struct TileGeom {
+  static constexpr int ROW_BYTES = NS * 128 * (BF16 ? 2 : 4);
+  // rows per tile: a power of two with TILE_BYTES <= 12 KB (16 warps x 12 KB = 192 KB)
+  static constexpr int R = (12288 / ROW_BYTES) >= 16  ? 16
+                           : (12288 / ROW_BYTES) >= 8 ? 8
+                           : (12288 / ROW_BYTES) >= 4 ? 4
+                           : (12288 / ROW_BYTES) >= 2 ? 2
+                                                      : 1;
+  static constexpr int TILE_BYTES = R * ROW_BYTES;
+};
+
+template <int NS, int BQ, int WARPS, bool BF16, bool MASKED>
+__global__ void __launch_bounds__(WARPS * 32, 1) scan_topk_kernel(const ScanParams p) {
+  using G = TileGeom<NS, BF16>;
+  constexpr int R = G::R;
+  constexpr int RG = (BQ >= 4 && R > 4) ? 4 : R;  // rows reduced together (register budget)
+  constexpr int NG = R / RG;
+  constexpr int ROW_BYTES = G::ROW_BYTES;
+  constexpr int TILE_BYTES = G::TILE_BYTES;
+  constexpr int LANES_PER_ROW = 32 / RG;  // lanes that end up holding one row's sums
+  constexpr uint32_t ALL_ROWS = (R == 32) ? 0xFFFFFFFFu : ((1u << R) - 1u);
+
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* tile = smem + (size_t)warp * TILE_BYTES;
+  uint64_t* cands_base = reinterpret_cast<uint64_t*>(smem + (size_t)WARPS * TILE_BYTES);
+  uint64_t* bars = cands_base + (size_t)WARPS * BQ * p.cap;
+  const uint32_t bar = smem_u32(&bars[warp]);
+  const uint32_t tile_s = smem_u32(tile);
+
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  __syncwarp();
+
+  // ---- queries -> registers; canonical self norm -----------------------------------
+  float4 q[BQ][NS];
+  float sq_nq[BQ];
+#pragma unroll
+  for (int b = 0; b < BQ; ++b) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      uint32_t j = 128u * s + 4u * lane;
+      const float* qb = p.queries + (size_t)b * p.dim;
+      bool live = (uint32_t)b < p.nq_valid;
+      float4 v;
+      v.x = (live && j + 0 < p.dim) ? __ldg(qb + j + 0) : 0.f;
+      v.y = (live && j + 1 < p.dim) ? __ldg(qb + j + 1) : 0.f;
+      v.z = (live && j + 2 < p.dim) ? __ldg(qb + j + 2) : 0.f;
+      v.w = (live && j + 3 < p.dim) ? __ldg(qb + j + 3) : 0.f;
+      q[b][s] = v;
+      a0 = __fmaf_rn(v.x, v.x, a0);
+      a1 = __fmaf_rn(v.y, v.y, a1);
+      a2 = __fmaf_rn(v.z, v.z, a2);
+      a3 = __fmaf_rn(v.w, v.w, a3);
+    }
+    float pl = __fadd_rn(__fadd_rn(a0, a1), __fadd_rn(a2, a3));
+    sq_nq[b] = __fsqrt_rn(butterfly_sum(pl));
+  }
+
+  // ---- per-warp candidate lists ------------------------------------------------------
+  uint64_t* lists = cands_base + (size_t)warp * BQ * p.cap;
+  uint32_t cnt[BQ];
+  uint64_t thresh[BQ];
+#pragma unroll
+  for (int b = 0; b < BQ; ++b) cnt[b] = 0, thresh[b] = 0;
+
+  const uint64_t total_tiles = (p.n_rows + R - 1) / R;
+  const uint64_t GW = (uint64_t)gridDim.x * WARPS;
+  const uint64_t policy = policy_evict_first();
+  const uint8_t* rows_b = reinterpret_cast<const uint8_t*>(p.rows);
+
+  // bits of the rows of tile t that must be scored
+  auto tile_bits = [&](uint64_t t) -> uint32_t {
+    uint64_t row0 = t * R;
+    uint64_t left = p.n_rows - row0;
+    uint32_t valid = left >= (uint64_t)R ? ALL_ROWS : ((1u << (uint32_t)left) - 1u);
+    if (MASKED) {
+      uint32_t w = __ldg(p.mask + (row0 >> 5));
+      uint32_t b = (w >> (uint32_t)(row0 & 31)) & ALL_ROWS;
+      if (p.mask_mode == 2) b = ~b;  // TSS_MASK_EXCLUDE
+      valid &= b;
+    }
+    return valid;
+  };
+  // first tile >= t0 of this warp's sequence (t0, t0+GW, ...) with any live row
+  auto next_live = [&](uint64_t t0, uint32_t& bits) -> uint64_t {
+    if constexpr (!MASKED) {
+      bits = t0 < total_tiles ? tile_bits(t0) : 0u;
+      return t0;
+    } else {
+    while (t0 < total_tiles) {
+      uint64_t tc = t0 + (uint64_t)lane * GW;
+      uint32_t b = tc < total_tiles ? tile_bits(tc) : 0u;
+      unsigned nz = __ballot_sync(FULL_MASK, b != 0u);
+      if (nz) {
+        int src = __ffs(nz) - 1;
+        bits = __shfl_sync(FULL_MASK, b, src);
+        return t0 + (uint64_t)src * GW;
+      }
+      t0 += 32 * GW;
+    }
+    bits = 0;
+    return t0;
+    }
+  };
+  auto issue = [&](uint64_t t, uint32_t bits) {
+    if (lane == 0) {
+      const uint8_t* src = rows_b + t * (uint64_t)TILE_BYTES;
+      uint32_t hi = 32 - __clz(bits);  // rows [0,hi) span every live row
+      if (!MASKED || bits == ((hi >= 32) ? 0xFFFFFFFFu : ((1u << hi) - 1u))) {
+        uint32_t bytes = hi * ROW_BYTES;
+        mbar_arrive_expect_tx(bar, bytes);
+        bulk_g2s(tile_s, src, bytes, bar, policy);
+      } else {  // sparse tile: fetch only the live rows
+        mbar_arrive_expect_tx(bar, __popc(bits) * ROW_BYTES);
+        for (uint32_t b = bits; b; b &= b - 1) {
+          uint32_t r = __ffs(b) - 1;
+          bulk_g2s(tile_s + r * ROW_BYTES, src + r * ROW_BYTES, ROW_BYTES, bar, policy);
+        }
+      }
+    }
+  };
+
+  uint32_t cur_bits = 0;
+  uint64_t t = next_live((uint64_t)blockIdx.x * WARPS + warp, cur_bits);
+  uint32_t phase = 0;
+  if (t < total_tiles) issue(t, cur_bits);
+
+  while (t < total_tiles) {
+    mbar_wait(bar, phase);
+    phase ^= 1;
+
+    float dots[BQ][NG], nrms[NG];
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+      float pd[BQ][RG], pn[RG];
+#pragma unroll
+      for (int r = 0; r < RG; ++r) {
+        const uint8_t* rp = tile + (g * RG + r) * ROW_BYTES;
+        float d[BQ][4];
+        float n0 = 0.f, n1 = 0.f, n2 = 0.f, n3 = 0.f;
+#pragma unroll
+        for (int b = 0; b < BQ; ++b) d[b][0] = d[b][1] = d[b][2] = d[b][3] = 0.f;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+          float4 e;
+          if (BF16) {
+            uint2 u = *reinterpret_cast<const uint2*>(rp + s * 256 + lane * 8);
+            e.x = __uint_as_float(u.x << 16);
+            e.y = __uint_as_float(u.x & 0xFFFF0000u);
+            e.z = __uint_as_float(u.y << 16);
+            e.w = __uint_as_float(u.y & 0xFFFF0000u);
+          } else {
+            e = *reinterpret_cast<const float4*>(rp + s * 512 + lane * 16);
+          }
+#pragma unroll
+          for (int b = 0; b < BQ; ++b) {
+            d[b][0] = __fmaf_rn(q[b][s].x, e.x, d[b][0]);
+            d[b][1] = __fmaf_rn(q[b][s].y, e.y, d[b][1]);
+            d[b][2] = __fmaf_rn(q[b][s].z, e.z, d[b][2]);
+            d[b][3] = __fmaf_rn(q[b][s].w, e.w, d[b][3]);
+          }
+          n0 = __fmaf_rn(e.x, e.x, n0);
+          n1 = __fmaf_rn(e.y, e.y, n1);
+          n2 = __fmaf_rn(e.z, e.z, n2);
+          n3 = __fmaf_rn(e.w, e.w, n3);
+        }
+#pragma unroll
+        for (int b = 0; b < BQ; ++b)
+          pd[b][r] = __fadd_rn(__fadd_rn(d[b][0], d[b][1]), __fadd_rn(d[b][2], d[b][3]));
+        pn[r] = __fadd_rn(__fadd_rn(n0, n1), __fadd_rn(n2, n3));
+      }
+#pragma unroll
+      for (int b = 0; b < BQ; ++b) dots[b][g] = reduce_rows<RG>(pd[b], lane);
+      nrms[g] = reduce_rows<RG>(pn, lane);
+    }
+    // every shared-memory read of this tile has been consumed by the shuffles
+    // above, so the buffer can be handed back to the TMA unit.
+    __syncwarp();
+    uint32_t nbits = 0;
+    const uint64_t tn = next_live(t + GW, nbits);
+    if (tn < total_tiles) issue(tn, nbits);
+
+    // ---- score + top-k for tile t (overlaps the copy just issued) -------------
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+      const uint32_t r_in_tile = g * RG + (lane / LANES_PER_ROW);
+      const uint64_t row_local = t * R + r_in_tile;
+      const bool owner = (lane % LANES_PER_ROW) == 0 && ((cur_bits >> r_in_tile) & 1u);
+      const uint32_t row_global = p.row_base + (uint32_t)row_local;
+#pragma unroll
+      for (int b = 0; b < BQ; ++b) {
+        if ((uint32_t)b < p.nq_valid) {
+          float s = finish_score(dots[b][g], sq_nq[b], nrms[g]);
+          warp_offer(pack_key(s, row_global), owner, lists + (size_t)b * p.cap, cnt[b], p.k, p.cap,
+                     thresh[b], lane);
+        }
+      }
+    }
+    t = tn;
+    cur_bits = nbits;
+  }
+
+  // ---- per-warp final prune: sorted, zero padded ---------------------------------
+#pragma unroll
+  for (int b = 0; b < BQ; ++b)
+    warp_prune(lists + (size_t)b * p.cap, cnt[b], p.k, p.cap, thresh[b], lane);
+  __syncthreads();
+
+  // ---- CTA merge: WARPS lists -> list of warp 0 --------------------------------------
+  const int tid = threadIdx.x, nthreads = WARPS * 32;
+  for (uint32_t b = 0; b < p.nq_valid; ++b)
+    block_merge_lists(cands_base + (size_t)b * p.cap, BQ * p.cap, WARPS, p.kp, tid, nthreads);
+  for (uint32_t idx = tid; idx < p.nq_valid * p.kp; idx += nthreads) {
+    uint32_t b = idx / p.kp, e = idx - b * p.kp;
+    uint64_t v = cands_base[(size_t)b * p.cap + e];
+    if (e >= p.k) v = 0;
+    p.partials[((size_t)b * gridDim.x + blockIdx.x) * p.kp + e] = v;
+  }
+
+  // ---- last CTA merges the per-CTA partials --------------------------------------------
+  __shared__ unsigned int s_ticket;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_ticket = atomicAdd(p.done_counter, 1u);
+  __syncthreads();
+  if (s_ticket != gridDim.x - 1) return;
+  __threadfence();
+
+  uint64_t* ws = reinterpret_cast<uint64_t*>(smem);
+  const uint32_t slots = p.smem_bytes / (p.kp * 8u);  // >= 2 by construction
+  for (uint32_t b = 0; b < p.nq_valid; ++b) {
+    for (uint32_t e = tid; e < p.kp; e += nthreads) ws[e] = 0;
+    const uint64_t* part = p.partials + (size_t)b * gridDim.x * p.kp;
+    for (uint32_t l0 = 0; l0 < gridDim.x; l0 += slots - 1) {
+      uint32_t c = min(slots - 1, gridDim.x - l0);
+      for (uint32_t idx = tid; idx < c * p.kp; idx += nthreads)
+        ws[p.kp + idx] = __ldcg(part + (size_t)l0 * p.kp + idx);
+      __syncthreads();
+      block_merge_lists(ws, p.kp, c + 1, p.kp, tid, nthreads);
+    }
+    for (uint32_t e = tid; e < p.k; e += nthreads) p.out_keys[(size_t)b * p.k + e] = ws[e];
+    __syncthreads();
+  }
+  if (tid == 0) *p.done_counter = 0;
+}
+
+}  // namespace tss

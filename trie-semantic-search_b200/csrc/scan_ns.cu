@@ -1,0 +1,58 @@
+// scan_ns.cu -- instantiates the K1 scan kernel for one stripe count.
+// Compiled once per supported NS with -DTSS_NS=<n> (see Makefile) so the
+// instances build in parallel.
+#include "scan.cuh"
+#include "scan_launch.h"
+
+#ifndef TSS_NS
+#error "compile with -DTSS_NS=<stripes>"
+#endif
+
+namespace tss {
+
+constexpr int kWarps = 16;
+constexpr int kMaxDevices = 64;
+
+template <int NS, int BQ, bool BF16, bool MASKED>
+static cudaError_t launch_one(const ScanParams& p, int grid, int device, cudaStream_t st) {
+  auto kern = scan_topk_kernel<NS, BQ, kWarps, BF16, MASKED>;
+  const size_t smem = (size_t)kWarps * TileGeom<NS, BF16>::TILE_BYTES +
+                      (size_t)kWarps * BQ * p.cap * 8 + (size_t)kWarps * 8;
+  if (smem > 232448) return cudaErrorInvalidConfiguration;
+  static bool attr_done[kMaxDevices] = {};
+  if (device < 0 || device >= kMaxDevices) return cudaErrorInvalidDevice;
+  if (!attr_done[device]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e != cudaSuccess) return e;
+    attr_done[device] = true;
+  }
+  ScanParams q = p;
+  q.smem_bytes = (uint32_t)smem;
+  kern<<<grid, kWarps * 32, smem, st>>>(q);
+  return cudaGetLastError();
+}
+
+template <int NS, int BQ>
+static cudaError_t launch_bq(const ScanParams& p, bool bf16, bool masked, int grid, int device,
+                             cudaStream_t st) {
+  if (bf16)
+    return masked ? launch_one<NS, BQ, true, true>(p, grid, device, st)
+                  : launch_one<NS, BQ, true, false>(p, grid, device, st);
+  return masked ? launch_one<NS, BQ, false, true>(p, grid, device, st)
+                : launch_one<NS, BQ, false, false>(p, grid, device, st);
+}
+
+#define TSS_CAT2(a, b) a##b
+#define TSS_CAT(a, b) TSS_CAT2(a, b)
+
+cudaError_t TSS_CAT(launch_scan_ns, TSS_NS)(const ScanParams& p, int bq, bool bf16, bool masked,
+                                            int grid, int device, cudaStream_t st) {
+  switch (bq) {
+    case 1: return launch_bq<TSS_NS, 1>(p, bf16, masked, grid, device, st);
+    case 2: return launch_bq<TSS_NS, 2>(p, bf16, masked, grid, device, st);
+    case 4: return launch_bq<TSS_NS, 4>(p, bf16, masked, grid, device, st);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace tss
