@@ -18,13 +18,15 @@ static cudaError_t launch_one(const ScanParams& p, int grid, int device, cudaStr
   auto kern = scan_topk_kernel<NS, BQ, kWarps, BF16, MASKED>;
   const size_t smem = (size_t)kWarps * TileGeom<NS, BF16>::TILE_BYTES +
                       (size_t)kWarps * BQ * p.cap * 8 + (size_t)kWarps * 8;
-  if (smem > 232448) return cudaErrorInvalidConfiguration;
-  static bool attr_done[kMaxDevices] = {};
+  // 227 KB per CTA minus the kernel's static shared memory (ticket word, padded)
+  if (smem > 232448 - 256) return cudaErrorInvalidConfiguration;
+  static size_t attr_bytes[kMaxDevices] = {};
   if (device < 0 || device >= kMaxDevices) return cudaErrorInvalidDevice;
-  if (!attr_done[device]) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+  if (attr_bytes[device] < smem) {
+    cudaError_t e =
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    attr_done[device] = true;
+    attr_bytes[device] = smem;
   }
   ScanParams q = p;
   q.smem_bytes = (uint32_t)smem;
