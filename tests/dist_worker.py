@@ -1,0 +1,67 @@
+"""Run under torchrun on >= 2 GPUs: sharded search (NCCL all-gather + merge) == oracle."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    import tss_loader
+    import orc
+    tss = tss_loader.load()
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt.copy_(torch.frombuffer(bytearray(tss.Comm.unique_id()), dtype=torch.uint8))
+    dist.broadcast(idt, 0)
+    comm = tss.Comm(idt.cpu().numpy().tobytes(), rank, world, local)
+
+    dim, seed = 384, 0x5EED
+    ok = True
+    for n, k, nq in [(200_003, 10, 5), (1000, 50, 2), (5, 10, 1), (300_000, 128, 3)]:
+        per = (n + world - 1) // world
+        b = min(rank * per, n)
+        cnt = min(per, n - b)
+        ix = tss.FlatIndex(dim, tss.TSS_F32, local)
+        ix.add_synthetic(b, cnt, seed)
+        ix.set_shard(b, comm)
+        ix.finalize()
+        q = orc.gen_rows(0, nq, dim, 0xBEEF)
+        got = ix.search(q, k)
+        # device-resident variant too
+        dq = tss.DeviceBuffer(local, q.nbytes).upload(q)
+        dk = tss.DeviceBuffer(local, nq * k * 8)
+        ix.search_device(dq, nq, k, dk)
+        ix.sync()
+        r2, s2 = tss.unpack_keys(dk.download(np.uint64, nq * k).reshape(nq, k))
+        rows = orc.gen_rows(0, n, dim, seed)
+        want = orc.cosine_topk(rows, q, k)
+        same = (np.array_equal(got[0], want[0]) and
+                np.array_equal(got[1].view(np.uint32), want[1].view(np.uint32)) and
+                np.array_equal(got[2], want[2]) and np.array_equal(r2, want[0]) and
+                np.array_equal(s2.view(np.uint32), want[1].view(np.uint32)))
+        if not same:
+            print(f"rank {rank}: MISMATCH n={n} k={k}", flush=True)
+        ok &= same
+        ix.close()
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    comm.close()
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank == 0:
+        print("DIST_OK" if int(flag.item()) == 1 else "DIST_FAILED", flush=True)
+    return 0 if int(flag.item()) == 1 else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())

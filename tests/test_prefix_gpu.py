@@ -1,0 +1,166 @@
+"""K4 parity: prefix-match kernel + posting scatter vs the literal trie restatement.
+
+Masks must match bit-exactly (north_star).  The flattened term array is what
+TrieNode trees export to: unique terms (tokens joined by ' '), byte-sorted, CSR postings.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ID = [bytes([i]) * 16 for i in range(8)]
+
+
+def _flatten(term_postings):
+    """dict term(bytes) -> [rows]  ->  (sorted terms, postings)"""
+    terms = sorted(term_postings)
+    return terms, [term_postings[t] for t in terms]
+
+
+def _bits(rows, n):
+    w = np.zeros((n + 31) // 32, dtype=np.uint32)
+    rows = np.asarray(sorted(set(int(r) for r in rows if 0 <= r < n)), dtype=np.int64)
+    if rows.size:
+        np.bitwise_or.at(w, rows >> 5, (np.uint32(1) << (rows & 31).astype(np.uint32)))
+    return w
+
+
+def test_k9_simple_demo_corpus(tss, orc):
+    # case-name trie of the three simple_demo.rs cases; row i <-> case i
+    names = ["brown v. board of education", "miranda v. arizona", "roe v. wade"]
+    terms, posts = _flatten({n.encode(): [i] for i, n in enumerate(names)})
+    t = tss.Terms(terms, posts)
+    assert t.size() == 3
+    m = tss.Mask(3)
+
+    def mask_of(prefix, kind=tss.TSS_PREFIX_TOKEN):
+        m.clear()
+        st = t.prefix_mask(prefix, m, kind)
+        return int(m.download()[0]), st
+
+    assert mask_of(b"brown")[0] == 0b001              # K9
+    assert mask_of(b"brown v.")[0] == 0b001           # K2's completion, as postings
+    assert mask_of(b"bro")[0] == 0                    # K3: token-level, not char-level
+    assert mask_of(b"bro", tss.TSS_PREFIX_CHAR)[0] == 0b001
+    assert mask_of(b"brown board")[0] == 0            # K4
+    bits, st = mask_of(b"roe v. wade")                # K1: exact node, no subtree
+    assert bits == 0b100 and st.exact_hi - st.exact_lo == 1 and st.sub_hi == st.sub_lo
+    bits, st = mask_of(b"")                           # K8/K9: root -> every posting
+    assert bits == 0b111 and (st.sub_lo, st.sub_hi) == (0, 3) and st.npostings == 3
+    assert mask_of(b"zzz")[0] == 0 and mask_of(b"a")[0] == 0
+    assert mask_of(b"m", tss.TSS_PREFIX_CHAR)[0] == 0b010
+
+
+def _random_terms(rng, nterms, vocab, n_rows):
+    tp = {}
+    zipf = rng.zipf(1.3, size=nterms * 4) % vocab
+    zi = 0
+    while len(tp) < nterms:
+        ntok = int(rng.integers(1, 5))
+        toks = [f"w{zipf[(zi + j) % zipf.size]:05d}" for j in range(ntok)]
+        zi += ntok
+        term = " ".join(toks).encode()
+        if term in tp:
+            continue
+        tp[term] = [int(r) for r in rng.integers(0, n_rows, size=int(rng.geometric(0.25)))]
+    return tp
+
+
+def test_token_prefix_masks_match_trie(tss, orc):
+    rng = np.random.default_rng(11)
+    n_rows = 40_000
+    tp = _random_terms(rng, 30_000, 600, n_rows)
+    terms, posts = _flatten(tp)
+    trie = orc.Trie()
+    for term, rows in tp.items():  # citation trie: case-preserving, whitespace tokenised
+        for r in rows:
+            trie.insert_citation(term.decode(), orc.docref(ID[0], r, -1))
+    t = tss.Terms(terms, posts)
+    m = tss.Mask(n_rows)
+    prefixes = [b"", b"w00001", b"w00001 w00002", b"w00000", b"w00003 w00001 w00000", b"w0000",
+                b"nope", b"w00001 ", terms[0], terms[-1], terms[len(terms) // 2],
+                terms[7].split(b" ")[0], b"w00002  w00001"]
+    prefixes += [b" ".join(terms[i].split(b" ")[:2]) for i in range(0, len(terms), 3001)]
+    for p in prefixes:
+        m.clear()
+        st = t.prefix_mask(p, m)
+        want_refs = trie.prefix_postings(orc.TRIE_CITATION, p.decode())
+        want = _bits([ref[1] for ref in want_refs], n_rows)
+        # the ABI takes the prefix already joined by single spaces (the shim normalises);
+        # un-normalised input is simply a different byte string
+        if p != b" ".join(p.split()):
+            continue
+        assert np.array_equal(m.download(), want), p
+        assert st.npostings == len(want_refs), p
+        assert m.popcount() == int(np.unpackbits(want.view(np.uint8)).sum())
+
+
+def test_char_prefix_masks_match_bruteforce(tss):
+    rng = np.random.default_rng(12)
+    n_rows = 10_000
+    tp = _random_terms(rng, 5_000, 300, n_rows)
+    tp[b"\xff\xff"] = [1]
+    tp[b"\xff\xffz"] = [2]
+    terms, posts = _flatten(tp)
+    t = tss.Terms(terms, posts)
+    m = tss.Mask(n_rows)
+    for p in [b"w", b"w0", b"w001", b"w00012 w", b"x", b"", b"\xff", b"\xff\xff", terms[10][:7]]:
+        m.clear()
+        t.prefix_mask(p, m, tss.TSS_PREFIX_CHAR)
+        want = _bits([r for term, rows in tp.items() if term.startswith(p) for r in rows], n_rows)
+        assert np.array_equal(m.download(), want), p
+
+
+def test_sharded_mask_and_accumulation(tss):
+    tp = {b"a b": [0, 5, 99], b"a c": [100, 150], b"d": [199, 3]}
+    terms, posts = _flatten(tp)
+    t = tss.Terms(terms, posts)
+    lo, hi = tss.Mask(100), tss.Mask(100)
+    t.prefix_mask(b"a", lo, row_base=0)
+    t.prefix_mask(b"a", hi, row_base=100)
+    assert np.array_equal(lo.download(), _bits([0, 5, 99], 100))
+    assert np.array_equal(hi.download(), _bits([0, 50], 100))
+    # masks accumulate until cleared (OR semantics)
+    t.prefix_mask(b"d", lo, row_base=0)
+    assert np.array_equal(lo.download(), _bits([0, 5, 99, 3], 100))
+
+
+def test_hybrid_prefix_filtered_topk(tss, orc):
+    """config-4 shape, reduced: prefix -> mask -> masked top-10 == oracle on the same mask."""
+    rng = np.random.default_rng(13)
+    n_rows, dim = 120_000, 384
+    tp = _random_terms(rng, 20_000, 400, n_rows)
+    terms, posts = _flatten(tp)
+    t = tss.Terms(terms, posts)
+    ix = tss.FlatIndex(dim)
+    ix.add_synthetic(0, n_rows, 0x5EED)
+    ix.finalize()
+    rows = orc.gen_rows(0, n_rows, dim, 0x5EED)
+    q = orc.gen_rows(0, 2, dim, 0xBEEF)
+    m = tss.Mask(n_rows)
+    for p in [b"w00001", b"w00000 w00001", b""]:
+        m.clear()
+        t.prefix_mask(p, m)
+        words = m.download()
+        got = ix.search(q, 10, m, tss.TSS_MASK_INCLUDE)
+        want = orc.cosine_topk(rows, q, 10, words, orc.MASK_INCLUDE)
+        for g, w in zip(got, want):
+            assert np.array_equal(g, w), p
+        got = ix.search(q, 10, m, tss.TSS_MASK_EXCLUDE)
+        want = orc.cosine_topk(rows, q, 10, words, orc.MASK_EXCLUDE)
+        for g, w in zip(got, want):
+            assert np.array_equal(g, w), p
+
+
+def test_terms_edge_cases(tss):
+    t = tss.Terms([], [])
+    m = tss.Mask(10)
+    st = t.prefix_mask(b"x", m)
+    assert m.popcount() == 0 and st.npostings == 0
+    one = tss.Terms([b"solo"], [[4, 4, 4]])  # duplicate postings are kept, the bit is set once
+    st = one.prefix_mask(b"solo", m)
+    assert m.popcount() == 1 and st.npostings == 3
+    with pytest.raises(tss.TssError):
+        tss.Terms([b"b", b"a"], [[], []])  # unsorted
+    with pytest.raises(tss.TssError):
+        tss.Terms([b"a", b"a"], [[], []])  # duplicate
