@@ -1,0 +1,323 @@
+// host_shim_test.cpp -- the C++ host shim (VectorIndex / TrieIndex / SearchEngine mirrors of
+// reference src/vector.rs, src/trie.rs, src/search.rs) against hand-derived KATs and the
+// CPU oracle.  `host_shim_test cpu` needs no GPU; `host_shim_test gpu` runs the device paths.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <random>
+#include <string>
+
+#include "../include/tss.h"
+#include "../oracle/oracle.h"
+#include "../trie-semantic-search_b200/host/tss_host.hpp"
+
+using namespace tss_host;
+
+static int g_fail = 0;
+#define CHECK(cond)                                                        \
+  do {                                                                     \
+    if (!(cond)) {                                                         \
+      printf("FAIL %s:%d: %s\n", __FILE__, __LINE__, #cond);               \
+      ++g_fail;                                                            \
+    }                                                                      \
+  } while (0)
+
+static CaseId cid(uint64_t v) { return CaseId::from_u64(v); }
+static orc_docref to_orc(const DocRef& d) {
+  orc_docref o;
+  memcpy(o.case_id, d.case_id.bytes.data(), 16);
+  o.paragraph_index = d.paragraph_index;
+  o.char_offset = d.char_offset ? (int64_t)*d.char_offset : -1;
+  return o;
+}
+static bool same_ref(const DocRef& d, const orc_docref& o) {
+  orc_docref mine = to_orc(d);
+  return memcmp(mine.case_id, o.case_id, 16) == 0 && mine.paragraph_index == o.paragraph_index &&
+         mine.char_offset == o.char_offset;
+}
+
+static void trie_kats() {
+  TrieIndex t;
+  const char* names[] = {"Brown v. Board of Education", "Miranda v. Arizona", "Roe v. Wade"};
+  const char* cits[] = {"347 U.S. 483 (1954)", "384 U.S. 436 (1966)", "410 U.S. 113 (1973)"};
+  for (int i = 0; i < 3; ++i) {
+    t.insert_case_name(names[i], cid(i + 1));
+    t.insert_citation(cits[i], DocRef{cid(i + 1), 0, std::nullopt});
+  }
+  auto r = t.search_one(TrieIndex::CaseName, "Brown v. Board of Education");  // K1
+  CHECK(r.exact_matches.size() == 1 && r.exact_matches[0] == (DocRef{cid(1), 0, std::nullopt}));
+  CHECK(r.prefix_completions.empty() && r.total_matches == 1);
+  r = t.search_one(TrieIndex::CaseName, "BROWN V.");  // K2
+  CHECK(r.exact_matches.empty() && r.prefix_completions.size() == 1 &&
+        r.prefix_completions[0] == "brown v. board of education" && r.total_matches == 1);
+  r = t.search_one(TrieIndex::CaseName, "bro");  // K3
+  CHECK(r.total_matches == 0 && r.exact_matches.empty() && r.prefix_completions.empty());
+  CHECK(t.search_one(TrieIndex::CaseName, "brown board").total_matches == 0);  // K4
+  r = t.search_one(TrieIndex::Citation, "347 U.S.");                           // K5
+  CHECK(r.prefix_completions.size() == 1 && r.prefix_completions[0] == "347 U.S. 483 (1954)");
+  CHECK(t.search_one(TrieIndex::Citation, "347 u.s.").total_matches == 0);
+  {
+    TrieIndex d;  // K6
+    d.insert_case_name("Same Name", cid(10));
+    d.insert_case_name("same name", cid(11));
+    auto e = d.search_one(TrieIndex::CaseName, "SAME NAME").exact_matches;
+    CHECK(e.size() == 2 && e[0].case_id == cid(10) && e[1].case_id == cid(11));
+    CHECK(d.trie(TrieIndex::CaseName).frequency({"same", "name"}) == 2);
+  }
+  r = t.search("brown v.");  // K7: cascade loses the case-name completion
+  CHECK(r.total_matches == 0);
+  CHECK(t.search("roe v. wade").exact_matches.size() == 1);
+  CHECK(t.search("384 U.S. 436 (1966)").exact_matches[0].case_id == cid(2));
+  r = t.search_one(TrieIndex::CaseName, "");  // K8
+  CHECK(r.exact_matches.empty() && r.prefix_completions.size() == 3);
+  {
+    TrieIndex many;
+    for (int i = 0; i < 25; ++i) many.insert_case_name("state v. person" + std::to_string(100 + i), cid(i));
+    auto m = many.search_one(TrieIndex::CaseName, "state v.");
+    CHECK(m.prefix_completions.size() == 10 && m.total_matches == 10);  // limit 10
+  }
+  {
+    TrieIndex c;  // content tokens are lower-cased, not re-split
+    c.insert_content({"Equal", "Protection", "Clause"}, DocRef{cid(1), 4, 17});
+    CHECK(c.search("equal PROTECTION").prefix_completions ==
+          std::vector<std::string>{"equal protection clause"});
+    CHECK(c.search("EQUAL protection clause").exact_matches[0] == (DocRef{cid(1), 4, 17}));
+  }
+  CHECK(t.get_completions("bro", 5).empty());  // TODO stub in the reference too
+  bool threw = false;
+  try {
+    TrieIndex::load_from_disk("x");
+  } catch (const SearchError& e) {
+    threw = e.kind == SearchError::NotSupported;
+  }
+  CHECK(threw);
+}
+
+static void trie_vs_oracle_random() {
+  std::mt19937 rng(42);
+  TrieIndex t;
+  orc_trie_index* o = orc_trie_new();
+  const char* vocab[] = {"state", "v.", "People", "united", "States", "doe", "Roe", "in", "re",
+                         "smith", "Jones", "co.", "inc.", "bank", "of", "america"};
+  std::vector<std::string> names;
+  for (int i = 0; i < 3000; ++i) {
+    int nt = 1 + rng() % 4;
+    std::string s;
+    for (int j = 0; j < nt; ++j) s += std::string(j ? "  " : " ") + vocab[rng() % 16];
+    names.push_back(s);
+    CaseId c = cid(i);
+    t.insert_case_name(s, c);
+    orc_trie_insert_case_name(o, s.c_str(), c.bytes.data());
+    DocRef ref{c, (size_t)(i % 7), i % 3 ? std::optional<size_t>(i) : std::nullopt};
+    orc_docref oref = to_orc(ref);
+    t.insert_citation(s, ref);
+    orc_trie_insert_citation(o, s.c_str(), &oref);
+  }
+  std::vector<std::string> queries = {"", "state", "STATE v.", "people", "People", "zzz", "state state"};
+  for (int i = 0; i < 200; ++i) queries.push_back(names[rng() % names.size()]);
+  for (int i = 0; i < 100; ++i) {
+    std::string s = names[rng() % names.size()];
+    queries.push_back(s.substr(0, s.find_last_of(' ') == std::string::npos ? s.size() : s.find_last_of(' ')));
+  }
+  for (const auto& q : queries) {
+    for (int w : {0, 2}) {
+      auto mine = t.search_one((TrieIndex::Which)w, q);
+      orc_trie_result* ref = orc_trie_search_one(o, w, q.c_str());
+      CHECK(mine.exact_matches.size() == ref->n_exact);
+      for (size_t i = 0; i < mine.exact_matches.size() && i < ref->n_exact; ++i)
+        CHECK(same_ref(mine.exact_matches[i], ref->exact_matches[i]));
+      CHECK(mine.prefix_completions.size() == ref->n_completions);
+      for (size_t i = 0; i < mine.prefix_completions.size() && i < ref->n_completions; ++i)
+        CHECK(mine.prefix_completions[i] == ref->completions[i]);
+      CHECK(mine.total_matches == ref->total_matches);
+      orc_trie_result_free(ref);
+    }
+    auto mine = t.search(q);
+    orc_trie_result* ref = orc_trie_search(o, q.c_str());
+    CHECK(mine.exact_matches.size() == ref->n_exact && mine.total_matches == ref->total_matches);
+    orc_trie_result_free(ref);
+  }
+  orc_trie_free(o);
+}
+
+static void no_gpu_is_loud() {
+  if (tss_device_count() > 0) return;
+  bool threw = false;
+  try {
+    VectorConfig vc;
+    vc.dimension = 384;
+    VectorIndex v(vc);
+  } catch (const SearchError& e) {
+    threw = e.kind == SearchError::VectorIndexFailed && std::string(e.category()) == "vector";
+  }
+  CHECK(threw);
+}
+
+// ---- GPU -------------------------------------------------------------------------------------
+static std::vector<float> synth(uint64_t row, uint32_t dim, uint64_t seed) {
+  std::vector<float> v(dim);
+  orc_gen_rows(v.data(), row, 1, dim, seed);
+  return v;
+}
+
+static void hnsw_vs_oracle() {
+  const uint32_t dim = 384, n = 5000, k = 50;
+  HnswIndex h(HnswConfig(), dim, 0, false);
+  std::vector<float> all((size_t)n * dim);
+  orc_gen_rows(all.data(), 0, n, dim, 7);
+  for (uint32_t i = 0; i < n; ++i)
+    h.add_vector(DocRef{cid(i / 3), i % 3, std::nullopt},
+                 std::vector<float>(all.begin() + (size_t)i * dim, all.begin() + (size_t)(i + 1) * dim));
+  CHECK(h.size() == n);
+  auto q = synth(1, dim, 9);
+  auto got = h.search(q, k);
+  std::vector<uint32_t> rows(k), counts(1);
+  std::vector<float> scores(k);
+  orc_cosine_topk(all.data(), n, dim, q.data(), 1, k, nullptr, ORC_MASK_NONE, 0, rows.data(),
+                  scores.data(), counts.data(), ORC_ORDER_CANONICAL, 0, 0);
+  CHECK(got.size() == counts[0]);
+  for (size_t i = 0; i < got.size(); ++i) {
+    CHECK(got[i].first.case_id == cid(rows[i] / 3) && got[i].first.paragraph_index == rows[i] % 3);
+    CHECK(got[i].second == 1.0f - scores[i]);  // distance, src/vector.rs:144
+  }
+  // incremental add after a search
+  h.add_vector(DocRef{cid(99999), 0, std::nullopt}, q);
+  auto again = h.search(q, 3);
+  CHECK(again[0].first.case_id == cid(99999) && std::fabs(again[0].second) < 1e-6f);
+  bool threw = false;
+  try {
+    h.add_vector(DocRef{cid(1), 0, std::nullopt}, std::vector<float>(10, 1.f));
+  } catch (const SearchError& e) {
+    threw = e.kind == SearchError::VectorIndexFailed;
+  }
+  CHECK(threw);
+  threw = false;
+  try {
+    h.search(std::vector<float>(7, 1.f), 3);
+  } catch (const SearchError& e) {
+    threw = e.kind == SearchError::HnswSearchError;
+  }
+  CHECK(threw);
+  auto batch = h.search_batch({q, synth(2, dim, 9), synth(3, dim, 9)}, 5);
+  CHECK(batch.size() == 3 && batch[0][0].first.case_id == cid(99999) && batch[2].size() == 5);
+}
+
+static void stub_embedding_behaviour() {
+  // the reference's EmbeddingModel returns zeros (src/vector.rs:173): every score is 0.0 and
+  // the order falls back to ascending row id
+  VectorConfig vc;
+  vc.dimension = 384;
+  VectorIndex v(vc);
+  for (int i = 0; i < 20; ++i) v.add_embedding(DocRef{cid(i), 0, std::nullopt}, synth(i, 384, 3));
+  auto r = v.search("anything", 5);
+  CHECK(r.size() == 5);
+  for (size_t i = 0; i < r.size(); ++i) CHECK(r[i].similarity_score == 0.0f && r[i].doc_ref.case_id == cid(i));
+  auto st = v.get_stats();
+  CHECK(st.total_vectors == 20 && st.cache_size == 1 && st.dimension == 384);
+  v.add_document(DocRef{cid(77), 0, std::nullopt}, "some text");  // embeds as zeros, still indexed
+  CHECK(v.get_stats().total_vectors == 21);
+}
+
+static void engine_hybrid() {
+  const uint32_t dim = 384;
+  VectorConfig vc;
+  vc.dimension = dim;
+  auto store = std::make_shared<MetadataStore>();
+  SearchEngineConfig sc;
+  sc.enable_query_cache = false;
+  SearchEngine eng(vc, TrieConfig(), sc, store);
+  const char* names[] = {"Brown v. Board of Education", "Miranda v. Arizona", "Roe v. Wade"};
+  // 60 cases x 2 paragraphs; cases 0..2 are the simple_demo ones
+  for (int c = 0; c < 60; ++c) {
+    CaseMetadata m;
+    m.id = cid(c);
+    m.name = c < 3 ? names[c] : "case " + std::to_string(c);
+    m.court = c % 2 ? "scotus" : "ca9";
+    m.decision_date = 1000 + c;
+    store->put(m);
+    eng.trie_index().insert_case_name(m.name, m.id);
+    for (int p = 0; p < 2; ++p)
+      eng.vector_index().add_embedding(DocRef{m.id, (size_t)p, std::nullopt}, synth(c * 2 + p, dim, 5));
+  }
+  // query text "miranda v. arizona" embeds next to case 7's paragraph 1
+  auto target = synth(7 * 2 + 1, dim, 5);
+  eng.vector_index().embedding_model().set_encoder([&](const std::string&) { return target; });
+  eng.freeze();
+
+  SearchQuery q;
+  q.query = "Miranda v. Arizona";
+  auto r = eng.search_with_params(q);
+  // M1 shape: trie exact hit first with weight 2.0, then semantic hits >= 0.5, de-duped by case
+  CHECK(r.size() >= 2 && r[0].case_metadata.id == cid(1) && r[0].score == 2.0f &&
+        r[0].match_type == MatchType::Exact);
+  CHECK(r[1].case_metadata.id == cid(7) && r[1].match_type == MatchType::Semantic &&
+        r[1].score > 0.99f);
+  for (size_t i = 2; i < r.size(); ++i) CHECK(r[i].score >= 0.5f);
+  CHECK(r[0].snippet.find("paragraph 0") != std::string::npos);
+  // the three policies agree whenever top-50 is not exhausted by seen cases
+  eng.set_mask_policy(SearchEngine::MaskPolicy::ExcludeOnDevice);
+  auto r2 = eng.search_with_params(q);
+  CHECK(r2.size() == r.size());
+  for (size_t i = 0; i < r.size() && i < r2.size(); ++i)
+    CHECK(r2[i].case_metadata.id == r[i].case_metadata.id && r2[i].score == r[i].score);
+  // prefix filter: only rows of cases under the prefix "miranda" are scored
+  eng.set_mask_policy(SearchEngine::MaskPolicy::PrefixFilter);
+  q.query = "miranda";
+  q.config.min_similarity = -1.0f;
+  auto r3 = eng.search_with_params(q);
+  CHECK(r3.size() == 1 && r3[0].case_metadata.id == cid(1) && r3[0].match_type == MatchType::Semantic);
+  eng.set_mask_policy(SearchEngine::MaskPolicy::PostHoc);
+  // filters are post-hoc (src/search.rs:233): court filter can empty the list
+  q = SearchQuery();
+  q.query = "Miranda v. Arizona";
+  q.court_filter = std::vector<std::string>{"ca9"};
+  for (auto& x : eng.search_with_params(q)) CHECK(x.case_metadata.court == "ca9");
+  q.court_filter.reset();
+  q.date_range = std::make_pair(1007, 1007);
+  auto rd = eng.search_with_params(q);
+  CHECK(rd.size() == 1 && rd[0].case_metadata.id == cid(7));
+  // M2: >= max_results exact hits skip the vector pass entirely
+  q = SearchQuery();
+  q.query = "Roe v. Wade";
+  q.config.max_results = 1;
+  auto rm = eng.search_with_params(q);
+  CHECK(rm.size() == 1 && rm[0].match_type == MatchType::Exact);
+  // validation, src/search.rs:284-300
+  bool threw = false;
+  try {
+    eng.search("a");
+  } catch (const SearchError& e) {
+    threw = e.kind == SearchError::InvalidSearchQuery;
+  }
+  CHECK(threw);
+  // semantic disabled
+  q = SearchQuery();
+  q.query = "Miranda v. Arizona";
+  q.config.enable_semantic = false;
+  CHECK(eng.search_with_params(q).size() == 1);
+  q.config.enable_semantic = true;
+  q.config.enable_prefix = false;
+  auto rs = eng.search_with_params(q);
+  CHECK(!rs.empty() && rs[0].case_metadata.id == cid(7) && rs[0].match_type == MatchType::Semantic);
+}
+
+int main(int argc, char** argv) {
+  std::string mode = argc > 1 ? argv[1] : "cpu";
+  try {
+    trie_kats();
+    trie_vs_oracle_random();
+    if (mode == "gpu") {
+      hnsw_vs_oracle();
+      stub_embedding_behaviour();
+      engine_hybrid();
+    } else {
+      no_gpu_is_loud();
+    }
+  } catch (const std::exception& e) {
+    printf("FAIL: exception: %s\n", e.what());
+    return 2;
+  }
+  printf(g_fail ? "HOST_SHIM_FAILED (%d)\n" : "HOST_SHIM_OK\n", g_fail);
+  return g_fail ? 1 : 0;
+}

@@ -760,10 +760,12 @@ int tss_prefix_mask(tss_terms* t, const char* prefix, uint32_t len, int kind, ts
   };
   const std::string p(prefix ? prefix : "", len);
   if (kind == TSS_PREFIX_TOKEN) {
-    if (len == 0) {  // zero tokens: node = root (never terminal), subtree = everything
+    if (len == 0) {
+      // zero tokens: node = root.  The root is terminal only if an empty token list was
+      // inserted (term ""), which sorts first; everything else is its subtree.
       fixed(0, 0);
-      fixed(1, 0);
-      fixed(2, 0);
+      push(1, std::string(1, '\0'));
+      push(2, std::string(1, '\0'));
       fixed(3, -2);
     } else {
       push(0, p);                      // first term >= P

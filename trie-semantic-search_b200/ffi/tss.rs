@@ -1,0 +1,210 @@
+//! tss.rs -- the Rust side of the boundary: `extern "C"` block for libtss.so plus the
+//! replacement bodies of the four `HnswIndex` methods (reference src/vector.rs:184-208).
+//!
+//! SOURCE ONLY: this build environment has no cargo/rustc and the
+//! reference crate does not compile as written (F3), so this file has never been compiled.
+//! It is the binding a maintainer drops into `src/` next to `vector.rs`; the same logic is
+//! exercised in C++ by `../host/tss_host.cpp` (tests/host_shim_test.cpp).
+//!
+//! build.rs:  println!("cargo:rustc-link-lib=dylib=tss");
+//!            println!("cargo:rustc-link-search=native={}", env!("TSS_LIB_DIR"));
+
+#![allow(non_camel_case_types, dead_code)]
+
+use crate::errors::{Result, SearchError};
+use crate::DocRef;
+use std::ffi::CStr;
+use std::os::raw::{c_char, c_int, c_void};
+
+#[repr(C)]
+pub struct tss_index { _p: [u8; 0] }
+#[repr(C)]
+pub struct tss_mask { _p: [u8; 0] }
+#[repr(C)]
+pub struct tss_terms { _p: [u8; 0] }
+#[repr(C)]
+pub struct tss_comm { _p: [u8; 0] }
+
+#[repr(C)]
+#[derive(Default, Debug, Clone, Copy)]
+pub struct tss_prefix_stats {
+    pub exact_lo: u64,
+    pub exact_hi: u64,
+    pub sub_lo: u64,
+    pub sub_hi: u64,
+    pub npostings: u64,
+}
+
+pub const TSS_OK: c_int = 0;
+pub const TSS_F32: c_int = 0;
+pub const TSS_BF16: c_int = 1;
+pub const TSS_MASK_NONE: c_int = 0;
+pub const TSS_MASK_INCLUDE: c_int = 1;
+pub const TSS_MASK_EXCLUDE: c_int = 2;
+pub const TSS_PREFIX_TOKEN: c_int = 0;
+pub const TSS_PREFIX_CHAR: c_int = 1;
+
+#[link(name = "tss")]
+extern "C" {
+    pub fn tss_abi_version() -> c_int;
+    pub fn tss_last_error() -> *const c_char;
+    pub fn tss_device_count() -> c_int;
+
+    pub fn tss_index_create(out: *mut *mut tss_index, dim: u32, storage: c_int, device: c_int) -> c_int;
+    pub fn tss_index_reserve(ix: *mut tss_index, nrows: u64) -> c_int;
+    pub fn tss_index_add(ix: *mut tss_index, rows: *const f32, nrows: u64) -> c_int;
+    pub fn tss_index_add_synthetic(ix: *mut tss_index, row_begin: u64, nrows: u64, seed: u64) -> c_int;
+    pub fn tss_index_finalize(ix: *mut tss_index) -> c_int;
+    pub fn tss_index_size(ix: *const tss_index) -> u64;
+    pub fn tss_index_dim(ix: *const tss_index) -> u32;
+    pub fn tss_index_destroy(ix: *mut tss_index);
+    pub fn tss_index_get_rows(ix: *mut tss_index, row_begin: u64, nrows: u64, out: *mut f32) -> c_int;
+    pub fn tss_index_search(
+        ix: *mut tss_index, queries: *const f32, nq: u32, k: u32, mask: *const tss_mask,
+        mask_mode: c_int, out_rows: *mut u32, out_scores: *mut f32, out_counts: *mut u32,
+    ) -> c_int;
+    pub fn tss_index_search_device(
+        ix: *mut tss_index, d_queries: *const f32, nq: u32, k: u32, mask: *const tss_mask,
+        mask_mode: c_int, d_out_keys: *mut u64,
+    ) -> c_int;
+    pub fn tss_unpack_keys(keys: *const u64, n: u64, out_rows: *mut u32, out_scores: *mut f32);
+
+    pub fn tss_comm_unique_id(out_id: *mut u8) -> c_int;
+    pub fn tss_comm_create(out: *mut *mut tss_comm, id: *const u8, rank: c_int, nranks: c_int, device: c_int) -> c_int;
+    pub fn tss_comm_destroy(c: *mut tss_comm);
+    pub fn tss_index_set_shard(ix: *mut tss_index, row_base: u64, comm: *mut tss_comm) -> c_int;
+
+    pub fn tss_mask_create(out: *mut *mut tss_mask, nbits: u64, device: c_int) -> c_int;
+    pub fn tss_mask_clear(m: *mut tss_mask) -> c_int;
+    pub fn tss_mask_set_rows(m: *mut tss_mask, rows: *const u32, n: u64, row_base: u64) -> c_int;
+    pub fn tss_mask_upload(m: *mut tss_mask, words: *const u32) -> c_int;
+    pub fn tss_mask_download(m: *const tss_mask, words: *mut u32) -> c_int;
+    pub fn tss_mask_popcount(m: *const tss_mask, out: *mut u64) -> c_int;
+    pub fn tss_mask_nbits(m: *const tss_mask) -> u64;
+    pub fn tss_mask_destroy(m: *mut tss_mask);
+
+    pub fn tss_terms_create(
+        out: *mut *mut tss_terms, pool: *const c_char, term_off: *const u64, post_off: *const u64,
+        post_rows: *const u32, nterms: u64, device: c_int,
+    ) -> c_int;
+    pub fn tss_terms_size(t: *const tss_terms) -> u64;
+    pub fn tss_terms_destroy(t: *mut tss_terms);
+    pub fn tss_prefix_mask(
+        t: *mut tss_terms, prefix: *const c_char, len: u32, kind: c_int, out: *mut tss_mask,
+        row_base: u64, stats: *mut tss_prefix_stats,
+    ) -> c_int;
+
+    pub fn tss_index_stream(ix: *mut tss_index) -> *mut c_void;
+    pub fn tss_index_sync(ix: *mut tss_index) -> c_int;
+    pub fn tss_launch_count() -> u64;
+}
+
+fn last_error() -> String {
+    unsafe { CStr::from_ptr(tss_last_error()).to_string_lossy().into_owned() }
+}
+
+/// Drop-in replacement for the stub `HnswIndex` of src/vector.rs:40-44.
+pub struct HnswIndex {
+    config: crate::config::HnswConfig,
+    ix: *mut tss_index,
+    dim: usize,
+    /// row id -> DocRef; the GPU only ever sees dense u32 row ids
+    doc_refs: Vec<DocRef>,
+    /// rows staged on the host until the next search
+    pending: Vec<f32>,
+    dirty: bool,
+}
+
+// the handle is externally synchronised by the tokio RwLock around VectorIndex
+// (src/search.rs:33-36,249-252)
+unsafe impl Send for HnswIndex {}
+unsafe impl Sync for HnswIndex {}
+
+impl HnswIndex {
+    /// src/vector.rs:185-188
+    pub async fn new(config: crate::config::HnswConfig, dimension: usize) -> Result<Self> {
+        let mut ix: *mut tss_index = std::ptr::null_mut();
+        let rc = unsafe { tss_index_create(&mut ix, dimension as u32, TSS_F32, 0) };
+        if rc != TSS_OK {
+            return Err(SearchError::VectorIndexFailed { reason: last_error() });
+        }
+        unsafe { tss_index_reserve(ix, config.max_elements.min(1 << 20) as u64) };
+        Ok(Self { config, ix, dim: dimension, doc_refs: Vec::new(), pending: Vec::new(), dirty: true })
+    }
+
+    /// src/vector.rs:190-193
+    pub async fn add_vector(&mut self, doc_ref: DocRef, embedding: Vec<f32>) -> Result<()> {
+        if embedding.len() != self.dim {
+            return Err(SearchError::VectorIndexFailed {
+                reason: format!("embedding has {} dims, index has {}", embedding.len(), self.dim),
+            });
+        }
+        self.doc_refs.push(doc_ref);
+        self.pending.extend_from_slice(&embedding);
+        self.dirty = true;
+        if self.pending.len() >= self.dim * 16384 {
+            self.flush()?;
+        }
+        Ok(())
+    }
+
+    fn flush(&mut self) -> Result<()> {
+        if !self.pending.is_empty() {
+            let n = (self.pending.len() / self.dim) as u64;
+            let rc = unsafe { tss_index_add(self.ix, self.pending.as_ptr(), n) };
+            if rc != TSS_OK {
+                return Err(SearchError::VectorIndexFailed { reason: last_error() });
+            }
+            self.pending.clear();
+        }
+        Ok(())
+    }
+
+    /// src/vector.rs:195-202 -- `&self` in the reference; the lazy flush needs `&mut`, which the
+    /// only caller already has (VectorIndex::search takes `&mut self`, src/vector.rs:128-132).
+    pub async fn search(&mut self, query_embedding: &[f32], top_k: usize) -> Result<Vec<(DocRef, f32)>> {
+        if query_embedding.len() != self.dim {
+            return Err(SearchError::HnswSearchError {
+                details: format!("query has {} dims, index has {}", query_embedding.len(), self.dim),
+            });
+        }
+        if top_k == 0 {
+            return Ok(Vec::new());
+        }
+        if self.dirty {
+            self.flush()?;
+            if unsafe { tss_index_finalize(self.ix) } != TSS_OK {
+                return Err(SearchError::VectorIndexFailed { reason: last_error() });
+            }
+            self.dirty = false;
+        }
+        let mut rows = vec![0u32; top_k];
+        let mut scores = vec![0f32; top_k];
+        let mut count = 0u32;
+        let rc = unsafe {
+            tss_index_search(
+                self.ix, query_embedding.as_ptr(), 1, top_k as u32, std::ptr::null(), TSS_MASK_NONE,
+                rows.as_mut_ptr(), scores.as_mut_ptr(), &mut count,
+            )
+        };
+        if rc != TSS_OK {
+            return Err(SearchError::HnswSearchError { details: last_error() });
+        }
+        // the ABI returns similarity; VectorIndex::search computes `1.0 - distance`
+        // (src/vector.rs:144), so hand it a distance
+        Ok((0..count as usize)
+            .map(|i| (self.doc_refs[rows[i] as usize].clone(), 1.0 - scores[i]))
+            .collect())
+    }
+
+    /// src/vector.rs:204-207
+    pub fn size(&self) -> usize {
+        self.doc_refs.len()
+    }
+}
+
+impl Drop for HnswIndex {
+    fn drop(&mut self) {
+        unsafe { tss_index_destroy(self.ix) }
+    }
+}

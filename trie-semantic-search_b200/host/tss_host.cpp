@@ -1,0 +1,483 @@
+// tss_host.cpp -- see tss_host.hpp.  Reference citations are into /root/reference/src.
+#include "tss_host.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <ctime>
+#include <unordered_set>
+
+#include "../../include/tss.h"
+
+namespace tss_host {
+
+namespace {
+[[noreturn]] void raise_tss(SearchError::Kind kind, const char* what, int rc) {
+  throw SearchError(kind, std::string(what) + ": libtss status " + std::to_string(rc) + ": " +
+                              tss_last_error());
+}
+bool is_ws(unsigned char c) { return c == ' ' || (c >= 9 && c <= 13); }
+}  // namespace
+
+// ---- core types -----------------------------------------------------------------------------
+CaseId CaseId::from_u64(uint64_t v) {
+  CaseId c;
+  for (int i = 0; i < 8; ++i) c.bytes[15 - i] = (uint8_t)(v >> (8 * i));
+  return c;
+}
+std::string CaseId::to_string() const {
+  char buf[40];
+  const uint8_t* b = bytes.data();
+  snprintf(buf, sizeof(buf),
+           "%02x%02x%02x%02x-%02x%02x-%02x%02x-%02x%02x-%02x%02x%02x%02x%02x%02x", b[0], b[1],
+           b[2], b[3], b[4], b[5], b[6], b[7], b[8], b[9], b[10], b[11], b[12], b[13], b[14],
+           b[15]);
+  return buf;
+}
+size_t CaseIdHash::operator()(const CaseId& c) const {
+  uint64_t a, b;
+  memcpy(&a, c.bytes.data(), 8);
+  memcpy(&b, c.bytes.data() + 8, 8);
+  return (size_t)(a * 0x9E3779B97F4A7C15ull ^ (b + 0x7F4A7C15ull + (a << 6) + (a >> 2)));
+}
+
+const char* SearchError::category() const {  // src/errors.rs:236-272
+  switch (kind) {
+    case VectorIndexFailed:
+    case HnswSearchError: return "vector";
+    case InvalidSearchQuery: return "search";
+    case NotSupported: return "system";
+  }
+  return "unknown";
+}
+
+// ---- HnswIndex ------------------------------------------------------------------------------
+HnswIndex::HnswIndex(const HnswConfig& config, size_t dimension, int device, bool bf16)
+    : config_(config), dim_(dimension), device_(device) {
+  int rc = tss_index_create(&ix_, (uint32_t)dimension, bf16 ? TSS_BF16 : TSS_F32, device);
+  if (rc) raise_tss(SearchError::VectorIndexFailed, "HnswIndex::new", rc);
+}
+HnswIndex::~HnswIndex() { tss_index_destroy(ix_); }
+
+void HnswIndex::add_vector(const DocRef& doc_ref, const std::vector<float>& embedding) {
+  if (embedding.size() != dim_)
+    throw SearchError(SearchError::VectorIndexFailed,
+                      "embedding has " + std::to_string(embedding.size()) + " dims, index has " +
+                          std::to_string(dim_));
+  for (float v : embedding)
+    if (!std::isfinite(v))
+      throw SearchError(SearchError::VectorIndexFailed, "embedding contains NaN or Inf");
+  if (row_docref_.size() >= config_.max_elements)
+    throw SearchError(SearchError::VectorIndexFailed, "max_elements reached");
+  uint32_t row = (uint32_t)row_docref_.size();
+  row_docref_.push_back(doc_ref);
+  case_rows_[doc_ref.case_id].push_back(row);
+  pending_.insert(pending_.end(), embedding.begin(), embedding.end());
+  ++pending_rows_;
+  dirty_ = true;
+  if (pending_rows_ >= 16384) flush();
+}
+
+void HnswIndex::flush() {
+  if (pending_rows_) {
+    int rc = tss_index_add(ix_, pending_.data(), pending_rows_);
+    if (rc) raise_tss(SearchError::VectorIndexFailed, "HnswIndex::add_vector", rc);
+    pending_.clear();
+    pending_rows_ = 0;
+  }
+}
+
+size_t HnswIndex::size() const { return row_docref_.size(); }
+
+const std::vector<uint32_t>* HnswIndex::rows_of_case(const CaseId& id) const {
+  auto it = case_rows_.find(id);
+  return it == case_rows_.end() ? nullptr : &it->second;
+}
+
+std::vector<std::vector<std::pair<DocRef, float>>> HnswIndex::search_batch(
+    const std::vector<std::vector<float>>& queries, size_t top_k) {
+  std::vector<std::vector<std::pair<DocRef, float>>> out(queries.size());
+  if (queries.empty()) return out;
+  std::vector<float> flat;
+  for (const auto& q : queries) {
+    if (q.size() != dim_)
+      throw SearchError(SearchError::HnswSearchError, "query dimension mismatch");
+    flat.insert(flat.end(), q.begin(), q.end());
+  }
+  if (dirty_) {
+    flush();
+    int rc = tss_index_finalize(ix_);
+    if (rc) raise_tss(SearchError::VectorIndexFailed, "HnswIndex finalize", rc);
+    dirty_ = false;
+  }
+  const uint32_t nq = (uint32_t)queries.size(), k = (uint32_t)top_k;
+  std::vector<uint32_t> rows((size_t)nq * k), counts(nq);
+  std::vector<float> scores((size_t)nq * k);
+  int rc = tss_index_search(ix_, flat.data(), nq, k, nullptr, TSS_MASK_NONE, rows.data(),
+                            scores.data(), counts.data());
+  if (rc) raise_tss(SearchError::HnswSearchError, "HnswIndex::search", rc);
+  for (uint32_t qi = 0; qi < nq; ++qi)
+    for (uint32_t j = 0; j < counts[qi]; ++j)
+      out[qi].emplace_back(row_docref_[rows[(size_t)qi * k + j]],
+                           1.0f - scores[(size_t)qi * k + j]);
+  return out;
+}
+
+std::vector<std::pair<DocRef, float>> HnswIndex::search_masked(
+    const std::vector<float>& query_embedding, size_t top_k, const tss_mask* mask, int mask_mode) {
+  if (query_embedding.size() != dim_)
+    throw SearchError(SearchError::HnswSearchError,
+                      "query has " + std::to_string(query_embedding.size()) + " dims, index has " +
+                          std::to_string(dim_));
+  if (top_k == 0) return {};
+  if (dirty_) {
+    flush();
+    int rc = tss_index_finalize(ix_);
+    if (rc) raise_tss(SearchError::VectorIndexFailed, "HnswIndex finalize", rc);
+    dirty_ = false;
+  }
+  const uint32_t k = (uint32_t)top_k;
+  std::vector<uint32_t> rows(k);
+  std::vector<float> scores(k);
+  uint32_t count = 0;
+  int rc = tss_index_search(ix_, query_embedding.data(), 1, k, mask, mask_mode, rows.data(),
+                            scores.data(), &count);
+  if (rc) raise_tss(SearchError::HnswSearchError, "HnswIndex::search", rc);
+  std::vector<std::pair<DocRef, float>> out;
+  out.reserve(count);
+  // the ABI returns similarity; the reference signature carries a distance that the caller
+  // turns back with 1.0 - distance (src/vector.rs:144)
+  for (uint32_t j = 0; j < count; ++j) out.emplace_back(row_docref_[rows[j]], 1.0f - scores[j]);
+  return out;
+}
+
+std::vector<std::pair<DocRef, float>> HnswIndex::search(const std::vector<float>& query_embedding,
+                                                        size_t top_k) {
+  return search_masked(query_embedding, top_k, nullptr, TSS_MASK_NONE);
+}
+
+// ---- embedding + cache -----------------------------------------------------------------------
+EmbeddingResult EmbeddingModel::encode(const std::string& text) const {
+  EmbeddingResult r;
+  r.embedding = encoder_ ? encoder_(text) : std::vector<float>(dim_, 0.0f);  // src/vector.rs:173
+  return r;
+}
+std::optional<std::vector<float>> VectorCache::get(const std::string& key) const {
+  auto it = cache_.find(key);
+  if (it == cache_.end()) return std::nullopt;
+  return it->second;
+}
+void VectorCache::insert(const std::string& key, std::vector<float> value) {
+  if (cache_.size() >= max_size_ && !cache_.empty()) cache_.erase(cache_.begin());  // :223-228
+  cache_[key] = std::move(value);
+}
+
+// ---- VectorIndex -----------------------------------------------------------------------------
+VectorIndex::VectorIndex(const VectorConfig& config)
+    : config_(config),
+      embedding_model_(config.model, config.dimension),
+      hnsw_index_(config.hnsw, config.dimension, config.device, config.bf16_storage),
+      vector_cache_(1000) {}  // src/vector.rs:72
+
+EmbeddingResult VectorIndex::generate_embedding(const std::string& text) {
+  if (auto cached = vector_cache_.get(text)) return EmbeddingResult{*cached, 0};  // :100-105
+  EmbeddingResult r = embedding_model_.encode(text);                              // :108
+  vector_cache_.insert(text, r.embedding);                                        // :111
+  return r;
+}
+void VectorIndex::add_document(const DocRef& doc_ref, const std::string& text) {
+  hnsw_index_.add_vector(doc_ref, generate_embedding(text).embedding);  // :122-123
+}
+void VectorIndex::add_embedding(const DocRef& doc_ref, const std::vector<float>& embedding) {
+  hnsw_index_.add_vector(doc_ref, embedding);
+}
+std::vector<VectorSearchResult> VectorIndex::search_masked(const std::string& query, size_t top_k,
+                                                           const tss_mask* mask, int mask_mode) {
+  EmbeddingResult q = generate_embedding(query);                                      // :134
+  auto neighbors = hnsw_index_.search_masked(q.embedding, top_k, mask, mask_mode);   // :137
+  std::vector<VectorSearchResult> out;
+  out.reserve(neighbors.size());
+  for (auto& n : neighbors)  // order preserved; similarity = 1.0 - distance  :140-147
+    out.push_back(VectorSearchResult{n.first, 1.0f - n.second, std::nullopt});
+  return out;
+}
+std::vector<VectorSearchResult> VectorIndex::search(const std::string& query, size_t top_k) {
+  return search_masked(query, top_k, nullptr, TSS_MASK_NONE);
+}
+VectorIndexStats VectorIndex::get_stats() const {
+  return VectorIndexStats{hnsw_index_.size(), vector_cache_.size(), config_.dimension};  // :153-159
+}
+
+// ---- TokenTrie ------------------------------------------------------------------------------
+std::vector<std::string> TokenTrie::tokenize(const std::string& text) const {
+  std::vector<std::string> out;
+  std::string cur;
+  for (unsigned char c : text) {
+    if (is_ws(c)) {
+      if (!cur.empty()) out.push_back(cur), cur.clear();
+    } else {
+      cur.push_back(lowercase_ && c >= 'A' && c <= 'Z' ? (char)(c + 32) : (char)c);
+    }
+  }
+  if (!cur.empty()) out.push_back(cur);
+  return out;
+}
+std::string TokenTrie::normalise_join(const std::vector<std::string>& tokens) const {
+  std::string s;
+  for (size_t i = 0; i < tokens.size(); ++i) {
+    if (tokens[i].empty())
+      throw SearchError(SearchError::NotSupported, "empty token in a trie key");
+    if (i) s.push_back(' ');
+    for (unsigned char c : tokens[i]) {
+      if (is_ws(c))  // the flattened form uses ' ' as the token separator
+        throw SearchError(SearchError::NotSupported, "token contains whitespace");
+      s.push_back(lowercase_ && c >= 'A' && c <= 'Z' ? (char)(c + 32) : (char)c);
+    }
+  }
+  return s;
+}
+void TokenTrie::insert_tokens(const std::vector<std::string>& tokens, const DocRef& ref) {
+  terms_[normalise_join(tokens)].push_back(ref);  // push, no de-dup: src/trie.rs:219
+}
+uint32_t TokenTrie::frequency(const std::vector<std::string>& tokens) const {
+  auto it = terms_.find(normalise_join(tokens));
+  return it == terms_.end() ? 0 : (uint32_t)it->second.size();  // += 1 per insert, :220
+}
+TrieSearchResult TokenTrie::search_tokens(const std::vector<std::string>& tokens) const {
+  TrieSearchResult r;
+  const std::string p = normalise_join(tokens);
+  // does the walk (src/trie.rs:227-238) reach a node?  A node exists iff some term equals P
+  // or continues it with a further token.
+  auto exact = terms_.find(p);
+  const std::string sub = p.empty() ? std::string() : p + " ";
+  auto it = p.empty() ? terms_.begin() : terms_.lower_bound(sub);
+  auto below = [&](const std::string& key) {
+    return p.empty() ? !key.empty() : key.compare(0, sub.size(), sub) == 0;
+  };
+  if (exact != terms_.end()) r.exact_matches = exact->second;  // :241-245
+  for (; it != terms_.end() && r.prefix_completions.size() < 10; ++it) {  // limit 10, :248
+    if (p.empty() && it->first.empty()) continue;  // the root itself is not "strictly longer"
+    if (!below(it->first)) break;
+    r.prefix_completions.push_back(it->first);  // path.join(" "), strictly longer :266-267
+  }
+  r.total_matches = r.exact_matches.size() + r.prefix_completions.size();  // :251
+  return r;
+}
+
+// ---- TrieIndex --------------------------------------------------------------------------------
+TrieIndex::TrieIndex(const TrieConfig& config)
+    : config_(config),
+      tries_{TokenTrie(true), TokenTrie(true), TokenTrie(false)} {}  // :147,171 lower; :190 as is
+TrieIndex::~TrieIndex() {
+  for (auto* t : frozen_) tss_terms_destroy(t);
+}
+void TrieIndex::insert_case_name(const std::string& case_name, const CaseId& case_id) {
+  DocRef ref{case_id, 0, std::nullopt};  // :148-152
+  tries_[CaseName].insert_tokens(tries_[CaseName].tokenize(case_name), ref);
+}
+void TrieIndex::insert_content(const std::vector<std::string>& tokens, const DocRef& ref) {
+  tries_[Content].insert_tokens(tokens, ref);  // tokens lower-cased, not re-split :171
+}
+void TrieIndex::insert_citation(const std::string& citation, const DocRef& ref) {
+  tries_[Citation].insert_tokens(tries_[Citation].tokenize(citation), ref);
+}
+TrieSearchResult TrieIndex::search_one(Which w, const std::string& query) const {
+  return tries_[w].search_tokens(tries_[w].tokenize(query));
+}
+TrieSearchResult TrieIndex::search(const std::string& query) const {
+  TrieSearchResult r = search_one(CaseName, query);  // :114-118
+  if (!r.exact_matches.empty()) return r;
+  r = search_one(Citation, query);  // :121-125
+  if (!r.exact_matches.empty()) return r;
+  return search_one(Content, query);  // :128-129
+}
+std::vector<std::string> TrieIndex::get_completions(const std::string&, size_t) const {
+  return {};  // TODO in the reference too, :133-136
+}
+TrieIndex TrieIndex::load_from_disk(const std::string&) {
+  throw SearchError(SearchError::NotSupported, "Loading trie from disk");  // :85-87
+}
+void TrieIndex::save_to_disk(const std::string&) const {}  // :91-94
+
+void TrieIndex::freeze(Which w, int device, const RowsOf& rows_of) {
+  std::string pool;
+  std::vector<uint64_t> term_off{0}, post_off{0};
+  std::vector<uint32_t> post_rows;
+  for (const auto& kv : tries_[w].terms()) {  // std::map iterates in byte order
+    pool += kv.first;
+    term_off.push_back(pool.size());
+    for (const DocRef& ref : kv.second)
+      if (const auto* rows = rows_of(ref.case_id))
+        post_rows.insert(post_rows.end(), rows->begin(), rows->end());
+    post_off.push_back(post_rows.size());
+  }
+  tss_terms_destroy(frozen_[w]);
+  frozen_[w] = nullptr;
+  int rc = tss_terms_create(&frozen_[w], pool.data(), term_off.data(), post_off.data(),
+                            post_rows.data(), term_off.size() - 1, device);
+  if (rc) raise_tss(SearchError::VectorIndexFailed, "TrieIndex::freeze", rc);
+}
+void TrieIndex::prefix_mask(Which w, const std::string& query, tss_mask* mask,
+                            uint64_t row_base) const {
+  if (!frozen_[w]) throw SearchError(SearchError::NotSupported, "TrieIndex::prefix_mask before freeze");
+  std::string p;
+  for (const auto& t : tries_[w].tokenize(query)) {
+    if (!p.empty()) p.push_back(' ');
+    p += t;
+  }
+  int rc = tss_prefix_mask(frozen_[w], p.data(), (uint32_t)p.size(), TSS_PREFIX_TOKEN, mask,
+                           row_base, nullptr);
+  if (rc) raise_tss(SearchError::HnswSearchError, "TrieIndex::prefix_mask", rc);
+}
+
+// ---- SearchEngine ----------------------------------------------------------------------------
+std::optional<CaseMetadata> MetadataStore::get_case_metadata(const CaseId& id) const {
+  auto it = map_.find(id);
+  if (it == map_.end()) return std::nullopt;
+  return it->second;
+}
+
+SearchEngine::SearchEngine(const VectorConfig& vc, const TrieConfig& tc,
+                           const SearchEngineConfig& sc, std::shared_ptr<MetadataStore> storage)
+    : config_(sc), trie_index_(tc), vector_index_(vc), storage_(std::move(storage)) {}
+SearchEngine::~SearchEngine() { tss_mask_destroy(mask_); }
+
+void SearchEngine::freeze() {
+  HnswIndex& h = vector_index_.hnsw();
+  auto rows_of = [&h](const CaseId& id) { return h.rows_of_case(id); };
+  for (int w = 0; w < 3; ++w) trie_index_.freeze((TrieIndex::Which)w, h.device(), rows_of);
+  tss_mask_destroy(mask_);
+  mask_ = nullptr;
+  mask_bits_ = h.size();
+  int rc = tss_mask_create(&mask_, mask_bits_ ? mask_bits_ : 1, h.device());
+  if (rc) raise_tss(SearchError::VectorIndexFailed, "SearchEngine::freeze", rc);
+}
+
+std::vector<SearchResult> SearchEngine::search(const std::string& query) {
+  SearchQuery q;
+  q.query = query;
+  q.max_results = config_.default_max_results;  // :152
+  return search_with_params(q);
+}
+
+void SearchEngine::validate_query(const SearchQuery& query) const {
+  if (query.query.size() < config_.min_query_length)  // :285-290
+    throw SearchError(SearchError::InvalidSearchQuery,
+                      "Invalid search query: " + query.query + " - Query too short: minimum " +
+                          std::to_string(config_.min_query_length) + " characters");
+  if (query.query.size() > config_.max_query_length)  // :292-297
+    throw SearchError(SearchError::InvalidSearchQuery,
+                      "Invalid search query: " + query.query + " - Query too long: maximum " +
+                          std::to_string(config_.max_query_length) + " characters");
+}
+
+std::vector<SearchResult> SearchEngine::search_with_params(const SearchQuery& query) {
+  if (config_.enable_query_cache) {  // key = query string only, :164-168,303-306
+    auto it = query_cache_.find(query.query);
+    if (it != query_cache_.end() &&
+        (int64_t)time(nullptr) - it->second.timestamp < (int64_t)config_.query_cache_ttl_seconds)
+      return it->second.results;
+  }
+  validate_query(query);                                           // :171
+  std::vector<SearchResult> results = execute_hybrid_search(query);  // :174
+  if (config_.enable_query_cache) {                                // :177-179,365-378
+    if (query_cache_.size() >= config_.query_cache_size && !query_cache_.empty())
+      query_cache_.erase(query_cache_.begin());
+    query_cache_[query.query] = Cached{results, (int64_t)time(nullptr)};
+  }
+  return results;
+}
+
+std::vector<SearchResult> SearchEngine::apply_filters(std::vector<SearchResult> results,
+                                                      const SearchQuery& query) const {
+  if (query.court_filter) {  // :261-263
+    const auto& cf = *query.court_filter;
+    results.erase(std::remove_if(results.begin(), results.end(),
+                                 [&](const SearchResult& r) {
+                                   return std::find(cf.begin(), cf.end(), r.case_metadata.court) ==
+                                          cf.end();
+                                 }),
+                  results.end());
+  }
+  if (query.date_range) {  // :266-271
+    auto [lo, hi] = *query.date_range;
+    results.erase(std::remove_if(results.begin(), results.end(),
+                                 [&](const SearchResult& r) {
+                                   return r.case_metadata.decision_date < lo ||
+                                          r.case_metadata.decision_date > hi;
+                                 }),
+                  results.end());
+  }
+  return results;
+}
+
+std::vector<SearchResult> SearchEngine::execute_hybrid_search(const SearchQuery& query) {
+  std::vector<SearchResult> all_results;
+  std::unordered_set<CaseId, CaseIdHash> seen_cases;  // :187
+  auto snippet = [](const DocRef& d) {              // :277-281
+    return "Snippet for case " + d.case_id.to_string() + " paragraph " +
+           std::to_string(d.paragraph_index);
+  };
+
+  // 1. trie search for exact matches, :190-206
+  if (query.config.enable_prefix) {
+    TrieSearchResult tr = trie_index_.search(query.query);
+    for (const DocRef& d : tr.exact_matches) {
+      auto meta = storage_->get_case_metadata(d.case_id);  // :193
+      if (!meta) continue;
+      if (seen_cases.insert(d.case_id).second)  // :194
+        all_results.push_back(
+            SearchResult{*meta, query.config.exact_match_weight, MatchType::Exact, snippet(d)});
+    }
+  }
+
+  // 2. vector search for semantic matches, :209-227
+  if (query.config.enable_semantic && all_results.size() < query.config.max_results) {
+    HnswIndex& h = vector_index_.hnsw();
+    const tss_mask* mask = nullptr;
+    int mode = TSS_MASK_NONE;
+    if (policy_ != MaskPolicy::PostHoc) {
+      if (!mask_ || mask_bits_ != h.size())
+        throw SearchError(SearchError::NotSupported, "SearchEngine::freeze() not called after the last insert");
+      int rc = tss_mask_clear(mask_);
+      if (rc) raise_tss(SearchError::HnswSearchError, "mask clear", rc);
+      if (policy_ == MaskPolicy::ExcludeOnDevice) {
+        std::vector<uint32_t> rows;
+        for (const CaseId& c : seen_cases)
+          if (const auto* r = h.rows_of_case(c)) rows.insert(rows.end(), r->begin(), r->end());
+        if (!rows.empty()) {
+          rc = tss_mask_set_rows(mask_, rows.data(), rows.size(), 0);
+          if (rc) raise_tss(SearchError::HnswSearchError, "mask set_rows", rc);
+          mask = mask_;
+          mode = TSS_MASK_EXCLUDE;
+        }
+      } else {  // PrefixFilter: rows at or below the node the query reaches, any of the tries
+        for (int w = 0; w < 3; ++w)
+          trie_index_.prefix_mask((TrieIndex::Which)w, query.query, mask_);
+        mask = mask_;
+        mode = TSS_MASK_INCLUDE;
+      }
+    }
+    auto vector_results = vector_index_.search_masked(query.query, kVectorTopK, mask, mode);  // :251
+    for (const VectorSearchResult& v : vector_results) {
+      if (v.similarity_score >= query.config.min_similarity) {       // :212
+        auto meta = storage_->get_case_metadata(v.doc_ref.case_id);  // :213
+        if (!meta) continue;
+        if (seen_cases.insert(v.doc_ref.case_id).second)             // :214
+          all_results.push_back(
+              SearchResult{*meta, v.similarity_score, MatchType::Semantic, snippet(v.doc_ref)});
+      }
+    }
+  }
+
+  // 3. stable sort by score desc (partial_cmp, Equal on incomparable), :230
+  std::stable_sort(all_results.begin(), all_results.end(),
+                   [](const SearchResult& a, const SearchResult& b) { return a.score > b.score; });
+  all_results = apply_filters(std::move(all_results), query);  // :233
+  size_t max_results = query.max_results.value_or(query.config.max_results);  // :236
+  if (all_results.size() > max_results) all_results.resize(max_results);      // :237
+  return all_results;
+}
+
+}  // namespace tss_host
