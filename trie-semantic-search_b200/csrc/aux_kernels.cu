@@ -2,6 +2,7 @@
 // check, row packing, mask ops, K4 prefix search + scatter, K5 gathered merge.
 #include "aux_kernels.cuh"
 #include "common.cuh"
+#include "scan.cuh"
 
 namespace tss {
 
@@ -225,45 +226,33 @@ cudaError_t launch_prefix_scatter(const TermsDev& t, const uint64_t* d_bounds, u
 }
 
 // ---- K5: merge of all-gathered per-rank top-k lists ---------------------------------------
-// one CTA per query: bitonic sort of P*k keys (padded to a power of two) in smem.
+// one warp per query: stage the P sorted lists of k keys in shared memory, then a warp
+// tournament (scan.cuh) picks the k best.  in [P][nq][k] -> out [nq][k].
 __global__ void merge_gathered_kernel(const uint64_t* in, uint64_t* out, uint32_t P, uint32_t nq,
-                                      uint32_t k, uint32_t npad) {
+                                      uint32_t k) {
   extern __shared__ uint64_t sk[];
-  const uint32_t qi = blockIdx.x;
-  const uint32_t n = P * k;
-  for (uint32_t i = threadIdx.x; i < npad; i += blockDim.x) {
-    uint64_t v = 0;
-    if (i < n) {
-      uint32_t r = i / k, e = i - r * k;
-      v = in[((size_t)r * nq + qi) * k + e];
-    }
-    sk[i] = v;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t wpc = blockDim.x >> 5;
+  const uint32_t qi = blockIdx.x * wpc + warp;
+  if (qi >= nq) return;
+  uint64_t* mine = sk + (size_t)warp * P * k;
+  for (uint32_t i = lane; i < P * k; i += 32) {
+    uint32_t r = i / k, e = i - r * k;
+    mine[i] = in[((size_t)r * nq + qi) * k + e];
   }
-  __syncthreads();
-  for (uint32_t size = 2; size <= npad; size <<= 1) {
-    for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
-      for (uint32_t i = threadIdx.x; i < (npad >> 1); i += blockDim.x) {
-        uint32_t lo = ((i & ~(stride - 1)) << 1) | (i & (stride - 1));
-        uint32_t hi = lo | stride;
-        bool desc = (lo & size) == 0;
-        uint64_t a = sk[lo], b = sk[hi];
-        if ((a < b) == desc) {
-          sk[lo] = b;
-          sk[hi] = a;
-        }
-      }
-      __syncthreads();
-    }
-  }
-  for (uint32_t e = threadIdx.x; e < k; e += blockDim.x) out[(size_t)qi * k + e] = sk[e];
+  __syncwarp();
+  warp_tournament<2>(mine, k, P, k, k, out + (size_t)qi * k, lane);
 }
 cudaError_t launch_merge_gathered(const uint64_t* in, uint64_t* out, uint32_t P, uint32_t nq,
                                   uint32_t k, cudaStream_t st) {
   if (!nq) return cudaSuccess;
-  uint32_t n = P * k, npad = 2;
-  while (npad < n) npad <<= 1;
-  if ((size_t)npad * 8 > 48 * 1024) return cudaErrorInvalidConfiguration;
-  merge_gathered_kernel<<<nq, 256, (size_t)npad * 8, st>>>(in, out, P, nq, k, npad);
+  if (P > 64) return cudaErrorInvalidConfiguration;
+  size_t per_warp = (size_t)P * k * 8;
+  if (per_warp > 48 * 1024) return cudaErrorInvalidConfiguration;
+  uint32_t wpc = (uint32_t)(48 * 1024 / per_warp);
+  if (wpc > 4) wpc = 4;
+  if (wpc > nq) wpc = nq;
+  merge_gathered_kernel<<<(nq + wpc - 1) / wpc, wpc * 32, per_warp * wpc, st>>>(in, out, P, nq, k);
   return cudaGetLastError();
 }
 

@@ -16,8 +16,11 @@ constexpr int kMaxDevices = 64;
 template <int NS, int BQ, bool BF16, bool MASKED>
 static cudaError_t launch_one(const ScanParams& p, int grid, int device, cudaStream_t st) {
   auto kern = scan_topk_kernel<NS, BQ, kWarps, BF16, MASKED>;
-  const size_t smem = (size_t)kWarps * TileGeom<NS, BF16>::TILE_BYTES +
-                      (size_t)kWarps * BQ * p.cap * 8 + (size_t)kWarps * 8;
+  size_t smem = (size_t)kWarps * TileGeom<NS, BF16>::TILE_BYTES +
+                (size_t)kWarps * BQ * p.cap * 8 + (size_t)kWarps * 8;
+  // the last CTA stages gridDim.x partial lists of kp keys in shared memory
+  if (grid > 256) return cudaErrorInvalidConfiguration;
+  if (smem < (size_t)grid * p.kp * 8) smem = (size_t)grid * p.kp * 8;
   // 227 KB per CTA minus the kernel's static shared memory (ticket word, padded)
   if (smem > 232448 - 256) return cudaErrorInvalidConfiguration;
   static size_t attr_bytes[kMaxDevices] = {};
