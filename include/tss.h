@@ -184,6 +184,9 @@ int tss_event_create(int device, void** out);
 int tss_event_record(tss_index* ix, void* ev);
 int tss_event_elapsed_ms(void* ev_a, void* ev_b, float* out_ms); /* synchronises on ev_b */
 int tss_event_destroy(void* ev);
+/* diagnostics: when d_buf (device, 256*8 u64) is non-NULL every scan CTA writes %globaltimer
+ * stamps of its phases into it (slot = cta*8 + phase); NULL switches it off. */
+int tss_index_debug_phases(tss_index* ix, void* d_buf);
 /* kernels launched by this library in this process so far (bench's gpu_launches). */
 uint64_t tss_launch_count(void);
 

@@ -38,7 +38,7 @@ ABI_SYMBOLS = [
     "tss_terms_create", "tss_terms_size", "tss_terms_destroy", "tss_prefix_mask",
     "tss_index_stream", "tss_index_sync", "tss_dev_alloc", "tss_dev_free", "tss_dev_h2d",
     "tss_dev_d2h", "tss_event_create", "tss_event_record", "tss_event_elapsed_ms",
-    "tss_event_destroy", "tss_launch_count",
+    "tss_event_destroy", "tss_launch_count", "tss_index_debug_phases",
 ]
 
 
@@ -110,6 +110,7 @@ def lib() -> C.CDLL:
         "tss_event_elapsed_ms": (i32, [vp, vp, pf]),
         "tss_event_destroy": (i32, [vp]),
         "tss_launch_count": (u64, []),
+        "tss_index_debug_phases": (i32, [vp, vp]),
     }
     del pu32
     for name, (res, args) in sig.items():

@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -134,7 +135,14 @@ struct tss_index {
   uint64_t* d_gather = nullptr;    // nranks x kWsQueries x k (lazy)
   uint64_t* d_merged = nullptr;    // kWsQueries x k (lazy)
   uint64_t* d_partials = nullptr;  // kMaxBq x num_sms x 128
-  unsigned int* d_counter = nullptr;
+  unsigned int* d_counter = nullptr;  // [0] done ticket, [1] dynamic tile claims
+  // tile schedule of the unmasked scan (see scan.cuh): share of tiles walked statically,
+  // tiles per dynamic claim, and how many warp-rounds at the very end are claimed one
+  // tile at a time (tail balancing)
+  float static_frac = 0.0f;
+  uint32_t dyn_chunk = 8;
+  float fine_rounds = 2.0f;
+  unsigned long long* d_dbg = nullptr;  // diagnostics (tss_index_debug_phases)
   float* h_queries = nullptr;  // pinned
   uint64_t* h_keys = nullptr;  // pinned
 };
@@ -213,7 +221,23 @@ int enqueue_scan(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
     p.mask_mode = mode;
     p.partials = ix->d_partials;
     p.done_counter = ix->d_counter;
+    p.tile_counter = ix->d_counter + 1;
+    {
+      // tiles per warp-round = num_sms * 16 warps; rows per tile from the storage geometry
+      const uint64_t tile_rows = 12288 / ix->row_bytes >= 16  ? 16
+                                 : 12288 / ix->row_bytes >= 8 ? 8
+                                 : 12288 / ix->row_bytes >= 4 ? 4
+                                 : 12288 / ix->row_bytes >= 2 ? 2
+                                                              : 1;
+      const uint64_t tiles = (ix->n_rows + tile_rows - 1) / tile_rows;
+      const uint64_t gw = (uint64_t)ix->num_sms * 16;
+      p.static_rounds = (uint32_t)((double)(tiles / gw) * ix->static_frac);
+      p.dyn_chunk = ix->dyn_chunk;
+      const uint64_t fine_tiles = (uint64_t)((double)gw * ix->fine_rounds);
+      p.fine_start = tiles > fine_tiles ? tiles - fine_tiles : 0;
+    }
     p.out_keys = d_out + (size_t)q0 * k;
+    p.dbg = ix->d_dbg;
     cudaError_t e = tss::launch_scan(ix->ns, p, bq, ix->storage == TSS_BF16, mode != TSS_MASK_NONE,
                                      ix->num_sms, ix->device, ix->stream);
     if (e != cudaSuccess) return cuda_fail(e, "scan_topk_kernel launch");
@@ -311,8 +335,12 @@ int tss_index_create(tss_index** out, uint32_t dim, int storage, int device) {
   ALLOC(cudaMalloc(&ix->d_queries, (size_t)kWsQueries * dim * sizeof(float)))
   ALLOC(cudaMalloc(&ix->d_keys, (size_t)kWsQueries * TSS_MAX_FUSED_K * sizeof(uint64_t)))
   ALLOC(cudaMalloc(&ix->d_partials, (size_t)kMaxBq * ix->num_sms * 128 * sizeof(uint64_t)))
-  ALLOC(cudaMalloc(&ix->d_counter, sizeof(unsigned int)))
-  ALLOC(cudaMemset(ix->d_counter, 0, sizeof(unsigned int)))
+  ALLOC(cudaMalloc(&ix->d_counter, 2 * sizeof(unsigned int)))
+  ALLOC(cudaMemset(ix->d_counter, 0, 2 * sizeof(unsigned int)))
+  if (const char* sf = getenv("TSS_STATIC_FRAC")) ix->static_frac = (float)atof(sf);
+  if (const char* sf = getenv("TSS_FINE_ROUNDS")) ix->fine_rounds = (float)atof(sf);
+  if (const char* sf = getenv("TSS_DYN_CHUNK")) ix->dyn_chunk = (uint32_t)atoi(sf);
+  if (ix->dyn_chunk < 1) ix->dyn_chunk = 1;
   ALLOC(cudaMallocHost(&ix->h_queries, (size_t)kWsQueries * dim * sizeof(float)))
   ALLOC(cudaMallocHost(&ix->h_keys, (size_t)kWsQueries * TSS_MAX_FUSED_K * sizeof(uint64_t)))
 #undef ALLOC
@@ -818,6 +846,11 @@ int tss_prefix_mask(tss_terms* t, const char* prefix, uint32_t len, int kind, ts
 }
 
 // ---- plumbing --------------------------------------------------------------------------------
+int tss_index_debug_phases(tss_index* ix, void* d_buf) {
+  if (!ix) return fail(TSS_ERR_INVALID_ARG, "index is NULL");
+  ix->d_dbg = reinterpret_cast<unsigned long long*>(d_buf);
+  return TSS_OK;
+}
 void* tss_index_stream(tss_index* ix) { return ix ? (void*)ix->stream : nullptr; }
 
 int tss_index_sync(tss_index* ix) {

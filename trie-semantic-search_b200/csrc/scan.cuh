@@ -38,9 +38,31 @@ struct ScanParams {
   int mask_mode;           // TSS_MASK_*
   uint64_t* partials;      // [BQ][gridDim.x][kp]
   unsigned int* done_counter;
+  unsigned int* tile_counter;  // dynamic tile claims (unmasked scans); zero between launches
+  uint32_t static_rounds;  // each warp first takes this many statically interleaved tiles
+  uint32_t dyn_chunk;      // tiles per dynamic claim before fine_start (>= 1)
+  uint64_t fine_start;     // from this tile on, dynamic claims are single tiles
   uint64_t* out_keys;      // [nq_valid][k]
   uint32_t smem_bytes;     // dynamic shared memory size of this launch
+  unsigned long long* dbg; // diagnostics: [gridDim.x][8] %globaltimer stamps, or null
 };
+
+__device__ __forceinline__ void dbg_stamp(const ScanParams& p, int slot) {
+  if (p.dbg && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    p.dbg[(size_t)blockIdx.x * 8 + slot] = t;
+  }
+}
+
+// max of a 64-bit key over the warp with two hardware REDUX ops (hi word, then the lo words
+// of the lanes that tie on hi).  All 32 lanes must call it.
+__device__ __forceinline__ uint64_t warp_max64(uint64_t v) {
+  const uint32_t hi = (uint32_t)(v >> 32), lo = (uint32_t)v;
+  const uint32_t mh = __reduce_max_sync(FULL_MASK, hi);
+  const uint32_t ml = __reduce_max_sync(FULL_MASK, hi == mh ? lo : 0u);
+  return ((uint64_t)mh << 32) | ml;
+}
 
 // ---- warp-level candidate list ----------------------------------------------------
 __device__ __forceinline__ void warp_bitonic_sort_desc(uint64_t* list, uint32_t cap, int lane) {
@@ -61,12 +83,30 @@ __device__ __forceinline__ void warp_bitonic_sort_desc(uint64_t* list, uint32_t 
   }
 }
 
-// sort the list, keep the best k, refresh the threshold
+// keep the best k of the list, sorted descending and zero padded; refresh the threshold
 __device__ __forceinline__ void warp_prune(uint64_t* list, uint32_t& n, uint32_t k, uint32_t cap,
                                            uint64_t& thresh, int lane) {
-  for (uint32_t i = n + lane; i < cap; i += 32) list[i] = 0;
-  __syncwarp();
-  warp_bitonic_sort_desc(list, cap, lane);
+  if (cap == 64) {
+    // small k: two keys per lane in registers, k rounds of "take the warp max"
+    uint64_t a = (uint32_t)lane < n ? list[lane] : 0;
+    uint64_t b = (uint32_t)lane + 32 < n ? list[lane + 32] : 0;
+    __syncwarp();
+    uint64_t mine = 0, mine2 = 0;  // lane j ends up holding sorted[j] (and sorted[j+32])
+    for (uint32_t j = 0; j < k; ++j) {
+      uint64_t g = warp_max64(a > b ? a : b);
+      if (g == 0) break;
+      if (a == g) a = 0;
+      else if (b == g) b = 0;
+      if ((j & 31) == (uint32_t)lane) (j < 32 ? mine : mine2) = g;
+    }
+    list[lane] = mine;
+    list[lane + 32] = mine2;
+    __syncwarp();
+  } else {
+    for (uint32_t i = n + lane; i < cap; i += 32) list[i] = 0;
+    __syncwarp();
+    warp_bitonic_sort_desc(list, cap, lane);
+  }
   if (n >= k) {
     n = k;
     thresh = list[k - 1];
@@ -143,12 +183,7 @@ __device__ __forceinline__ void warp_tournament(const uint64_t* lists, uint32_t 
         if (v > best) best = v, bi = i;
       }
     }
-    uint64_t g = best;
-#pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) {
-      uint64_t o = __shfl_xor_sync(FULL_MASK, g, m);
-      g = o > g ? o : g;
-    }
+    const uint64_t g = warp_max64(best);
     if (lane == 0) out[j] = g;
     if (g != 0 && best == g) {
 #pragma unroll
@@ -190,6 +225,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_topk_kernel(const ScanPara
   const uint32_t bar = smem_u32(&bars[warp]);
   const uint32_t tile_s = smem_u32(tile);
 
+  dbg_stamp(p, 0);
   if (lane == 0) {
     mbar_init(bar, 1);
     fence_barrier_init();
@@ -286,8 +322,53 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_topk_kernel(const ScanPara
     }
   };
 
+  dbg_stamp(p, 1);
+  // ---- tile schedule -------------------------------------------------------------------
+  // Unmasked: every warp first walks `static_rounds` statically interleaved tiles
+  // (tile = warp_id + round * GW, no atomics), then claims the remaining tiles one at a
+  // time from a global counter, so SMs that stream faster take more of the tail and all
+  // CTAs finish together.  The claim for the tile after next is issued right after a
+  // copy is launched, so the atomic's latency hides behind a whole tile of work.
+  // Masked: static interleave with 32-tile look-ahead skipping of dead tiles.
+  const uint64_t gw = (uint64_t)blockIdx.x * WARPS + warp;
+  const uint64_t dyn_base = (uint64_t)p.static_rounds * GW;
+  uint32_t round = 0, claim_raw = 0, claim_size = 0;
+  uint64_t claim_t = 0, q_next = 0, q_end = 0, last_seen = 0;
+  bool claim_dyn = false;
+  auto claim = [&]() {
+    claim_dyn = false;
+    if (round < p.static_rounds) {
+      claim_t = gw + (uint64_t)round * GW;
+      ++round;
+    } else if (q_next < q_end) {
+      claim_t = q_next++;  // rest of the chunk claimed earlier
+    } else {
+      claim_size = last_seen >= p.fine_start ? 1u : p.dyn_chunk;
+      if (lane == 0) claim_raw = atomicAdd(p.tile_counter, claim_size);
+      claim_dyn = true;
+    }
+  };
+  auto resolve = [&](uint32_t& bits) -> uint64_t {
+    uint64_t tt = claim_t;
+    if (claim_dyn) {
+      tt = dyn_base + __shfl_sync(FULL_MASK, claim_raw, 0);
+      q_next = tt + 1;
+      q_end = tt + claim_size;
+      last_seen = tt;
+    }
+    bits = tt < total_tiles ? tile_bits(tt) : 0u;
+    return tt;
+  };
+
   uint32_t cur_bits = 0;
-  uint64_t t = next_live((uint64_t)blockIdx.x * WARPS + warp, cur_bits);
+  uint64_t t;
+  if constexpr (MASKED) {
+    t = next_live(gw, cur_bits);
+  } else {
+    claim();
+    t = resolve(cur_bits);
+    claim();
+  }
   uint32_t phase = 0;
   if (t < total_tiles) issue(t, cur_bits);
 
@@ -343,8 +424,14 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_topk_kernel(const ScanPara
     // above, so the buffer can be handed back to the TMA unit.
     __syncwarp();
     uint32_t nbits = 0;
-    const uint64_t tn = next_live(t + GW, nbits);
+    uint64_t tn;
+    if constexpr (MASKED) {
+      tn = next_live(t + GW, nbits);
+    } else {
+      tn = resolve(nbits);
+    }
     if (tn < total_tiles) issue(tn, nbits);
+    if constexpr (!MASKED) claim();
 
     // ---- score + top-k for tile t (overlaps the copy just issued) -------------
 #pragma unroll
@@ -366,11 +453,13 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_topk_kernel(const ScanPara
     cur_bits = nbits;
   }
 
+  dbg_stamp(p, 2);
   // ---- per-warp final prune: sorted, zero padded ---------------------------------
 #pragma unroll
   for (int b = 0; b < BQ; ++b)
     warp_prune(lists + (size_t)b * p.cap, cnt[b], p.k, p.cap, thresh[b], lane);
   __syncthreads();
+  dbg_stamp(p, 3);
 
   // ---- CTA merge: tournament over the WARPS sorted lists, one warp per query -------------
   const int tid = threadIdx.x, nthreads = WARPS * 32;
@@ -386,6 +475,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_topk_kernel(const ScanPara
   __syncthreads();
   if (tid == 0) s_ticket = atomicAdd(p.done_counter, 1u);
   __syncthreads();
+  dbg_stamp(p, 4);
   if (s_ticket != gridDim.x - 1) return;
   __threadfence();
 
@@ -394,16 +484,35 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_topk_kernel(const ScanPara
   uint64_t* ws = reinterpret_cast<uint64_t*>(smem);
   for (uint32_t b = 0; b < p.nq_valid; ++b) {
     const uint64_t* part = p.partials + (size_t)b * gridDim.x * p.kp;
-    for (uint32_t idx = tid; idx < gridDim.x * p.kp; idx += nthreads) {
-      uint32_t e = idx % p.kp;
-      ws[idx] = e < p.k ? __ldcg(part + idx) : 0;
+    const uint32_t total_keys = gridDim.x * p.k;
+    for (uint32_t i0 = tid; i0 < total_keys; i0 += 4 * nthreads) {
+      uint64_t v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {  // all four loads in flight before the first store
+        uint32_t idx = i0 + u * nthreads;
+        uint32_t l = idx / p.k, e = idx - l * p.k;
+        v[u] = idx < total_keys ? __ldcg(part + (size_t)l * p.kp + e) : 0;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        uint32_t idx = i0 + u * nthreads;
+        if (idx < total_keys) ws[idx] = v[u];
+      }
     }
     __syncthreads();
-    if (warp == 0)
-      warp_tournament<8>(ws, p.kp, gridDim.x, p.k, p.k, p.out_keys + (size_t)b * p.k, lane);
+    if (warp == 0) {
+      if (gridDim.x <= 160)
+        warp_tournament<5>(ws, p.k, gridDim.x, p.k, p.k, p.out_keys + (size_t)b * p.k, lane);
+      else
+        warp_tournament<8>(ws, p.k, gridDim.x, p.k, p.k, p.out_keys + (size_t)b * p.k, lane);
+    }
     __syncthreads();
   }
-  if (tid == 0) *p.done_counter = 0;
+  dbg_stamp(p, 5);
+  if (tid == 0) {
+    *p.done_counter = 0;
+    *p.tile_counter = 0;
+  }
 }
 
 }  // namespace tss
