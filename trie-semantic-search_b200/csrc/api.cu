@@ -19,6 +19,7 @@
 
 #include "../../include/tss.h"
 #include "aux_kernels.cuh"
+#include "gemm_topk.cuh"
 #include "scan.cuh"
 #include "scan_launch.h"
 
@@ -84,6 +85,38 @@ constexpr int kNcclUint64 = 5;
 constexpr uint32_t kMaxBq = 4;           // queries per scan launch
 constexpr uint32_t kWsQueries = 1024;    // device query/result workspace, in queries
 constexpr size_t kStageBytes = 64u << 20;  // upload staging buffer
+constexpr uint32_t kGemmCandCap = 16384;   // survivors kept per query by the K2 epilogue
+constexpr uint32_t kGemmMaxSample = 8192;  // tiles sampled by the K2 threshold pass
+
+typedef CUresult (*TmapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                 const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+TmapEncodeFn g_tmap_encode = nullptr;
+int load_tmap_encode() {
+  if (g_tmap_encode) return TSS_OK;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn)
+    return fail(TSS_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  g_tmap_encode = reinterpret_cast<TmapEncodeFn>(fn);
+  return TSS_OK;
+}
+// 2-D bf16 tensor map over a row-major [rows][kpad] matrix, box = 64 elements x box_rows,
+// 128-byte swizzle (what the UMMA K-major descriptors in gemm_topk.cu expect)
+int make_tmap(CUtensorMap* out, const void* base, uint64_t rows, uint32_t kpad, uint32_t box_rows) {
+  cuuint64_t dims[2] = {kpad, rows ? rows : 1};
+  cuuint64_t strides[1] = {(cuuint64_t)kpad * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_tmap_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims,
+                             strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(TSS_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return TSS_OK;
+}
 
 }  // namespace
 
@@ -145,6 +178,25 @@ struct tss_index {
   unsigned long long* d_dbg = nullptr;  // diagnostics (tss_index_debug_phases)
   float* h_queries = nullptr;  // pinned
   uint64_t* h_keys = nullptr;  // pinned
+  // K2 (tensor-core) workspace, allocated on first large-batch search of a bf16 index
+  struct Gemm {
+    bool ready = false;
+    uint64_t norm_rows = 0;        // rows covered by d_inv_norm
+    const void* norm_base = nullptr;
+    float* d_inv_norm = nullptr;   // [capacity]
+    uint64_t inv_norm_cap = 0;
+    uint16_t* d_qbf16 = nullptr;   // [kWsQueries][kpad]
+    float* d_inv_q = nullptr;      // [kWsQueries]
+    float* d_thr = nullptr;        // [kWsQueries]
+    float* d_tile_max = nullptr;   // [kGemmMaxSample][kWsQueries]
+    uint64_t* d_cand = nullptr;    // [kWsQueries][kGemmCandCap]
+    uint32_t* d_cand_count = nullptr;
+    uint32_t* h_cand_count = nullptr;  // pinned
+    CUtensorMap tmap_q, tmap_e;
+    uint64_t tmap_rows = 0;
+    const void* tmap_base = nullptr;
+  } gemm;
+  uint32_t gemm_min_nq = 32;  // batches at least this large use K2 (bf16 storage, D <= 384)
 };
 
 namespace {
@@ -263,9 +315,128 @@ int enqueue_gather_merge(tss_index* ix, const uint64_t* d_local, uint32_t nq, ui
 
 int ensure_gather_ws(tss_index* ix) {
   if (!ix->comm || ix->d_gather) return TSS_OK;
-  CU(cudaMalloc(&ix->d_gather,
-                (size_t)ix->comm->nranks * kWsQueries * TSS_MAX_FUSED_K * sizeof(uint64_t)));
-  CU(cudaMalloc(&ix->d_merged, (size_t)kWsQueries * TSS_MAX_FUSED_K * sizeof(uint64_t)));
+  CU(cudaMalloc(&ix->d_gather, (size_t)ix->comm->nranks * kWsQueries * TSS_MAX_K * sizeof(uint64_t)));
+  CU(cudaMalloc(&ix->d_merged, (size_t)kWsQueries * TSS_MAX_K * sizeof(uint64_t)));
+  return TSS_OK;
+}
+
+bool gemm_eligible(const tss_index* ix, uint32_t nq, uint32_t k, int mode) {
+  return ix->storage == TSS_BF16 && ix->ns <= 3 && mode == TSS_MASK_NONE &&
+         nq >= ix->gemm_min_nq && ix->n_rows >= 4ull * 256 * k && k <= TSS_MAX_K;
+}
+
+int ensure_gemm_ws(tss_index* ix) {
+  tss_index::Gemm& g = ix->gemm;
+  int rc = load_tmap_encode();
+  if (rc) return rc;
+  const uint32_t kpad = ix->stride_elems;
+  if (!g.ready) {
+    CU(cudaMalloc(&g.d_qbf16, (size_t)kWsQueries * kpad * 2));
+    CU(cudaMalloc(&g.d_inv_q, kWsQueries * sizeof(float)));
+    CU(cudaMalloc(&g.d_thr, kWsQueries * sizeof(float)));
+    CU(cudaMalloc(&g.d_tile_max, (size_t)kGemmMaxSample * kWsQueries * sizeof(float)));
+    CU(cudaMalloc(&g.d_cand, (size_t)kWsQueries * kGemmCandCap * sizeof(uint64_t)));
+    CU(cudaMalloc(&g.d_cand_count, kWsQueries * sizeof(uint32_t)));
+    CU(cudaMallocHost(&g.h_cand_count, kWsQueries * sizeof(uint32_t)));
+    if ((rc = make_tmap(&g.tmap_q, g.d_qbf16, kWsQueries, kpad, 128))) return rc;
+    g.ready = true;
+  }
+  if (g.inv_norm_cap < ix->n_rows) {
+    cudaFree(g.d_inv_norm);
+    g.d_inv_norm = nullptr;
+    CU(cudaMalloc(&g.d_inv_norm, (size_t)ix->capacity * sizeof(float)));
+    g.inv_norm_cap = ix->capacity;
+    g.norm_rows = 0;
+  }
+  if (g.norm_rows != ix->n_rows || g.norm_base != ix->d_rows) {
+    cudaError_t e =
+        tss::launch_row_inv_norm(ix->d_rows, ix->n_rows, ix->stride_elems, g.d_inv_norm, ix->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "row_inv_norm launch");
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    g.norm_rows = ix->n_rows;
+    g.norm_base = ix->d_rows;
+  }
+  if (g.tmap_rows != ix->n_rows || g.tmap_base != ix->d_rows) {
+    if ((rc = make_tmap(&g.tmap_e, ix->d_rows, ix->n_rows, kpad, 256))) return rc;
+    g.tmap_rows = ix->n_rows;
+    g.tmap_base = ix->d_rows;
+  }
+  return TSS_OK;
+}
+
+int enqueue_scan(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
+                 const tss_mask* mask, int mode, uint64_t* d_out);
+
+// K2: nq <= kWsQueries device-resident fp32 queries -> d_out (nq x k local keys).
+// Synchronises the stream once to check the survivor lists for overflow; queries whose list
+// overflowed (adversarially clustered scores) are redone exactly by the K1 scan.
+int enqueue_gemm(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k, uint64_t* d_out) {
+  int rc = ensure_gemm_ws(ix);
+  if (rc) return rc;
+  tss_index::Gemm& g = ix->gemm;
+  const uint32_t kpad = ix->stride_elems;
+  const uint32_t nq_pad = (nq + 127) / 128 * 128, mb = nq_pad / 128;
+  const uint32_t num_tiles = (uint32_t)((ix->n_rows + 255) / 256);
+  uint32_t sample = k * 8 > 1024 ? k * 8 : 1024;
+  if (sample > kGemmMaxSample) sample = kGemmMaxSample;
+  if (sample > num_tiles) sample = num_tiles;
+  int nslices = ix->num_sms / (int)mb;
+  if (nslices < 1) return fail(TSS_ERR_INVALID_ARG, "batch of %u queries exceeds one K2 launch", nq);
+  const int grid = nslices * (int)mb;
+  cudaError_t e;
+  e = tss::launch_prep_queries(d_queries, nq, ix->dim, kpad, nq_pad, g.d_qbf16, g.d_inv_q, ix->stream);
+  if (e != cudaSuccess) return cuda_fail(e, "prep_queries launch");
+  CU(cudaMemsetAsync(g.d_cand_count, 0, nq_pad * sizeof(uint32_t), ix->stream));
+  tss::GemmParams p{};
+  p.n_rows = ix->n_rows;
+  p.row_base = (uint32_t)ix->row_base;
+  p.inv_norm = g.d_inv_norm;
+  p.mb = mb;
+  p.num_tiles = num_tiles;
+  p.sample_stride = num_tiles / sample;
+  p.sample_count = sample;
+  p.tile_max = g.d_tile_max;
+  p.thr = g.d_thr;
+  p.cand = g.d_cand;
+  p.cand_count = g.d_cand_count;
+  p.cand_cap = kGemmCandCap;
+  const int kb = (int)(kpad / 64);
+  p.mode = 0;
+  if ((e = tss::launch_gemm_topk(kb, g.tmap_q, g.tmap_e, p, grid, ix->stream)) != cudaSuccess)
+    return cuda_fail(e, "gemm_topk_kernel (threshold pass) launch");
+  if ((e = tss::launch_threshold(g.d_tile_max, sample, nq_pad, nq, k, g.d_thr, ix->stream)) != cudaSuccess)
+    return cuda_fail(e, "threshold_kernel launch");
+  p.mode = 1;
+  if ((e = tss::launch_gemm_topk(kb, g.tmap_q, g.tmap_e, p, grid, ix->stream)) != cudaSuccess)
+    return cuda_fail(e, "gemm_topk_kernel (collect pass) launch");
+  if ((e = tss::launch_select(g.d_cand, g.d_cand_count, kGemmCandCap, g.d_inv_q, nq, k, d_out,
+                              ix->stream)) != cudaSuccess)
+    return cuda_fail(e, "select_kernel launch");
+  g_launches.fetch_add(5, std::memory_order_relaxed);
+  CU(cudaMemcpyAsync(g.h_cand_count, g.d_cand_count, nq * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                     ix->stream));
+  CU(cudaStreamSynchronize(ix->stream));
+  for (uint32_t qi = 0; qi < nq; ++qi) {
+    if (g.h_cand_count[qi] <= kGemmCandCap) continue;
+    if (k > TSS_MAX_FUSED_K)
+      return fail(TSS_ERR_STATE, "K2 survivor list overflowed for query %u and k=%u > %u has no "
+                  "exact fallback", qi, k, TSS_MAX_FUSED_K);
+    if ((rc = enqueue_scan(ix, d_queries + (size_t)qi * ix->dim, 1, k, nullptr, TSS_MASK_NONE,
+                           d_out + (size_t)qi * k)))
+      return rc;
+  }
+  return TSS_OK;
+}
+
+// local (per-shard) search of nq device-resident queries: picks K2 or K1
+int enqueue_local(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
+                  const tss_mask* mask, int mode, uint64_t* d_out) {
+  if (!gemm_eligible(ix, nq, k, mode)) return enqueue_scan(ix, d_queries, nq, k, mask, mode, d_out);
+  for (uint32_t q0 = 0; q0 < nq; q0 += kWsQueries) {
+    uint32_t n = nq - q0 < kWsQueries ? nq - q0 : kWsQueries;
+    int rc = enqueue_gemm(ix, d_queries + (size_t)q0 * ix->dim, n, k, d_out + (size_t)q0 * k);
+    if (rc) return rc;
+  }
   return TSS_OK;
 }
 
@@ -273,9 +444,15 @@ int validate_search(const tss_index* ix, const void* queries, uint32_t nq, uint3
   if (!ix) return fail(TSS_ERR_INVALID_ARG, "index is NULL");
   if (!queries && nq) return fail(TSS_ERR_INVALID_ARG, "queries is NULL");
   if (k == 0 || k > TSS_MAX_K) return fail(TSS_ERR_INVALID_ARG, "k=%u outside [1,%u]", k, TSS_MAX_K);
-  if (k > TSS_MAX_FUSED_K)
-    return fail(TSS_ERR_INVALID_ARG, "k=%u > %u is not implemented yet", k, TSS_MAX_FUSED_K);
   if (!ix->finalized) return fail(TSS_ERR_STATE, "search before tss_index_finalize");
+  return TSS_OK;
+}
+int check_k_path(const tss_index* ix, uint32_t nq, uint32_t k, int mode) {
+  if (k > TSS_MAX_FUSED_K && !gemm_eligible(ix, nq, k, mode))
+    return fail(TSS_ERR_INVALID_ARG,
+                "k=%u > %u needs the tensor-core path: bf16 storage, dim <= 384, no mask, nq >= %u "
+                "and at least %llu rows", k, TSS_MAX_FUSED_K, ix->gemm_min_nq,
+                (unsigned long long)(4ull * 256 * k));
   return TSS_OK;
 }
 
@@ -333,7 +510,7 @@ int tss_index_create(tss_index** out, uint32_t dim, int storage, int device) {
   ALLOC(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking))
   ALLOC(cudaMalloc(&ix->d_flag, sizeof(int)))
   ALLOC(cudaMalloc(&ix->d_queries, (size_t)kWsQueries * dim * sizeof(float)))
-  ALLOC(cudaMalloc(&ix->d_keys, (size_t)kWsQueries * TSS_MAX_FUSED_K * sizeof(uint64_t)))
+  ALLOC(cudaMalloc(&ix->d_keys, (size_t)kWsQueries * TSS_MAX_K * sizeof(uint64_t)))
   ALLOC(cudaMalloc(&ix->d_partials, (size_t)kMaxBq * ix->num_sms * 128 * sizeof(uint64_t)))
   ALLOC(cudaMalloc(&ix->d_counter, 2 * sizeof(unsigned int)))
   ALLOC(cudaMemset(ix->d_counter, 0, 2 * sizeof(unsigned int)))
@@ -342,7 +519,8 @@ int tss_index_create(tss_index** out, uint32_t dim, int storage, int device) {
   if (const char* sf = getenv("TSS_DYN_CHUNK")) ix->dyn_chunk = (uint32_t)atoi(sf);
   if (ix->dyn_chunk < 1) ix->dyn_chunk = 1;
   ALLOC(cudaMallocHost(&ix->h_queries, (size_t)kWsQueries * dim * sizeof(float)))
-  ALLOC(cudaMallocHost(&ix->h_keys, (size_t)kWsQueries * TSS_MAX_FUSED_K * sizeof(uint64_t)))
+  ALLOC(cudaMallocHost(&ix->h_keys, (size_t)kWsQueries * TSS_MAX_K * sizeof(uint64_t)))
+  if (const char* sf = getenv("TSS_GEMM_MIN_NQ")) ix->gemm_min_nq = (uint32_t)atoi(sf);
 #undef ALLOC
   *out = ix;
   return TSS_OK;
@@ -363,6 +541,14 @@ void tss_index_destroy(tss_index* ix) {
   cudaFree(ix->d_counter);
   if (ix->h_queries) cudaFreeHost(ix->h_queries);
   if (ix->h_keys) cudaFreeHost(ix->h_keys);
+  cudaFree(ix->gemm.d_inv_norm);
+  cudaFree(ix->gemm.d_qbf16);
+  cudaFree(ix->gemm.d_inv_q);
+  cudaFree(ix->gemm.d_thr);
+  cudaFree(ix->gemm.d_tile_max);
+  cudaFree(ix->gemm.d_cand);
+  cudaFree(ix->gemm.d_cand_count);
+  if (ix->gemm.h_cand_count) cudaFreeHost(ix->gemm.h_cand_count);
   if (ix->stream) cudaStreamDestroy(ix->stream);
   delete ix;
 }
@@ -475,13 +661,14 @@ int tss_index_search_device(tss_index* ix, const float* d_queries, uint32_t nq, 
   if (rc) return rc;
   if (!d_out_keys) return fail(TSS_ERR_INVALID_ARG, "d_out_keys is NULL");
   if ((rc = check_mask(ix, mask, mask_mode))) return rc;
+  if ((rc = check_k_path(ix, nq, k, mask_mode))) return rc;
   if (!nq) return TSS_OK;
   DeviceGuard g(ix->device);
-  if (!ix->comm) return enqueue_scan(ix, d_queries, nq, k, mask, mask_mode, d_out_keys);
+  if (!ix->comm) return enqueue_local(ix, d_queries, nq, k, mask, mask_mode, d_out_keys);
   if ((rc = ensure_gather_ws(ix))) return rc;
   for (uint32_t q0 = 0; q0 < nq; q0 += kWsQueries) {
     uint32_t n = nq - q0 < kWsQueries ? nq - q0 : kWsQueries;
-    if ((rc = enqueue_scan(ix, d_queries + (size_t)q0 * ix->dim, n, k, mask, mask_mode, ix->d_keys)))
+    if ((rc = enqueue_local(ix, d_queries + (size_t)q0 * ix->dim, n, k, mask, mask_mode, ix->d_keys)))
       return rc;
     if ((rc = enqueue_gather_merge(ix, ix->d_keys, n, k, d_out_keys + (size_t)q0 * k))) return rc;
   }
@@ -513,6 +700,7 @@ int tss_index_search(tss_index* ix, const float* queries, uint32_t nq, uint32_t 
   if (!out_rows || !out_scores || !out_counts)
     return fail(TSS_ERR_INVALID_ARG, "output pointer is NULL");
   if ((rc = check_mask(ix, mask, mask_mode))) return rc;
+  if ((rc = check_k_path(ix, nq, k, mask_mode))) return rc;
   if (!nq) return TSS_OK;
   for (uint64_t i = 0; i < (uint64_t)nq * ix->dim; ++i)
     if (!std::isfinite(queries[i]))
@@ -525,7 +713,12 @@ int tss_index_search(tss_index* ix, const float* queries, uint32_t nq, uint32_t 
     size_t qbytes = (size_t)n * ix->dim * sizeof(float);
     memcpy(ix->h_queries, queries + (size_t)q0 * ix->dim, qbytes);
     CU(cudaMemcpyAsync(ix->d_queries, ix->h_queries, qbytes, cudaMemcpyHostToDevice, ix->stream));
-    if ((rc = enqueue_scan(ix, ix->d_queries, n, k, mask, mask_mode, ix->d_keys))) return rc;
+    // a large batch of a bf16 index takes the tensor-core path as a whole (nq, not n, decides)
+    if (gemm_eligible(ix, nq, k, mask_mode))
+      rc = enqueue_gemm(ix, ix->d_queries, n, k, ix->d_keys);
+    else
+      rc = enqueue_scan(ix, ix->d_queries, n, k, mask, mask_mode, ix->d_keys);
+    if (rc) return rc;
     const uint64_t* d_res = ix->d_keys;
     if (ix->comm) {
       if ((rc = enqueue_gather_merge(ix, ix->d_keys, n, k, ix->d_merged))) return rc;

@@ -1,0 +1,450 @@
+// gemm_topk.cu -- K2: tcgen05/TMEM bf16 GEMM scoring with a fused threshold top-k epilogue.
+//
+// Large query batches really are a dense contraction S = Q . E^T (B x N, K = D), so this
+// path runs on the 5th-generation tensor cores.  It replaces the body of HnswIndex::search
+// (reference src/vector.rs:195-202, a stub) for nq >= 32 over a bf16 index.
+//
+// Per CTA (one per SM, 192 threads, cta_group::1):
+//   * 128 queries (one UMMA M tile) stay resident in shared memory for the whole kernel as
+//     K/64 swizzle-128B K-major tiles (TMA, 96 KB at D = 384);
+//   * corpus tiles of 256 rows stream through a 3-stage ring of 256 x 64 bf16 boxes
+//     (TMA 2-D tensor map over the row-major matrix, swizzle 128B, 32 KB per stage);
+//   * one elected thread issues tcgen05.mma (M128 N256 K16, fp32 accumulate) into one of two
+//     256-column TMEM accumulators; tcgen05.commit frees the smem stage / publishes the tile;
+//   * four epilogue warps read the accumulator with tcgen05.ld (lane = query, column =
+//     corpus row), scale by the row's 1/norm and either
+//       mode 0: keep the per-tile maximum  (threshold pass over a strided tile sample), or
+//       mode 1: append (score,row) keys that reach the query's threshold to a global list.
+//     The epilogue of tile t overlaps the MMAs of tile t+1 (double-buffered TMEM).
+//
+// The threshold of a query is the k-th largest of >= k per-tile maxima: k distinct rows score
+// at least that much, so it is a valid lower bound of the global k-th best score and no row
+// below it can be in the top-k.  The exact top-k is then selected from the (few thousand)
+// survivors.  The N x B score matrix is never materialised.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+#include "gemm_topk.cuh"
+
+namespace tss {
+
+namespace {
+
+constexpr int kBlockM = 128;      // queries per CTA (UMMA M)
+constexpr int kBlockN = 256;      // corpus rows per tile (UMMA N)
+constexpr int kBlockK = 64;       // bf16 elements per k-block = 128 bytes = one swizzle atom row
+constexpr int kUmmaK = 16;        // K per tcgen05.mma for 16-bit inputs
+constexpr int kStages = 3;
+constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KB
+constexpr int kBTileBytes = kBlockN * kBlockK * 2;  // 32 KB
+constexpr int kThreads = 192;     // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2..5 epilogue
+constexpr int kTmemCols = 512;    // two 256-column fp32 accumulators
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                            int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+// K-major, swizzle-128B shared-memory matrix descriptor (sm_100 format):
+// start address >> 4 | SBO (8 rows x 128 B = 1024) >> 4 at bit 32 | version 1 at bit 46 |
+// layout SWIZZLE_128B (2) at bit 61.  LBO is unused for a single swizzle atom along K.
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  uint64_t d = (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(1024u >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// instruction descriptor, kind::f16: D fp32 (bit 4), A bf16 (bit 7), B bf16 (bit 10),
+// both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kBlockN >> 3) << 17) |
+                            ((uint32_t)(kBlockM >> 4) << 24);
+
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                     uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(kIdesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+}  // namespace
+
+template <int KB>  // k-blocks of 64 elements (D padded to KB*64)
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_e,
+                 const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // swizzle-128B tiles need 1024-byte alignment
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t sA = smem_base;                         // KB tiles of 16 KB
+  const uint32_t sB = sA + KB * kATileBytes;             // kStages tiles of 32 KB
+  uint8_t* tail = smem + KB * kATileBytes + kStages * kBTileBytes;
+  float* s_ninv = reinterpret_cast<float*>(tail);        // [2][256] inverse row norms
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail + 2 * kBlockN * sizeof(float));
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 16);
+  const uint32_t bar_full = smem_u32(&bars[0]);        // [kStages]
+  const uint32_t bar_empty = smem_u32(&bars[kStages]); // [kStages]
+  const uint32_t bar_a = smem_u32(&bars[2 * kStages]);
+  const uint32_t bar_tfull = smem_u32(&bars[2 * kStages + 1]);   // [2]
+  const uint32_t bar_tempty = smem_u32(&bars[2 * kStages + 3]);  // [2]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t m_blk = blockIdx.x % p.mb;
+  const uint32_t slice = blockIdx.x / p.mb, nslices = gridDim.x / p.mb;
+  // this CTA's tile list: i = slice, slice + nslices, ... < count; tile = i * stride
+  const uint32_t count = p.mode == 0 ? p.sample_count : p.num_tiles;
+  const uint32_t stride = p.mode == 0 ? p.sample_stride : 1u;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmap_q);
+    prefetch_tmap(&tmap_e);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_a, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_tfull + 8 * a, 1);
+      mbar_init(bar_tempty + 8 * a, 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {  // TMEM allocation is warp-wide
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(s_tmem)),
+                 "n"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar_a, KB * kATileBytes);
+      for (int kb = 0; kb < KB; ++kb)
+        tma_load_2d(sA + kb * kATileBytes, &tmap_q, bar_a, kb * kBlockK, (int)(m_blk * kBlockM));
+      uint32_t s = 0, ph = 0;
+      for (uint32_t i = slice; i < count; i += nslices) {
+        const int row0 = (int)(i * stride * kBlockN);
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(bar_empty + 8 * s, ph ^ 1);
+          mbar_arrive_expect_tx(bar_full + 8 * s, kBTileBytes);
+          tma_load_2d(sB + s * kBTileBytes, &tmap_e, bar_full + 8 * s, kb * kBlockK, row0);
+          if (++s == kStages) s = 0, ph ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one elected lane) =====
+    if (lane == 0) {
+      mbar_wait(bar_a, 0);
+      uint32_t s = 0, ph = 0, it = 0;
+      for (uint32_t i = slice; i < count; i += nslices, ++it) {
+        const uint32_t acc = it & 1u, use = it >> 1;
+        mbar_wait(bar_tempty + 8 * acc, (use & 1u) ^ 1u);  // epilogue drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * kBlockN;
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(bar_full + 8 * s, ph);
+          tc_fence_after();
+          const uint64_t adesc = make_desc(sA + kb * kATileBytes);
+          const uint64_t bdesc = make_desc(sB + s * kBTileBytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k)  // +32 bytes along K per step (>> 4 = 2)
+            umma(tmem_d, adesc + 2 * k, bdesc + 2 * k, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(bar_empty + 8 * s);  // smem stage reusable once these MMAs retire
+          if (++s == kStages) s = 0, ph ^= 1;
+        }
+        umma_commit(bar_tfull + 8 * acc);  // accumulator complete
+      }
+    }
+  } else {
+    // ===== epilogue: warps 2..5 own TMEM lanes 32*(warp%4) .. +31 =====
+    const uint32_t lane_base = 32u * (warp & 3);
+    const uint32_t q_local = lane_base + lane;            // query within the block
+    const uint32_t q = m_blk * kBlockM + q_local;         // query within the batch (may be >= nq)
+    const uint32_t et = threadIdx.x - 64;                 // 0..127 among epilogue threads
+    const float thr = (p.mode == 1) ? p.thr[q] : 0.f;
+    uint32_t it = 0;
+    for (uint32_t i = slice; i < count; i += nslices, ++it) {
+      const uint32_t acc = it & 1u, use = it >> 1;
+      const uint64_t row0 = (uint64_t)i * stride * kBlockN;
+      float* ninv = s_ninv + acc * kBlockN;
+      {
+        uint64_t r = row0 + 2 * et;
+        float2 v;
+        v.x = r < p.n_rows ? __ldg(p.inv_norm + r) : 0.f;
+        v.y = r + 1 < p.n_rows ? __ldg(p.inv_norm + r + 1) : 0.f;
+        *reinterpret_cast<float2*>(ninv + 2 * et) = v;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(bar_tfull + 8 * acc, use & 1u);
+      tc_fence_after();
+      const uint64_t left = p.n_rows - row0;
+      const uint32_t ncols = left >= (uint64_t)kBlockN ? kBlockN : (uint32_t)left;
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (uint32_t c = 0; c < kBlockN; c += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + (lane_base << 16) + acc * kBlockN + c, r);
+        tmem_ld_wait();
+        if (c >= ncols) continue;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float v = __uint_as_float(r[j]) * ninv[c + j];
+          if (p.mode == 0) {
+            if (c + j < ncols) mx = fmaxf(mx, v);
+          } else if (v >= thr && c + j < ncols) {
+            uint32_t pos = atomicAdd(p.cand_count + q, 1u);
+            if (pos < p.cand_cap)
+              p.cand[(size_t)q * p.cand_cap + pos] =
+                  pack_key(v, p.row_base + (uint32_t)(row0 + c + j));
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_tempty + 8 * acc);
+      if (p.mode == 0) p.tile_max[(size_t)i * (p.mb * kBlockM) + q] = mx;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "n"(kTmemCols)
+                 : "memory");
+  }
+}
+
+// ---- small kernels around it ------------------------------------------------------------
+// fp32 queries -> bf16 [mb*128][kpad] (zero padded) + per-query 1/|q| (of the bf16-rounded query)
+__global__ void prep_queries_kernel(const float* q, uint32_t nq, uint32_t dim, uint32_t kpad,
+                                    uint32_t nq_pad, uint16_t* out, float* inv_qnorm) {
+  const uint32_t qi = blockIdx.x;
+  if (qi >= nq_pad) return;
+  float ss = 0.f;
+  for (uint32_t j = threadIdx.x; j < kpad; j += blockDim.x) {
+    float v = (qi < nq && j < dim) ? q[(size_t)qi * dim + j] : 0.f;
+    uint32_t u = __float_as_uint(v);
+    u += 0x7FFFu + ((u >> 16) & 1u);
+    uint16_t h = (uint16_t)(u >> 16);
+    out[(size_t)qi * kpad + j] = h;
+    float w = __uint_as_float((uint32_t)h << 16);
+    ss = fmaf(w, w, ss);
+  }
+  __shared__ float red[32];
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) ss += __shfl_xor_sync(FULL_MASK, ss, m);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (uint32_t w = 0; w < (blockDim.x + 31) / 32; ++w) t += red[w];
+    inv_qnorm[qi] = t > 0.f ? rsqrtf(t) : 0.f;
+  }
+}
+
+// 1/|e| of every stored bf16 row (one warp per row)
+__global__ void row_inv_norm_kernel(const uint16_t* rows, uint64_t n_rows, uint32_t stride_elems,
+                                    float* out) {
+  const uint64_t r = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= n_rows) return;
+  const uint16_t* row = rows + r * stride_elems;
+  float ss = 0.f;
+  for (uint32_t j = lane; j < stride_elems; j += 32) {
+    float w = __uint_as_float((uint32_t)row[j] << 16);
+    ss = fmaf(w, w, ss);
+  }
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) ss += __shfl_xor_sync(FULL_MASK, ss, m);
+  if (lane == 0) out[r] = ss > 0.f ? rsqrtf(ss) : 0.f;
+}
+
+// block-wide bitonic sort (descending) of n (power of two) u64 keys in shared memory
+__device__ void block_bitonic_desc(uint64_t* sk, uint32_t n) {
+  for (uint32_t size = 2; size <= n; size <<= 1) {
+    for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+      for (uint32_t i = threadIdx.x; i < (n >> 1); i += blockDim.x) {
+        uint32_t lo = ((i & ~(stride - 1)) << 1) | (i & (stride - 1));
+        uint32_t hi = lo | stride;
+        bool desc = (lo & size) == 0;
+        uint64_t a = sk[lo], b = sk[hi];
+        if ((a < b) == desc) {
+          sk[lo] = b;
+          sk[hi] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// thr[q] = k-th largest of the sample_count per-tile maxima of query q (+inf for padding queries)
+__global__ void threshold_kernel(const float* tile_max, uint32_t sample_count, uint32_t nq_pad,
+                                 uint32_t nq, uint32_t k, uint32_t npad, float* thr) {
+  extern __shared__ uint64_t sk[];
+  const uint32_t q = blockIdx.x;
+  for (uint32_t i = threadIdx.x; i < npad; i += blockDim.x) {
+    uint64_t key = 0;
+    if (i < sample_count) {
+      float v = tile_max[(size_t)i * nq_pad + q];
+      key = (uint64_t)orderable_bits(__float_as_uint(v)) + 1;  // 0 stays "missing"
+    }
+    sk[i] = key;
+  }
+  __syncthreads();
+  block_bitonic_desc(sk, npad);
+  if (threadIdx.x == 0) {
+    float t = -INFINITY;  // fewer than k maxima: keep everything
+    if (q >= nq) {
+      t = INFINITY;
+    } else if (k <= sample_count && sk[k - 1] != 0) {
+      uint32_t o = (uint32_t)(sk[k - 1] - 1);
+      uint32_t u = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
+      t = __uint_as_float(u);
+    }
+    thr[q] = t;
+  }
+}
+
+// exact top-k of each query's survivor list; scores are scaled by 1/|q| first
+__global__ void select_kernel(const uint64_t* cand, const uint32_t* cand_count, uint32_t cand_cap,
+                              const float* inv_qnorm, uint32_t k, uint64_t* out) {
+  extern __shared__ uint64_t sk[];
+  const uint32_t q = blockIdx.x;
+  uint32_t cnt = cand_count[q];
+  if (cnt > cand_cap) cnt = cand_cap;
+  uint32_t npad = 2;
+  while (npad < cnt) npad <<= 1;
+  const float iq = inv_qnorm[q];
+  for (uint32_t i = threadIdx.x; i < npad; i += blockDim.x) {
+    uint64_t key = 0;
+    if (i < cnt) {
+      uint64_t c = cand[(size_t)q * cand_cap + i];
+      uint32_t o = (uint32_t)(c >> 32);
+      uint32_t u = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
+      float s = __uint_as_float(u) * iq;
+      if (!isfinite(s)) s = 0.f;
+      if (s == 0.f) s = 0.f;
+      key = ((uint64_t)orderable_bits(__float_as_uint(s)) << 32) | (c & 0xFFFFFFFFull);
+    }
+    sk[i] = key;
+  }
+  __syncthreads();
+  block_bitonic_desc(sk, npad);
+  for (uint32_t e = threadIdx.x; e < k; e += blockDim.x)
+    out[(size_t)q * k + e] = e < npad ? sk[e] : 0;
+}
+
+// ---- host side ------------------------------------------------------------------------------
+size_t gemm_smem_bytes(int kb) {
+  return 1024 + (size_t)kb * kATileBytes + (size_t)kStages * kBTileBytes + 2 * kBlockN * 4 + 16 * 8 + 16;
+}
+
+cudaError_t launch_gemm_topk(int kb, const CUtensorMap& tmap_q, const CUtensorMap& tmap_e,
+                             const GemmParams& p, int grid, cudaStream_t st) {
+  const size_t smem = gemm_smem_bytes(kb);
+  cudaError_t e;
+#define TSS_GEMM_CASE(KBV)                                                                        \
+  case KBV:                                                                                        \
+    e = cudaFuncSetAttribute(gemm_topk_kernel<KBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                             (int)smem);                                                          \
+    if (e != cudaSuccess) return e;                                                               \
+    gemm_topk_kernel<KBV><<<grid, kThreads, smem, st>>>(tmap_q, tmap_e, p);                       \
+    break;
+  switch (kb) {
+    TSS_GEMM_CASE(2)
+    TSS_GEMM_CASE(4)
+    TSS_GEMM_CASE(6)
+    default: return cudaErrorInvalidValue;
+  }
+#undef TSS_GEMM_CASE
+  return cudaGetLastError();
+}
+
+cudaError_t launch_prep_queries(const float* q, uint32_t nq, uint32_t dim, uint32_t kpad,
+                                uint32_t nq_pad, uint16_t* out, float* inv_qnorm, cudaStream_t st) {
+  prep_queries_kernel<<<nq_pad, 128, 0, st>>>(q, nq, dim, kpad, nq_pad, out, inv_qnorm);
+  return cudaGetLastError();
+}
+cudaError_t launch_row_inv_norm(const void* rows, uint64_t n_rows, uint32_t stride_elems, float* out,
+                                cudaStream_t st) {
+  if (!n_rows) return cudaSuccess;
+  const uint64_t blocks = (n_rows * 32 + 255) / 256;
+  row_inv_norm_kernel<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const uint16_t*>(rows),
+                                                        n_rows, stride_elems, out);
+  return cudaGetLastError();
+}
+cudaError_t launch_threshold(const float* tile_max, uint32_t sample_count, uint32_t nq_pad,
+                             uint32_t nq, uint32_t k, float* thr, cudaStream_t st) {
+  uint32_t npad = 2;
+  while (npad < sample_count) npad <<= 1;
+  if ((size_t)npad * 8 > 96 * 1024) return cudaErrorInvalidConfiguration;
+  cudaError_t e = cudaFuncSetAttribute(threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       96 * 1024);
+  if (e != cudaSuccess) return e;
+  threshold_kernel<<<nq_pad, 256, (size_t)npad * 8, st>>>(tile_max, sample_count, nq_pad, nq, k,
+                                                          npad, thr);
+  return cudaGetLastError();
+}
+cudaError_t launch_select(const uint64_t* cand, const uint32_t* cand_count, uint32_t cand_cap,
+                          const float* inv_qnorm, uint32_t nq, uint32_t k, uint64_t* out,
+                          cudaStream_t st) {
+  uint32_t npad = 2;
+  while (npad < cand_cap) npad <<= 1;
+  cudaError_t e = cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)((size_t)npad * 8));
+  if (e != cudaSuccess) return e;
+  select_kernel<<<nq, 512, (size_t)npad * 8, st>>>(cand, cand_count, cand_cap, inv_qnorm, k, out);
+  return cudaGetLastError();
+}
+
+}  // namespace tss

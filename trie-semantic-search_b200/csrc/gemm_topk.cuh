@@ -1,0 +1,37 @@
+// gemm_topk.cuh -- host-visible interface of the K2 tensor-core path (see gemm_topk.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tss {
+
+struct GemmParams {
+  uint64_t n_rows;         // rows in this shard
+  uint32_t row_base;       // global id of local row 0
+  const float* inv_norm;   // [n_rows] 1/|row|
+  uint32_t mb;             // 128-query blocks in this launch (grid = nslices * mb)
+  uint32_t num_tiles;      // ceil(n_rows / 256)
+  int mode;                // 0 = per-tile maxima over the sample, 1 = collect survivors
+  uint32_t sample_stride, sample_count;  // mode 0: tiles j * stride, j < count
+  float* tile_max;         // mode 0 out: [sample_count][mb*128]
+  const float* thr;        // mode 1 in:  [mb*128]
+  uint64_t* cand;          // mode 1 out: [mb*128][cand_cap] packed keys (unscaled by 1/|q|)
+  uint32_t* cand_count;    // [mb*128]
+  uint32_t cand_cap;
+};
+
+size_t gemm_smem_bytes(int kb);
+cudaError_t launch_gemm_topk(int kb, const CUtensorMap& tmap_q, const CUtensorMap& tmap_e,
+                             const GemmParams& p, int grid, cudaStream_t st);
+cudaError_t launch_prep_queries(const float* q, uint32_t nq, uint32_t dim, uint32_t kpad,
+                                uint32_t nq_pad, uint16_t* out, float* inv_qnorm, cudaStream_t st);
+cudaError_t launch_row_inv_norm(const void* rows, uint64_t n_rows, uint32_t stride_elems, float* out,
+                                cudaStream_t st);
+cudaError_t launch_threshold(const float* tile_max, uint32_t sample_count, uint32_t nq_pad,
+                             uint32_t nq, uint32_t k, float* thr, cudaStream_t st);
+cudaError_t launch_select(const uint64_t* cand, const uint32_t* cand_count, uint32_t cand_cap,
+                          const float* inv_qnorm, uint32_t nq, uint32_t k, uint64_t* out,
+                          cudaStream_t st);
+
+}  // namespace tss
