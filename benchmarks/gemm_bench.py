@@ -1,0 +1,56 @@
+"""BASELINE config 3: synthetic N x 384 bf16, 1024-query batch, tcgen05 GEMM scoring + top-100.
+Reports queries/s, achieved TFLOP/s (2*B*N*D algorithmic) against MEASURED_PEAKS.json, and
+recall@k vs the fp32 exact oracle on a query subset (CPU, bounded rows if --recall-rows)."""
+import argparse, json, os, sys, time
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import tss_loader
+tss = tss_loader.load()
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--rows", type=int, default=10_000_000)
+ap.add_argument("--nq", type=int, default=1024)
+ap.add_argument("--k", type=int, default=100)
+ap.add_argument("--iters", type=int, default=5)
+ap.add_argument("--recall-queries", type=int, default=0)
+a = ap.parse_args()
+dim = 384
+ix = tss.FlatIndex(dim, tss.TSS_BF16)
+ix.reserve(a.rows)
+ix.add_synthetic(0, a.rows, 0x5EED)
+ix.finalize()
+rng = np.random.default_rng(1)
+import orc
+q = orc.gen_rows(0, a.nq, dim, 0xBEEF)
+dq = tss.DeviceBuffer(0, q.nbytes).upload(q)
+dk = tss.DeviceBuffer(0, a.nq * a.k * 8)
+for _ in range(2):
+    ix.search_device(dq, a.nq, a.k, dk)
+ix.sync()
+e0, e1 = tss.Event(0), tss.Event(0)
+l0 = tss.launch_count()
+e0.record(ix)
+for _ in range(a.iters):
+    ix.search_device(dq, a.nq, a.k, dk)
+e1.record(ix)
+ix.sync()
+ms = e0.elapsed_ms(e1) / a.iters
+flops = 2.0 * a.nq * a.rows * dim
+peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+out = {"rows": a.rows, "nq": a.nq, "k": a.k, "ms_per_batch": ms, "queries_per_s": a.nq / ms * 1e3,
+       "achieved_tflops_algorithmic": flops / ms / 1e9, "peak_tflops_burst": peaks["bf16_tflops"],
+       "frac_of_burst": flops / ms / 1e9 / peaks["bf16_tflops"],
+       "frac_of_sustained": flops / ms / 1e9 / peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]),
+       "launches_per_batch": (tss.launch_count() - l0) / a.iters}
+if a.recall_queries:
+    keys = dk.download(np.uint64, a.nq * a.k).reshape(a.nq, a.k)
+    gr, gs = tss.unpack_keys(keys)
+    nqr = a.recall_queries
+    t = time.time()
+    er, es, _ = orc.cosine_topk_synth(0, a.rows, dim, 0x5EED, q[:nqr], a.k)
+    out["recall_at_k_vs_fp32_exact"] = float(np.mean([len(set(gr[i].tolist()) & set(er[i].tolist())) / a.k for i in range(nqr)]))
+    out["recall_at_10_vs_fp32_exact"] = float(np.mean([len(set(gr[i][:10].tolist()) & set(er[i][:10].tolist())) / 10 for i in range(nqr)]))
+    out["recall_queries"] = nqr
+    out["oracle_seconds"] = time.time() - t
+print(json.dumps(out))

@@ -229,21 +229,49 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       const uint32_t ncols = left >= (uint64_t)kBlockN ? kBlockN : (uint32_t)left;
       float mx = -INFINITY;
 #pragma unroll 1
-      for (uint32_t c = 0; c < kBlockN; c += 32) {
-        uint32_t r[32];
-        tmem_ld32(tmem_base + (lane_base << 16) + acc * kBlockN + c, r);
+      for (uint32_t c = 0; c < kBlockN; c += 64) {
+        uint32_t r[2][32];
+        const uint32_t taddr = tmem_base + (lane_base << 16) + acc * kBlockN + c;
+        tmem_ld32(taddr, r[0]);
+        tmem_ld32(taddr + 32, r[1]);
         tmem_ld_wait();
-        if (c >= ncols) continue;
+        if (c >= ncols) continue;  // warp-uniform: the loads above stay converged
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float v = __uint_as_float(r[j]) * ninv[c + j];
+        for (int h = 0; h < 2; ++h) {
+          const uint32_t cb = c + 32 * h;
+          // branch-free common case: scale by 1/|row| and take the chunk maximum; only a chunk
+          // whose maximum reaches the threshold is walked element by element
+          float v[32];
+          float m = -INFINITY;
+          const float4* nv = reinterpret_cast<const float4*>(ninv + cb);
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 w = nv[j4];
+            v[4 * j4 + 0] = __uint_as_float(r[h][4 * j4 + 0]) * w.x;
+            v[4 * j4 + 1] = __uint_as_float(r[h][4 * j4 + 1]) * w.y;
+            v[4 * j4 + 2] = __uint_as_float(r[h][4 * j4 + 2]) * w.z;
+            v[4 * j4 + 3] = __uint_as_float(r[h][4 * j4 + 3]) * w.w;
+          }
+          if (cb + 32 > ncols) {  // last, partial tile of the corpus only
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (cb + j >= ncols) v[j] = -INFINITY;
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) m = fmaxf(m, v[j]);
           if (p.mode == 0) {
-            if (c + j < ncols) mx = fmaxf(mx, v);
-          } else if (v >= thr && c + j < ncols) {
-            uint32_t pos = atomicAdd(p.cand_count + q, 1u);
-            if (pos < p.cand_cap)
-              p.cand[(size_t)q * p.cand_cap + pos] =
-                  pack_key(v, p.row_base + (uint32_t)(row0 + c + j));
+            mx = fmaxf(mx, m);
+          } else if (m >= thr) {
+            // rare: some element of this chunk survives (unrolled so v[] stays in registers)
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (v[j] >= thr) {
+                uint32_t pos = atomicAdd(p.cand_count + q, 1u);
+                if (pos < p.cand_cap)
+                  p.cand[(size_t)q * p.cand_cap + pos] =
+                      pack_key(v[j], p.row_base + (uint32_t)(row0 + cb + j));
+              }
+            }
           }
         }
       }
