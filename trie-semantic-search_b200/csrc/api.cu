@@ -190,8 +190,9 @@ struct tss_index {
     float* d_thr = nullptr;        // [kWsQueries]
     float* d_tile_max = nullptr;   // [kGemmMaxSample][kWsQueries]
     uint64_t* d_cand = nullptr;    // [kWsQueries][kGemmCandCap]
-    uint32_t* d_cand_count = nullptr;
-    uint32_t* h_cand_count = nullptr;  // pinned
+    uint32_t* d_cand_count = nullptr;  // [kWsQueries][nslices]
+    uint32_t* d_overflow = nullptr;    // [kWsQueries]
+    uint32_t* h_cand_count = nullptr;  // pinned copy of d_overflow
     CUtensorMap tmap_q, tmap_e;
     uint64_t tmap_rows = 0;
     const void* tmap_base = nullptr;
@@ -336,7 +337,8 @@ int ensure_gemm_ws(tss_index* ix) {
     CU(cudaMalloc(&g.d_thr, kWsQueries * sizeof(float)));
     CU(cudaMalloc(&g.d_tile_max, (size_t)kGemmMaxSample * kWsQueries * sizeof(float)));
     CU(cudaMalloc(&g.d_cand, (size_t)kWsQueries * kGemmCandCap * sizeof(uint64_t)));
-    CU(cudaMalloc(&g.d_cand_count, kWsQueries * sizeof(uint32_t)));
+    CU(cudaMalloc(&g.d_cand_count, (size_t)kWsQueries * 256 * sizeof(uint32_t)));
+    CU(cudaMalloc(&g.d_overflow, kWsQueries * sizeof(uint32_t)));
     CU(cudaMallocHost(&g.h_cand_count, kWsQueries * sizeof(uint32_t)));
     if ((rc = make_tmap(&g.tmap_q, g.d_qbf16, kWsQueries, kpad, 128))) return rc;
     g.ready = true;
@@ -377,19 +379,23 @@ int enqueue_gemm(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
   const uint32_t kpad = ix->stride_elems;
   const uint32_t nq_pad = (nq + 127) / 128 * 128, mb = nq_pad / 128;
   const uint32_t num_tiles = (uint32_t)((ix->n_rows + 255) / 256);
-  uint32_t sample = k * 8 > 1024 ? k * 8 : 1024;
-  if (sample > kGemmMaxSample) sample = kGemmMaxSample;
+  // the threshold pass yields two maxima per sampled tile (one per 128-row half)
+  uint32_t sample = k * 4 > 1024 ? k * 4 : 1024;
+  if (sample > kGemmMaxSample / 2) sample = kGemmMaxSample / 2;
   if (sample > num_tiles) sample = num_tiles;
   int nslices = ix->num_sms / (int)mb;
+  if (nslices > 128) nslices = 128;
   if (nslices < 1) return fail(TSS_ERR_INVALID_ARG, "batch of %u queries exceeds one K2 launch", nq);
   const int grid = nslices * (int)mb;
   cudaError_t e;
   e = tss::launch_prep_queries(d_queries, nq, ix->dim, kpad, nq_pad, g.d_qbf16, g.d_inv_q, ix->stream);
   if (e != cudaSuccess) return cuda_fail(e, "prep_queries launch");
-  CU(cudaMemsetAsync(g.d_cand_count, 0, nq_pad * sizeof(uint32_t), ix->stream));
+  const uint32_t nsub = (uint32_t)nslices * 2;
+  const uint32_t cap_s = kGemmCandCap / nsub;
   tss::GemmParams p{};
   p.n_rows = ix->n_rows;
   p.row_base = (uint32_t)ix->row_base;
+  p.rows_bytes = ix->d_rows;
   p.inv_norm = g.d_inv_norm;
   p.mb = mb;
   p.num_tiles = num_tiles;
@@ -399,25 +405,26 @@ int enqueue_gemm(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
   p.thr = g.d_thr;
   p.cand = g.d_cand;
   p.cand_count = g.d_cand_count;
-  p.cand_cap = kGemmCandCap;
+  p.cand_cap = cap_s;
+  if (const char* dbg = getenv("TSS_GEMM_DEBUG")) p.debug = (uint32_t)atoi(dbg);
   const int kb = (int)(kpad / 64);
   p.mode = 0;
   if ((e = tss::launch_gemm_topk(kb, g.tmap_q, g.tmap_e, p, grid, ix->stream)) != cudaSuccess)
     return cuda_fail(e, "gemm_topk_kernel (threshold pass) launch");
-  if ((e = tss::launch_threshold(g.d_tile_max, sample, nq_pad, nq, k, g.d_thr, ix->stream)) != cudaSuccess)
+  if ((e = tss::launch_threshold(g.d_tile_max, sample * 2, nq_pad, nq, k, g.d_thr, ix->stream)) != cudaSuccess)
     return cuda_fail(e, "threshold_kernel launch");
   p.mode = 1;
   if ((e = tss::launch_gemm_topk(kb, g.tmap_q, g.tmap_e, p, grid, ix->stream)) != cudaSuccess)
     return cuda_fail(e, "gemm_topk_kernel (collect pass) launch");
-  if ((e = tss::launch_select(g.d_cand, g.d_cand_count, kGemmCandCap, g.d_inv_q, nq, k, d_out,
-                              ix->stream)) != cudaSuccess)
+  if ((e = tss::launch_select(g.d_cand, g.d_cand_count, nsub, cap_s, g.d_inv_q, nq, k,
+                              d_out, g.d_overflow, ix->stream)) != cudaSuccess)
     return cuda_fail(e, "select_kernel launch");
   g_launches.fetch_add(5, std::memory_order_relaxed);
-  CU(cudaMemcpyAsync(g.h_cand_count, g.d_cand_count, nq * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+  CU(cudaMemcpyAsync(g.h_cand_count, g.d_overflow, nq * sizeof(uint32_t), cudaMemcpyDeviceToHost,
                      ix->stream));
   CU(cudaStreamSynchronize(ix->stream));
   for (uint32_t qi = 0; qi < nq; ++qi) {
-    if (g.h_cand_count[qi] <= kGemmCandCap) continue;
+    if (!g.h_cand_count[qi]) continue;
     if (k > TSS_MAX_FUSED_K)
       return fail(TSS_ERR_STATE, "K2 survivor list overflowed for query %u and k=%u > %u has no "
                   "exact fallback", qi, k, TSS_MAX_FUSED_K);
@@ -548,6 +555,7 @@ void tss_index_destroy(tss_index* ix) {
   cudaFree(ix->gemm.d_tile_max);
   cudaFree(ix->gemm.d_cand);
   cudaFree(ix->gemm.d_cand_count);
+  cudaFree(ix->gemm.d_overflow);
   if (ix->gemm.h_cand_count) cudaFreeHost(ix->gemm.h_cand_count);
   if (ix->stream) cudaStreamDestroy(ix->stream);
   delete ix;

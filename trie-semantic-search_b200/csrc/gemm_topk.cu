@@ -4,14 +4,14 @@
 // path runs on the 5th-generation tensor cores.  It replaces the body of HnswIndex::search
 // (reference src/vector.rs:195-202, a stub) for nq >= 32 over a bf16 index.
 //
-// Per CTA (one per SM, 192 threads, cta_group::1):
+// Per CTA (one per SM, 320 threads, cta_group::1):
 //   * 128 queries (one UMMA M tile) stay resident in shared memory for the whole kernel as
 //     K/64 swizzle-128B K-major tiles (TMA, 96 KB at D = 384);
 //   * corpus tiles of 256 rows stream through a 3-stage ring of 256 x 64 bf16 boxes
 //     (TMA 2-D tensor map over the row-major matrix, swizzle 128B, 32 KB per stage);
 //   * one elected thread issues tcgen05.mma (M128 N256 K16, fp32 accumulate) into one of two
 //     256-column TMEM accumulators; tcgen05.commit frees the smem stage / publishes the tile;
-//   * four epilogue warps read the accumulator with tcgen05.ld (lane = query, column =
+//   * eight epilogue warps read the accumulator with tcgen05.ld (lane = query, column =
 //     corpus row), scale by the row's 1/norm and either
 //       mode 0: keep the per-tile maximum  (threshold pass over a strided tile sample), or
 //       mode 1: append (score,row) keys that reach the query's threshold to a global list.
@@ -36,10 +36,10 @@ constexpr int kBlockM = 128;      // queries per CTA (UMMA M)
 constexpr int kBlockN = 256;      // corpus rows per tile (UMMA N)
 constexpr int kBlockK = 64;       // bf16 elements per k-block = 128 bytes = one swizzle atom row
 constexpr int kUmmaK = 16;        // K per tcgen05.mma for 16-bit inputs
-constexpr int kStages = 3;
+constexpr int kStages = 4;
 constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KB
 constexpr int kBTileBytes = kBlockN * kBlockK * 2;  // 32 KB
-constexpr int kThreads = 192;     // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2..5 epilogue
+constexpr int kThreads = 320;     // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2..9 epilogue
 constexpr int kTmemCols = 512;    // two 256-column fp32 accumulators
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
@@ -49,6 +49,10 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "[%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
       "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
+}
+// contiguous global -> L2 prefetch (no shared-memory destination, no completion signal)
+__device__ __forceinline__ void prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -113,10 +117,12 @@ template <int KB>  // k-blocks of 64 elements (D padded to KB*64)
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_e,
                  const GemmParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  // swizzle-128B tiles need 1024-byte alignment
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // swizzle-128B tiles need 1024-byte alignment; the kernel has no static shared memory, so
+  // the dynamic window starts on its own allocation boundary (checked, not assumed)
+  const uint32_t smem_base = smem_u32(smem_raw);
+  if ((smem_base & 1023u) != 0) __trap();
+  uint8_t* smem = smem_raw;
   const uint32_t sA = smem_base;                         // KB tiles of 16 KB
   const uint32_t sB = sA + KB * kATileBytes;             // kStages tiles of 32 KB
   uint8_t* tail = smem + KB * kATileBytes + kStages * kBTileBytes;
@@ -146,7 +152,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     mbar_init(bar_a, 1);
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
-      mbar_init(bar_tempty + 8 * a, 128);
+      mbar_init(bar_tempty + 8 * a, 256);
     }
     fence_barrier_init();
   }
@@ -169,12 +175,33 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       for (int kb = 0; kb < KB; ++kb)
         tma_load_2d(sA + kb * kATileBytes, &tmap_q, bar_a, kb * kBlockK, (int)(m_blk * kBlockM));
       uint32_t s = 0, ph = 0;
+      // The 2-D boxes below touch 128 bytes of every 768-byte row, which is a poor DRAM
+      // access pattern (a page is re-opened once per k-block).  A tile's rows are one
+      // contiguous byte range, so the CTA that owns query block 0 of each slice pulls whole
+      // tiles into L2 a few tiles ahead with sequential bulk prefetches; the boxes then hit L2.
+      constexpr uint32_t kPrefetchAhead = 4;
+      const uint32_t tile_bytes = kBlockN * KB * kBlockK * 2;
+      auto prefetch_tile = [&](uint32_t ii) {
+        if (m_blk != 0 || ii >= count) return;
+        const uint64_t r0 = (uint64_t)ii * stride * kBlockN;
+        if (r0 >= p.n_rows) return;
+        const uint64_t rows_left = p.n_rows - r0;
+        const uint32_t bytes =
+            rows_left >= (uint64_t)kBlockN ? tile_bytes : (uint32_t)rows_left * (KB * kBlockK * 2);
+        prefetch_l2(p.rows_bytes + r0 * (uint64_t)(KB * kBlockK * 2), bytes);
+      };
+      for (uint32_t a = 0; a < kPrefetchAhead; ++a) prefetch_tile(slice + a * nslices);
       for (uint32_t i = slice; i < count; i += nslices) {
+        prefetch_tile(i + kPrefetchAhead * nslices);
         const int row0 = (int)(i * stride * kBlockN);
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(bar_empty + 8 * s, ph ^ 1);
-          mbar_arrive_expect_tx(bar_full + 8 * s, kBTileBytes);
-          tma_load_2d(sB + s * kBTileBytes, &tmap_e, bar_full + 8 * s, kb * kBlockK, row0);
+          if (p.debug & 4) {
+            mbar_arrive(bar_full + 8 * s);
+          } else {
+            mbar_arrive_expect_tx(bar_full + 8 * s, kBTileBytes);
+            tma_load_2d(sB + s * kBTileBytes, &tmap_e, bar_full + 8 * s, kb * kBlockK, row0);
+          }
           if (++s == kStages) s = 0, ph ^= 1;
         }
       }
@@ -196,7 +223,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           const uint64_t bdesc = make_desc(sB + s * kBTileBytes);
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k)  // +32 bytes along K per step (>> 4 = 2)
-            umma(tmem_d, adesc + 2 * k, bdesc + 2 * k, (kb | k) != 0 ? 1u : 0u);
+            if (!(p.debug & 2)) umma(tmem_d, adesc + 2 * k, bdesc + 2 * k, (kb | k) != 0 ? 1u : 0u);
           umma_commit(bar_empty + 8 * s);  // smem stage reusable once these MMAs retire
           if (++s == kStages) s = 0, ph ^= 1;
         }
@@ -204,45 +231,48 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       }
     }
   } else {
-    // ===== epilogue: warps 2..5 own TMEM lanes 32*(warp%4) .. +31 =====
+    // ===== epilogue: warps 2..9.  Warp w may touch TMEM lanes 32*(w%4)..+31 only, so two
+    // warps share each lane quadrant and split the tile's 256 columns between them:
+    // thread = (query, column half).  Two warps per scheduler also hide each other's latency.
     const uint32_t lane_base = 32u * (warp & 3);
+    const uint32_t half = (uint32_t)(warp - 2) >> 2;       // 0: columns 0..127, 1: 128..255
     const uint32_t q_local = lane_base + lane;            // query within the block
     const uint32_t q = m_blk * kBlockM + q_local;         // query within the batch (may be >= nq)
-    const uint32_t et = threadIdx.x - 64;                 // 0..127 among epilogue threads
+    const uint32_t et = threadIdx.x - 64;                 // 0..255 among epilogue threads
     const float thr = (p.mode == 1) ? p.thr[q] : 0.f;
+    // survivors of (query, slice, half) go to a list only this thread writes: no atomics
+    const uint32_t sub = slice * 2 + half, nsub = nslices * 2;
+    uint64_t* my_cand = p.cand + ((size_t)q * nsub + sub) * p.cand_cap;
+    uint32_t my_count = 0;
     uint32_t it = 0;
     for (uint32_t i = slice; i < count; i += nslices, ++it) {
       const uint32_t acc = it & 1u, use = it >> 1;
       const uint64_t row0 = (uint64_t)i * stride * kBlockN;
       float* ninv = s_ninv + acc * kBlockN;
       {
-        uint64_t r = row0 + 2 * et;
-        float2 v;
-        v.x = r < p.n_rows ? __ldg(p.inv_norm + r) : 0.f;
-        v.y = r + 1 < p.n_rows ? __ldg(p.inv_norm + r + 1) : 0.f;
-        *reinterpret_cast<float2*>(ninv + 2 * et) = v;
+        uint64_t r = row0 + et;
+        ninv[et] = r < p.n_rows ? __ldg(p.inv_norm + r) : 0.f;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(bar_tfull + 8 * acc, use & 1u);
       tc_fence_after();
       const uint64_t left = p.n_rows - row0;
       const uint32_t ncols = left >= (uint64_t)kBlockN ? kBlockN : (uint32_t)left;
       float mx = -INFINITY;
 #pragma unroll 1
-      for (uint32_t c = 0; c < kBlockN; c += 64) {
+      for (uint32_t c = half * 128; c < half * 128 + 128; c += 64) {
         uint32_t r[2][32];
         const uint32_t taddr = tmem_base + (lane_base << 16) + acc * kBlockN + c;
         tmem_ld32(taddr, r[0]);
         tmem_ld32(taddr + 32, r[1]);
         tmem_ld_wait();
-        if (c >= ncols) continue;  // warp-uniform: the loads above stay converged
+        if (c >= ncols || (p.debug & 1)) continue;  // warp-uniform: the loads above stay converged
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const uint32_t cb = c + 32 * h;
-          // branch-free common case: scale by 1/|row| and take the chunk maximum; only a chunk
-          // whose maximum reaches the threshold is walked element by element
+          // branch-free common case: scale by 1/|row|, maxima of the four groups of 8 and of
+          // the chunk; only a chunk (then a group) whose maximum reaches the threshold is walked
           float v[32];
-          float m = -INFINITY;
           const float4* nv = reinterpret_cast<const float4*>(ninv + cb);
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
@@ -257,19 +287,28 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             for (int j = 0; j < 32; ++j)
               if (cb + j >= ncols) v[j] = -INFINITY;
           }
+          float gm[4];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) m = fmaxf(m, v[j]);
+          for (int g = 0; g < 4; ++g) {
+            float a = fmaxf(fmaxf(v[8 * g + 0], v[8 * g + 1]), fmaxf(v[8 * g + 2], v[8 * g + 3]));
+            float b = fmaxf(fmaxf(v[8 * g + 4], v[8 * g + 5]), fmaxf(v[8 * g + 6], v[8 * g + 7]));
+            gm[g] = fmaxf(a, b);
+          }
+          const float m = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
           if (p.mode == 0) {
             mx = fmaxf(mx, m);
           } else if (m >= thr) {
-            // rare: some element of this chunk survives (unrolled so v[] stays in registers)
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (v[j] >= thr) {
-                uint32_t pos = atomicAdd(p.cand_count + q, 1u);
-                if (pos < p.cand_cap)
-                  p.cand[(size_t)q * p.cand_cap + pos] =
-                      pack_key(v[j], p.row_base + (uint32_t)(row0 + cb + j));
+            for (int g = 0; g < 4; ++g) {
+              if (gm[g] >= thr) {
+#pragma unroll
+                for (int j = 8 * g; j < 8 * g + 8; ++j) {
+                  if (v[j] >= thr) {
+                    if (my_count < p.cand_cap)
+                      my_cand[my_count] = pack_key(v[j], p.row_base + (uint32_t)(row0 + cb + j));
+                    ++my_count;
+                  }
+                }
               }
             }
           }
@@ -277,8 +316,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       }
       tc_fence_before();
       mbar_arrive(bar_tempty + 8 * acc);
-      if (p.mode == 0) p.tile_max[(size_t)i * (p.mb * kBlockM) + q] = mx;
+      // each (tile, half) is its own sample for the threshold: 128 distinct rows
+      if (p.mode == 0) p.tile_max[((size_t)i * 2 + half) * (p.mb * kBlockM) + q] = mx;
     }
+    if (p.mode == 1) p.cand_count[(size_t)q * nsub + sub] = my_count;
   }
 
   tc_fence_before();
@@ -383,38 +424,56 @@ __global__ void threshold_kernel(const float* tile_max, uint32_t sample_count, u
   }
 }
 
-// exact top-k of each query's survivor list; scores are scaled by 1/|q| first
-__global__ void select_kernel(const uint64_t* cand, const uint32_t* cand_count, uint32_t cand_cap,
-                              const float* inv_qnorm, uint32_t k, uint64_t* out) {
+// exact top-k of each query's survivors (nslices private lists of <= cap_s keys); scores are
+// scaled by 1/|q| first.  overflow[q] = 1 when some list was too short to hold its survivors.
+__global__ void select_kernel(const uint64_t* cand, const uint32_t* cand_count, uint32_t nslices,
+                              uint32_t cap_s, const float* inv_qnorm, uint32_t k, uint64_t* out,
+                              uint32_t* overflow) {
   extern __shared__ uint64_t sk[];
+  __shared__ uint32_t s_off[257];
+  __shared__ uint32_t s_over;
   const uint32_t q = blockIdx.x;
-  uint32_t cnt = cand_count[q];
-  if (cnt > cand_cap) cnt = cand_cap;
+  if (threadIdx.x == 0) {
+    uint32_t off = 0, over = 0;
+    for (uint32_t sl = 0; sl < nslices; ++sl) {
+      uint32_t c = cand_count[(size_t)q * nslices + sl];
+      if (c > cap_s) c = cap_s, over = 1;
+      s_off[sl] = off;
+      off += c;
+    }
+    s_off[nslices] = off;
+    s_over = over;
+  }
+  __syncthreads();
+  const uint32_t cnt = s_off[nslices];
   uint32_t npad = 2;
   while (npad < cnt) npad <<= 1;
   const float iq = inv_qnorm[q];
-  for (uint32_t i = threadIdx.x; i < npad; i += blockDim.x) {
-    uint64_t key = 0;
-    if (i < cnt) {
-      uint64_t c = cand[(size_t)q * cand_cap + i];
-      uint32_t o = (uint32_t)(c >> 32);
-      uint32_t u = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
-      float s = __uint_as_float(u) * iq;
-      if (!isfinite(s)) s = 0.f;
-      if (s == 0.f) s = 0.f;
-      key = ((uint64_t)orderable_bits(__float_as_uint(s)) << 32) | (c & 0xFFFFFFFFull);
+  for (uint32_t i = threadIdx.x; i < npad; i += blockDim.x) sk[i] = 0;
+  __syncthreads();
+  for (uint32_t sl = 0; sl < nslices; ++sl) {
+    const uint32_t o = s_off[sl], c = s_off[sl + 1] - o;
+    const uint64_t* src = cand + ((size_t)q * nslices + sl) * cap_s;
+    for (uint32_t i = threadIdx.x; i < c; i += blockDim.x) {
+      uint64_t key = src[i];
+      uint32_t ob = (uint32_t)(key >> 32);
+      uint32_t u = (ob & 0x80000000u) ? (ob & 0x7FFFFFFFu) : ~ob;
+      float sc = __uint_as_float(u) * iq;
+      if (!isfinite(sc)) sc = 0.f;
+      if (sc == 0.f) sc = 0.f;
+      sk[o + i] = ((uint64_t)orderable_bits(__float_as_uint(sc)) << 32) | (key & 0xFFFFFFFFull);
     }
-    sk[i] = key;
   }
   __syncthreads();
   block_bitonic_desc(sk, npad);
   for (uint32_t e = threadIdx.x; e < k; e += blockDim.x)
     out[(size_t)q * k + e] = e < npad ? sk[e] : 0;
+  if (threadIdx.x == 0) overflow[q] = s_over;
 }
 
 // ---- host side ------------------------------------------------------------------------------
 size_t gemm_smem_bytes(int kb) {
-  return 1024 + (size_t)kb * kATileBytes + (size_t)kStages * kBTileBytes + 2 * kBlockN * 4 + 16 * 8 + 16;
+  return (size_t)kb * kATileBytes + (size_t)kStages * kBTileBytes + 2 * kBlockN * 4 + 16 * 8 + 16;
 }
 
 cudaError_t launch_gemm_topk(int kb, const CUtensorMap& tmap_q, const CUtensorMap& tmap_e,
@@ -463,15 +522,17 @@ cudaError_t launch_threshold(const float* tile_max, uint32_t sample_count, uint3
                                                           npad, thr);
   return cudaGetLastError();
 }
-cudaError_t launch_select(const uint64_t* cand, const uint32_t* cand_count, uint32_t cand_cap,
-                          const float* inv_qnorm, uint32_t nq, uint32_t k, uint64_t* out,
-                          cudaStream_t st) {
+cudaError_t launch_select(const uint64_t* cand, const uint32_t* cand_count, uint32_t nslices,
+                          uint32_t cap_s, const float* inv_qnorm, uint32_t nq, uint32_t k,
+                          uint64_t* out, uint32_t* overflow, cudaStream_t st) {
+  if (nslices > 256) return cudaErrorInvalidConfiguration;
   uint32_t npad = 2;
-  while (npad < cand_cap) npad <<= 1;
+  while (npad < nslices * cap_s) npad <<= 1;
   cudaError_t e = cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)((size_t)npad * 8));
   if (e != cudaSuccess) return e;
-  select_kernel<<<nq, 512, (size_t)npad * 8, st>>>(cand, cand_count, cand_cap, inv_qnorm, k, out);
+  select_kernel<<<nq, 512, (size_t)npad * 8, st>>>(cand, cand_count, nslices, cap_s, inv_qnorm, k,
+                                                   out, overflow);
   return cudaGetLastError();
 }
 

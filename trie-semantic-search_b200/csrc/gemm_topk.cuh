@@ -9,16 +9,18 @@ namespace tss {
 struct GemmParams {
   uint64_t n_rows;         // rows in this shard
   uint32_t row_base;       // global id of local row 0
+  const uint8_t* rows_bytes;  // the bf16 matrix itself (for contiguous L2 prefetches)
   const float* inv_norm;   // [n_rows] 1/|row|
   uint32_t mb;             // 128-query blocks in this launch (grid = nslices * mb)
   uint32_t num_tiles;      // ceil(n_rows / 256)
   int mode;                // 0 = per-tile maxima over the sample, 1 = collect survivors
   uint32_t sample_stride, sample_count;  // mode 0: tiles j * stride, j < count
-  float* tile_max;         // mode 0 out: [sample_count][mb*128]
+  float* tile_max;         // mode 0 out: [sample_count*2][mb*128] (one maximum per half tile)
   const float* thr;        // mode 1 in:  [mb*128]
-  uint64_t* cand;          // mode 1 out: [mb*128][cand_cap] packed keys (unscaled by 1/|q|)
-  uint32_t* cand_count;    // [mb*128]
-  uint32_t cand_cap;
+  uint64_t* cand;          // mode 1 out: [mb*128][nslices*2][cand_cap] keys (unscaled by 1/|q|)
+  uint32_t* cand_count;    // [mb*128][nslices*2] survivors seen (may exceed cand_cap)
+  uint32_t cand_cap;       // per (query, slice, column half) list
+  uint32_t debug;          // diagnostics: 1 = no epilogue math, 2 = no MMA issue, 4 = no corpus TMA
 };
 
 size_t gemm_smem_bytes(int kb);
@@ -30,8 +32,8 @@ cudaError_t launch_row_inv_norm(const void* rows, uint64_t n_rows, uint32_t stri
                                 cudaStream_t st);
 cudaError_t launch_threshold(const float* tile_max, uint32_t sample_count, uint32_t nq_pad,
                              uint32_t nq, uint32_t k, float* thr, cudaStream_t st);
-cudaError_t launch_select(const uint64_t* cand, const uint32_t* cand_count, uint32_t cand_cap,
-                          const float* inv_qnorm, uint32_t nq, uint32_t k, uint64_t* out,
-                          cudaStream_t st);
+cudaError_t launch_select(const uint64_t* cand, const uint32_t* cand_count, uint32_t nslices,
+                          uint32_t cap_s, const float* inv_qnorm, uint32_t nq, uint32_t k,
+                          uint64_t* out, uint32_t* overflow, cudaStream_t st);
 
 }  // namespace tss
