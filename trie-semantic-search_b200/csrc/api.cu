@@ -193,7 +193,7 @@ struct tss_index {
     uint32_t* d_cand_count = nullptr;  // [kWsQueries][nslices]
     uint32_t* d_overflow = nullptr;    // [kWsQueries]
     uint32_t* h_cand_count = nullptr;  // pinned copy of d_overflow
-    CUtensorMap tmap_q, tmap_e;
+    CUtensorMap tmap_q, tmap_e, tmap_e_half;  // corpus boxes of 256 rows / 128 rows (cluster 2)
     uint64_t tmap_rows = 0;
     const void* tmap_base = nullptr;
   } gemm;
@@ -360,6 +360,7 @@ int ensure_gemm_ws(tss_index* ix) {
   }
   if (g.tmap_rows != ix->n_rows || g.tmap_base != ix->d_rows) {
     if ((rc = make_tmap(&g.tmap_e, ix->d_rows, ix->n_rows, kpad, 256))) return rc;
+    if ((rc = make_tmap(&g.tmap_e_half, ix->d_rows, ix->n_rows, kpad, 128))) return rc;
     g.tmap_rows = ix->n_rows;
     g.tmap_base = ix->d_rows;
   }
@@ -379,18 +380,23 @@ int enqueue_gemm(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
   const uint32_t kpad = ix->stride_elems;
   const uint32_t nq_pad = (nq + 127) / 128 * 128, mb = nq_pad / 128;
   const uint32_t num_tiles = (uint32_t)((ix->n_rows + 255) / 256);
-  // the threshold pass yields two maxima per sampled tile (one per 128-row half)
-  uint32_t sample = k * 4 > 1024 ? k * 4 : 1024;
-  if (sample > kGemmMaxSample / 2) sample = kGemmMaxSample / 2;
+  // the threshold pass yields `split` maxima per sampled tile (one per column part)
+  const uint32_t split = (uint32_t)tss::gemm_col_split();
+  uint32_t sample = k * 8 / split > 1024 ? k * 8 / split : 1024;
+  if (sample > kGemmMaxSample / split) sample = kGemmMaxSample / split;
   if (sample > num_tiles) sample = num_tiles;
   int nslices = ix->num_sms / (int)mb;
-  if (nslices > 128) nslices = 128;
+  if (nslices * (int)tss::gemm_col_split() > 256) nslices = 256 / tss::gemm_col_split();
   if (nslices < 1) return fail(TSS_ERR_INVALID_ARG, "batch of %u queries exceeds one K2 launch", nq);
   const int grid = nslices * (int)mb;
+  // CTA pairs that share corpus tiles by TMA multicast need an even number of query blocks
+  int cluster = (mb % 2 == 0) ? 2 : 1;
+  if (const char* cl = getenv("TSS_GEMM_CLUSTER")) cluster = atoi(cl) == 2 && mb % 2 == 0 ? 2 : 1;
+  const CUtensorMap& tmap_e = cluster == 2 ? g.tmap_e_half : g.tmap_e;
   cudaError_t e;
   e = tss::launch_prep_queries(d_queries, nq, ix->dim, kpad, nq_pad, g.d_qbf16, g.d_inv_q, ix->stream);
   if (e != cudaSuccess) return cuda_fail(e, "prep_queries launch");
-  const uint32_t nsub = (uint32_t)nslices * 2;
+  const uint32_t nsub = (uint32_t)nslices * split;
   const uint32_t cap_s = kGemmCandCap / nsub;
   tss::GemmParams p{};
   p.n_rows = ix->n_rows;
@@ -409,12 +415,12 @@ int enqueue_gemm(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
   if (const char* dbg = getenv("TSS_GEMM_DEBUG")) p.debug = (uint32_t)atoi(dbg);
   const int kb = (int)(kpad / 64);
   p.mode = 0;
-  if ((e = tss::launch_gemm_topk(kb, g.tmap_q, g.tmap_e, p, grid, ix->stream)) != cudaSuccess)
+  if ((e = tss::launch_gemm_topk(kb, cluster, g.tmap_q, tmap_e, p, grid, ix->stream)) != cudaSuccess)
     return cuda_fail(e, "gemm_topk_kernel (threshold pass) launch");
-  if ((e = tss::launch_threshold(g.d_tile_max, sample * 2, nq_pad, nq, k, g.d_thr, ix->stream)) != cudaSuccess)
+  if ((e = tss::launch_threshold(g.d_tile_max, sample * split, nq_pad, nq, k, g.d_thr, ix->stream)) != cudaSuccess)
     return cuda_fail(e, "threshold_kernel launch");
   p.mode = 1;
-  if ((e = tss::launch_gemm_topk(kb, g.tmap_q, g.tmap_e, p, grid, ix->stream)) != cudaSuccess)
+  if ((e = tss::launch_gemm_topk(kb, cluster, g.tmap_q, tmap_e, p, grid, ix->stream)) != cudaSuccess)
     return cuda_fail(e, "gemm_topk_kernel (collect pass) launch");
   if ((e = tss::launch_select(g.d_cand, g.d_cand_count, nsub, cap_s, g.d_inv_q, nq, k,
                               d_out, g.d_overflow, ix->stream)) != cudaSuccess)

@@ -4,14 +4,14 @@
 // path runs on the 5th-generation tensor cores.  It replaces the body of HnswIndex::search
 // (reference src/vector.rs:195-202, a stub) for nq >= 32 over a bf16 index.
 //
-// Per CTA (one per SM, 320 threads, cta_group::1):
+// Per CTA (one per SM, 576 threads, cta_group::1):
 //   * 128 queries (one UMMA M tile) stay resident in shared memory for the whole kernel as
 //     K/64 swizzle-128B K-major tiles (TMA, 96 KB at D = 384);
 //   * corpus tiles of 256 rows stream through a 3-stage ring of 256 x 64 bf16 boxes
 //     (TMA 2-D tensor map over the row-major matrix, swizzle 128B, 32 KB per stage);
 //   * one elected thread issues tcgen05.mma (M128 N256 K16, fp32 accumulate) into one of two
 //     256-column TMEM accumulators; tcgen05.commit frees the smem stage / publishes the tile;
-//   * eight epilogue warps read the accumulator with tcgen05.ld (lane = query, column =
+//   * sixteen epilogue warps read the accumulator with tcgen05.ld (lane = query, column =
 //     corpus row), scale by the row's 1/norm and either
 //       mode 0: keep the per-tile maximum  (threshold pass over a strided tile sample), or
 //       mode 1: append (score,row) keys that reach the query's threshold to a global list.
@@ -39,7 +39,9 @@ constexpr int kUmmaK = 16;        // K per tcgen05.mma for 16-bit inputs
 constexpr int kStages = 4;
 constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KB
 constexpr int kBTileBytes = kBlockN * kBlockK * 2;  // 32 KB
-constexpr int kThreads = 320;     // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2..9 epilogue
+constexpr int kColSplit = 4;      // epilogue warps per TMEM lane quadrant (each takes 256/4 columns)
+constexpr int kEpiThreads = 128 * kColSplit;
+constexpr int kThreads = 64 + kEpiThreads;  // warp 0 TMA, warp 1 MMA + TMEM alloc, rest epilogue
 constexpr int kTmemCols = 512;    // two 256-column fp32 accumulators
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
@@ -53,6 +55,31 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
 // contiguous global -> L2 prefetch (no shared-memory destination, no completion signal)
 __device__ __forceinline__ void prefetch_l2(const void* src, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+// same, multicast to every CTA of the cluster named in cta_mask (same smem / barrier offsets)
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                               int c0, int c1, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      ".multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+      "[%0], %1;" ::"r"(bar),
+      "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -113,7 +140,11 @@ __device__ __forceinline__ void tmem_ld_wait() {
 
 }  // namespace
 
-template <int KB>  // k-blocks of 64 elements (D padded to KB*64)
+// KB: k-blocks of 64 elements (D padded to KB*64).  CL: CTAs per cluster (1 or 2).  With
+// CL == 2 the two CTAs of a cluster score different query blocks against the SAME corpus
+// tiles: each loads half of every 256-row stage and multicasts it into both CTAs' shared
+// memory, which halves the L2 -> SM traffic per CTA (the bound of the CL == 1 kernel).
+template <int KB, int CL>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_e,
                  const GemmParams p) {
@@ -136,8 +167,11 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   const uint32_t bar_tempty = smem_u32(&bars[2 * kStages + 3]);  // [2]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t m_blk = blockIdx.x % p.mb;
-  const uint32_t slice = blockIdx.x / p.mb, nslices = gridDim.x / p.mb;
+  const uint32_t rank = CL > 1 ? cluster_rank() : 0u;
+  const uint32_t cluster_id = blockIdx.x / CL, groups = p.mb / CL;  // clusters per slice
+  const uint32_t m_blk = (cluster_id % groups) * CL + rank;
+  const uint32_t slice = cluster_id / groups, nslices = (gridDim.x / CL) / groups;
+  constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
   // this CTA's tile list: i = slice, slice + nslices, ... < count; tile = i * stride
   const uint32_t count = p.mode == 0 ? p.sample_count : p.num_tiles;
   const uint32_t stride = p.mode == 0 ? p.sample_stride : 1u;
@@ -147,12 +181,12 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     prefetch_tmap(&tmap_e);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_empty + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, CL);  // every CTA that reads the stage must release it
     }
     mbar_init(bar_a, 1);
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
-      mbar_init(bar_tempty + 8 * a, 256);
+      mbar_init(bar_tempty + 8 * a, kEpiThreads);
     }
     fence_barrier_init();
   }
@@ -165,6 +199,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // peer barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
 
@@ -198,9 +233,15 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           mbar_wait(bar_empty + 8 * s, ph ^ 1);
           if (p.debug & 4) {
             mbar_arrive(bar_full + 8 * s);
-          } else {
+          } else if (CL == 1) {
             mbar_arrive_expect_tx(bar_full + 8 * s, kBTileBytes);
             tma_load_2d(sB + s * kBTileBytes, &tmap_e, bar_full + 8 * s, kb * kBlockK, row0);
+          } else {
+            // my barrier counts the whole stage: my slice of the rows plus the peers' multicasts
+            mbar_arrive_expect_tx(bar_full + 8 * s, kBTileBytes);
+            constexpr int kRowsPer = kBlockN / CL;
+            tma_load_2d_mc(sB + s * kBTileBytes + rank * (kBTileBytes / CL), &tmap_e,
+                           bar_full + 8 * s, kb * kBlockK, row0 + (int)rank * kRowsPer, kMask);
           }
           if (++s == kStages) s = 0, ph ^= 1;
         }
@@ -224,24 +265,27 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k)  // +32 bytes along K per step (>> 4 = 2)
             if (!(p.debug & 2)) umma(tmem_d, adesc + 2 * k, bdesc + 2 * k, (kb | k) != 0 ? 1u : 0u);
-          umma_commit(bar_empty + 8 * s);  // smem stage reusable once these MMAs retire
+          // smem stage reusable once these MMAs retire (in every CTA of the cluster)
+          if (CL == 1) umma_commit(bar_empty + 8 * s);
+          else umma_commit_mc(bar_empty + 8 * s, kMask);
           if (++s == kStages) s = 0, ph ^= 1;
         }
         umma_commit(bar_tfull + 8 * acc);  // accumulator complete
       }
     }
   } else {
-    // ===== epilogue: warps 2..9.  Warp w may touch TMEM lanes 32*(w%4)..+31 only, so two
-    // warps share each lane quadrant and split the tile's 256 columns between them:
-    // thread = (query, column half).  Two warps per scheduler also hide each other's latency.
+    // ===== epilogue: warps 2...  Warp w may touch TMEM lanes 32*(w%4)..+31 only, so
+    // kColSplit warps share each lane quadrant and split the tile's 256 columns between them:
+    // thread = (query, column part).  Several warps per scheduler hide each other's latency.
+    constexpr uint32_t kColsPer = kBlockN / kColSplit;
     const uint32_t lane_base = 32u * (warp & 3);
-    const uint32_t half = (uint32_t)(warp - 2) >> 2;       // 0: columns 0..127, 1: 128..255
+    const uint32_t part = (uint32_t)(warp - 2) >> 2;      // which kColsPer-column part
     const uint32_t q_local = lane_base + lane;            // query within the block
     const uint32_t q = m_blk * kBlockM + q_local;         // query within the batch (may be >= nq)
-    const uint32_t et = threadIdx.x - 64;                 // 0..255 among epilogue threads
+    const uint32_t et = threadIdx.x - 64;                 // 0..kEpiThreads-1
     const float thr = (p.mode == 1) ? p.thr[q] : 0.f;
-    // survivors of (query, slice, half) go to a list only this thread writes: no atomics
-    const uint32_t sub = slice * 2 + half, nsub = nslices * 2;
+    // survivors of (query, slice, part) go to a list only this thread writes: no atomics
+    const uint32_t sub = slice * kColSplit + part, nsub = nslices * kColSplit;
     uint64_t* my_cand = p.cand + ((size_t)q * nsub + sub) * p.cand_cap;
     uint32_t my_count = 0;
     uint32_t it = 0;
@@ -249,65 +293,59 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       const uint32_t acc = it & 1u, use = it >> 1;
       const uint64_t row0 = (uint64_t)i * stride * kBlockN;
       float* ninv = s_ninv + acc * kBlockN;
-      {
+      if (et < (uint32_t)kBlockN) {
         uint64_t r = row0 + et;
         ninv[et] = r < p.n_rows ? __ldg(p.inv_norm + r) : 0.f;
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       mbar_wait(bar_tfull + 8 * acc, use & 1u);
       tc_fence_after();
       const uint64_t left = p.n_rows - row0;
       const uint32_t ncols = left >= (uint64_t)kBlockN ? kBlockN : (uint32_t)left;
       float mx = -INFINITY;
 #pragma unroll 1
-      for (uint32_t c = half * 128; c < half * 128 + 128; c += 64) {
-        uint32_t r[2][32];
-        const uint32_t taddr = tmem_base + (lane_base << 16) + acc * kBlockN + c;
-        tmem_ld32(taddr, r[0]);
-        tmem_ld32(taddr + 32, r[1]);
+      for (uint32_t cb = part * kColsPer; cb < (part + 1) * kColsPer; cb += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + (lane_base << 16) + acc * kBlockN + cb, r);
         tmem_ld_wait();
-        if (c >= ncols || (p.debug & 1)) continue;  // warp-uniform: the loads above stay converged
+        if (cb >= ncols || (p.debug & 1)) continue;  // warp-uniform: the load above stays converged
+        // branch-free common case: scale by 1/|row|, maxima of the four groups of 8 and of
+        // the chunk; only a chunk (then a group) whose maximum reaches the threshold is walked
+        float v[32];
+        const float4* nv = reinterpret_cast<const float4*>(ninv + cb);
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const uint32_t cb = c + 32 * h;
-          // branch-free common case: scale by 1/|row|, maxima of the four groups of 8 and of
-          // the chunk; only a chunk (then a group) whose maximum reaches the threshold is walked
-          float v[32];
-          const float4* nv = reinterpret_cast<const float4*>(ninv + cb);
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 w = nv[j4];
+          v[4 * j4 + 0] = __uint_as_float(r[4 * j4 + 0]) * w.x;
+          v[4 * j4 + 1] = __uint_as_float(r[4 * j4 + 1]) * w.y;
+          v[4 * j4 + 2] = __uint_as_float(r[4 * j4 + 2]) * w.z;
+          v[4 * j4 + 3] = __uint_as_float(r[4 * j4 + 3]) * w.w;
+        }
+        if (cb + 32 > ncols) {  // last, partial tile of the corpus only
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 w = nv[j4];
-            v[4 * j4 + 0] = __uint_as_float(r[h][4 * j4 + 0]) * w.x;
-            v[4 * j4 + 1] = __uint_as_float(r[h][4 * j4 + 1]) * w.y;
-            v[4 * j4 + 2] = __uint_as_float(r[h][4 * j4 + 2]) * w.z;
-            v[4 * j4 + 3] = __uint_as_float(r[h][4 * j4 + 3]) * w.w;
-          }
-          if (cb + 32 > ncols) {  // last, partial tile of the corpus only
+          for (int j = 0; j < 32; ++j)
+            if (cb + j >= ncols) v[j] = -INFINITY;
+        }
+        float gm[4];
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (cb + j >= ncols) v[j] = -INFINITY;
-          }
-          float gm[4];
+        for (int g = 0; g < 4; ++g) {
+          float a = fmaxf(fmaxf(v[8 * g + 0], v[8 * g + 1]), fmaxf(v[8 * g + 2], v[8 * g + 3]));
+          float b = fmaxf(fmaxf(v[8 * g + 4], v[8 * g + 5]), fmaxf(v[8 * g + 6], v[8 * g + 7]));
+          gm[g] = fmaxf(a, b);
+        }
+        const float m = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
+        if (p.mode == 0) {
+          mx = fmaxf(mx, m);
+        } else if (m >= thr) {
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            float a = fmaxf(fmaxf(v[8 * g + 0], v[8 * g + 1]), fmaxf(v[8 * g + 2], v[8 * g + 3]));
-            float b = fmaxf(fmaxf(v[8 * g + 4], v[8 * g + 5]), fmaxf(v[8 * g + 6], v[8 * g + 7]));
-            gm[g] = fmaxf(a, b);
-          }
-          const float m = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
-          if (p.mode == 0) {
-            mx = fmaxf(mx, m);
-          } else if (m >= thr) {
+            if (gm[g] >= thr) {
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              if (gm[g] >= thr) {
-#pragma unroll
-                for (int j = 8 * g; j < 8 * g + 8; ++j) {
-                  if (v[j] >= thr) {
-                    if (my_count < p.cand_cap)
-                      my_cand[my_count] = pack_key(v[j], p.row_base + (uint32_t)(row0 + cb + j));
-                    ++my_count;
-                  }
+              for (int j = 8 * g; j < 8 * g + 8; ++j) {
+                if (v[j] >= thr) {
+                  if (my_count < p.cand_cap)
+                    my_cand[my_count] = pack_key(v[j], p.row_base + (uint32_t)(row0 + cb + j));
+                  ++my_count;
                 }
               }
             }
@@ -316,14 +354,15 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       }
       tc_fence_before();
       mbar_arrive(bar_tempty + 8 * acc);
-      // each (tile, half) is its own sample for the threshold: 128 distinct rows
-      if (p.mode == 0) p.tile_max[((size_t)i * 2 + half) * (p.mb * kBlockM) + q] = mx;
+      // each (tile, part) is its own sample for the threshold: kColsPer distinct rows
+      if (p.mode == 0) p.tile_max[((size_t)i * kColSplit + part) * (p.mb * kBlockM) + q] = mx;
     }
     if (p.mode == 1) p.cand_count[(size_t)q * nsub + sub] = my_count;
   }
 
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // no CTA exits while a peer may still write into it
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
@@ -472,21 +511,40 @@ __global__ void select_kernel(const uint64_t* cand, const uint32_t* cand_count, 
 }
 
 // ---- host side ------------------------------------------------------------------------------
+int gemm_col_split() { return kColSplit; }
 size_t gemm_smem_bytes(int kb) {
   return (size_t)kb * kATileBytes + (size_t)kStages * kBTileBytes + 2 * kBlockN * 4 + 16 * 8 + 16;
 }
 
-cudaError_t launch_gemm_topk(int kb, const CUtensorMap& tmap_q, const CUtensorMap& tmap_e,
-                             const GemmParams& p, int grid, cudaStream_t st) {
+template <int KB, int CL>
+static cudaError_t launch_gemm_inst(const CUtensorMap& tmap_q, const CUtensorMap& tmap_e,
+                                    const GemmParams& p, int grid, size_t smem, cudaStream_t st) {
+  auto kern = gemm_topk_kernel<KB, CL>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, tmap_q, tmap_e, p);
+}
+
+cudaError_t launch_gemm_topk(int kb, int cluster, const CUtensorMap& tmap_q,
+                             const CUtensorMap& tmap_e, const GemmParams& p, int grid,
+                             cudaStream_t st) {
   const size_t smem = gemm_smem_bytes(kb);
-  cudaError_t e;
-#define TSS_GEMM_CASE(KBV)                                                                        \
-  case KBV:                                                                                        \
-    e = cudaFuncSetAttribute(gemm_topk_kernel<KBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                             (int)smem);                                                          \
-    if (e != cudaSuccess) return e;                                                               \
-    gemm_topk_kernel<KBV><<<grid, kThreads, smem, st>>>(tmap_q, tmap_e, p);                       \
-    break;
+#define TSS_GEMM_CASE(KBV)                                                               \
+  case KBV:                                                                               \
+    return cluster == 2 ? launch_gemm_inst<KBV, 2>(tmap_q, tmap_e, p, grid, smem, st)     \
+                        : launch_gemm_inst<KBV, 1>(tmap_q, tmap_e, p, grid, smem, st);
   switch (kb) {
     TSS_GEMM_CASE(2)
     TSS_GEMM_CASE(4)
@@ -494,7 +552,6 @@ cudaError_t launch_gemm_topk(int kb, const CUtensorMap& tmap_q, const CUtensorMa
     default: return cudaErrorInvalidValue;
   }
 #undef TSS_GEMM_CASE
-  return cudaGetLastError();
 }
 
 cudaError_t launch_prep_queries(const float* q, uint32_t nq, uint32_t dim, uint32_t kpad,

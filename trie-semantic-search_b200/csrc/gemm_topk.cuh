@@ -15,17 +15,20 @@ struct GemmParams {
   uint32_t num_tiles;      // ceil(n_rows / 256)
   int mode;                // 0 = per-tile maxima over the sample, 1 = collect survivors
   uint32_t sample_stride, sample_count;  // mode 0: tiles j * stride, j < count
-  float* tile_max;         // mode 0 out: [sample_count*2][mb*128] (one maximum per half tile)
+  float* tile_max;         // mode 0 out: [sample_count*split][mb*128] (one maximum per tile part)
   const float* thr;        // mode 1 in:  [mb*128]
-  uint64_t* cand;          // mode 1 out: [mb*128][nslices*2][cand_cap] keys (unscaled by 1/|q|)
-  uint32_t* cand_count;    // [mb*128][nslices*2] survivors seen (may exceed cand_cap)
-  uint32_t cand_cap;       // per (query, slice, column half) list
+  uint64_t* cand;          // mode 1 out: [mb*128][nslices*split][cand_cap] keys (unscaled by 1/|q|)
+  uint32_t* cand_count;    // [mb*128][nslices*split] survivors seen (may exceed cand_cap)
+  uint32_t cand_cap;       // per (query, slice, column part) list
   uint32_t debug;          // diagnostics: 1 = no epilogue math, 2 = no MMA issue, 4 = no corpus TMA
 };
 
 size_t gemm_smem_bytes(int kb);
-cudaError_t launch_gemm_topk(int kb, const CUtensorMap& tmap_q, const CUtensorMap& tmap_e,
-                             const GemmParams& p, int grid, cudaStream_t st);
+int gemm_col_split();  // survivor lists / threshold samples per (slice, tile)
+// cluster: 1, or 2 (needs an even mb; tmap_e must then have a 128-row box)
+cudaError_t launch_gemm_topk(int kb, int cluster, const CUtensorMap& tmap_q,
+                             const CUtensorMap& tmap_e, const GemmParams& p, int grid,
+                             cudaStream_t st);
 cudaError_t launch_prep_queries(const float* q, uint32_t nq, uint32_t dim, uint32_t kpad,
                                 uint32_t nq_pad, uint16_t* out, float* inv_qnorm, cudaStream_t st);
 cudaError_t launch_row_inv_norm(const void* rows, uint64_t n_rows, uint32_t stride_elems, float* out,
