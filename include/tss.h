@@ -133,6 +133,10 @@ void tss_unpack_keys(const uint64_t* keys, uint64_t n, uint32_t* out_rows, float
 int tss_comm_unique_id(uint8_t out_id[128]);
 int tss_comm_create(tss_comm** out, const uint8_t id[128], int rank, int nranks, int device);
 void tss_comm_destroy(tss_comm* c);
+/* Collective over the comm the first time a comm is attached to an index (the ranks map each
+ * other's exchange buffers with CUDA IPC so the scan kernel can push its top-k straight into
+ * peer memory over NVLink and merge in its last CTA; TSS_FUSED_XCHG=0 or an IPC failure falls
+ * back to ncclAllGather + a merge kernel).  comm == NULL detaches. */
 int tss_index_set_shard(tss_index* ix, uint64_t row_base, tss_comm* comm /* nullable */);
 
 /* ---- masks ------------------------------------------------------------------*/

@@ -168,7 +168,7 @@ struct tss_index {
   uint64_t* d_gather = nullptr;    // nranks x kWsQueries x k (lazy)
   uint64_t* d_merged = nullptr;    // kWsQueries x k (lazy)
   uint64_t* d_partials = nullptr;  // kMaxBq x num_sms x 128
-  unsigned int* d_counter = nullptr;  // [0] done ticket, [1] dynamic tile claims
+  unsigned int* d_counter = nullptr;  // [0] done ticket, [1] tile claims, [2] exchange status
   // tile schedule of the unmasked scan (see scan.cuh): share of tiles walked statically,
   // tiles per dynamic claim, and how many warp-rounds at the very end are claimed one
   // tile at a time (tail balancing)
@@ -198,6 +198,15 @@ struct tss_index {
     const void* tmap_base = nullptr;
   } gemm;
   uint32_t gemm_min_nq = 32;  // batches at least this large use K2 (bf16 storage, D <= 384)
+  // fused sharded merge: exchange buffers of all ranks mapped with CUDA IPC (<= 8 ranks)
+  struct Xchg {
+    bool ready = false;
+    tss_comm* comm = nullptr;
+    uint8_t* local = nullptr;
+    uint8_t* peer[8] = {};
+    uint32_t seq = 0;
+    bool suppress = false;  // a rank-local redo (K2 overflow fallback) must not exchange
+  } xchg;
 };
 
 namespace {
@@ -291,6 +300,13 @@ int enqueue_scan(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
     }
     p.out_keys = d_out + (size_t)q0 * k;
     p.dbg = ix->d_dbg;
+    if (ix->comm && ix->xchg.ready && !ix->xchg.suppress) {
+      for (int r = 0; r < ix->comm->nranks; ++r) p.xchg_peer[r] = ix->xchg.peer[r];
+      p.xchg_nranks = (uint32_t)ix->comm->nranks;
+      p.xchg_rank = (uint32_t)ix->comm->rank;
+      p.xchg_seq = ++ix->xchg.seq;
+      p.xchg_status = ix->d_counter + 2;
+    }
     cudaError_t e = tss::launch_scan(ix->ns, p, bq, ix->storage == TSS_BF16, mode != TSS_MASK_NONE,
                                      ix->num_sms, ix->device, ix->stream);
     if (e != cudaSuccess) return cuda_fail(e, "scan_topk_kernel launch");
@@ -434,17 +450,25 @@ int enqueue_gemm(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
     if (k > TSS_MAX_FUSED_K)
       return fail(TSS_ERR_STATE, "K2 survivor list overflowed for query %u and k=%u > %u has no "
                   "exact fallback", qi, k, TSS_MAX_FUSED_K);
-    if ((rc = enqueue_scan(ix, d_queries + (size_t)qi * ix->dim, 1, k, nullptr, TSS_MASK_NONE,
-                           d_out + (size_t)qi * k)))
-      return rc;
+    ix->xchg.suppress = true;
+    rc = enqueue_scan(ix, d_queries + (size_t)qi * ix->dim, 1, k, nullptr, TSS_MASK_NONE,
+                      d_out + (size_t)qi * k);
+    ix->xchg.suppress = false;
+    if (rc) return rc;
   }
   return TSS_OK;
 }
 
-// local (per-shard) search of nq device-resident queries: picks K2 or K1
+// local (per-shard) search of nq device-resident queries: picks K2 or K1.  *merged is set
+// when d_out already holds the GLOBAL result (the K1 scan of a sharded index exchanges and
+// merges inside its last CTA; K2 leaves that to NCCL + merge_gathered_kernel).
 int enqueue_local(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
-                  const tss_mask* mask, int mode, uint64_t* d_out) {
-  if (!gemm_eligible(ix, nq, k, mode)) return enqueue_scan(ix, d_queries, nq, k, mask, mode, d_out);
+                  const tss_mask* mask, int mode, uint64_t* d_out, bool* merged) {
+  *merged = false;
+  if (!gemm_eligible(ix, nq, k, mode)) {
+    *merged = ix->comm && ix->xchg.ready;
+    return enqueue_scan(ix, d_queries, nq, k, mask, mode, d_out);
+  }
   for (uint32_t q0 = 0; q0 < nq; q0 += kWsQueries) {
     uint32_t n = nq - q0 < kWsQueries ? nq - q0 : kWsQueries;
     int rc = enqueue_gemm(ix, d_queries + (size_t)q0 * ix->dim, n, k, d_out + (size_t)q0 * k);
@@ -525,8 +549,8 @@ int tss_index_create(tss_index** out, uint32_t dim, int storage, int device) {
   ALLOC(cudaMalloc(&ix->d_queries, (size_t)kWsQueries * dim * sizeof(float)))
   ALLOC(cudaMalloc(&ix->d_keys, (size_t)kWsQueries * TSS_MAX_K * sizeof(uint64_t)))
   ALLOC(cudaMalloc(&ix->d_partials, (size_t)kMaxBq * ix->num_sms * 128 * sizeof(uint64_t)))
-  ALLOC(cudaMalloc(&ix->d_counter, 2 * sizeof(unsigned int)))
-  ALLOC(cudaMemset(ix->d_counter, 0, 2 * sizeof(unsigned int)))
+  ALLOC(cudaMalloc(&ix->d_counter, 4 * sizeof(unsigned int)))
+  ALLOC(cudaMemset(ix->d_counter, 0, 4 * sizeof(unsigned int)))
   if (const char* sf = getenv("TSS_STATIC_FRAC")) ix->static_frac = (float)atof(sf);
   if (const char* sf = getenv("TSS_FINE_ROUNDS")) ix->fine_rounds = (float)atof(sf);
   if (const char* sf = getenv("TSS_DYN_CHUNK")) ix->dyn_chunk = (uint32_t)atoi(sf);
@@ -554,6 +578,9 @@ void tss_index_destroy(tss_index* ix) {
   cudaFree(ix->d_counter);
   if (ix->h_queries) cudaFreeHost(ix->h_queries);
   if (ix->h_keys) cudaFreeHost(ix->h_keys);
+  for (int r = 0; r < 8; ++r)
+    if (ix->xchg.peer[r] && ix->xchg.peer[r] != ix->xchg.local) cudaIpcCloseMemHandle(ix->xchg.peer[r]);
+  cudaFree(ix->xchg.local);
   cudaFree(ix->gemm.d_inv_norm);
   cudaFree(ix->gemm.d_qbf16);
   cudaFree(ix->gemm.d_inv_q);
@@ -678,13 +705,18 @@ int tss_index_search_device(tss_index* ix, const float* d_queries, uint32_t nq, 
   if ((rc = check_k_path(ix, nq, k, mask_mode))) return rc;
   if (!nq) return TSS_OK;
   DeviceGuard g(ix->device);
-  if (!ix->comm) return enqueue_local(ix, d_queries, nq, k, mask, mask_mode, d_out_keys);
+  bool merged = false;
+  if (!ix->comm) return enqueue_local(ix, d_queries, nq, k, mask, mask_mode, d_out_keys, &merged);
   if ((rc = ensure_gather_ws(ix))) return rc;
   for (uint32_t q0 = 0; q0 < nq; q0 += kWsQueries) {
     uint32_t n = nq - q0 < kWsQueries ? nq - q0 : kWsQueries;
-    if ((rc = enqueue_local(ix, d_queries + (size_t)q0 * ix->dim, n, k, mask, mask_mode, ix->d_keys)))
+    const bool fused = ix->xchg.ready && !gemm_eligible(ix, nq, k, mask_mode);
+    uint64_t* d_local = fused ? d_out_keys + (size_t)q0 * k : ix->d_keys;
+    if ((rc = enqueue_local(ix, d_queries + (size_t)q0 * ix->dim, n, k, mask, mask_mode, d_local,
+                            &merged)))
       return rc;
-    if ((rc = enqueue_gather_merge(ix, ix->d_keys, n, k, d_out_keys + (size_t)q0 * k))) return rc;
+    if (!merged && (rc = enqueue_gather_merge(ix, ix->d_keys, n, k, d_out_keys + (size_t)q0 * k)))
+      return rc;
   }
   return TSS_OK;
 }
@@ -728,19 +760,28 @@ int tss_index_search(tss_index* ix, const float* queries, uint32_t nq, uint32_t 
     memcpy(ix->h_queries, queries + (size_t)q0 * ix->dim, qbytes);
     CU(cudaMemcpyAsync(ix->d_queries, ix->h_queries, qbytes, cudaMemcpyHostToDevice, ix->stream));
     // a large batch of a bf16 index takes the tensor-core path as a whole (nq, not n, decides)
-    if (gemm_eligible(ix, nq, k, mask_mode))
+    bool merged = false;
+    if (gemm_eligible(ix, nq, k, mask_mode)) {
       rc = enqueue_gemm(ix, ix->d_queries, n, k, ix->d_keys);
-    else
+    } else {
+      merged = ix->comm && ix->xchg.ready;
       rc = enqueue_scan(ix, ix->d_queries, n, k, mask, mask_mode, ix->d_keys);
+    }
     if (rc) return rc;
     const uint64_t* d_res = ix->d_keys;
-    if (ix->comm) {
+    if (ix->comm && !merged) {
       if ((rc = enqueue_gather_merge(ix, ix->d_keys, n, k, ix->d_merged))) return rc;
       d_res = ix->d_merged;
     }
     CU(cudaMemcpyAsync(ix->h_keys, d_res, (size_t)n * k * sizeof(uint64_t), cudaMemcpyDeviceToHost,
                        ix->stream));
+    unsigned int xstatus = 0;
+    if (merged)
+      CU(cudaMemcpyAsync(&xstatus, ix->d_counter + 2, sizeof(xstatus), cudaMemcpyDeviceToHost,
+                         ix->stream));
     CU(cudaStreamSynchronize(ix->stream));
+    if (xstatus)
+      return fail(TSS_ERR_NCCL, "a rank of the shard group did not deliver its top-k within 5 s");
     tss_unpack_keys(ix->h_keys, (uint64_t)n * k, out_rows + (size_t)q0 * k,
                     out_scores + (size_t)q0 * k);
     for (uint32_t qi = 0; qi < n; ++qi) {
@@ -795,6 +836,58 @@ void tss_comm_destroy(tss_comm* c) {
   delete c;
 }
 
+namespace {
+// Map every rank's exchange buffer into this process (CUDA IPC; handles travel over the comm's
+// own all-gather).  Failure is not an error: the sharded search then uses NCCL + a merge kernel.
+int setup_xchg(tss_index* ix, tss_comm* comm) {
+  tss_index::Xchg& x = ix->xchg;
+  if (x.ready && x.comm == comm) return TSS_OK;
+  x.ready = false;
+  const char* env = getenv("TSS_FUSED_XCHG");
+  if ((env && atoi(env) == 0) || comm->nranks < 2 || comm->nranks > (int)tss::kXchgMaxRanks)
+    return TSS_OK;
+  if (!x.local) {
+    CU(cudaMalloc(&x.local, tss::kXchgBytes));
+    CU(cudaMemset(x.local, 0, tss::kXchgBytes));
+  }
+  cudaIpcMemHandle_t mine;
+  CU(cudaIpcGetMemHandle(&mine, x.local));
+  uint8_t* d_h = nullptr;
+  CU(cudaMalloc(&d_h, sizeof(mine) * (size_t)(comm->nranks + 1)));
+  std::vector<cudaIpcMemHandle_t> all(comm->nranks);
+  cudaError_t e = cudaMemcpyAsync(d_h, &mine, sizeof(mine), cudaMemcpyHostToDevice, ix->stream);
+  int nrc = 0;
+  if (e == cudaSuccess)
+    nrc = g_nccl.AllGather(d_h, d_h + sizeof(mine), sizeof(mine), /*ncclUint8*/ 1, comm->comm,
+                           ix->stream);
+  if (e == cudaSuccess && nrc == 0)
+    e = cudaMemcpyAsync(all.data(), d_h + sizeof(mine), sizeof(mine) * comm->nranks,
+                        cudaMemcpyDeviceToHost, ix->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ix->stream);
+  cudaFree(d_h);
+  if (nrc != 0) return fail(TSS_ERR_NCCL, "ncclAllGather (IPC handles): %s", g_nccl.GetErrorString(nrc));
+  if (e != cudaSuccess) return cuda_fail(e, "IPC handle exchange");
+  bool ok = true;
+  for (int r = 0; r < comm->nranks; ++r) {
+    if (r == comm->rank) {
+      x.peer[r] = x.local;
+      continue;
+    }
+    void* ptr = nullptr;
+    if (cudaIpcOpenMemHandle(&ptr, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      cudaGetLastError();
+      ok = false;
+      break;
+    }
+    x.peer[r] = static_cast<uint8_t*>(ptr);
+  }
+  x.comm = comm;
+  x.ready = ok;
+  x.seq = 0;
+  return TSS_OK;
+}
+}  // namespace
+
 int tss_index_set_shard(tss_index* ix, uint64_t row_base, tss_comm* comm) {
   if (!ix) return fail(TSS_ERR_INVALID_ARG, "index is NULL");
   if (row_base + ix->n_rows >= 0xFFFFFFFFull)
@@ -805,6 +898,11 @@ int tss_index_set_shard(tss_index* ix, uint64_t row_base, tss_comm* comm) {
     return fail(TSS_ERR_INVALID_ARG, "at most %d ranks", 48 * 1024 / (TSS_MAX_FUSED_K * 8));
   ix->row_base = row_base;
   ix->comm = comm;
+  if (comm) {  // collective over the comm the first time a given comm is attached
+    DeviceGuard g(ix->device);
+    int rc = setup_xchg(ix, comm);
+    if (rc) return rc;
+  }
   return TSS_OK;
 }
 

@@ -45,7 +45,35 @@ struct ScanParams {
   uint64_t* out_keys;      // [nq_valid][k]
   uint32_t smem_bytes;     // dynamic shared memory size of this launch
   unsigned long long* dbg; // diagnostics: [gridDim.x][8] %globaltimer stamps, or null
+  // fused sharded merge (K5 inside the scan): exchange buffers of every rank of the shard
+  // group, mapped into this process with CUDA IPC; xchg_nranks == 0 switches it off
+  uint8_t* xchg_peer[8];
+  uint32_t xchg_nranks, xchg_rank, xchg_seq;
+  unsigned int* xchg_status;  // set to 1 when a peer never showed up (5 s), instead of hanging
 };
+
+// exchange buffer layout (bytes): [0,256) one u32 arrival flag per source rank, then
+// keys[parity 2][source rank 8][query 4][128] u64
+constexpr uint32_t kXchgKeysOffset = 256;
+constexpr uint32_t kXchgMaxRanks = 8, kXchgMaxQ = 4, kXchgMaxK = 128;
+constexpr size_t kXchgBytes =
+    kXchgKeysOffset + (size_t)2 * kXchgMaxRanks * kXchgMaxQ * kXchgMaxK * sizeof(uint64_t);
+__host__ __device__ __forceinline__ size_t xchg_key_index(uint32_t parity, uint32_t rank, uint32_t qb) {
+  return ((size_t)(parity * kXchgMaxRanks + rank) * kXchgMaxQ + qb) * kXchgMaxK;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint64_t ld_relaxed_sys(const uint64_t* p) {
+  uint64_t v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
 
 __device__ __forceinline__ void dbg_stamp(const ScanParams& p, int slot) {
   if (p.dbg && threadIdx.x == 0) {
@@ -500,13 +528,62 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_topk_kernel(const ScanPara
       }
     }
     __syncthreads();
+    // sharded + fused: the local result goes to a staging row in shared memory instead
+    uint64_t* fin = ws + (size_t)gridDim.x * p.k + (size_t)b * kXchgMaxK;
+    uint64_t* dst = p.xchg_nranks ? fin : p.out_keys + (size_t)b * p.k;
     if (warp == 0) {
       if (gridDim.x <= 160)
-        warp_tournament<5>(ws, p.k, gridDim.x, p.k, p.k, p.out_keys + (size_t)b * p.k, lane);
+        warp_tournament<5>(ws, p.k, gridDim.x, p.k, p.k, dst, lane);
       else
-        warp_tournament<8>(ws, p.k, gridDim.x, p.k, p.k, p.out_keys + (size_t)b * p.k, lane);
+        warp_tournament<8>(ws, p.k, gridDim.x, p.k, p.k, dst, lane);
     }
     __syncthreads();
+    if (p.xchg_nranks) {
+      // push this shard's k keys for query b straight into every rank's exchange buffer
+      // (peer memory over NVLink), own buffer included
+      const uint32_t parity = p.xchg_seq & 1u;
+      for (uint32_t idx = tid; idx < p.xchg_nranks * p.k; idx += nthreads) {
+        uint32_t r = idx / p.k, e = idx - r * p.k;
+        uint64_t* keys = reinterpret_cast<uint64_t*>(p.xchg_peer[r] + kXchgKeysOffset);
+        keys[xchg_key_index(parity, p.xchg_rank, b) + e] = fin[e];
+      }
+    }
+  }
+  if (p.xchg_nranks) {
+    // publish: everything this CTA wrote to the peers is visible before the flag is
+    __threadfence_system();
+    __syncthreads();
+    if ((uint32_t)tid < p.xchg_nranks)
+      st_release_sys(reinterpret_cast<uint32_t*>(p.xchg_peer[tid]) + p.xchg_rank, p.xchg_seq);
+    // wait until every rank's keys for this sequence number have landed here.  The ranks
+    // run on different GPUs and each only ever waits for the others' previous work.
+    if ((uint32_t)tid < p.xchg_nranks) {
+      const uint32_t* flag = reinterpret_cast<const uint32_t*>(p.xchg_peer[p.xchg_rank]) + tid;
+      unsigned long long t0, t1;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+      while ((int32_t)(ld_acquire_sys(flag) - p.xchg_seq) < 0) {
+        __nanosleep(64);
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 5000000000ull) {  // a rank died: report, do not spin forever
+          atomicExch(p.xchg_status, 1u);
+          break;
+        }
+      }
+    }
+    __syncthreads();
+    const uint32_t parity = p.xchg_seq & 1u;
+    const uint64_t* mine =
+        reinterpret_cast<const uint64_t*>(p.xchg_peer[p.xchg_rank] + kXchgKeysOffset);
+    // stage the P lists of every query in shared memory, one warp per query merges them
+    for (uint32_t idx = tid; idx < p.nq_valid * p.xchg_nranks * p.k; idx += nthreads) {
+      uint32_t b = idx / (p.xchg_nranks * p.k), rem = idx - b * (p.xchg_nranks * p.k);
+      uint32_t r = rem / p.k, e = rem - r * p.k;
+      ws[idx] = ld_relaxed_sys(mine + xchg_key_index(parity, r, b) + e);
+    }
+    __syncthreads();
+    if ((uint32_t)warp < p.nq_valid)
+      warp_tournament<1>(ws + (size_t)warp * p.xchg_nranks * p.k, p.k, p.xchg_nranks, p.k, p.k,
+                         p.out_keys + (size_t)warp * p.k, lane);
   }
   dbg_stamp(p, 5);
   if (tid == 0) {

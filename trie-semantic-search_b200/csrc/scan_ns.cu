@@ -20,7 +20,11 @@ static cudaError_t launch_one(const ScanParams& p, int grid, int device, cudaStr
                 (size_t)kWarps * BQ * p.cap * 8 + (size_t)kWarps * 8;
   // the last CTA stages gridDim.x partial lists of kp keys in shared memory
   if (grid > 256) return cudaErrorInvalidConfiguration;
-  if (smem < (size_t)grid * p.kp * 8) smem = (size_t)grid * p.kp * 8;
+  // (+ the staging rows and peer lists of the fused sharded merge)
+  const size_t merge_bytes = (size_t)grid * p.kp * 8 + (size_t)kXchgMaxQ * kXchgMaxK * 8;
+  const size_t xchg_bytes = (size_t)kXchgMaxQ * kXchgMaxRanks * kXchgMaxK * 8;
+  if (smem < merge_bytes) smem = merge_bytes;
+  if (smem < xchg_bytes) smem = xchg_bytes;
   // 227 KB per CTA minus the kernel's static shared memory (ticket word, padded)
   if (smem > 232448 - 256) return cudaErrorInvalidConfiguration;
   static size_t attr_bytes[kMaxDevices] = {};
