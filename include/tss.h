@@ -97,6 +97,12 @@ int tss_index_finalize(tss_index* ix);
 uint64_t tss_index_size(const tss_index* ix);
 uint32_t tss_index_dim(const tss_index* ix);
 void tss_index_destroy(tss_index* ix);
+/* On-disk form: a 64-byte header + the padded rows exactly as they sit in
+ * HBM, so tss_index_load is file -> pinned buffer -> HBM with no repacking.  These fill in
+ * VectorIndex::save_to_disk / load_from_disk (src/vector.rs:83-95, TODO stubs); the row ->
+ * DocRef table stays with the caller.  The loaded index is finalized. */
+int tss_index_save(tss_index* ix, const char* path);
+int tss_index_load(tss_index** out, const char* path, int device);
 /* copy stored rows back (fp32; bf16 storage is widened). Test utility. */
 int tss_index_get_rows(tss_index* ix, uint64_t row_begin, uint64_t nrows, float* out);
 

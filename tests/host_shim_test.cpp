@@ -201,6 +201,18 @@ static void hnsw_vs_oracle() {
   CHECK(threw);
   auto batch = h.search_batch({q, synth(2, dim, 9), synth(3, dim, 9)}, 5);
   CHECK(batch.size() == 3 && batch[0][0].first.case_id == cid(99999) && batch[2].size() == 5);
+  // N1: save -> load -> same answers, DocRefs included
+  const std::string path = "/tmp/tss_host_shim_test_index";
+  h.save(path);
+  auto h2 = HnswIndex::load(HnswConfig(), path, 0);
+  CHECK(h2->size() == h.size() && h2->dimension() == dim);
+  auto a = h.search(q, 20), b = h2->search(q, 20);
+  CHECK(a.size() == b.size());
+  for (size_t i = 0; i < a.size() && i < b.size(); ++i)
+    CHECK(a[i].first == b[i].first && a[i].second == b[i].second);
+  CHECK(h2->rows_of_case(cid(5)) && h2->rows_of_case(cid(5))->size() == 3);
+  remove((path + ".tssidx").c_str());
+  remove((path + ".docrefs").c_str());
 }
 
 static void stub_embedding_behaviour() {

@@ -79,3 +79,19 @@ def test_terms_validation_runs_before_any_device_call(tss):
     rc = L.tss_terms_create(C.byref(p), pool.ctypes.data, toff.ctypes.data, poff.ctypes.data,
                             rows.ctypes.data, 2, 0)
     assert rc == tss.TSS_ERR_INVALID_ARG and b"byte-sorted" in L.tss_last_error()
+
+
+def test_index_load_rejects_bad_files_before_touching_a_device(tss, tmp_path):
+    import ctypes as C
+    import struct
+    L = tss.lib()
+    p = C.c_void_p()
+    bad = tmp_path / "bad.tssidx"
+    bad.write_bytes(b"NOTANIDX" + b"\0" * 56)
+    assert L.tss_index_load(C.byref(p), str(bad).encode(), 0) == tss.TSS_ERR_INVALID_ARG
+    assert b"TSSIDX01" in L.tss_last_error()
+    assert L.tss_index_load(C.byref(p), str(tmp_path / "missing").encode(), 0) == tss.TSS_ERR_INVALID_ARG
+    hdr = b"TSSIDX01" + struct.pack("<IIIIQQ", 384, 0, 999, 0, 10, 1536) + b"\0" * 24
+    bad.write_bytes(hdr)
+    assert L.tss_index_load(C.byref(p), str(bad).encode(), 0) == tss.TSS_ERR_INVALID_ARG
+    assert b"inconsistent" in L.tss_last_error()

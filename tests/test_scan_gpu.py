@@ -251,3 +251,30 @@ def test_full_size_properties_1m(tss, orc):
     assert np.array_equal(r, r2) and np.array_equal(s, s2)
     # the oracle streaming the same generator agrees on the whole top-k
     _assert_same((r, s, c), orc.cosine_topk_synth(0, n, dim, SEED, q, k))
+
+
+@pytest.mark.parametrize("storage", ["f32", "bf16"])
+def test_save_load_round_trip(tss, orc, tmp_path, storage):
+    """N1: on-disk index -> load -> identical search results; truncated files are rejected."""
+    import os
+    n, dim = 33_333, 200  # dim pads to 256 in storage
+    rows = orc.gen_rows(0, n, dim, SEED)
+    q = orc.gen_rows(0, 3, dim, 0xBEEF)
+    st = tss.TSS_F32 if storage == "f32" else tss.TSS_BF16
+    ix = tss.FlatIndex(dim, st)
+    ix.add(rows)
+    ix.finalize()
+    want = ix.search(q, 10)
+    path = str(tmp_path / "idx.tssidx")
+    ix.save(path)
+    assert os.path.getsize(path) == 64 + n * 256 * (4 if storage == "f32" else 2)
+    ix2 = tss.FlatIndex.load(path)
+    assert ix2.size() == n and ix2.dim == dim
+    got = ix2.search(q, 10)
+    for g, w in zip(got, want):
+        assert np.array_equal(g, w)
+    assert np.array_equal(ix2.get_rows(5, 7), ix.get_rows(5, 7))
+    with open(path, "r+b") as f:
+        f.truncate(64 + 1000)
+    with pytest.raises(tss.TssError):
+        tss.FlatIndex.load(path)

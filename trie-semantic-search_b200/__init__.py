@@ -39,6 +39,7 @@ ABI_SYMBOLS = [
     "tss_index_stream", "tss_index_sync", "tss_dev_alloc", "tss_dev_free", "tss_dev_h2d",
     "tss_dev_d2h", "tss_event_create", "tss_event_record", "tss_event_elapsed_ms",
     "tss_event_destroy", "tss_launch_count", "tss_index_debug_phases",
+    "tss_index_save", "tss_index_load",
 ]
 
 
@@ -111,6 +112,8 @@ def lib() -> C.CDLL:
         "tss_event_destroy": (i32, [vp]),
         "tss_launch_count": (u64, []),
         "tss_index_debug_phases": (i32, [vp, vp]),
+        "tss_index_save": (i32, [vp, C.c_char_p]),
+        "tss_index_load": (i32, [C.POINTER(vp), C.c_char_p, i32]),
     }
     del pu32
     for name, (res, args) in sig.items():
@@ -327,6 +330,19 @@ class FlatIndex:
         p = C.c_void_p()
         _check(lib().tss_index_create(C.byref(p), dim, storage, device))
         self.handle, self.dim, self.device, self.storage = p.value, dim, device, storage
+
+    def save(self, path: str) -> None:
+        _check(lib().tss_index_save(self.handle, path.encode()))
+
+    @classmethod
+    def load(cls, path: str, device: int = 0) -> "FlatIndex":
+        p = C.c_void_p()
+        _check(lib().tss_index_load(C.byref(p), path.encode(), device))
+        self = cls.__new__(cls)
+        self.handle, self.device = p.value, device
+        self.dim = int(lib().tss_index_dim(p.value))
+        self.storage = None
+        return self
 
     def reserve(self, nrows: int) -> None:
         _check(lib().tss_index_reserve(self.handle, int(nrows)))

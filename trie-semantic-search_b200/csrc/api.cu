@@ -695,6 +695,100 @@ int tss_index_get_rows(tss_index* ix, uint64_t row_begin, uint64_t nrows, float*
   return TSS_OK;
 }
 
+// ---- on-disk format (VectorIndex::save_to_disk / load_from_disk,
+// reference src/vector.rs:83-95 are TODO stubs) ---------------------------------------------
+// 64-byte header + the padded rows exactly as they sit in HBM, so loading is a straight
+// file -> pinned buffer -> HBM copy with no repacking.
+namespace {
+struct IndexFileHeader {
+  char magic[8];  // "TSSIDX01"
+  uint32_t dim, storage, stride_elems, reserved;
+  uint64_t n_rows, row_bytes;
+  uint8_t pad[24];
+};
+static_assert(sizeof(IndexFileHeader) == 64, "header is 64 bytes");
+constexpr size_t kIoChunk = 32u << 20;
+}  // namespace
+
+int tss_index_save(tss_index* ix, const char* path) {
+  if (!ix || !path) return fail(TSS_ERR_INVALID_ARG, "NULL argument");
+  DeviceGuard g(ix->device);
+  CU(cudaStreamSynchronize(ix->stream));
+  FILE* f = fopen(path, "wb");
+  if (!f) return fail(TSS_ERR_INVALID_ARG, "cannot open %s for writing", path);
+  IndexFileHeader h{};
+  memcpy(h.magic, "TSSIDX01", 8);
+  h.dim = ix->dim;
+  h.storage = (uint32_t)ix->storage;
+  h.stride_elems = ix->stride_elems;
+  h.n_rows = ix->n_rows;
+  h.row_bytes = ix->row_bytes;
+  bool ok = fwrite(&h, sizeof(h), 1, f) == 1;
+  void* hbuf = nullptr;
+  if (ok && cudaMallocHost(&hbuf, kIoChunk) != cudaSuccess) ok = false;
+  const size_t total = (size_t)ix->n_rows * ix->row_bytes;
+  for (size_t off = 0; ok && off < total; off += kIoChunk) {
+    size_t n = total - off < kIoChunk ? total - off : kIoChunk;
+    ok = cudaMemcpy(hbuf, ix->d_rows + off, n, cudaMemcpyDeviceToHost) == cudaSuccess &&
+         fwrite(hbuf, 1, n, f) == n;
+  }
+  if (hbuf) cudaFreeHost(hbuf);
+  ok = (fclose(f) == 0) && ok;
+  if (!ok) return fail(TSS_ERR_STATE, "writing %s failed", path);
+  return TSS_OK;
+}
+
+int tss_index_load(tss_index** out, const char* path, int device) {
+  if (!out || !path) return fail(TSS_ERR_INVALID_ARG, "NULL argument");
+  *out = nullptr;
+  FILE* f = fopen(path, "rb");
+  if (!f) return fail(TSS_ERR_INVALID_ARG, "cannot open %s", path);
+  IndexFileHeader h{};
+  if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, "TSSIDX01", 8) != 0) {
+    fclose(f);
+    return fail(TSS_ERR_INVALID_ARG, "%s is not a TSSIDX01 file", path);
+  }
+  const int ns = h.dim ? tss::storage_stripes_for_dim(h.dim) : 0;
+  const uint64_t elem = h.storage == TSS_BF16 ? 2 : 4;
+  if (!ns || (h.storage != TSS_F32 && h.storage != TSS_BF16) ||
+      h.stride_elems != (uint32_t)ns * 128u || h.row_bytes != h.stride_elems * elem ||
+      h.n_rows >= 0xFFFFFFFFull) {
+    fclose(f);
+    return fail(TSS_ERR_INVALID_ARG, "%s: inconsistent header", path);
+  }
+  tss_index* ix = nullptr;
+  int rc = tss_index_create(&ix, h.dim, (int)h.storage, device);
+  if (rc) {
+    fclose(f);
+    return rc;
+  }
+  DeviceGuard g(device);
+  rc = ensure_capacity(ix, h.n_rows ? h.n_rows : 1);
+  void* hbuf = nullptr;
+  if (!rc && cudaMallocHost(&hbuf, kIoChunk) != cudaSuccess) rc = fail(TSS_ERR_OOM, "pinned buffer");
+  const size_t total = (size_t)h.n_rows * h.row_bytes;
+  for (size_t off = 0; !rc && off < total; off += kIoChunk) {
+    size_t n = total - off < kIoChunk ? total - off : kIoChunk;
+    if (fread(hbuf, 1, n, f) != n)
+      rc = fail(TSS_ERR_INVALID_ARG, "%s is truncated", path);
+    else if (cudaMemcpy(ix->d_rows + off, hbuf, n, cudaMemcpyHostToDevice) != cudaSuccess)
+      rc = fail(TSS_ERR_CUDA, "upload of %s failed", path);
+  }
+  if (hbuf) cudaFreeHost(hbuf);
+  fclose(f);
+  if (rc) {
+    tss_index_destroy(ix);
+    return rc;
+  }
+  ix->n_rows = h.n_rows;
+  if ((rc = tss_index_finalize(ix))) {
+    tss_index_destroy(ix);
+    return rc;
+  }
+  *out = ix;
+  return TSS_OK;
+}
+
 // ---- search ---------------------------------------------------------------------------
 int tss_index_search_device(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
                             const tss_mask* mask, int mask_mode, uint64_t* d_out_keys) {

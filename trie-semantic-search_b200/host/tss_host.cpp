@@ -90,6 +90,70 @@ void HnswIndex::flush() {
 
 size_t HnswIndex::size() const { return row_docref_.size(); }
 
+void HnswIndex::make_searchable() {
+  if (!dirty_) return;
+  flush();
+  int rc = tss_index_finalize(ix_);
+  if (rc) raise_tss(SearchError::VectorIndexFailed, "HnswIndex finalize", rc);
+  dirty_ = false;
+}
+
+namespace {
+struct DocRefRecord {
+  uint8_t case_id[16];
+  uint64_t paragraph_index;
+  int64_t char_offset;  // -1 = None
+};
+}  // namespace
+
+void HnswIndex::save(const std::string& path) {
+  make_searchable();
+  int rc = tss_index_save(ix_, (path + ".tssidx").c_str());
+  if (rc) raise_tss(SearchError::VectorIndexFailed, "HnswIndex::save", rc);
+  FILE* f = fopen((path + ".docrefs").c_str(), "wb");
+  if (!f) throw SearchError(SearchError::VectorIndexFailed, "cannot write " + path + ".docrefs");
+  uint64_t n = row_docref_.size();
+  bool ok = fwrite(&n, sizeof(n), 1, f) == 1;
+  for (const DocRef& d : row_docref_) {
+    DocRefRecord r;
+    memcpy(r.case_id, d.case_id.bytes.data(), 16);
+    r.paragraph_index = d.paragraph_index;
+    r.char_offset = d.char_offset ? (int64_t)*d.char_offset : -1;
+    ok = ok && fwrite(&r, sizeof(r), 1, f) == 1;
+  }
+  ok = (fclose(f) == 0) && ok;
+  if (!ok) throw SearchError(SearchError::VectorIndexFailed, "writing " + path + ".docrefs failed");
+}
+
+std::unique_ptr<HnswIndex> HnswIndex::load(const HnswConfig& config, const std::string& path,
+                                           int device) {
+  std::unique_ptr<HnswIndex> h(new HnswIndex());
+  h->config_ = config;
+  h->device_ = device;
+  int rc = tss_index_load(&h->ix_, (path + ".tssidx").c_str(), device);
+  if (rc) raise_tss(SearchError::VectorIndexFailed, "HnswIndex::load", rc);
+  h->dim_ = tss_index_dim(h->ix_);
+  FILE* f = fopen((path + ".docrefs").c_str(), "rb");
+  if (!f) throw SearchError(SearchError::VectorIndexFailed, "cannot read " + path + ".docrefs");
+  uint64_t n = 0;
+  bool ok = fread(&n, sizeof(n), 1, f) == 1 && n == tss_index_size(h->ix_);
+  for (uint64_t i = 0; ok && i < n; ++i) {
+    DocRefRecord r;
+    ok = fread(&r, sizeof(r), 1, f) == 1;
+    if (!ok) break;
+    DocRef d;
+    memcpy(d.case_id.bytes.data(), r.case_id, 16);
+    d.paragraph_index = (size_t)r.paragraph_index;
+    if (r.char_offset >= 0) d.char_offset = (size_t)r.char_offset;
+    h->case_rows_[d.case_id].push_back((uint32_t)i);
+    h->row_docref_.push_back(d);
+  }
+  fclose(f);
+  if (!ok) throw SearchError(SearchError::VectorIndexFailed, path + ".docrefs does not match the index");
+  h->dirty_ = false;
+  return h;
+}
+
 const std::vector<uint32_t>* HnswIndex::rows_of_case(const CaseId& id) const {
   auto it = case_rows_.find(id);
   return it == case_rows_.end() ? nullptr : &it->second;
@@ -177,8 +241,22 @@ void VectorCache::insert(const std::string& key, std::vector<float> value) {
 VectorIndex::VectorIndex(const VectorConfig& config)
     : config_(config),
       embedding_model_(config.model, config.dimension),
-      hnsw_index_(config.hnsw, config.dimension, config.device, config.bf16_storage),
+      hnsw_index_(new HnswIndex(config.hnsw, config.dimension, config.device, config.bf16_storage)),
       vector_cache_(1000) {}  // src/vector.rs:72
+VectorIndex::VectorIndex(const VectorConfig& config, std::unique_ptr<HnswIndex> loaded)
+    : config_(config),
+      embedding_model_(config.model, config.dimension),
+      hnsw_index_(std::move(loaded)),
+      vector_cache_(1000) {}
+
+void VectorIndex::save_to_disk(const std::string& path) { hnsw_index_->save(path); }
+std::unique_ptr<VectorIndex> VectorIndex::load_from_disk(const VectorConfig& config,
+                                                         const std::string& path) {
+  auto h = HnswIndex::load(config.hnsw, path, config.device);
+  if (h->dimension() != config.dimension)
+    throw SearchError(SearchError::VectorIndexFailed, "index file dimension differs from config");
+  return std::unique_ptr<VectorIndex>(new VectorIndex(config, std::move(h)));
+}
 
 EmbeddingResult VectorIndex::generate_embedding(const std::string& text) {
   if (auto cached = vector_cache_.get(text)) return EmbeddingResult{*cached, 0};  // :100-105
@@ -187,15 +265,15 @@ EmbeddingResult VectorIndex::generate_embedding(const std::string& text) {
   return r;
 }
 void VectorIndex::add_document(const DocRef& doc_ref, const std::string& text) {
-  hnsw_index_.add_vector(doc_ref, generate_embedding(text).embedding);  // :122-123
+  hnsw_index_->add_vector(doc_ref, generate_embedding(text).embedding);  // :122-123
 }
 void VectorIndex::add_embedding(const DocRef& doc_ref, const std::vector<float>& embedding) {
-  hnsw_index_.add_vector(doc_ref, embedding);
+  hnsw_index_->add_vector(doc_ref, embedding);
 }
 std::vector<VectorSearchResult> VectorIndex::search_masked(const std::string& query, size_t top_k,
                                                            const tss_mask* mask, int mask_mode) {
   EmbeddingResult q = generate_embedding(query);                                      // :134
-  auto neighbors = hnsw_index_.search_masked(q.embedding, top_k, mask, mask_mode);   // :137
+  auto neighbors = hnsw_index_->search_masked(q.embedding, top_k, mask, mask_mode);   // :137
   std::vector<VectorSearchResult> out;
   out.reserve(neighbors.size());
   for (auto& n : neighbors)  // order preserved; similarity = 1.0 - distance  :140-147
@@ -206,7 +284,7 @@ std::vector<VectorSearchResult> VectorIndex::search(const std::string& query, si
   return search_masked(query, top_k, nullptr, TSS_MASK_NONE);
 }
 VectorIndexStats VectorIndex::get_stats() const {
-  return VectorIndexStats{hnsw_index_.size(), vector_cache_.size(), config_.dimension};  // :153-159
+  return VectorIndexStats{hnsw_index_->size(), vector_cache_.size(), config_.dimension};  // :153-159
 }
 
 // ---- TokenTrie ------------------------------------------------------------------------------

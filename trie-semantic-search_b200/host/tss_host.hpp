@@ -125,6 +125,10 @@ class HnswIndex {
                                                       int mask_mode);
   std::vector<std::vector<std::pair<DocRef, float>>> search_batch(
       const std::vector<std::vector<float>>& queries, size_t top_k);
+  // on-disk form: <path>.tssidx (tss_index_save) + <path>.docrefs
+  void save(const std::string& path);
+  static std::unique_ptr<HnswIndex> load(const HnswConfig& config, const std::string& path,
+                                         int device);
   const std::vector<uint32_t>* rows_of_case(const CaseId& id) const;
   const DocRef& doc_ref_of_row(uint32_t row) const { return row_docref_[row]; }
   tss_index* handle() { return ix_; }
@@ -132,10 +136,12 @@ class HnswIndex {
   size_t dimension() const { return dim_; }
 
  private:
+  HnswIndex() = default;
   void flush();
+  void make_searchable();
   HnswConfig config_;
-  size_t dim_;
-  int device_;
+  size_t dim_ = 0;
+  int device_ = 0;
   tss_index* ix_ = nullptr;
   std::vector<DocRef> row_docref_;  // row -> DocRef (stays on the host)
   std::unordered_map<CaseId, std::vector<uint32_t>, CaseIdHash> case_rows_;
@@ -195,13 +201,18 @@ class VectorIndex {  // src/vector.rs:27-160
   std::vector<VectorSearchResult> search_masked(const std::string& query, size_t top_k,
                                                 const tss_mask* mask, int mask_mode);
   VectorIndexStats get_stats() const;  // :153-159
+  // src/vector.rs:83-95 are TODO stubs (save = Ok(()), load = Self::new); here they persist
+  void save_to_disk(const std::string& path);
+  static std::unique_ptr<VectorIndex> load_from_disk(const VectorConfig& config,
+                                                     const std::string& path);
   EmbeddingModel& embedding_model() { return embedding_model_; }
-  HnswIndex& hnsw() { return hnsw_index_; }
+  HnswIndex& hnsw() { return *hnsw_index_; }
 
  private:
+  VectorIndex(const VectorConfig& config, std::unique_ptr<HnswIndex> loaded);
   VectorConfig config_;
   EmbeddingModel embedding_model_;
-  HnswIndex hnsw_index_;
+  std::unique_ptr<HnswIndex> hnsw_index_;
   VectorCache vector_cache_;
 };
 
