@@ -278,3 +278,26 @@ def test_save_load_round_trip(tss, orc, tmp_path, storage):
         f.truncate(64 + 1000)
     with pytest.raises(tss.TssError):
         tss.FlatIndex.load(path)
+
+
+@pytest.mark.parametrize("k", [129, 300, 1024])
+def test_large_k_rounds_on_the_scan_path(tss, orc, k):
+    """k > 128 on an fp32 index: exact, by rounds of 128 that exclude what was already found."""
+    n = 5000
+    rows = orc.gen_rows(0, n, 384, SEED)
+    rows[4000:4100] = rows[17]  # ties across a round boundary
+    q = orc.gen_rows(0, 2, 384, 0xBEEF)
+    q[1] = rows[17]
+    ix = _mk_index(tss, rows)
+    _assert_same(ix.search(q, k), orc.cosine_topk(rows, q, k))
+    bits = np.random.default_rng(k).random(n) < 0.5
+    words = np.zeros((n + 31) // 32, dtype=np.uint32)
+    idx = np.nonzero(bits)[0]
+    np.bitwise_or.at(words, idx >> 5, (np.uint32(1) << (idx & 31).astype(np.uint32)))
+    m = tss.Mask(n)
+    m.upload(words)
+    _assert_same(ix.search(q, k, m, tss.TSS_MASK_INCLUDE),
+                 orc.cosine_topk(rows, q, k, words, orc.MASK_INCLUDE))
+    _assert_same(ix.search(q, k, m, tss.TSS_MASK_EXCLUDE),
+                 orc.cosine_topk(rows, q, k, words, orc.MASK_EXCLUDE))
+    assert np.array_equal(m.download(), words)  # the caller's mask is untouched

@@ -198,6 +198,8 @@ struct tss_index {
     const void* tmap_base = nullptr;
   } gemm;
   uint32_t gemm_min_nq = 32;  // batches at least this large use K2 (bf16 storage, D <= 384)
+  uint32_t* d_round_mask = nullptr;  // scratch mask of the k > 128 scan rounds
+  uint64_t round_mask_words = 0;
   // fused sharded merge: exchange buffers of all ranks mapped with CUDA IPC (<= 8 ranks)
   struct Xchg {
     bool ready = false;
@@ -385,6 +387,8 @@ int ensure_gemm_ws(tss_index* ix) {
 
 int enqueue_scan(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
                  const tss_mask* mask, int mode, uint64_t* d_out);
+int enqueue_scan_rounds(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
+                        const tss_mask* mask, int mode, uint64_t* d_out);
 
 // K2: nq <= kWsQueries device-resident fp32 queries -> d_out (nq x k local keys).
 // Synchronises the stream once to check the survivor lists for overflow; queries whose list
@@ -447,16 +451,61 @@ int enqueue_gemm(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
   CU(cudaStreamSynchronize(ix->stream));
   for (uint32_t qi = 0; qi < nq; ++qi) {
     if (!g.h_cand_count[qi]) continue;
-    if (k > TSS_MAX_FUSED_K)
-      return fail(TSS_ERR_STATE, "K2 survivor list overflowed for query %u and k=%u > %u has no "
-                  "exact fallback", qi, k, TSS_MAX_FUSED_K);
     ix->xchg.suppress = true;
-    rc = enqueue_scan(ix, d_queries + (size_t)qi * ix->dim, 1, k, nullptr, TSS_MASK_NONE,
-                      d_out + (size_t)qi * k);
+    if (k > TSS_MAX_FUSED_K)
+      rc = enqueue_scan_rounds(ix, d_queries + (size_t)qi * ix->dim, 1, k, nullptr, TSS_MASK_NONE,
+                               d_out + (size_t)qi * k);
+    else
+      rc = enqueue_scan(ix, d_queries + (size_t)qi * ix->dim, 1, k, nullptr, TSS_MASK_NONE,
+                        d_out + (size_t)qi * k);
     ix->xchg.suppress = false;
     if (rc) return rc;
   }
   return TSS_OK;
+}
+
+// k > TSS_MAX_FUSED_K on the scan path: rounds of 128, each excluding what the previous rounds
+// found (exact; ceil(k/128) scans per query, one query at a time because the exclusions differ).
+int enqueue_scan_rounds(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
+                        const tss_mask* mask, int mode, uint64_t* d_out) {
+  const uint64_t words = (ix->n_rows + 31) / 32 + 1;
+  if (ix->round_mask_words < words) {
+    cudaFree(ix->d_round_mask);
+    ix->d_round_mask = nullptr;
+    CU(cudaMalloc(&ix->d_round_mask, words * sizeof(uint32_t)));
+    ix->round_mask_words = words;
+  }
+  tss_mask scratch;
+  scratch.device = ix->device;
+  scratch.nbits = ix->n_rows;
+  scratch.nwords = words - 1;
+  scratch.d_words = ix->d_round_mask;
+  // NONE -> exclude what was found; EXCLUDE -> same on a copy; INCLUDE -> clear found bits of a copy
+  const int round_mode = mode == TSS_MASK_INCLUDE ? TSS_MASK_INCLUDE : TSS_MASK_EXCLUDE;
+  const bool saved = ix->xchg.suppress;
+  ix->xchg.suppress = true;  // rounds are rank-local; the caller merges across ranks
+  int rc = TSS_OK;
+  for (uint32_t qi = 0; qi < nq && !rc; ++qi) {
+    if (mode == TSS_MASK_NONE)
+      CU(cudaMemsetAsync(ix->d_round_mask, 0, words * sizeof(uint32_t), ix->stream));
+    else
+      CU(cudaMemcpyAsync(ix->d_round_mask, mask->d_words, (words - 1) * sizeof(uint32_t),
+                         cudaMemcpyDeviceToDevice, ix->stream));
+    for (uint32_t done = 0; done < k && !rc; done += TSS_MAX_FUSED_K) {
+      const uint32_t kr = k - done < TSS_MAX_FUSED_K ? k - done : TSS_MAX_FUSED_K;
+      uint64_t* dst = d_out + (size_t)qi * k + done;
+      rc = enqueue_scan(ix, d_queries + (size_t)qi * ix->dim, 1, kr, &scratch, round_mode, dst);
+      if (rc) break;
+      cudaError_t e = tss::launch_mask_update_from_keys(ix->d_round_mask, ix->n_rows, dst, kr,
+                                                        ix->row_base, round_mode == TSS_MASK_EXCLUDE,
+                                                        ix->stream);
+      if (e != cudaSuccess) rc = cuda_fail(e, "mask_update_from_keys launch");
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
+  }
+  ix->xchg.suppress = saved;
+  scratch.d_words = nullptr;  // borrowed
+  return rc;
 }
 
 // local (per-shard) search of nq device-resident queries: picks K2 or K1.  *merged is set
@@ -466,6 +515,7 @@ int enqueue_local(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k
                   const tss_mask* mask, int mode, uint64_t* d_out, bool* merged) {
   *merged = false;
   if (!gemm_eligible(ix, nq, k, mode)) {
+    if (k > TSS_MAX_FUSED_K) return enqueue_scan_rounds(ix, d_queries, nq, k, mask, mode, d_out);
     *merged = ix->comm && ix->xchg.ready;
     return enqueue_scan(ix, d_queries, nq, k, mask, mode, d_out);
   }
@@ -485,11 +535,11 @@ int validate_search(const tss_index* ix, const void* queries, uint32_t nq, uint3
   return TSS_OK;
 }
 int check_k_path(const tss_index* ix, uint32_t nq, uint32_t k, int mode) {
-  if (k > TSS_MAX_FUSED_K && !gemm_eligible(ix, nq, k, mode))
-    return fail(TSS_ERR_INVALID_ARG,
-                "k=%u > %u needs the tensor-core path: bf16 storage, dim <= 384, no mask, nq >= %u "
-                "and at least %llu rows", k, TSS_MAX_FUSED_K, ix->gemm_min_nq,
-                (unsigned long long)(4ull * 256 * k));
+  (void)nq;
+  (void)mode;
+  if (k > TSS_MAX_FUSED_K && ix->comm && (uint64_t)ix->comm->nranks * k * 8 > 48 * 1024)
+    return fail(TSS_ERR_INVALID_ARG, "k=%u over %d ranks exceeds the merge kernel (ranks*k <= 6144)",
+                k, ix->comm->nranks);
   return TSS_OK;
 }
 
@@ -581,6 +631,7 @@ void tss_index_destroy(tss_index* ix) {
   for (int r = 0; r < 8; ++r)
     if (ix->xchg.peer[r] && ix->xchg.peer[r] != ix->xchg.local) cudaIpcCloseMemHandle(ix->xchg.peer[r]);
   cudaFree(ix->xchg.local);
+  cudaFree(ix->d_round_mask);
   cudaFree(ix->gemm.d_inv_norm);
   cudaFree(ix->gemm.d_qbf16);
   cudaFree(ix->gemm.d_inv_q);
@@ -804,7 +855,7 @@ int tss_index_search_device(tss_index* ix, const float* d_queries, uint32_t nq, 
   if ((rc = ensure_gather_ws(ix))) return rc;
   for (uint32_t q0 = 0; q0 < nq; q0 += kWsQueries) {
     uint32_t n = nq - q0 < kWsQueries ? nq - q0 : kWsQueries;
-    const bool fused = ix->xchg.ready && !gemm_eligible(ix, nq, k, mask_mode);
+    const bool fused = ix->xchg.ready && !gemm_eligible(ix, nq, k, mask_mode) && k <= TSS_MAX_FUSED_K;
     uint64_t* d_local = fused ? d_out_keys + (size_t)q0 * k : ix->d_keys;
     if ((rc = enqueue_local(ix, d_queries + (size_t)q0 * ix->dim, n, k, mask, mask_mode, d_local,
                             &merged)))
@@ -857,6 +908,8 @@ int tss_index_search(tss_index* ix, const float* queries, uint32_t nq, uint32_t 
     bool merged = false;
     if (gemm_eligible(ix, nq, k, mask_mode)) {
       rc = enqueue_gemm(ix, ix->d_queries, n, k, ix->d_keys);
+    } else if (k > TSS_MAX_FUSED_K) {
+      rc = enqueue_scan_rounds(ix, ix->d_queries, n, k, mask, mask_mode, ix->d_keys);
     } else {
       merged = ix->comm && ix->xchg.ready;
       rc = enqueue_scan(ix, ix->d_queries, n, k, mask, mask_mode, ix->d_keys);

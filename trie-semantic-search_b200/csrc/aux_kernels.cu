@@ -124,6 +124,26 @@ cudaError_t launch_mask_set_rows(uint32_t* words, uint64_t nbits, const uint32_t
   return cudaGetLastError();
 }
 
+// set (or clear) the bits of the rows named by packed keys (0 = empty slot)
+__global__ void mask_update_from_keys_kernel(uint32_t* words, uint64_t nbits, const uint64_t* keys,
+                                             uint32_t n, uint64_t row_base, int set) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    uint64_t key = keys[i];
+    if (!key) continue;
+    uint64_t r = (uint64_t)(0xFFFFFFFFu - (uint32_t)key) - row_base;
+    if (r >= nbits) continue;
+    if (set) atomicOr(words + (r >> 5), 1u << (uint32_t)(r & 31));
+    else atomicAnd(words + (r >> 5), ~(1u << (uint32_t)(r & 31)));
+  }
+}
+cudaError_t launch_mask_update_from_keys(uint32_t* words, uint64_t nbits, const uint64_t* keys,
+                                         uint32_t n, uint64_t row_base, bool set, cudaStream_t st) {
+  if (!n) return cudaSuccess;
+  mask_update_from_keys_kernel<<<(n + 255) / 256, 256, 0, st>>>(words, nbits, keys, n, row_base,
+                                                                set ? 1 : 0);
+  return cudaGetLastError();
+}
+
 __global__ void mask_popcount_kernel(const uint32_t* words, uint64_t nwords,
                                      unsigned long long* out) {
   unsigned long long c = 0;

@@ -21,6 +21,8 @@ cudaError_t launch_unpack_rows(const void* src, float* dst, uint64_t nrows, uint
 // masks
 cudaError_t launch_mask_set_rows(uint32_t* words, uint64_t nbits, const uint32_t* rows, uint64_t n,
                                  uint64_t row_base, cudaStream_t st);
+cudaError_t launch_mask_update_from_keys(uint32_t* words, uint64_t nbits, const uint64_t* keys,
+                                         uint32_t n, uint64_t row_base, bool set, cudaStream_t st);
 cudaError_t launch_mask_popcount(const uint32_t* words, uint64_t nwords, unsigned long long* out,
                                  cudaStream_t st);
 
