@@ -197,7 +197,7 @@ struct tss_index {
     uint64_t tmap_rows = 0;
     const void* tmap_base = nullptr;
   } gemm;
-  uint32_t gemm_min_nq = 32;  // batches at least this large use K2 (bf16 storage, D <= 384)
+  uint32_t gemm_min_nq = 16;  // batches at least this large use K2 (bf16 storage, D <= 384)
   uint32_t* d_round_mask = nullptr;  // scratch mask of the k > 128 scan rounds
   uint64_t round_mask_words = 0;
   // fused sharded merge: exchange buffers of all ranks mapped with CUDA IPC (<= 8 ranks)
@@ -355,7 +355,7 @@ int ensure_gemm_ws(tss_index* ix) {
     CU(cudaMalloc(&g.d_thr, kWsQueries * sizeof(float)));
     CU(cudaMalloc(&g.d_tile_max, (size_t)kGemmMaxSample * kWsQueries * sizeof(float)));
     CU(cudaMalloc(&g.d_cand, (size_t)kWsQueries * kGemmCandCap * sizeof(uint64_t)));
-    CU(cudaMalloc(&g.d_cand_count, (size_t)kWsQueries * 256 * sizeof(uint32_t)));
+    CU(cudaMalloc(&g.d_cand_count, (size_t)kWsQueries * 1024 * sizeof(uint32_t)));
     CU(cudaMalloc(&g.d_overflow, kWsQueries * sizeof(uint32_t)));
     CU(cudaMallocHost(&g.h_cand_count, kWsQueries * sizeof(uint32_t)));
     if ((rc = make_tmap(&g.tmap_q, g.d_qbf16, kWsQueries, kpad, 128))) return rc;
@@ -406,7 +406,7 @@ int enqueue_gemm(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
   if (sample > kGemmMaxSample / split) sample = kGemmMaxSample / split;
   if (sample > num_tiles) sample = num_tiles;
   int nslices = ix->num_sms / (int)mb;
-  if (nslices * (int)tss::gemm_col_split() > 256) nslices = 256 / tss::gemm_col_split();
+  if (nslices * (int)tss::gemm_col_split() > 1024) nslices = 1024 / tss::gemm_col_split();
   if (nslices < 1) return fail(TSS_ERR_INVALID_ARG, "batch of %u queries exceeds one K2 launch", nq);
   const int grid = nslices * (int)mb;
   // CTA pairs that share corpus tiles by TMA multicast need an even number of query blocks

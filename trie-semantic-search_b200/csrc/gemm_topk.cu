@@ -2,7 +2,7 @@
 //
 // Large query batches really are a dense contraction S = Q . E^T (B x N, K = D), so this
 // path runs on the 5th-generation tensor cores.  It replaces the body of HnswIndex::search
-// (reference src/vector.rs:195-202, a stub) for nq >= 32 over a bf16 index.
+// (reference src/vector.rs:195-202, a stub) for nq >= 16 over a bf16 index.
 //
 // Per CTA (one per SM, 576 threads, cta_group::1):
 //   * 128 queries (one UMMA M tile) stay resident in shared memory for the whole kernel as
@@ -355,7 +355,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       tc_fence_before();
       mbar_arrive(bar_tempty + 8 * acc);
       // each (tile, part) is its own sample for the threshold: kColsPer distinct rows
-      if (p.mode == 0) p.tile_max[((size_t)i * kColSplit + part) * (p.mb * kBlockM) + q] = mx;
+      if (p.mode == 0)
+        p.tile_max[(size_t)q * (p.sample_count * kColSplit) + (size_t)i * kColSplit + part] = mx;
     }
     if (p.mode == 1) p.cand_count[(size_t)q * nsub + sub] = my_count;
   }
@@ -435,74 +436,124 @@ __device__ void block_bitonic_desc(uint64_t* sk, uint32_t n) {
   }
 }
 
-// thr[q] = k-th largest of the sample_count per-tile maxima of query q (+inf for padding queries)
-__global__ void threshold_kernel(const float* tile_max, uint32_t sample_count, uint32_t nq_pad,
-                                 uint32_t nq, uint32_t k, uint32_t npad, float* thr) {
-  extern __shared__ uint64_t sk[];
-  const uint32_t q = blockIdx.x;
-  for (uint32_t i = threadIdx.x; i < npad; i += blockDim.x) {
-    uint64_t key = 0;
-    if (i < sample_count) {
-      float v = tile_max[(size_t)i * nq_pad + q];
-      key = (uint64_t)orderable_bits(__float_as_uint(v)) + 1;  // 0 stays "missing"
+// k-th largest (1-based) of the n 32-bit keys fetch(i), i < n, by a 4-pass 8-bit radix select.
+// hist: 256 shared counters; s_sel: 2 shared words.  All threads of the block call it.
+template <class Fetch>
+__device__ uint32_t block_radix_kth(uint32_t n, uint32_t k, Fetch fetch, uint32_t* hist,
+                                    uint32_t* s_sel) {
+  uint32_t prefix = 0, mask = 0, remaining = k;
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    for (uint32_t b = threadIdx.x; b < 256; b += blockDim.x) hist[b] = 0;
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+      uint32_t v = fetch(i);
+      if ((v & mask) == prefix) atomicAdd(&hist[(v >> shift) & 255u], 1u);
     }
-    sk[i] = key;
-  }
-  __syncthreads();
-  block_bitonic_desc(sk, npad);
-  if (threadIdx.x == 0) {
-    float t = -INFINITY;  // fewer than k maxima: keep everything
-    if (q >= nq) {
-      t = INFINITY;
-    } else if (k <= sample_count && sk[k - 1] != 0) {
-      uint32_t o = (uint32_t)(sk[k - 1] - 1);
-      uint32_t u = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
-      t = __uint_as_float(u);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t cum = 0, b = 255;
+      for (;; --b) {
+        if (cum + hist[b] >= remaining || b == 0) break;
+        cum += hist[b];
+      }
+      s_sel[0] = b;
+      s_sel[1] = remaining - cum;
     }
-    thr[q] = t;
+    __syncthreads();
+    prefix |= s_sel[0] << shift;
+    mask |= 255u << shift;
+    remaining = s_sel[1];
+    __syncthreads();
   }
+  return prefix;
 }
 
-// exact top-k of each query's survivors (nslices private lists of <= cap_s keys); scores are
-// scaled by 1/|q| first.  overflow[q] = 1 when some list was too short to hold its survivors.
-__global__ void select_kernel(const uint64_t* cand, const uint32_t* cand_count, uint32_t nslices,
+// thr[q] = k-th largest of the `count` per-tile-part maxima of query q (+inf for padding
+// queries, -inf when there are fewer than k maxima: keep everything).  tile_max is [nq_pad][count].
+__global__ void threshold_kernel(const float* tile_max, uint32_t count, uint32_t nq, uint32_t k,
+                                 float* thr) {
+  __shared__ uint32_t hist[256];
+  __shared__ uint32_t s_sel[2];
+  const uint32_t q = blockIdx.x;
+  const float* mine = tile_max + (size_t)q * count;
+  float t;
+  if (q >= nq) {
+    t = INFINITY;
+  } else if (k > count) {
+    t = -INFINITY;
+  } else {
+    uint32_t o = block_radix_kth(
+        count, k, [&](uint32_t i) { return orderable_bits(__float_as_uint(mine[i])); }, hist, s_sel);
+    uint32_t u = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
+    t = __uint_as_float(u);
+  }
+  if (threadIdx.x == 0) thr[q] = t;
+}
+
+// exact top-k of each query's survivors (nsub private lists of <= cap_s keys each).  A radix
+// select over the score words finds the k-th score; only keys at or above it (about k of the
+// few thousand survivors) are scaled by 1/|q|, sorted and written.  overflow[q] = 1 when some
+// list was too short to hold its survivors, or the ties at the k-th score do not fit the
+// sorter: the query is then redone by the exact scan.
+constexpr uint32_t kSelectSort = 2048;
+constexpr uint32_t kSelectMaxLists = 1024;
+__global__ void select_kernel(const uint64_t* cand, const uint32_t* cand_count, uint32_t nsub,
                               uint32_t cap_s, const float* inv_qnorm, uint32_t k, uint64_t* out,
                               uint32_t* overflow) {
-  extern __shared__ uint64_t sk[];
-  __shared__ uint32_t s_off[257];
-  __shared__ uint32_t s_over;
+  __shared__ uint64_t sk[kSelectSort];
+  __shared__ uint32_t s_off[kSelectMaxLists + 1];
+  __shared__ uint32_t hist[256];
+  __shared__ uint32_t s_sel[2];
+  __shared__ uint32_t s_over, s_n;
   const uint32_t q = blockIdx.x;
   if (threadIdx.x == 0) {
     uint32_t off = 0, over = 0;
-    for (uint32_t sl = 0; sl < nslices; ++sl) {
-      uint32_t c = cand_count[(size_t)q * nslices + sl];
+    for (uint32_t sl = 0; sl < nsub; ++sl) {
+      uint32_t c = cand_count[(size_t)q * nsub + sl];
       if (c > cap_s) c = cap_s, over = 1;
       s_off[sl] = off;
       off += c;
     }
-    s_off[nslices] = off;
+    s_off[nsub] = off;
     s_over = over;
+    s_n = 0;
   }
   __syncthreads();
-  const uint32_t cnt = s_off[nslices];
-  uint32_t npad = 2;
-  while (npad < cnt) npad <<= 1;
+  const uint32_t cnt = s_off[nsub];
+  const uint64_t* base = cand + (size_t)q * nsub * cap_s;
+  // candidate i of the concatenated lists (binary search over the list offsets)
+  auto key_at = [&](uint32_t i) -> uint64_t {
+    uint32_t lo = 0, hi = nsub;
+    while (hi - lo > 1) {
+      uint32_t mid = (lo + hi) >> 1;
+      if (s_off[mid] <= i) lo = mid;
+      else hi = mid;
+    }
+    return base[(size_t)lo * cap_s + (i - s_off[lo])];
+  };
+  uint32_t kth = 0;  // orderable score word of the k-th best survivor (0: keep all)
+  if (cnt > k)
+    kth = block_radix_kth(cnt, k, [&](uint32_t i) { return (uint32_t)(key_at(i) >> 32); }, hist, s_sel);
   const float iq = inv_qnorm[q];
-  for (uint32_t i = threadIdx.x; i < npad; i += blockDim.x) sk[i] = 0;
-  __syncthreads();
-  for (uint32_t sl = 0; sl < nslices; ++sl) {
-    const uint32_t o = s_off[sl], c = s_off[sl + 1] - o;
-    const uint64_t* src = cand + ((size_t)q * nslices + sl) * cap_s;
-    for (uint32_t i = threadIdx.x; i < c; i += blockDim.x) {
-      uint64_t key = src[i];
-      uint32_t ob = (uint32_t)(key >> 32);
+  for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
+    const uint64_t key = key_at(i);
+    const uint32_t ob = (uint32_t)(key >> 32);
+    if (ob < kth) continue;
+    const uint32_t pos = atomicAdd(&s_n, 1u);
+    if (pos < kSelectSort) {
       uint32_t u = (ob & 0x80000000u) ? (ob & 0x7FFFFFFFu) : ~ob;
       float sc = __uint_as_float(u) * iq;
       if (!isfinite(sc)) sc = 0.f;
       if (sc == 0.f) sc = 0.f;
-      sk[o + i] = ((uint64_t)orderable_bits(__float_as_uint(sc)) << 32) | (key & 0xFFFFFFFFull);
+      sk[pos] = ((uint64_t)orderable_bits(__float_as_uint(sc)) << 32) | (key & 0xFFFFFFFFull);
     }
   }
+  __syncthreads();
+  uint32_t m = s_n;
+  if (m > kSelectSort) m = kSelectSort, s_over = 1;  // (benign race: every writer stores 1)
+  uint32_t npad = 2;
+  while (npad < m) npad <<= 1;
+  for (uint32_t i = m + threadIdx.x; i < npad; i += blockDim.x) sk[i] = 0;
   __syncthreads();
   block_bitonic_desc(sk, npad);
   for (uint32_t e = threadIdx.x; e < k; e += blockDim.x)
@@ -567,29 +618,16 @@ cudaError_t launch_row_inv_norm(const void* rows, uint64_t n_rows, uint32_t stri
                                                         n_rows, stride_elems, out);
   return cudaGetLastError();
 }
-cudaError_t launch_threshold(const float* tile_max, uint32_t sample_count, uint32_t nq_pad,
-                             uint32_t nq, uint32_t k, float* thr, cudaStream_t st) {
-  uint32_t npad = 2;
-  while (npad < sample_count) npad <<= 1;
-  if ((size_t)npad * 8 > 96 * 1024) return cudaErrorInvalidConfiguration;
-  cudaError_t e = cudaFuncSetAttribute(threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       96 * 1024);
-  if (e != cudaSuccess) return e;
-  threshold_kernel<<<nq_pad, 256, (size_t)npad * 8, st>>>(tile_max, sample_count, nq_pad, nq, k,
-                                                          npad, thr);
+cudaError_t launch_threshold(const float* tile_max, uint32_t count, uint32_t nq_pad, uint32_t nq,
+                             uint32_t k, float* thr, cudaStream_t st) {
+  threshold_kernel<<<nq_pad, 256, 0, st>>>(tile_max, count, nq, k, thr);
   return cudaGetLastError();
 }
 cudaError_t launch_select(const uint64_t* cand, const uint32_t* cand_count, uint32_t nslices,
                           uint32_t cap_s, const float* inv_qnorm, uint32_t nq, uint32_t k,
                           uint64_t* out, uint32_t* overflow, cudaStream_t st) {
-  if (nslices > 256) return cudaErrorInvalidConfiguration;
-  uint32_t npad = 2;
-  while (npad < nslices * cap_s) npad <<= 1;
-  cudaError_t e = cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)((size_t)npad * 8));
-  if (e != cudaSuccess) return e;
-  select_kernel<<<nq, 512, (size_t)npad * 8, st>>>(cand, cand_count, nslices, cap_s, inv_qnorm, k,
-                                                   out, overflow);
+  if (nslices > kSelectMaxLists || k > kSelectSort) return cudaErrorInvalidConfiguration;
+  select_kernel<<<nq, 256, 0, st>>>(cand, cand_count, nslices, cap_s, inv_qnorm, k, out, overflow);
   return cudaGetLastError();
 }
 

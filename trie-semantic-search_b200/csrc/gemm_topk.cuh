@@ -15,7 +15,7 @@ struct GemmParams {
   uint32_t num_tiles;      // ceil(n_rows / 256)
   int mode;                // 0 = per-tile maxima over the sample, 1 = collect survivors
   uint32_t sample_stride, sample_count;  // mode 0: tiles j * stride, j < count
-  float* tile_max;         // mode 0 out: [sample_count*split][mb*128] (one maximum per tile part)
+  float* tile_max;         // mode 0 out: [mb*128][sample_count*split] (one maximum per tile part)
   const float* thr;        // mode 1 in:  [mb*128]
   uint64_t* cand;          // mode 1 out: [mb*128][nslices*split][cand_cap] keys (unscaled by 1/|q|)
   uint32_t* cand_count;    // [mb*128][nslices*split] survivors seen (may exceed cand_cap)
