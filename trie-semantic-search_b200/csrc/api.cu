@@ -83,6 +83,7 @@ int load_nccl() {
 constexpr int kNcclUint64 = 5;
 
 constexpr uint32_t kMaxBq = 4;           // queries per scan launch
+constexpr uint32_t kScanSlots = 4;       // scan workspace slots (launches in flight under PDL)
 constexpr uint32_t kWsQueries = 1024;    // device query/result workspace, in queries
 constexpr size_t kStageBytes = 64u << 20;  // upload staging buffer
 constexpr uint32_t kGemmCandCap = 16384;   // survivors kept per query by the K2 epilogue
@@ -167,8 +168,14 @@ struct tss_index {
   uint64_t* d_keys = nullptr;      // kWsQueries x TSS_MAX_FUSED_K local results
   uint64_t* d_gather = nullptr;    // nranks x kWsQueries x k (lazy)
   uint64_t* d_merged = nullptr;    // kWsQueries x k (lazy)
-  uint64_t* d_partials = nullptr;  // kMaxBq x num_sms x 128
-  unsigned int* d_counter = nullptr;  // [0] done ticket, [1] tile claims, [2] exchange status
+  // Scan workspaces come in kScanSlots slots used round-robin, because consecutive scans
+  // overlap under programmatic dependent launch: d_partials[slot][kMaxBq][num_sms][128] and
+  // d_counter[slot*4 + {0 done ticket, 1 tile claims, 2 generation}]; d_counter[16] is the
+  // exchange status word.
+  uint64_t* d_partials = nullptr;
+  unsigned int* d_counter = nullptr;
+  uint32_t launch_no = 0;
+  bool pdl = true;
   // tile schedule of the unmasked scan (see scan.cuh): share of tiles walked statically,
   // tiles per dynamic claim, and how many warp-rounds at the very end are claimed one
   // tile at a time (tail balancing)
@@ -283,9 +290,15 @@ int enqueue_scan(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
     p.cap = cap;
     p.mask = mode != TSS_MASK_NONE ? mask->d_words : nullptr;
     p.mask_mode = mode;
-    p.partials = ix->d_partials;
-    p.done_counter = ix->d_counter;
-    p.tile_counter = ix->d_counter + 1;
+    const uint32_t no = ++ix->launch_no;  // 1, 2, ...
+    const uint32_t slot = no % kScanSlots;
+    p.partials = ix->d_partials + (size_t)slot * kMaxBq * ix->num_sms * 128;
+    p.done_counter = ix->d_counter + slot * 4;
+    p.tile_counter = ix->d_counter + slot * 4 + 1;
+    p.slot_gen = ix->d_counter + slot * 4 + 2;
+    p.launch_no = no;
+    p.expect_gen = no > kScanSlots ? no - kScanSlots : 0;
+    p.pdl = ix->pdl ? 1 : 0;
     {
       // tiles per warp-round = num_sms * 16 warps; rows per tile from the storage geometry
       const uint64_t tile_rows = 12288 / ix->row_bytes >= 16  ? 16
@@ -307,7 +320,7 @@ int enqueue_scan(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
       p.xchg_nranks = (uint32_t)ix->comm->nranks;
       p.xchg_rank = (uint32_t)ix->comm->rank;
       p.xchg_seq = ++ix->xchg.seq;
-      p.xchg_status = ix->d_counter + 2;
+      p.xchg_status = ix->d_counter + 16;
     }
     cudaError_t e = tss::launch_scan(ix->ns, p, bq, ix->storage == TSS_BF16, mode != TSS_MASK_NONE,
                                      ix->num_sms, ix->device, ix->stream);
@@ -598,9 +611,10 @@ int tss_index_create(tss_index** out, uint32_t dim, int storage, int device) {
   ALLOC(cudaMalloc(&ix->d_flag, sizeof(int)))
   ALLOC(cudaMalloc(&ix->d_queries, (size_t)kWsQueries * dim * sizeof(float)))
   ALLOC(cudaMalloc(&ix->d_keys, (size_t)kWsQueries * TSS_MAX_K * sizeof(uint64_t)))
-  ALLOC(cudaMalloc(&ix->d_partials, (size_t)kMaxBq * ix->num_sms * 128 * sizeof(uint64_t)))
-  ALLOC(cudaMalloc(&ix->d_counter, 4 * sizeof(unsigned int)))
-  ALLOC(cudaMemset(ix->d_counter, 0, 4 * sizeof(unsigned int)))
+  ALLOC(cudaMalloc(&ix->d_partials, (size_t)kScanSlots * kMaxBq * ix->num_sms * 128 * sizeof(uint64_t)))
+  ALLOC(cudaMalloc(&ix->d_counter, 32 * sizeof(unsigned int)))
+  ALLOC(cudaMemset(ix->d_counter, 0, 32 * sizeof(unsigned int)))
+  if (const char* sf = getenv("TSS_PDL")) ix->pdl = atoi(sf) != 0;
   if (const char* sf = getenv("TSS_STATIC_FRAC")) ix->static_frac = (float)atof(sf);
   if (const char* sf = getenv("TSS_FINE_ROUNDS")) ix->fine_rounds = (float)atof(sf);
   if (const char* sf = getenv("TSS_DYN_CHUNK")) ix->dyn_chunk = (uint32_t)atoi(sf);
@@ -924,7 +938,7 @@ int tss_index_search(tss_index* ix, const float* queries, uint32_t nq, uint32_t 
                        ix->stream));
     unsigned int xstatus = 0;
     if (merged)
-      CU(cudaMemcpyAsync(&xstatus, ix->d_counter + 2, sizeof(xstatus), cudaMemcpyDeviceToHost,
+      CU(cudaMemcpyAsync(&xstatus, ix->d_counter + 16, sizeof(xstatus), cudaMemcpyDeviceToHost,
                          ix->stream));
     CU(cudaStreamSynchronize(ix->stream));
     if (xstatus)

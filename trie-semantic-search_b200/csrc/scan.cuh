@@ -50,6 +50,12 @@ struct ScanParams {
   uint8_t* xchg_peer[8];
   uint32_t xchg_nranks, xchg_rank, xchg_seq;
   unsigned int* xchg_status;  // set to 1 when a peer never showed up (5 s), instead of hanging
+  uint32_t pdl;               // launched with programmatic stream serialization
+  // workspace slot hand-over: consecutive launches overlap under PDL, so the slot (partials +
+  // counters) of this launch may still be in use by the launch that had it kSlots launches
+  // ago.  slot_gen holds the number of the last launch that finished with the slot.
+  unsigned int* slot_gen;
+  uint32_t launch_no, expect_gen;
 };
 
 // exchange buffer layout (bytes): [0,256) one u32 arrival flag per source rank, then
@@ -350,6 +356,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_topk_kernel(const ScanPara
     }
   };
 
+  // the previous user of this workspace slot must have finished (normally long ago)
+  if (threadIdx.x == 0)
+    while (ld_acquire_sys(p.slot_gen) != p.expect_gen) __nanosleep(32);
+  __syncthreads();
   dbg_stamp(p, 1);
   // ---- tile schedule -------------------------------------------------------------------
   // Unmasked: every warp first walks `static_rounds` statically interleaved tiles
@@ -482,6 +492,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_topk_kernel(const ScanPara
   }
 
   dbg_stamp(p, 2);
+  // The scan of the next query batch depends on nothing this launch still has to do (its
+  // workspaces alternate by launch parity), so let it start filling SMs as our CTAs retire:
+  // its prologue and first tiles overlap our merges and the last CTA's exchange.
+  if (p.pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   // ---- per-warp final prune: sorted, zero padded ---------------------------------
 #pragma unroll
   for (int b = 0; b < BQ; ++b)
@@ -589,6 +603,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_topk_kernel(const ScanPara
   if (tid == 0) {
     *p.done_counter = 0;
     *p.tile_counter = 0;
+    __threadfence();
+    st_release_sys(p.slot_gen, p.launch_no);  // hand the slot to launch_no + kSlots
   }
 }
 

@@ -37,8 +37,17 @@ static cudaError_t launch_one(const ScanParams& p, int grid, int device, cudaStr
   }
   ScanParams q = p;
   q.smem_bytes = (uint32_t)smem;
-  kern<<<grid, kWarps * 32, smem, st>>>(q);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kWarps * 32);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = q.pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, q);
 }
 
 template <int NS, int BQ>
