@@ -66,6 +66,7 @@ typedef struct tss_index tss_index; /* replaces HnswIndex, src/vector.rs:40-44 *
 typedef struct tss_mask tss_mask;   /* device bitmask over the rows of one shard */
 typedef struct tss_terms tss_terms; /* flattened, byte-sorted term array + CSR postings */
 typedef struct tss_comm tss_comm;   /* one rank of a row-sharded index (NCCL) */
+typedef struct tss_columns tss_columns; /* per-row metadata columns of one shard (N3) */
 
 /* ---- library --------------------------------------------------------------*/
 int tss_abi_version(void);
@@ -153,11 +154,26 @@ int tss_mask_clear(tss_mask* m);
  * this is how the shim turns seen_cases (src/search.rs:187-206) into an
  * EXCLUDE mask. */
 int tss_mask_set_rows(tss_mask* m, const uint32_t* rows, uint64_t n, uint64_t row_base);
+int tss_mask_clear_rows(tss_mask* m, const uint32_t* rows, uint64_t n, uint64_t row_base);
 int tss_mask_upload(tss_mask* m, const uint32_t* words /* ceil(nbits/32) */);
 int tss_mask_download(const tss_mask* m, uint32_t* words /* ceil(nbits/32) */);
 int tss_mask_popcount(const tss_mask* m, uint64_t* out);
 uint64_t tss_mask_nbits(const tss_mask* m);
 void tss_mask_destroy(tss_mask* m);
+
+/* ---- metadata pre-filter --------------------------------------------
+ * SearchEngine::apply_filters (src/search.rs:255-274) drops results AFTER the top-50 + sort, so
+ * a selective court / date filter can return fewer than max_results.  With the two columns the
+ * filter reads resident on the device (u16 court id assigned by the host, i32 decision date in
+ * days), tss_filter_mask writes the rows that pass -- date in [date_lo, date_hi] AND (no court
+ * list OR court in the list), the same conjunction as apply_filters -- into a mask that the
+ * search takes as TSS_MASK_INCLUDE.  combine_and != 0 intersects with the mask's current
+ * content (e.g. a prefix mask) instead of overwriting it.  6 bytes per row of traffic. */
+int tss_columns_create(tss_columns** out, const uint16_t* court_ids, const int32_t* dates,
+                       uint64_t nrows, int device);
+void tss_columns_destroy(tss_columns* c);
+int tss_filter_mask(tss_columns* c, const uint16_t* allowed_courts, uint32_t n_allowed,
+                    int32_t date_lo, int32_t date_hi, tss_mask* mask, int combine_and);
 
 /* ---- flattened trie ---------------------------------------------------------
  * tss_terms_create <- the populated TrieNode tree (src/trie.rs:51-57,211-221),

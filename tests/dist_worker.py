@@ -53,6 +53,26 @@ def main():
             print(f"rank {rank}: MISMATCH n={n} k={k}", flush=True)
         ok &= same
         ix.close()
+    # K2 (tensor-core path) on a sharded bf16 index: local GEMM top-k, NCCL all-gather, merge
+    n, k, nq = 400_000, 10, 64
+    per = (n + world - 1) // world
+    b = min(rank * per, n)
+    cnt = min(per, n - b)
+    ix = tss.FlatIndex(dim, tss.TSS_BF16, local)
+    ix.add_synthetic(b, cnt, seed)
+    ix.set_shard(b, comm)
+    ix.finalize()
+    q = orc.gen_rows(0, nq, dim, 0xBEEF)
+    rows = orc.gen_rows(0, n, dim, seed)
+    q[0] = rows[123_456] + 0.125 * q[0]
+    gr, gs, gc = ix.search(q, k)
+    want = orc.cosine_topk(rows, q, k, bf16=True)
+    hits = sum(len(set(g.tolist()) & set(w.tolist())) for g, w in zip(gr, want[0]))
+    same = bool(np.all(gc == k)) and gr[0][0] == 123_456 and hits >= 0.97 * nq * k
+    if not same:
+        print(f"rank {rank}: K2 sharded MISMATCH recall {hits / (nq * k):.3f}", flush=True)
+    ok &= same
+    ix.close()
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     comm.close()

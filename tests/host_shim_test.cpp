@@ -289,6 +289,40 @@ static void engine_hybrid() {
   q.date_range = std::make_pair(1007, 1007);
   auto rd = eng.search_with_params(q);
   CHECK(rd.size() == 1 && rd[0].case_metadata.id == cid(7));
+  // N3: the same court filter applied on the device BEFORE top-k cannot be starved: with
+  // min_similarity -1 the semantic pass fills max_results with ca9 cases only
+  {
+    SearchQuery f;
+    f.query = "nothing in the trie";
+    f.court_filter = std::vector<std::string>{"ca9"};
+    f.config.min_similarity = -1.0f;
+    auto post = eng.search_with_params(f);          // post-hoc: top-50 then filter
+    eng.set_prefilter(true);
+    auto pre = eng.search_with_params(f);
+    CHECK(pre.size() == 10);
+    for (auto& x : pre) CHECK(x.case_metadata.court == "ca9");
+    for (size_t i = 0; i + 1 < pre.size(); ++i) CHECK(pre[i].score >= pre[i + 1].score);
+    CHECK(post.size() <= pre.size());
+    if (!post.empty()) CHECK(pre[0].case_metadata.id == post[0].case_metadata.id);
+    f.court_filter = std::vector<std::string>{"no such court"};
+    CHECK(eng.search_with_params(f).empty());
+    f.court_filter.reset();
+    f.date_range = std::make_pair(1010, 1012);
+    auto dr = eng.search_with_params(f);
+    CHECK(dr.size() == 3);
+    for (auto& x : dr) CHECK(x.case_metadata.decision_date >= 1010 && x.case_metadata.decision_date <= 1012);
+    eng.set_mask_policy(SearchEngine::MaskPolicy::ExcludeOnDevice);
+    f.query = "Miranda v. Arizona";  // exact trie hit (case 1, scotus, date 1001) + filter
+    f.date_range = std::make_pair(1000, 1005);
+    auto both = eng.search_with_params(f);
+    CHECK(!both.empty() && both[0].match_type == MatchType::Exact);
+    for (auto& x : both) CHECK(x.case_metadata.decision_date >= 1000 && x.case_metadata.decision_date <= 1005);
+    size_t n1 = 0;
+    for (auto& x : both) n1 += x.case_metadata.id == cid(1);
+    CHECK(n1 == 1);
+    eng.set_mask_policy(SearchEngine::MaskPolicy::PostHoc);
+    eng.set_prefilter(false);
+  }
   // M2: >= max_results exact hits skip the vector pass entirely
   q = SearchQuery();
   q.query = "Roe v. Wade";

@@ -40,6 +40,7 @@ ABI_SYMBOLS = [
     "tss_dev_d2h", "tss_event_create", "tss_event_record", "tss_event_elapsed_ms",
     "tss_event_destroy", "tss_launch_count", "tss_index_debug_phases",
     "tss_index_save", "tss_index_load",
+    "tss_mask_clear_rows", "tss_columns_create", "tss_columns_destroy", "tss_filter_mask",
 ]
 
 
@@ -112,6 +113,10 @@ def lib() -> C.CDLL:
         "tss_event_destroy": (i32, [vp]),
         "tss_launch_count": (u64, []),
         "tss_index_debug_phases": (i32, [vp, vp]),
+        "tss_mask_clear_rows": (i32, [vp, vp, u64, u64]),
+        "tss_columns_create": (i32, [C.POINTER(vp), vp, vp, u64, i32]),
+        "tss_columns_destroy": (None, [vp]),
+        "tss_filter_mask": (i32, [vp, vp, u32, C.c_int32, C.c_int32, vp, i32]),
         "tss_index_save": (i32, [vp, C.c_char_p]),
         "tss_index_load": (i32, [C.POINTER(vp), C.c_char_p, i32]),
     }
@@ -241,6 +246,10 @@ class Mask:
         r = np.ascontiguousarray(rows, dtype=np.uint32)
         _check(lib().tss_mask_set_rows(self.handle, r.ctypes.data, r.size, int(row_base)))
 
+    def clear_rows(self, rows, row_base: int = 0) -> None:
+        r = np.ascontiguousarray(rows, dtype=np.uint32)
+        _check(lib().tss_mask_clear_rows(self.handle, r.ctypes.data, r.size, int(row_base)))
+
     def upload(self, words) -> None:
         w = np.ascontiguousarray(words, dtype=np.uint32)
         assert w.size == (self.nbits + 31) // 32
@@ -259,6 +268,35 @@ class Mask:
     def close(self) -> None:
         if self.handle:
             lib().tss_mask_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Columns:
+    """Per-row metadata columns (u16 court id, i32 decision date) for the pre-filter (N3)."""
+
+    def __init__(self, court_ids, dates, device: int = 0):
+        c = np.ascontiguousarray(court_ids, dtype=np.uint16)
+        d = np.ascontiguousarray(dates, dtype=np.int32)
+        assert c.size == d.size
+        p = C.c_void_p()
+        _check(lib().tss_columns_create(C.byref(p), c.ctypes.data, d.ctypes.data, c.size, device))
+        self.handle, self.nrows = p.value, c.size
+
+    def filter_mask(self, mask: "Mask", allowed_courts=(), date_lo: int = -2**31,
+                    date_hi: int = 2**31 - 1, combine_and: bool = False) -> None:
+        a = np.ascontiguousarray(list(allowed_courts), dtype=np.uint16)
+        _check(lib().tss_filter_mask(self.handle, a.ctypes.data if a.size else None, a.size,
+                                     int(date_lo), int(date_hi), mask.handle, int(combine_and)))
+
+    def close(self) -> None:
+        if self.handle:
+            lib().tss_columns_destroy(self.handle)
             self.handle = None
 
     def __del__(self):

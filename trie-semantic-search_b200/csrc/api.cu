@@ -133,6 +133,14 @@ struct tss_mask {
   unsigned long long* d_scratch = nullptr;
 };
 
+struct tss_columns {
+  int device = 0;
+  uint64_t nrows = 0;
+  uint16_t* d_court = nullptr;
+  int32_t* d_date = nullptr;
+  uint32_t* d_allow = nullptr;  // 65 536-bit allow set of the current call
+};
+
 struct tss_terms {
   int device = 0;
   uint64_t nterms = 0, pool_bytes = 0, nposts = 0;
@@ -1109,7 +1117,8 @@ int tss_mask_clear(tss_mask* m) {
   return TSS_OK;
 }
 
-int tss_mask_set_rows(tss_mask* m, const uint32_t* rows, uint64_t n, uint64_t row_base) {
+namespace {
+int mask_update_rows(tss_mask* m, const uint32_t* rows, uint64_t n, uint64_t row_base, bool set) {
   if (!m) return fail(TSS_ERR_INVALID_ARG, "mask is NULL");
   if (!n) return TSS_OK;
   if (!rows) return fail(TSS_ERR_INVALID_ARG, "rows is NULL");
@@ -1117,10 +1126,79 @@ int tss_mask_set_rows(tss_mask* m, const uint32_t* rows, uint64_t n, uint64_t ro
   uint32_t* d_rows = nullptr;
   CU(cudaMalloc(&d_rows, (size_t)n * sizeof(uint32_t)));
   cudaError_t e = cudaMemcpy(d_rows, rows, (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = tss::launch_mask_set_rows(m->d_words, m->nbits, d_rows, n, row_base, 0);
+  if (e == cudaSuccess)
+    e = tss::launch_mask_set_rows(m->d_words, m->nbits, d_rows, n, row_base, set, 0);
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
   cudaFree(d_rows);
   if (e != cudaSuccess) return cuda_fail(e, "mask_set_rows");
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return TSS_OK;
+}
+}  // namespace
+
+int tss_mask_set_rows(tss_mask* m, const uint32_t* rows, uint64_t n, uint64_t row_base) {
+  return mask_update_rows(m, rows, n, row_base, true);
+}
+int tss_mask_clear_rows(tss_mask* m, const uint32_t* rows, uint64_t n, uint64_t row_base) {
+  return mask_update_rows(m, rows, n, row_base, false);
+}
+
+// ---- N3: columnar metadata pre-filter ----------------------------------------------------------
+int tss_columns_create(tss_columns** out, const uint16_t* court_ids, const int32_t* dates,
+                       uint64_t nrows, int device) {
+  if (!out) return fail(TSS_ERR_INVALID_ARG, "out is NULL");
+  *out = nullptr;
+  if (nrows && (!court_ids || !dates)) return fail(TSS_ERR_INVALID_ARG, "column pointer is NULL");
+  int ndev = tss_device_count();
+  if (ndev == 0) return fail(TSS_ERR_CUDA, "no CUDA device visible (libtss has no CPU path)");
+  if (device < 0 || device >= ndev) return fail(TSS_ERR_INVALID_ARG, "device %d of %d", device, ndev);
+  DeviceGuard g(device);
+  tss_columns* c = new (std::nothrow) tss_columns();
+  if (!c) return fail(TSS_ERR_OOM, "host allocation failed");
+  c->device = device;
+  c->nrows = nrows;
+  cudaError_t e = cudaMalloc(&c->d_court, (nrows + 1) * sizeof(uint16_t));
+  if (e == cudaSuccess) e = cudaMalloc(&c->d_date, (nrows + 1) * sizeof(int32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&c->d_allow, 2048 * sizeof(uint32_t));
+  if (e == cudaSuccess && nrows)
+    e = cudaMemcpy(c->d_court, court_ids, nrows * sizeof(uint16_t), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && nrows)
+    e = cudaMemcpy(c->d_date, dates, nrows * sizeof(int32_t), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    tss_columns_destroy(c);
+    return cuda_fail(e, "columns upload");
+  }
+  *out = c;
+  return TSS_OK;
+}
+
+void tss_columns_destroy(tss_columns* c) {
+  if (!c) return;
+  DeviceGuard g(c->device);
+  cudaFree(c->d_court);
+  cudaFree(c->d_date);
+  cudaFree(c->d_allow);
+  delete c;
+}
+
+int tss_filter_mask(tss_columns* c, const uint16_t* allowed_courts, uint32_t n_allowed,
+                    int32_t date_lo, int32_t date_hi, tss_mask* mask, int combine_and) {
+  if (!c || !mask) return fail(TSS_ERR_INVALID_ARG, "NULL argument");
+  if (n_allowed && !allowed_courts) return fail(TSS_ERR_INVALID_ARG, "allowed_courts is NULL");
+  if (c->device != mask->device) return fail(TSS_ERR_INVALID_ARG, "columns and mask on different devices");
+  if (mask->nbits < c->nrows)
+    return fail(TSS_ERR_INVALID_ARG, "mask has %llu bits, columns have %llu rows",
+                (unsigned long long)mask->nbits, (unsigned long long)c->nrows);
+  DeviceGuard g(c->device);
+  if (n_allowed) {
+    std::vector<uint32_t> bits(2048, 0);
+    for (uint32_t i = 0; i < n_allowed; ++i) bits[allowed_courts[i] >> 5] |= 1u << (allowed_courts[i] & 31);
+    CU(cudaMemcpy(c->d_allow, bits.data(), 2048 * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  }
+  cudaError_t e = tss::launch_filter_mask(c->d_court, c->d_date, c->nrows, c->d_allow, n_allowed == 0,
+                                          date_lo, date_hi, mask->d_words, combine_and != 0, 0);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return cuda_fail(e, "filter_mask");
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return TSS_OK;
 }

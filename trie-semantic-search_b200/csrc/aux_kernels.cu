@@ -109,18 +109,20 @@ cudaError_t launch_unpack_rows(const void* src, float* dst, uint64_t nrows, uint
 
 // ---- masks -----------------------------------------------------------------------------
 __global__ void mask_set_rows_kernel(uint32_t* words, uint64_t nbits, const uint32_t* rows,
-                                     uint64_t n, uint64_t row_base) {
+                                     uint64_t n, uint64_t row_base, int set) {
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n;
        i += (uint64_t)gridDim.x * blockDim.x) {
     uint64_t r = (uint64_t)rows[i] - row_base;  // wraps to huge if below the shard
-    if (r < nbits) atomicOr(words + (r >> 5), 1u << (uint32_t)(r & 31));
+    if (r >= nbits) continue;
+    if (set) atomicOr(words + (r >> 5), 1u << (uint32_t)(r & 31));
+    else atomicAnd(words + (r >> 5), ~(1u << (uint32_t)(r & 31)));
   }
 }
 cudaError_t launch_mask_set_rows(uint32_t* words, uint64_t nbits, const uint32_t* rows, uint64_t n,
-                                 uint64_t row_base, cudaStream_t st) {
+                                 uint64_t row_base, bool set, cudaStream_t st) {
   if (!n) return cudaSuccess;
   int grid = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
-  mask_set_rows_kernel<<<grid, 256, 0, st>>>(words, nbits, rows, n, row_base);
+  mask_set_rows_kernel<<<grid, 256, 0, st>>>(words, nbits, rows, n, row_base, set ? 1 : 0);
   return cudaGetLastError();
 }
 
@@ -141,6 +143,46 @@ cudaError_t launch_mask_update_from_keys(uint32_t* words, uint64_t nbits, const 
   if (!n) return cudaSuccess;
   mask_update_from_keys_kernel<<<(n + 255) / 256, 256, 0, st>>>(words, nbits, keys, n, row_base,
                                                                 set ? 1 : 0);
+  return cudaGetLastError();
+}
+
+// N3: columnar metadata pre-filter.  One thread builds one 32-row mask word: a row passes when
+// its date lies in [lo,hi] and (no court list, or its court id is in the 65 536-bit allow set).
+__global__ void filter_mask_kernel(const uint16_t* court, const int32_t* date, uint64_t nrows,
+                                   const uint32_t* allow_bits, int any_court, int32_t lo, int32_t hi,
+                                   uint32_t* words, int combine_and) {
+  __shared__ uint32_t s_allow[2048];
+  if (!any_court)
+    for (uint32_t i = threadIdx.x; i < 2048; i += blockDim.x) s_allow[i] = allow_bits[i];
+  __syncthreads();
+  const uint64_t nwords = (nrows + 31) / 32;
+  for (uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < nwords;
+       w += (uint64_t)gridDim.x * blockDim.x) {
+    uint32_t bits = 0;
+    const uint64_t r0 = w * 32;
+#pragma unroll 4
+    for (uint32_t j = 0; j < 32; ++j) {
+      const uint64_t r = r0 + j;
+      if (r >= nrows) break;
+      const int32_t d = date[r];
+      bool ok = d >= lo && d <= hi;
+      if (ok && !any_court) {
+        const uint32_t c = court[r];
+        ok = (s_allow[c >> 5] >> (c & 31)) & 1u;
+      }
+      bits |= (uint32_t)ok << j;
+    }
+    words[w] = combine_and ? (words[w] & bits) : bits;
+  }
+}
+cudaError_t launch_filter_mask(const uint16_t* court, const int32_t* date, uint64_t nrows,
+                               const uint32_t* allow_bits, bool any_court, int32_t lo, int32_t hi,
+                               uint32_t* words, bool combine_and, cudaStream_t st) {
+  if (!nrows) return cudaSuccess;
+  const uint64_t nwords = (nrows + 31) / 32;
+  int grid = (int)((nwords + 255) / 256 < 148 * 8 ? (nwords + 255) / 256 : 148 * 8);
+  filter_mask_kernel<<<grid, 256, 0, st>>>(court, date, nrows, allow_bits, any_court ? 1 : 0, lo, hi,
+                                           words, combine_and ? 1 : 0);
   return cudaGetLastError();
 }
 

@@ -20,7 +20,11 @@ cudaError_t launch_unpack_rows(const void* src, float* dst, uint64_t nrows, uint
 
 // masks
 cudaError_t launch_mask_set_rows(uint32_t* words, uint64_t nbits, const uint32_t* rows, uint64_t n,
-                                 uint64_t row_base, cudaStream_t st);
+                                 uint64_t row_base, bool set, cudaStream_t st);
+// N3: metadata columns -> mask words (overwrite or AND)
+cudaError_t launch_filter_mask(const uint16_t* court, const int32_t* date, uint64_t nrows,
+                               const uint32_t* allow_bits, bool any_court, int32_t lo, int32_t hi,
+                               uint32_t* words, bool combine_and, cudaStream_t st);
 cudaError_t launch_mask_update_from_keys(uint32_t* words, uint64_t nbits, const uint64_t* keys,
                                          uint32_t n, uint64_t row_base, bool set, cudaStream_t st);
 cudaError_t launch_mask_popcount(const uint32_t* words, uint64_t nwords, unsigned long long* out,

@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <climits>
 #include <ctime>
 #include <unordered_set>
 
@@ -419,7 +420,10 @@ std::optional<CaseMetadata> MetadataStore::get_case_metadata(const CaseId& id) c
 SearchEngine::SearchEngine(const VectorConfig& vc, const TrieConfig& tc,
                            const SearchEngineConfig& sc, std::shared_ptr<MetadataStore> storage)
     : config_(sc), trie_index_(tc), vector_index_(vc), storage_(std::move(storage)) {}
-SearchEngine::~SearchEngine() { tss_mask_destroy(mask_); }
+SearchEngine::~SearchEngine() {
+  tss_mask_destroy(mask_);
+  tss_columns_destroy(columns_);
+}
 
 void SearchEngine::freeze() {
   HnswIndex& h = vector_index_.hnsw();
@@ -430,6 +434,26 @@ void SearchEngine::freeze() {
   mask_bits_ = h.size();
   int rc = tss_mask_create(&mask_, mask_bits_ ? mask_bits_ : 1, h.device());
   if (rc) raise_tss(SearchError::VectorIndexFailed, "SearchEngine::freeze", rc);
+  // N3 columns: court id (dictionary, 65535 = unknown) and decision date of every row's case
+  std::vector<uint16_t> court(h.size(), 65535);
+  std::vector<int32_t> date(h.size(), 0);
+  court_ids_.clear();
+  for (uint32_t r = 0; r < h.size(); ++r) {
+    auto meta = storage_->get_case_metadata(h.doc_ref_of_row(r).case_id);
+    if (!meta) continue;
+    auto it = court_ids_.find(meta->court);
+    if (it == court_ids_.end()) {
+      if (court_ids_.size() >= 65535)
+        throw SearchError(SearchError::NotSupported, "more than 65535 distinct courts");
+      it = court_ids_.emplace(meta->court, (uint16_t)court_ids_.size()).first;
+    }
+    court[r] = it->second;
+    date[r] = meta->decision_date;
+  }
+  tss_columns_destroy(columns_);
+  columns_ = nullptr;
+  rc = tss_columns_create(&columns_, court.data(), date.data(), h.size(), h.device());
+  if (rc) raise_tss(SearchError::VectorIndexFailed, "SearchEngine::freeze (columns)", rc);
 }
 
 std::vector<SearchResult> SearchEngine::search(const std::string& query) {
@@ -515,26 +539,50 @@ std::vector<SearchResult> SearchEngine::execute_hybrid_search(const SearchQuery&
     HnswIndex& h = vector_index_.hnsw();
     const tss_mask* mask = nullptr;
     int mode = TSS_MASK_NONE;
-    if (policy_ != MaskPolicy::PostHoc) {
+    const bool filtered = prefilter_ && (query.court_filter || query.date_range);
+    if (policy_ != MaskPolicy::PostHoc || filtered) {
       if (!mask_ || mask_bits_ != h.size())
         throw SearchError(SearchError::NotSupported, "SearchEngine::freeze() not called after the last insert");
       int rc = tss_mask_clear(mask_);
       if (rc) raise_tss(SearchError::HnswSearchError, "mask clear", rc);
-      if (policy_ == MaskPolicy::ExcludeOnDevice) {
-        std::vector<uint32_t> rows;
+      std::vector<uint32_t> seen_rows;
+      if (policy_ == MaskPolicy::ExcludeOnDevice)
         for (const CaseId& c : seen_cases)
-          if (const auto* r = h.rows_of_case(c)) rows.insert(rows.end(), r->begin(), r->end());
-        if (!rows.empty()) {
-          rc = tss_mask_set_rows(mask_, rows.data(), rows.size(), 0);
-          if (rc) raise_tss(SearchError::HnswSearchError, "mask set_rows", rc);
-          mask = mask_;
-          mode = TSS_MASK_EXCLUDE;
-        }
-      } else {  // PrefixFilter: rows at or below the node the query reaches, any of the tries
+          if (const auto* r = h.rows_of_case(c)) seen_rows.insert(seen_rows.end(), r->begin(), r->end());
+      bool have_include = false;
+      if (policy_ == MaskPolicy::PrefixFilter) {  // rows at or below the node the query reaches
         for (int w = 0; w < 3; ++w)
           trie_index_.prefix_mask((TrieIndex::Which)w, query.query, mask_);
+        have_include = true;
+      }
+      if (filtered) {  // N3: the filter's rows, intersected with the prefix rows if any
+        std::vector<uint16_t> allowed;
+        if (query.court_filter) {
+          for (const auto& name : *query.court_filter) {
+            auto it = court_ids_.find(name);
+            if (it != court_ids_.end()) allowed.push_back(it->second);
+          }
+          if (allowed.empty()) allowed.push_back(65535);  // no known court: nothing passes
+        }
+        int32_t lo = INT32_MIN, hi = INT32_MAX;
+        if (query.date_range) lo = query.date_range->first, hi = query.date_range->second;
+        rc = tss_filter_mask(columns_, allowed.data(), (uint32_t)allowed.size(), lo, hi, mask_,
+                             have_include ? 1 : 0);
+        if (rc) raise_tss(SearchError::HnswSearchError, "filter mask", rc);
+        have_include = true;
+      }
+      if (have_include) {
+        if (!seen_rows.empty()) {  // seen cases leave the include set
+          rc = tss_mask_clear_rows(mask_, seen_rows.data(), seen_rows.size(), 0);
+          if (rc) raise_tss(SearchError::HnswSearchError, "mask clear_rows", rc);
+        }
         mask = mask_;
         mode = TSS_MASK_INCLUDE;
+      } else if (!seen_rows.empty()) {  // ExcludeOnDevice alone
+        rc = tss_mask_set_rows(mask_, seen_rows.data(), seen_rows.size(), 0);
+        if (rc) raise_tss(SearchError::HnswSearchError, "mask set_rows", rc);
+        mask = mask_;
+        mode = TSS_MASK_EXCLUDE;
       }
     }
     auto vector_results = vector_index_.search_masked(query.query, kVectorTopK, mask, mode);  // :251

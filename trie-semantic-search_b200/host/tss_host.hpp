@@ -26,6 +26,7 @@ extern "C" {
 struct tss_index;
 struct tss_mask;
 struct tss_terms;
+struct tss_columns;
 }
 
 namespace tss_host {
@@ -318,6 +319,9 @@ class SearchEngine {
   TrieIndex& trie_index() { return trie_index_; }
   VectorIndex& vector_index() { return vector_index_; }
   void set_mask_policy(MaskPolicy p) { policy_ = p; }
+  // N3: apply court_filter / date_range on the device BEFORE top-k (an include mask built from
+  // per-row court-id / date columns) instead of after it; off = reference behaviour (:233)
+  void set_prefilter(bool on) { prefilter_ = on; }
   // call after the last insert: exports the tries to the device
   void freeze();
   static constexpr size_t kVectorTopK = 50;  // hard-coded in search_vector, :251
@@ -332,6 +336,9 @@ class SearchEngine {
   VectorIndex vector_index_;
   std::shared_ptr<MetadataStore> storage_;
   MaskPolicy policy_ = MaskPolicy::PostHoc;
+  bool prefilter_ = false;
+  tss_columns* columns_ = nullptr;
+  std::unordered_map<std::string, uint16_t> court_ids_;
   tss_mask* mask_ = nullptr;
   uint64_t mask_bits_ = 0;
   struct Cached {
