@@ -323,6 +323,26 @@ static void engine_hybrid() {
     eng.set_mask_policy(SearchEngine::MaskPolicy::PostHoc);
     eng.set_prefilter(false);
   }
+  // N4: a batch of queries gives, per query, exactly what search_with_params gives
+  {
+    std::vector<SearchQuery> qs(7);
+    const char* texts[] = {"Miranda v. Arizona", "Roe v. Wade", "nothing here", "case 12",
+                           "brown v.", "CASE 33", "Miranda v. Arizona"};
+    for (int i = 0; i < 7; ++i) qs[i].query = texts[i];
+    qs[2].config.min_similarity = -1.0f;
+    qs[3].court_filter = std::vector<std::string>{"ca9"};
+    qs[5].config.enable_semantic = false;
+    qs[6].max_results = 1;
+    auto batch = eng.search_batch(qs);
+    CHECK(batch.size() == 7);
+    for (int i = 0; i < 7; ++i) {
+      auto one = eng.search_with_params(qs[i]);
+      CHECK(one.size() == batch[i].size());
+      for (size_t j = 0; j < one.size() && j < batch[i].size(); ++j)
+        CHECK(one[j].case_metadata.id == batch[i][j].case_metadata.id &&
+              one[j].score == batch[i][j].score && one[j].match_type == batch[i][j].match_type);
+    }
+  }
   // M2: >= max_results exact hits skip the vector pass entirely
   q = SearchQuery();
   q.query = "Roe v. Wade";

@@ -8,7 +8,10 @@
 // with its own 1-D TMA bulk copy (cp.async.bulk -> UBLKCP) signalled on its own
 // mbarrier: no producer warp, no CTA-wide barrier in the steady state.  While
 // a warp's tile is in flight the SM's other warps compute, so up to
-// WARPS x TILE_BYTES (192 KB) per SM are outstanding against HBM.
+// WARPS x TILE_BYTES (192 KB) per SM are outstanding against HBM.  Tiles are
+// claimed dynamically (chunks of 8, single tiles at the very end) so every
+// CTA finishes at the same time; launches overlap under programmatic
+// dependent launch (workspace slot ring, see ScanParams::slot_gen).
 //
 // Arithmetic is DESIGN.md section 3's canonical order (lane l owns elements 4l..4l+3
 // of every 128-element stripe, 4 sub-accumulators, xor butterfly), so scores
@@ -160,39 +163,6 @@ __device__ __forceinline__ void warp_offer(uint64_t key, bool valid, uint64_t* l
   if (c) list[n + __popc(m & ((1u << lane) - 1u))] = key;
   n += __popc(m);
   __syncwarp();
-}
-
-// ---- block-level merge of L descending-sorted lists of kp keys -------------------
-// list i lives at base + i*stride; the merged top-kp ends up in list 0.
-__device__ __forceinline__ void block_merge_lists(uint64_t* base, uint32_t stride, uint32_t L,
-                                                  uint32_t kp, int tid, int nthreads) {
-  for (uint32_t step = 1; step < L; step <<= 1) {
-    // pairs (a = i*2*step, b = a + step) with b < L
-    uint32_t npairs = (L - step + 2 * step - 1) / (2 * step);
-    for (uint32_t idx = tid; idx < npairs * kp; idx += nthreads) {
-      uint32_t pi = idx / kp, e = idx - pi * kp;
-      uint64_t* A = base + (size_t)(pi * 2 * step) * stride;
-      uint64_t* B = A + (size_t)step * stride;
-      uint64_t a = A[e], b = B[kp - 1 - e];
-      A[e] = a > b ? a : b;  // bitonic sequence holding the top kp of A u B
-    }
-    __syncthreads();
-    for (uint32_t s = kp >> 1; s > 0; s >>= 1) {
-      uint32_t half = kp >> 1;
-      for (uint32_t idx = tid; idx < npairs * half; idx += nthreads) {
-        uint32_t pi = idx / half, i = idx - pi * half;
-        uint64_t* A = base + (size_t)(pi * 2 * step) * stride;
-        uint32_t lo = ((i & ~(s - 1)) << 1) | (i & (s - 1));
-        uint32_t hi = lo | s;
-        uint64_t a = A[lo], b = A[hi];
-        if (a < b) {
-          A[lo] = b;
-          A[hi] = a;
-        }
-      }
-      __syncthreads();
-    }
-  }
 }
 
 // ---- warp tournament: k-way merge of L descending-sorted lists ----------------------

@@ -491,6 +491,54 @@ std::vector<SearchResult> SearchEngine::search_with_params(const SearchQuery& qu
   return results;
 }
 
+std::vector<std::vector<SearchResult>> SearchEngine::search_batch(
+    const std::vector<SearchQuery>& queries) {
+  auto snippet = [](const DocRef& d) {
+    return "Snippet for case " + d.case_id.to_string() + " paragraph " +
+           std::to_string(d.paragraph_index);
+  };
+  const size_t n = queries.size();
+  std::vector<std::vector<SearchResult>> all(n);
+  std::vector<std::unordered_set<CaseId, CaseIdHash>> seen(n);
+  std::vector<size_t> need;  // queries that run the semantic pass
+  std::vector<std::vector<float>> embeddings;
+  for (size_t i = 0; i < n; ++i) {
+    const SearchQuery& q = queries[i];
+    validate_query(q);
+    if (q.config.enable_prefix) {  // :190-206
+      for (const DocRef& d : trie_index_.search(q.query).exact_matches) {
+        auto meta = storage_->get_case_metadata(d.case_id);
+        if (meta && seen[i].insert(d.case_id).second)
+          all[i].push_back(SearchResult{*meta, q.config.exact_match_weight, MatchType::Exact, snippet(d)});
+      }
+    }
+    if (q.config.enable_semantic && all[i].size() < q.config.max_results) {  // :209
+      need.push_back(i);
+      embeddings.push_back(vector_index_.generate_embedding(q.query).embedding);
+    }
+  }
+  auto hits = vector_index_.hnsw().search_batch(embeddings, kVectorTopK);  // one device call
+  for (size_t j = 0; j < need.size(); ++j) {
+    const size_t i = need[j];
+    const SearchQuery& q = queries[i];
+    for (const auto& h : hits[j]) {
+      const float sim = 1.0f - h.second;  // :144
+      if (sim < q.config.min_similarity) continue;  // :212
+      auto meta = storage_->get_case_metadata(h.first.case_id);
+      if (meta && seen[i].insert(h.first.case_id).second)
+        all[i].push_back(SearchResult{*meta, sim, MatchType::Semantic, snippet(h.first)});
+    }
+  }
+  for (size_t i = 0; i < n; ++i) {
+    std::stable_sort(all[i].begin(), all[i].end(),
+                     [](const SearchResult& a, const SearchResult& b) { return a.score > b.score; });
+    all[i] = apply_filters(std::move(all[i]), queries[i]);
+    size_t max_results = queries[i].max_results.value_or(queries[i].config.max_results);
+    if (all[i].size() > max_results) all[i].resize(max_results);
+  }
+  return all;
+}
+
 std::vector<SearchResult> SearchEngine::apply_filters(std::vector<SearchResult> results,
                                                       const SearchQuery& query) const {
   if (query.court_filter) {  // :261-263

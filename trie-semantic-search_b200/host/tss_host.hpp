@@ -316,6 +316,12 @@ class SearchEngine {
   ~SearchEngine();
   std::vector<SearchResult> search(const std::string& query);                 // :149-159
   std::vector<SearchResult> search_with_params(const SearchQuery& query);     // :162-182
+  // N4: many queries at once.  The trie pass and the merge run per query exactly as in
+  // search_with_params (PostHoc policy, no query cache); the semantic pass of all queries that
+  // need one is a single batched tss_index_search, so the corpus is streamed once per 4
+  // queries (K1) or once per batch (K2) instead of once per query behind the write lock
+  // (src/search.rs:249-252).
+  std::vector<std::vector<SearchResult>> search_batch(const std::vector<SearchQuery>& queries);
   TrieIndex& trie_index() { return trie_index_; }
   VectorIndex& vector_index() { return vector_index_; }
   void set_mask_policy(MaskPolicy p) { policy_ = p; }
