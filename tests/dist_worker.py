@@ -53,6 +53,35 @@ def main():
             print(f"rank {rank}: MISMATCH n={n} k={k}", flush=True)
         ok &= same
         ix.close()
+    # stress: hundreds of back-to-back tiny sharded scans.  Launches overlap under programmatic
+    # dependent launch, so their peer-memory exchanges must still happen in launch order.
+    n, k, reps = 300, 10, 400
+    per = (n + world - 1) // world
+    b = min(rank * per, n)
+    cnt = min(per, n - b)
+    ix = tss.FlatIndex(dim, tss.TSS_F32, local)
+    ix.add_synthetic(b, cnt, seed)
+    ix.set_shard(b, comm)
+    ix.finalize()
+    q = orc.gen_rows(0, 4, dim, 0xBEEF)
+    rows = orc.gen_rows(0, n, dim, seed)
+    want = orc.cosine_topk(rows, q, k)
+    dq = tss.DeviceBuffer(local, q.nbytes).upload(q)
+    dk = tss.DeviceBuffer(local, reps * k * 8)
+
+    class _Off:
+        def __init__(self, ptr):
+            self.ptr = ptr
+    for i in range(reps):
+        ix.search_device(_Off(dq.ptr + (i % 4) * dim * 4), 1, k, _Off(dk.ptr + i * k * 8))
+    ix.sync()
+    rr, ss = tss.unpack_keys(dk.download(np.uint64, reps * k).reshape(reps, k))
+    same = all(np.array_equal(rr[i], want[0][i % 4]) and
+               np.array_equal(ss[i].view(np.uint32), want[1][i % 4].view(np.uint32)) for i in range(reps))
+    if not same:
+        print(f"rank {rank}: back-to-back sharded scans MISMATCH", flush=True)
+    ok &= same
+    ix.close()
     # K2 (tensor-core path) on a sharded bf16 index: local GEMM top-k, NCCL all-gather, merge
     n, k, nq = 400_000, 10, 64
     per = (n + world - 1) // world

@@ -192,7 +192,8 @@ struct tss_index {
   float fine_rounds = 2.0f;
   unsigned long long* d_dbg = nullptr;  // diagnostics (tss_index_debug_phases)
   float* h_queries = nullptr;  // pinned
-  uint64_t* h_keys = nullptr;  // pinned
+  uint64_t* h_keys = nullptr;  // pinned + mapped: the scan writes its result straight into it
+  unsigned int* h_status = nullptr;  // pinned + mapped exchange status word
   // K2 (tensor-core) workspace, allocated on first large-batch search of a bf16 index
   struct Gemm {
     bool ready = false;
@@ -277,9 +278,10 @@ int check_mask(const tss_index* ix, const tss_mask* mask, int mode) {
   return TSS_OK;
 }
 
-// enqueue the scan for nq device-resident queries -> d_out (nq x k local keys)
+// enqueue the scan for nq device-resident queries -> d_out (nq x k local keys).  A single
+// query of <= 384 dims may instead be handed over from host memory inside the kernel parameters.
 int enqueue_scan(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
-                 const tss_mask* mask, int mode, uint64_t* d_out) {
+                 const tss_mask* mask, int mode, uint64_t* d_out, const float* h_inline_query) {
   const uint32_t kp = tss::kp_for_k(k), cap = tss::cap_for_k(k);
   const uint32_t bq_max = (uint32_t)tss::max_bq_for_k(k);
   for (uint32_t q0 = 0; q0 < nq;) {
@@ -292,6 +294,10 @@ int enqueue_scan(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
     p.row_base = (uint32_t)ix->row_base;
     p.dim = ix->dim;
     p.queries = d_queries + (size_t)q0 * ix->dim;
+    if (h_inline_query && nq == 1 && ix->dim <= 384) {
+      memcpy(p.q_inline, h_inline_query, ix->dim * sizeof(float));
+      p.use_inline = 1;
+    }
     p.nq_valid = take;
     p.k = k;
     p.kp = kp;
@@ -328,7 +334,8 @@ int enqueue_scan(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
       p.xchg_nranks = (uint32_t)ix->comm->nranks;
       p.xchg_rank = (uint32_t)ix->comm->rank;
       p.xchg_seq = ++ix->xchg.seq;
-      p.xchg_status = ix->d_counter + 16;
+      p.xchg_status = ix->h_status;  // mapped pinned: the host reads it without a copy
+      p.xchg_turn = ix->d_counter + 17;
     }
     cudaError_t e = tss::launch_scan(ix->ns, p, bq, ix->storage == TSS_BF16, mode != TSS_MASK_NONE,
                                      ix->num_sms, ix->device, ix->stream);
@@ -407,7 +414,8 @@ int ensure_gemm_ws(tss_index* ix) {
 }
 
 int enqueue_scan(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
-                 const tss_mask* mask, int mode, uint64_t* d_out);
+                 const tss_mask* mask, int mode, uint64_t* d_out,
+                 const float* h_inline_query = nullptr);
 int enqueue_scan_rounds(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
                         const tss_mask* mask, int mode, uint64_t* d_out);
 
@@ -629,6 +637,8 @@ int tss_index_create(tss_index** out, uint32_t dim, int storage, int device) {
   if (ix->dyn_chunk < 1) ix->dyn_chunk = 1;
   ALLOC(cudaMallocHost(&ix->h_queries, (size_t)kWsQueries * dim * sizeof(float)))
   ALLOC(cudaMallocHost(&ix->h_keys, (size_t)kWsQueries * TSS_MAX_K * sizeof(uint64_t)))
+  ALLOC(cudaMallocHost(&ix->h_status, 64))
+  *ix->h_status = 0;
   if (const char* sf = getenv("TSS_GEMM_MIN_NQ")) ix->gemm_min_nq = (uint32_t)atoi(sf);
 #undef ALLOC
   *out = ix;
@@ -650,6 +660,7 @@ void tss_index_destroy(tss_index* ix) {
   cudaFree(ix->d_counter);
   if (ix->h_queries) cudaFreeHost(ix->h_queries);
   if (ix->h_keys) cudaFreeHost(ix->h_keys);
+  if (ix->h_status) cudaFreeHost(ix->h_status);
   for (int r = 0; r < 8; ++r)
     if (ix->xchg.peer[r] && ix->xchg.peer[r] != ix->xchg.local) cudaIpcCloseMemHandle(ix->xchg.peer[r]);
   cudaFree(ix->xchg.local);
@@ -924,33 +935,44 @@ int tss_index_search(tss_index* ix, const float* queries, uint32_t nq, uint32_t 
   for (uint32_t q0 = 0; q0 < nq; q0 += kWsQueries) {
     uint32_t n = nq - q0 < kWsQueries ? nq - q0 : kWsQueries;
     size_t qbytes = (size_t)n * ix->dim * sizeof(float);
-    memcpy(ix->h_queries, queries + (size_t)q0 * ix->dim, qbytes);
-    CU(cudaMemcpyAsync(ix->d_queries, ix->h_queries, qbytes, cudaMemcpyHostToDevice, ix->stream));
+    const float* hq = queries + (size_t)q0 * ix->dim;
     // a large batch of a bf16 index takes the tensor-core path as a whole (nq, not n, decides)
+    const bool gemm = gemm_eligible(ix, nq, k, mask_mode);
+    const bool rounds = !gemm && k > TSS_MAX_FUSED_K;
+    // scan path: a lone query travels in the kernel parameters, and the last CTA writes the
+    // result straight into mapped pinned host memory -- no H2D / D2H copy operations at all
+    const bool inline_q = !gemm && !rounds && n == 1 && ix->dim <= 384;
+    if (!inline_q) {
+      memcpy(ix->h_queries, hq, qbytes);
+      CU(cudaMemcpyAsync(ix->d_queries, ix->h_queries, qbytes, cudaMemcpyHostToDevice, ix->stream));
+    }
     bool merged = false;
-    if (gemm_eligible(ix, nq, k, mask_mode)) {
+    bool direct = false;  // result already lands in h_keys
+    if (gemm) {
       rc = enqueue_gemm(ix, ix->d_queries, n, k, ix->d_keys);
-    } else if (k > TSS_MAX_FUSED_K) {
+    } else if (rounds) {
       rc = enqueue_scan_rounds(ix, ix->d_queries, n, k, mask, mask_mode, ix->d_keys);
     } else {
       merged = ix->comm && ix->xchg.ready;
-      rc = enqueue_scan(ix, ix->d_queries, n, k, mask, mask_mode, ix->d_keys);
+      direct = !ix->comm || merged;
+      rc = enqueue_scan(ix, ix->d_queries, n, k, mask, mask_mode, direct ? ix->h_keys : ix->d_keys,
+                        inline_q ? hq : nullptr);
     }
     if (rc) return rc;
-    const uint64_t* d_res = ix->d_keys;
-    if (ix->comm && !merged) {
-      if ((rc = enqueue_gather_merge(ix, ix->d_keys, n, k, ix->d_merged))) return rc;
-      d_res = ix->d_merged;
-    }
-    CU(cudaMemcpyAsync(ix->h_keys, d_res, (size_t)n * k * sizeof(uint64_t), cudaMemcpyDeviceToHost,
-                       ix->stream));
-    unsigned int xstatus = 0;
-    if (merged)
-      CU(cudaMemcpyAsync(&xstatus, ix->d_counter + 16, sizeof(xstatus), cudaMemcpyDeviceToHost,
+    if (!direct) {
+      const uint64_t* d_res = ix->d_keys;
+      if (ix->comm && !merged) {
+        if ((rc = enqueue_gather_merge(ix, ix->d_keys, n, k, ix->d_merged))) return rc;
+        d_res = ix->d_merged;
+      }
+      CU(cudaMemcpyAsync(ix->h_keys, d_res, (size_t)n * k * sizeof(uint64_t), cudaMemcpyDeviceToHost,
                          ix->stream));
+    }
     CU(cudaStreamSynchronize(ix->stream));
-    if (xstatus)
+    if (merged && *ix->h_status) {
+      *ix->h_status = 0;
       return fail(TSS_ERR_NCCL, "a rank of the shard group did not deliver its top-k within 5 s");
+    }
     tss_unpack_keys(ix->h_keys, (uint64_t)n * k, out_rows + (size_t)q0 * k,
                     out_scores + (size_t)q0 * k);
     for (uint32_t qi = 0; qi < n; ++qi) {
@@ -1053,6 +1075,7 @@ int setup_xchg(tss_index* ix, tss_comm* comm) {
   x.comm = comm;
   x.ready = ok;
   x.seq = 0;
+  CU(cudaMemset(ix->d_counter + 17, 0, sizeof(unsigned int)));
   return TSS_OK;
 }
 }  // namespace

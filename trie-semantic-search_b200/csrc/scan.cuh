@@ -53,12 +53,19 @@ struct ScanParams {
   uint8_t* xchg_peer[8];
   uint32_t xchg_nranks, xchg_rank, xchg_seq;
   unsigned int* xchg_status;  // set to 1 when a peer never showed up (5 s), instead of hanging
+  // exchanges of consecutive launches must happen in launch order on each GPU (launches
+  // overlap under PDL): *xchg_turn is the sequence number of the last finished exchange
+  unsigned int* xchg_turn;
   uint32_t pdl;               // launched with programmatic stream serialization
   // workspace slot hand-over: consecutive launches overlap under PDL, so the slot (partials +
   // counters) of this launch may still be in use by the launch that had it kSlots launches
   // ago.  slot_gen holds the number of the last launch that finished with the slot.
   unsigned int* slot_gen;
   uint32_t launch_no, expect_gen;
+  // a single query of <= 384 dims can ride in the kernel parameters (no H2D copy before the
+  // launch): use_inline != 0 -> query 0 is q_inline, `queries` is not read
+  uint32_t use_inline;
+  float q_inline[384];
 };
 
 // exchange buffer layout (bytes): [0,256) one u32 arrival flag per source rank, then
@@ -211,7 +218,7 @@ struct TileGeom {
 };
 
 template <int NS, int BQ, int WARPS, bool BF16, bool MASKED>
-__global__ void __launch_bounds__(WARPS * 32, 1) scan_topk_kernel(const ScanParams p) {
+__global__ void __launch_bounds__(WARPS * 32, 1) scan_topk_kernel(const __grid_constant__ ScanParams p) {
   using G = TileGeom<NS, BF16>;
   constexpr int R = G::R;
   constexpr int RG = (BQ >= 4 && R > 4) ? 4 : R;  // rows reduced together (register budget)
@@ -248,10 +255,17 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_topk_kernel(const ScanPara
       const float* qb = p.queries + (size_t)b * p.dim;
       bool live = (uint32_t)b < p.nq_valid;
       float4 v;
-      v.x = (live && j + 0 < p.dim) ? __ldg(qb + j + 0) : 0.f;
-      v.y = (live && j + 1 < p.dim) ? __ldg(qb + j + 1) : 0.f;
-      v.z = (live && j + 2 < p.dim) ? __ldg(qb + j + 2) : 0.f;
-      v.w = (live && j + 3 < p.dim) ? __ldg(qb + j + 3) : 0.f;
+      if (p.use_inline) {  // (b == 0 only: nq_valid == 1)
+        v.x = (live && j + 0 < p.dim) ? p.q_inline[(j + 0) % 384] : 0.f;
+        v.y = (live && j + 1 < p.dim) ? p.q_inline[(j + 1) % 384] : 0.f;
+        v.z = (live && j + 2 < p.dim) ? p.q_inline[(j + 2) % 384] : 0.f;
+        v.w = (live && j + 3 < p.dim) ? p.q_inline[(j + 3) % 384] : 0.f;
+      } else {
+        v.x = (live && j + 0 < p.dim) ? __ldg(qb + j + 0) : 0.f;
+        v.y = (live && j + 1 < p.dim) ? __ldg(qb + j + 1) : 0.f;
+        v.z = (live && j + 2 < p.dim) ? __ldg(qb + j + 2) : 0.f;
+        v.w = (live && j + 3 < p.dim) ? __ldg(qb + j + 3) : 0.f;
+      }
       q[b][s] = v;
       a0 = __fmaf_rn(v.x, v.x, a0);
       a1 = __fmaf_rn(v.y, v.y, a1);
@@ -491,6 +505,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_topk_kernel(const ScanPara
   if (s_ticket != gridDim.x - 1) return;
   __threadfence();
 
+  if (p.xchg_nranks) {  // wait for this GPU's previous exchange (normally long finished)
+    if (tid == 0)
+      while (ld_acquire_sys(p.xchg_turn) != p.xchg_seq - 1) __nanosleep(32);
+    __syncthreads();
+  }
   // stage every partial in shared memory (the launcher sized it for gridDim.x * kp keys
   // per query pass), then one warp per query runs the tournament
   uint64_t* ws = reinterpret_cast<uint64_t*>(smem);
@@ -575,6 +594,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_topk_kernel(const ScanPara
     *p.tile_counter = 0;
     __threadfence();
     st_release_sys(p.slot_gen, p.launch_no);  // hand the slot to launch_no + kSlots
+    if (p.xchg_nranks) st_release_sys(p.xchg_turn, p.xchg_seq);
   }
 }
 
