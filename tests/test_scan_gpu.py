@@ -301,3 +301,26 @@ def test_large_k_rounds_on_the_scan_path(tss, orc, k):
     _assert_same(ix.search(q, k, m, tss.TSS_MASK_EXCLUDE),
                  orc.cosine_topk(rows, q, k, words, orc.MASK_EXCLUDE))
     assert np.array_equal(m.download(), words)  # the caller's mask is untouched
+
+
+def test_back_to_back_launches_overlap_safely(tss, orc):
+    """Hundreds of queued scans (they overlap under programmatic dependent launch and rotate
+    through the workspace slots) each produce their own exact result."""
+    class _Off:
+        def __init__(self, ptr):
+            self.ptr = ptr
+    for n in (40, 3000, 200_000):
+        rows = orc.gen_rows(0, n, 384, SEED)
+        ix = _mk_index(tss, rows)
+        q = orc.gen_rows(0, 6, 384, 0xBEEF)
+        want = orc.cosine_topk(rows, q, 10)
+        reps = 300
+        dq = tss.DeviceBuffer(0, q.nbytes).upload(q)
+        dk = tss.DeviceBuffer(0, reps * 10 * 8)
+        for i in range(reps):
+            ix.search_device(_Off(dq.ptr + (i % 6) * 384 * 4), 1, 10, _Off(dk.ptr + i * 80))
+        ix.sync()
+        r, s = tss.unpack_keys(dk.download(np.uint64, reps * 10).reshape(reps, 10))
+        for i in range(reps):
+            assert np.array_equal(r[i], want[0][i % 6]), (n, i)
+            assert np.array_equal(s[i].view(np.uint32), want[1][i % 6].view(np.uint32))
