@@ -102,3 +102,21 @@ def test_small_batches_keep_using_the_scan(tss, orc):
     want = orc.cosine_topk(rows, q, 10, bf16=True)
     assert np.array_equal(got[0], want[0])
     assert np.array_equal(got[1].view(np.uint32), want[1].view(np.uint32))
+
+
+@pytest.mark.parametrize("dim", [64, 100, 256, 300])
+def test_other_dimensions(tss, orc, dim):
+    """D < 384 pads to 128 / 256 / 384 columns: 2, 4 or 6 k-blocks of the same kernel."""
+    n, nq, k = 80_000, 130, 10
+    rng = np.random.default_rng(dim)
+    rows = rng.standard_normal((n, dim)).astype(np.float32)
+    q = rng.standard_normal((nq, dim)).astype(np.float32)
+    q[5] = rows[777] + 0.1 * q[5]
+    ix = tss.FlatIndex(dim, tss.TSS_BF16)
+    ix.add(rows)
+    ix.finalize()
+    gr, gs, gc = ix.search(q, k)
+    assert np.all(gc == k) and gr[5][0] == 777
+    wi, ws = _f64_topk(_bf16(rows), _bf16(q), k)
+    assert _recall(gr, wi) >= 0.99
+    np.testing.assert_allclose(gs[:, 0], ws[:, 0], rtol=3e-5, atol=1e-6)
