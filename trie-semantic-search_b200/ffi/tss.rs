@@ -24,6 +24,8 @@ pub struct tss_mask { _p: [u8; 0] }
 pub struct tss_terms { _p: [u8; 0] }
 #[repr(C)]
 pub struct tss_comm { _p: [u8; 0] }
+#[repr(C)]
+pub struct tss_columns { _p: [u8; 0] }
 
 #[repr(C)]
 #[derive(Default, Debug, Clone, Copy)]
@@ -92,6 +94,18 @@ extern "C" {
     pub fn tss_prefix_mask(
         t: *mut tss_terms, prefix: *const c_char, len: u32, kind: c_int, out: *mut tss_mask,
         row_base: u64, stats: *mut tss_prefix_stats,
+    ) -> c_int;
+
+    pub fn tss_index_save(ix: *mut tss_index, path: *const c_char) -> c_int;
+    pub fn tss_index_load(out: *mut *mut tss_index, path: *const c_char, device: c_int) -> c_int;
+    pub fn tss_mask_clear_rows(m: *mut tss_mask, rows: *const u32, n: u64, row_base: u64) -> c_int;
+    pub fn tss_columns_create(
+        out: *mut *mut tss_columns, court_ids: *const u16, dates: *const i32, nrows: u64, device: c_int,
+    ) -> c_int;
+    pub fn tss_columns_destroy(c: *mut tss_columns);
+    pub fn tss_filter_mask(
+        c: *mut tss_columns, allowed_courts: *const u16, n_allowed: u32, date_lo: i32, date_hi: i32,
+        mask: *mut tss_mask, combine_and: c_int,
     ) -> c_int;
 
     pub fn tss_index_stream(ix: *mut tss_index) -> *mut c_void;
