@@ -301,43 +301,57 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_topk_kernel(const __grid_c
     }
     return valid;
   };
-  // first tile >= t0 of this warp's sequence (t0, t0+GW, ...) with any live row
-  auto next_live = [&](uint64_t t0, uint32_t& bits) -> uint64_t {
-    if constexpr (!MASKED) {
-      bits = t0 < total_tiles ? tile_bits(t0) : 0u;
-      return t0;
-    } else {
-    while (t0 < total_tiles) {
-      uint64_t tc = t0 + (uint64_t)lane * GW;
-      uint32_t b = tc < total_tiles ? tile_bits(tc) : 0u;
-      unsigned nz = __ballot_sync(FULL_MASK, b != 0u);
-      if (nz) {
-        int src = __ffs(nz) - 1;
-        bits = __shfl_sync(FULL_MASK, b, src);
-        return t0 + (uint64_t)src * GW;
-      }
-      t0 += 32 * GW;
-    }
-    bits = 0;
-    return t0;
-    }
-  };
+  // unmasked: one contiguous bulk copy of the tile's valid rows
   auto issue = [&](uint64_t t, uint32_t bits) {
     if (lane == 0) {
-      const uint8_t* src = rows_b + t * (uint64_t)TILE_BYTES;
-      uint32_t hi = 32 - __clz(bits);  // rows [0,hi) span every live row
-      if (!MASKED || bits == ((hi >= 32) ? 0xFFFFFFFFu : ((1u << hi) - 1u))) {
-        uint32_t bytes = hi * ROW_BYTES;
-        mbar_arrive_expect_tx(bar, bytes);
-        bulk_g2s(tile_s, src, bytes, bar, policy);
-      } else {  // sparse tile: fetch only the live rows
-        mbar_arrive_expect_tx(bar, __popc(bits) * ROW_BYTES);
-        for (uint32_t b = bits; b; b &= b - 1) {
-          uint32_t r = __ffs(b) - 1;
-          bulk_g2s(tile_s + r * ROW_BYTES, src + r * ROW_BYTES, ROW_BYTES, bar, policy);
+      const uint32_t bytes = (32 - __clz(bits)) * ROW_BYTES;  // bits = low `valid rows` ones
+      mbar_arrive_expect_tx(bar, bytes);
+      bulk_g2s(tile_s, rows_b + t * (uint64_t)TILE_BYTES, bytes, bar, policy);
+    }
+  };
+  // masked: pack the live rows of as many of this warp's next tiles (m_next, m_next + GW, ...)
+  // as fit into the R slots of the buffer, one bulk copy per live row (or per contiguous run
+  // from row 0), issued by the lane that examined the tile; slot_rows[s] = local row of slot s.
+  // A sparse mask therefore still keeps a whole buffer of bytes in flight per warp.
+  uint32_t* slot_rows = reinterpret_cast<uint32_t*>(bars + WARPS) + warp * 16;
+  uint64_t m_next = (uint64_t)blockIdx.x * WARPS + warp;
+  auto gather = [&]() -> uint32_t {
+    while (m_next < total_tiles) {
+      const uint64_t tc = m_next + (uint64_t)lane * GW;
+      const uint32_t b = tc < total_tiles ? tile_bits(tc) : 0u;
+      const uint32_t pc = __popc(b);
+      uint32_t inc = pc;  // inclusive prefix sum of the live-row counts over the lanes
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        uint32_t v = __shfl_up_sync(FULL_MASK, inc, d);
+        if (lane >= d) inc += v;
+      }
+      // whole tiles only: the lanes whose running total still fits form a prefix (lane 0 always)
+      const unsigned takem = __ballot_sync(FULL_MASK, inc <= (uint32_t)R);
+      const int ntake = takem == FULL_MASK ? 32 : __ffs(~takem) - 1;
+      const uint32_t total = __shfl_sync(FULL_MASK, inc, ntake - 1);
+      m_next += (uint64_t)ntake * GW;
+      if (total == 0) continue;  // nothing live in these tiles
+      if (lane == 0) mbar_arrive_expect_tx(bar, total * ROW_BYTES);
+      __syncwarp();
+      if (lane < ntake && pc) {
+        uint32_t slot = inc - pc;
+        const uint8_t* src = rows_b + tc * (uint64_t)TILE_BYTES;
+        if (b == (1u << pc) - 1u) {  // rows 0..pc-1: contiguous in HBM and in the buffer
+          bulk_g2s(tile_s + slot * ROW_BYTES, src, pc * ROW_BYTES, bar, policy);
+          for (uint32_t r = 0; r < pc; ++r) slot_rows[slot + r] = (uint32_t)(tc * R + r);
+        } else {
+          for (uint32_t bb = b; bb; bb &= bb - 1) {
+            const uint32_t r = __ffs(bb) - 1;
+            bulk_g2s(tile_s + slot * ROW_BYTES, src + r * ROW_BYTES, ROW_BYTES, bar, policy);
+            slot_rows[slot++] = (uint32_t)(tc * R + r);
+          }
         }
       }
+      __syncwarp();
+      return total;
     }
+    return 0u;
   };
 
   // the previous user of this workspace slot must have finished (normally long ago)
@@ -382,22 +396,30 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_topk_kernel(const __grid_c
     return tt;
   };
 
+  // unmasked: t = tile in the buffer, cur_bits = its valid rows.  masked: cur_bits = number of
+  // packed rows in the buffer and t is just "0 = buffer in flight / total_tiles = done".
   uint32_t cur_bits = 0;
   uint64_t t;
+  uint32_t phase = 0;
   if constexpr (MASKED) {
-    t = next_live(gw, cur_bits);
+    cur_bits = gather();
+    t = cur_bits ? 0 : total_tiles;
   } else {
     claim();
     t = resolve(cur_bits);
     claim();
+    if (t < total_tiles) issue(t, cur_bits);
   }
-  uint32_t phase = 0;
-  if (t < total_tiles) issue(t, cur_bits);
 
   while (t < total_tiles) {
     mbar_wait(bar, phase);
     phase ^= 1;
 
+    uint32_t my_row[NG];  // masked: local row held by the slot this lane will score
+    if constexpr (MASKED) {
+#pragma unroll
+      for (int g = 0; g < NG; ++g) my_row[g] = slot_rows[g * RG + (lane / LANES_PER_ROW)];
+    }
     float dots[BQ][NG], nrms[NG];
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
@@ -448,20 +470,28 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_topk_kernel(const __grid_c
     uint32_t nbits = 0;
     uint64_t tn;
     if constexpr (MASKED) {
-      tn = next_live(t + GW, nbits);
+      nbits = gather();
+      tn = nbits ? 0 : total_tiles;
     } else {
       tn = resolve(nbits);
+      if (tn < total_tiles) issue(tn, nbits);
+      claim();
     }
-    if (tn < total_tiles) issue(tn, nbits);
-    if constexpr (!MASKED) claim();
 
     // ---- score + top-k for tile t (overlaps the copy just issued) -------------
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
       const uint32_t r_in_tile = g * RG + (lane / LANES_PER_ROW);
-      const uint64_t row_local = t * R + r_in_tile;
-      const bool owner = (lane % LANES_PER_ROW) == 0 && ((cur_bits >> r_in_tile) & 1u);
-      const uint32_t row_global = p.row_base + (uint32_t)row_local;
+      uint32_t row_local;
+      bool owner = (lane % LANES_PER_ROW) == 0;
+      if constexpr (MASKED) {
+        row_local = my_row[g];
+        owner = owner && r_in_tile < cur_bits;
+      } else {
+        row_local = (uint32_t)(t * R + r_in_tile);
+        owner = owner && ((cur_bits >> r_in_tile) & 1u);
+      }
+      const uint32_t row_global = p.row_base + row_local;
 #pragma unroll
       for (int b = 0; b < BQ; ++b) {
         if ((uint32_t)b < p.nq_valid) {

@@ -17,7 +17,8 @@ template <int NS, int BQ, bool BF16, bool MASKED>
 static cudaError_t launch_one(const ScanParams& p, int grid, int device, cudaStream_t st) {
   auto kern = scan_topk_kernel<NS, BQ, kWarps, BF16, MASKED>;
   size_t smem = (size_t)kWarps * TileGeom<NS, BF16>::TILE_BYTES +
-                (size_t)kWarps * BQ * p.cap * 8 + (size_t)kWarps * 8;
+                (size_t)kWarps * BQ * p.cap * 8 + (size_t)kWarps * 8 +
+                (size_t)kWarps * 16 * 4;  // + per-warp slot -> row table of the masked scan
   // the last CTA stages gridDim.x partial lists of kp keys in shared memory
   if (grid > 256) return cudaErrorInvalidConfiguration;
   // (+ the staging rows and peer lists of the fused sharded merge)
