@@ -134,6 +134,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr)
       : "memory");
 }
+// two fp32 multiplies in one instruction (SASS FMUL2): v = {bits(a0)*b.x, bits(a1)*b.y}
+__device__ __forceinline__ void mul2(uint32_t a0, uint32_t a1, float bx, float by, float& v0,
+                                     float& v1) {
+  unsigned long long ra, rb, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "r"(a0), "r"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(bx), "f"(by));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(v0), "=f"(v1) : "l"(rd));
+}
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -316,10 +325,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
           const float4 w = nv[j4];
-          v[4 * j4 + 0] = __uint_as_float(r[4 * j4 + 0]) * w.x;
-          v[4 * j4 + 1] = __uint_as_float(r[4 * j4 + 1]) * w.y;
-          v[4 * j4 + 2] = __uint_as_float(r[4 * j4 + 2]) * w.z;
-          v[4 * j4 + 3] = __uint_as_float(r[4 * j4 + 3]) * w.w;
+          mul2(r[4 * j4 + 0], r[4 * j4 + 1], w.x, w.y, v[4 * j4 + 0], v[4 * j4 + 1]);
+          mul2(r[4 * j4 + 2], r[4 * j4 + 3], w.z, w.w, v[4 * j4 + 2], v[4 * j4 + 3]);
         }
         if (cb + 32 > ncols) {  // last, partial tile of the corpus only
 #pragma unroll
