@@ -432,6 +432,16 @@ class FlatIndex:
                                       scores.ctypes.data, counts.ctypes.data))
         return rows, scores, counts
 
+    def search_into(self, q_ptr: int, nq: int, k: int, rows_ptr: int, scores_ptr: int,
+                    counts_ptr: int, mask: Optional[Mask] = None,
+                    mask_mode: int = TSS_MASK_NONE) -> None:
+        """tss_index_search on caller-owned host buffers given as raw addresses (no per-call
+        numpy allocation or conversion): for latency-sensitive callers and bench.py's e2e leg."""
+        rc = lib().tss_index_search(self.handle, q_ptr, nq, k, mask.handle if mask else None,
+                                    mask_mode, rows_ptr, scores_ptr, counts_ptr)
+        if rc != TSS_OK:
+            _check(rc)
+
     def search_device(self, d_queries: DeviceBuffer, nq: int, k: int, d_out_keys: DeviceBuffer,
                       mask: Optional[Mask] = None, mask_mode: int = TSS_MASK_NONE) -> None:
         _check(lib().tss_index_search_device(self.handle, d_queries.ptr, nq, k,
