@@ -44,6 +44,15 @@ post_rows = rng.integers(0, N, size=int(post_off[-1]), dtype=np.uint32)
 build_s = time.time() - t0
 
 terms = tss.Terms.from_arrays(pool, term_off, post_off, post_rows)
+# N2: the same structure built on the device from the tokenised postings (one tuple per posting)
+vocab = [b"w%06d" % i for i in range(200_000)]
+tuple_of_posting = np.repeat(np.arange(T), npost)
+perm = rng.permutation(tuple_of_posting.size)          # postings arrive in arbitrary order
+ids_dev = (tok[tuple_of_posting[perm]] + 1).astype(np.uint32)
+t0 = time.time()
+built = tss.Terms.build(vocab, ids_dev, post_rows[perm])
+device_build_s = time.time() - t0
+assert built.size() == T
 ix = tss.FlatIndex(dim)
 ix.reserve(N); ix.add_synthetic(0, N, 0x5EED); ix.finalize()
 mask = tss.Mask(N)
@@ -52,7 +61,9 @@ q = orc.gen_rows(0, 4, dim, 0xBEEF)
 # postings under each first token -> pick prefixes by selectivity
 first = tok[:, 0]
 per_first = np.bincount(first, weights=npost, minlength=200_000)
-out = {"rows": N, "terms": int(T), "postings": int(post_off[-1]), "host_build_seconds": build_s, "cases": []}
+out = {"rows": N, "terms": int(T), "postings": int(post_off[-1]), "host_build_seconds": build_s,
+       "device_build_seconds_incl_h2d_and_validation": device_build_s, "cases": []}
+mask_b = tss.Mask(N)
 dense = []
 for _ in range(3):
     ix.search(q[0], k)
@@ -71,6 +82,8 @@ for target in (N * 1e-5, N * 1e-3, N * 1e-1):
     np.bitwise_or.at(want, want_rows >> 5, np.uint32(1) << (want_rows & 31).astype(np.uint32))
     mask.clear(); st = terms.prefix_mask(prefix, mask)
     ok = bool(np.array_equal(mask.download(), want))
+    mask_b.clear(); built.prefix_mask(prefix, mask_b)
+    ok = ok and bool(np.array_equal(mask_b.download(), want))  # device-built trie: same mask
     for _ in range(2):
         mask.clear(); terms.prefix_mask(prefix, mask, want_stats=False); ix.search(q[0], k, mask, tss.TSS_MASK_INCLUDE)
     tm = ts = 0.0

@@ -194,6 +194,19 @@ typedef struct tss_prefix_stats {
 int tss_terms_create(tss_terms** out, const char* pool, const uint64_t* term_off,
                      const uint64_t* post_off, const uint32_t* post_rows, uint64_t nterms,
                      int device);
+/* N2: build the same structure on the device from tokenised postings instead
+ * of TrieNode::insert's one-HashMap-hop-per-token (src/trie.rs:211-221).  The vocabulary is V
+ * unique tokens in byte order (pool + offsets[V+1]; no byte <= 0x20, so tuple order equals the
+ * byte order of the ' '-joined strings); posting i is the tuple token_ids[i*max_tokens ..]
+ * (id = vocabulary index + 1, 0 = padding at the end; an all-zero tuple is the root) with row
+ * rows[i].  Postings of a term keep their input order (document_refs.push, src/trie.rs:219). */
+int tss_terms_build(tss_terms** out, const char* vocab_pool, const uint64_t* vocab_off,
+                    uint32_t vocab_size, const uint32_t* token_ids, uint32_t max_tokens,
+                    const uint32_t* rows, uint64_t n_postings, int device);
+int tss_terms_sizes(const tss_terms* t, uint64_t* nterms, uint64_t* pool_bytes, uint64_t* npostings);
+/* copy the flattened arrays back (caller-allocated per tss_terms_sizes) */
+int tss_terms_export(const tss_terms* t, char* pool, uint64_t* term_off, uint64_t* post_off,
+                     uint32_t* post_rows);
 uint64_t tss_terms_size(const tss_terms* t);
 void tss_terms_destroy(tss_terms* t);
 int tss_prefix_mask(tss_terms* t, const char* prefix, uint32_t len, int kind, tss_mask* out,

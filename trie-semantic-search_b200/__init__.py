@@ -41,6 +41,7 @@ ABI_SYMBOLS = [
     "tss_event_destroy", "tss_launch_count", "tss_index_debug_phases",
     "tss_index_save", "tss_index_load",
     "tss_mask_clear_rows", "tss_columns_create", "tss_columns_destroy", "tss_filter_mask",
+    "tss_terms_build", "tss_terms_sizes", "tss_terms_export",
 ]
 
 
@@ -117,6 +118,9 @@ def lib() -> C.CDLL:
         "tss_columns_create": (i32, [C.POINTER(vp), vp, vp, u64, i32]),
         "tss_columns_destroy": (None, [vp]),
         "tss_filter_mask": (i32, [vp, vp, u32, C.c_int32, C.c_int32, vp, i32]),
+        "tss_terms_build": (i32, [C.POINTER(vp), vp, vp, u32, vp, u32, vp, u64, i32]),
+        "tss_terms_sizes": (i32, [vp, pu64, pu64, pu64]),
+        "tss_terms_export": (i32, [vp, vp, vp, vp, vp]),
         "tss_index_save": (i32, [vp, C.c_char_p]),
         "tss_index_load": (i32, [C.POINTER(vp), C.c_char_p, i32]),
     }
@@ -334,6 +338,41 @@ class Terms:
         _check(lib().tss_terms_create(C.byref(p), pool_buf.ctypes.data, toff.ctypes.data,
                                       poff.ctypes.data, rows_buf.ctypes.data, toff.size - 1, device))
         self.handle, self.device = p.value, device
+
+    @classmethod
+    def build(cls, vocab: Sequence[bytes], token_ids, rows, device: int = 0) -> "Terms":
+        """N2: device-side construction from tokenised postings (token id = vocab index + 1)."""
+        self = cls.__new__(cls)
+        vpool = b"".join(vocab)
+        voff = np.zeros(len(vocab) + 1, dtype=np.uint64)
+        np.cumsum([len(v) for v in vocab], out=voff[1:])
+        ids = np.ascontiguousarray(token_ids, dtype=np.uint32)
+        if ids.ndim == 1:
+            ids = ids.reshape(-1, 1)
+        r = np.ascontiguousarray(rows, dtype=np.uint32)
+        assert ids.shape[0] == r.size
+        vbuf = np.frombuffer(vpool, dtype=np.uint8) if vpool else np.zeros(1, dtype=np.uint8)
+        p = C.c_void_p()
+        _check(lib().tss_terms_build(C.byref(p), vbuf.ctypes.data, voff.ctypes.data, len(vocab),
+                                     ids.ctypes.data if ids.size else None, ids.shape[1],
+                                     r.ctypes.data if r.size else None, r.size, device))
+        self.handle, self.device = p.value, device
+        return self
+
+    def export(self):
+        """-> (terms: list[bytes], postings: list[list[int]]) copied back from the device"""
+        nt, pb, npst = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        _check(lib().tss_terms_sizes(self.handle, C.byref(nt), C.byref(pb), C.byref(npst)))
+        pool = np.zeros(max(pb.value, 1), dtype=np.uint8)
+        toff = np.zeros(nt.value + 1, dtype=np.uint64)
+        poff = np.zeros(nt.value + 1, dtype=np.uint64)
+        rows = np.zeros(max(npst.value, 1), dtype=np.uint32)
+        _check(lib().tss_terms_export(self.handle, pool.ctypes.data, toff.ctypes.data,
+                                      poff.ctypes.data, rows.ctypes.data))
+        raw = pool.tobytes()
+        terms = [raw[int(toff[i]):int(toff[i + 1])] for i in range(nt.value)]
+        posts = [rows[int(poff[i]):int(poff[i + 1])].tolist() for i in range(nt.value)]
+        return terms, posts
 
     def size(self) -> int:
         return int(lib().tss_terms_size(self.handle))

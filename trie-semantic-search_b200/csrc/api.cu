@@ -20,6 +20,7 @@
 #include "../../include/tss.h"
 #include "aux_kernels.cuh"
 #include "gemm_topk.cuh"
+#include "terms_build.cuh"
 #include "scan.cuh"
 #include "scan_launch.h"
 
@@ -1310,6 +1311,96 @@ int tss_terms_create(tss_terms** out, const char* pool, const uint64_t* term_off
     return cuda_fail(e, "terms upload");
   }
   *out = t;
+  return TSS_OK;
+}
+
+// ---- N2: build the flattened trie on the device -------------------------------------------------
+int tss_terms_build(tss_terms** out, const char* vocab_pool, const uint64_t* vocab_off,
+                    uint32_t vocab_size, const uint32_t* token_ids, uint32_t max_tokens,
+                    const uint32_t* rows, uint64_t n_postings, int device) {
+  if (!out) return fail(TSS_ERR_INVALID_ARG, "out is NULL");
+  *out = nullptr;
+  if (!vocab_off || (vocab_size && !vocab_pool))
+    return fail(TSS_ERR_INVALID_ARG, "vocabulary is NULL");
+  if (n_postings && (!token_ids || !rows || !max_tokens))
+    return fail(TSS_ERR_INVALID_ARG, "postings are NULL");
+  if (n_postings >= 0x7FFFFFFFull) return fail(TSS_ERR_INVALID_ARG, "at most 2^31-1 postings per build");
+  if (vocab_off[0] != 0) return fail(TSS_ERR_INVALID_ARG, "vocab_off must start at 0");
+  // token ids follow byte order only if the vocabulary is byte-sorted, and tuple order equals
+  // the byte order of the ' '-joined strings only if no token holds a byte <= ' '
+  for (uint32_t i = 0; i < vocab_size; ++i) {
+    if (vocab_off[i + 1] <= vocab_off[i])
+      return fail(TSS_ERR_INVALID_ARG, "vocabulary token %u is empty or offsets decrease", i);
+    for (uint64_t b = vocab_off[i]; b < vocab_off[i + 1]; ++b)
+      if ((unsigned char)vocab_pool[b] <= 0x20)
+        return fail(TSS_ERR_INVALID_ARG, "vocabulary token %u holds a byte <= 0x20", i);
+    if (i) {
+      uint64_t la = vocab_off[i] - vocab_off[i - 1], lb = vocab_off[i + 1] - vocab_off[i];
+      int c = memcmp(vocab_pool + vocab_off[i - 1], vocab_pool + vocab_off[i], la < lb ? la : lb);
+      if (c > 0 || (c == 0 && la >= lb))
+        return fail(TSS_ERR_INVALID_ARG, "vocabulary not strictly byte-sorted at token %u", i);
+    }
+  }
+  for (uint64_t i = 0; i < n_postings; ++i) {
+    bool ended = false;
+    for (uint32_t j = 0; j < max_tokens; ++j) {
+      uint32_t id = token_ids[i * max_tokens + j];
+      if (id > vocab_size) return fail(TSS_ERR_INVALID_ARG, "posting %llu: token id %u > vocabulary", (unsigned long long)i, id);
+      if (id && ended) return fail(TSS_ERR_INVALID_ARG, "posting %llu: token after padding", (unsigned long long)i);
+      if (!id) ended = true;
+    }
+  }
+  int ndev = tss_device_count();
+  if (ndev == 0) return fail(TSS_ERR_CUDA, "no CUDA device visible (libtss has no CPU path)");
+  if (device < 0 || device >= ndev) return fail(TSS_ERR_INVALID_ARG, "device %d of %d", device, ndev);
+  DeviceGuard g(device);
+  tss_terms* t = new (std::nothrow) tss_terms();
+  if (!t) return fail(TSS_ERR_OOM, "host allocation failed");
+  t->device = device;
+  t->key_cap = 4096;
+  cudaError_t e = cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaMalloc(&t->d_keys, t->key_cap);
+  if (e == cudaSuccess) e = cudaMallocHost(&t->h_keys, t->key_cap);
+  if (e == cudaSuccess) e = cudaMalloc(&t->d_bounds, 8 * sizeof(uint64_t));
+  tss::BuiltTerms b;
+  if (e == cudaSuccess)
+    e = tss::build_terms_device(vocab_pool, vocab_off, vocab_size, token_ids, max_tokens, rows,
+                                n_postings, t->stream, &b);
+  if (e != cudaSuccess) {
+    tss_terms_destroy(t);
+    return cuda_fail(e, "terms build");
+  }
+  g_launches.fetch_add(2 * max_tokens + 6, std::memory_order_relaxed);
+  t->d_pool = b.d_pool;
+  t->d_term_off = b.d_term_off;
+  t->d_post_off = b.d_post_off;
+  t->d_post_rows = b.d_post_rows;
+  t->nterms = b.nterms;
+  t->pool_bytes = b.pool_bytes;
+  t->nposts = b.nposts;
+  *out = t;
+  return TSS_OK;
+}
+
+int tss_terms_sizes(const tss_terms* t, uint64_t* nterms, uint64_t* pool_bytes, uint64_t* npostings) {
+  if (!t) return fail(TSS_ERR_INVALID_ARG, "terms is NULL");
+  if (nterms) *nterms = t->nterms;
+  if (pool_bytes) *pool_bytes = t->pool_bytes;
+  if (npostings) *npostings = t->nposts;
+  return TSS_OK;
+}
+
+int tss_terms_export(const tss_terms* t, char* pool, uint64_t* term_off, uint64_t* post_off,
+                     uint32_t* post_rows) {
+  if (!t || !term_off || !post_off) return fail(TSS_ERR_INVALID_ARG, "NULL argument");
+  if ((t->pool_bytes && !pool) || (t->nposts && !post_rows))
+    return fail(TSS_ERR_INVALID_ARG, "NULL argument");
+  DeviceGuard g(t->device);
+  CU(cudaStreamSynchronize(t->stream));
+  if (t->pool_bytes) CU(cudaMemcpy(pool, t->d_pool, t->pool_bytes, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(term_off, t->d_term_off, (t->nterms + 1) * 8, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(post_off, t->d_post_off, (t->nterms + 1) * 8, cudaMemcpyDeviceToHost));
+  if (t->nposts) CU(cudaMemcpy(post_rows, t->d_post_rows, t->nposts * 4, cudaMemcpyDeviceToHost));
   return TSS_OK;
 }
 

@@ -96,6 +96,14 @@ extern "C" {
         row_base: u64, stats: *mut tss_prefix_stats,
     ) -> c_int;
 
+    pub fn tss_terms_build(
+        out: *mut *mut tss_terms, vocab_pool: *const c_char, vocab_off: *const u64, vocab_size: u32,
+        token_ids: *const u32, max_tokens: u32, rows: *const u32, n_postings: u64, device: c_int,
+    ) -> c_int;
+    pub fn tss_terms_sizes(t: *const tss_terms, nterms: *mut u64, pool_bytes: *mut u64, npostings: *mut u64) -> c_int;
+    pub fn tss_terms_export(
+        t: *const tss_terms, pool: *mut c_char, term_off: *mut u64, post_off: *mut u64, post_rows: *mut u32,
+    ) -> c_int;
     pub fn tss_index_save(ix: *mut tss_index, path: *const c_char) -> c_int;
     pub fn tss_index_load(out: *mut *mut tss_index, path: *const c_char, device: c_int) -> c_int;
     pub fn tss_mask_clear_rows(m: *mut tss_mask, rows: *const u32, n: u64, row_base: u64) -> c_int;
