@@ -141,7 +141,7 @@ def cpu_baseline(orc, args, queries):
         orc.cosine_topk(rows, queries[nqs % len(queries)], args.k)
         nqs += 1
         dt = time.perf_counter() - t0
-        if dt > 10.0 or nqs >= 200:
+        if dt > 10.0 or nqs >= 1000:
             break
     qps_sample = nqs / dt
     scale = n / args.rows
