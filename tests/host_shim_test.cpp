@@ -7,6 +7,7 @@
 #include <cstring>
 #include <random>
 #include <string>
+#include <thread>
 
 #include "../include/tss.h"
 #include "../oracle/oracle.h"
@@ -342,6 +343,41 @@ static void engine_hybrid() {
         CHECK(one[j].case_metadata.id == batch[i][j].case_metadata.id &&
               one[j].score == batch[i][j].score && one[j].match_type == batch[i][j].match_type);
     }
+  }
+  // N4: the micro-batcher answers concurrent submitters with batched device calls
+  {
+    QueryBatcher batcher(eng, 16, 2000);
+    const char* texts[] = {"Miranda v. Arizona", "Roe v. Wade", "nothing here", "case 12", "x"};
+    std::vector<std::thread> threads;
+    std::vector<std::vector<std::future<std::vector<SearchResult>>>> futs(4);
+    for (int t = 0; t < 4; ++t)
+      threads.emplace_back([&, t] {
+        for (int i = 0; i < 10; ++i) {
+          SearchQuery q;
+          q.query = texts[(t + i) % 5];
+          futs[t].push_back(batcher.submit(q));
+        }
+      });
+    for (auto& th : threads) th.join();
+    size_t answered = 0, rejected = 0;
+    for (int t = 0; t < 4; ++t)
+      for (int i = 0; i < 10; ++i) {
+        SearchQuery q;
+        q.query = texts[(t + i) % 5];
+        try {
+          auto got = futs[t][i].get();
+          auto want = eng.search_with_params(q);
+          CHECK(got.size() == want.size());
+          for (size_t j = 0; j < got.size() && j < want.size(); ++j)
+            CHECK(got[j].case_metadata.id == want[j].case_metadata.id && got[j].score == want[j].score);
+          ++answered;
+        } catch (const SearchError& e) {
+          CHECK(e.kind == SearchError::InvalidSearchQuery && q.query == "x");
+          ++rejected;
+        }
+      }
+    CHECK(answered == 32 && rejected == 8);
+    CHECK(batcher.queries_run() == 40 && batcher.batches_run() < 40);
   }
   // M2: >= max_results exact hits skip the vector pass entirely
   q = SearchQuery();

@@ -654,4 +654,64 @@ std::vector<SearchResult> SearchEngine::execute_hybrid_search(const SearchQuery&
   return all_results;
 }
 
+// ---- QueryBatcher ------------------------------------------------------------------------------
+QueryBatcher::QueryBatcher(SearchEngine& engine, size_t max_batch, uint64_t max_wait_us)
+    : engine_(engine), max_batch_(max_batch ? max_batch : 1), max_wait_us_(max_wait_us),
+      worker_([this] { run(); }) {}
+
+QueryBatcher::~QueryBatcher() {
+  {
+    std::lock_guard<std::mutex> l(mu_);
+    stop_ = true;
+  }
+  cv_.notify_all();
+  worker_.join();
+}
+
+std::future<std::vector<SearchResult>> QueryBatcher::submit(SearchQuery query) {
+  std::promise<std::vector<SearchResult>> p;
+  auto f = p.get_future();
+  {
+    std::lock_guard<std::mutex> l(mu_);
+    queue_.emplace_back(std::move(query), std::move(p));
+  }
+  cv_.notify_all();
+  return f;
+}
+
+void QueryBatcher::run() {
+  for (;;) {
+    std::vector<SearchQuery> batch;
+    std::vector<std::promise<std::vector<SearchResult>>> promises;
+    {
+      std::unique_lock<std::mutex> l(mu_);
+      cv_.wait(l, [&] { return stop_ || !queue_.empty(); });
+      if (queue_.empty()) return;  // stop_ and nothing left to answer
+      if (queue_.size() < max_batch_ && max_wait_us_)  // give the batch a moment to fill
+        cv_.wait_for(l, std::chrono::microseconds(max_wait_us_),
+                     [&] { return stop_ || queue_.size() >= max_batch_; });
+      while (!queue_.empty() && batch.size() < max_batch_) {
+        batch.push_back(std::move(queue_.front().first));
+        promises.push_back(std::move(queue_.front().second));
+        queue_.pop_front();
+      }
+    }
+    try {
+      auto results = engine_.search_batch(batch);
+      for (size_t i = 0; i < promises.size(); ++i) promises[i].set_value(std::move(results[i]));
+    } catch (...) {
+      // one bad query (e.g. too short) must not fail its batch mates: answer one by one
+      for (size_t i = 0; i < promises.size(); ++i) {
+        try {
+          promises[i].set_value(engine_.search_batch({batch[i]})[0]);
+        } catch (...) {
+          promises[i].set_exception(std::current_exception());
+        }
+      }
+    }
+    ++batches_;
+    queries_ += batch.size();
+  }
+}
+
 }  // namespace tss_host

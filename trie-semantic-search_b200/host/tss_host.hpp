@@ -11,8 +11,13 @@
 #pragma once
 
 #include <array>
+#include <condition_variable>
 #include <cstdint>
+#include <deque>
 #include <functional>
+#include <future>
+#include <mutex>
+#include <thread>
 #include <map>
 #include <memory>
 #include <optional>
@@ -352,6 +357,35 @@ class SearchEngine {
     int64_t timestamp;
   };
   std::unordered_map<std::string, Cached> query_cache_;  // QueryCache :104-116,344-385
+};
+
+// ---- N4: micro-batcher in front of the engine ---------------------------------------------------
+// The reference funnels every vector search through one tokio write lock
+// (src/search.rs:249-252): concurrent requests queue and each streams the corpus on its own.
+// QueryBatcher owns the engine on one worker thread; callers submit() from any thread and get
+// a future; the worker drains up to max_batch queued queries (waiting at most max_wait_us for
+// the batch to fill) and answers them with ONE SearchEngine::search_batch call.
+class QueryBatcher {
+ public:
+  QueryBatcher(SearchEngine& engine, size_t max_batch = 64, uint64_t max_wait_us = 200);
+  ~QueryBatcher();
+  QueryBatcher(const QueryBatcher&) = delete;
+  QueryBatcher& operator=(const QueryBatcher&) = delete;
+  std::future<std::vector<SearchResult>> submit(SearchQuery query);
+  size_t batches_run() const { return batches_; }
+  size_t queries_run() const { return queries_; }
+
+ private:
+  void run();
+  SearchEngine& engine_;
+  size_t max_batch_;
+  uint64_t max_wait_us_;
+  std::mutex mu_;
+  std::condition_variable cv_;
+  std::deque<std::pair<SearchQuery, std::promise<std::vector<SearchResult>>>> queue_;
+  bool stop_ = false;
+  size_t batches_ = 0, queries_ = 0;
+  std::thread worker_;
 };
 
 }  // namespace tss_host
