@@ -433,6 +433,8 @@ int enqueue_gemm(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
   // the threshold pass yields `split` maxima per sampled tile (one per column part)
   const uint32_t split = (uint32_t)tss::gemm_col_split();
   uint32_t sample = k * 8 / split > 1024 ? k * 8 / split : 1024;
+  if (const char* sm = getenv("TSS_GEMM_SAMPLE")) sample = (uint32_t)atoi(sm);
+  if (sample < (k + split - 1) / split) sample = (k + split - 1) / split;
   if (sample > kGemmMaxSample / split) sample = kGemmMaxSample / split;
   if (sample > num_tiles) sample = num_tiles;
   int nslices = ix->num_sms / (int)mb;
@@ -462,6 +464,8 @@ int enqueue_gemm(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
   p.cand = g.d_cand;
   p.cand_count = g.d_cand_count;
   p.cand_cap = cap_s;
+  p.prefetch_ahead = 4;
+  if (const char* pf = getenv("TSS_GEMM_PREFETCH")) p.prefetch_ahead = (uint32_t)atoi(pf);
   if (const char* dbg = getenv("TSS_GEMM_DEBUG")) p.debug = (uint32_t)atoi(dbg);
   const int kb = (int)(kpad / 64);
   p.mode = 0;
@@ -972,7 +976,7 @@ int tss_index_search(tss_index* ix, const float* queries, uint32_t nq, uint32_t 
     CU(cudaStreamSynchronize(ix->stream));
     if (merged && *ix->h_status) {
       *ix->h_status = 0;
-      return fail(TSS_ERR_NCCL, "a rank of the shard group did not deliver its top-k within 5 s");
+      return fail(TSS_ERR_NCCL, "a rank of the shard group did not deliver its top-k within 20 s");
     }
     tss_unpack_keys(ix->h_keys, (uint64_t)n * k, out_rows + (size_t)q0 * k,
                     out_scores + (size_t)q0 * k);

@@ -223,7 +223,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       // access pattern (a page is re-opened once per k-block).  A tile's rows are one
       // contiguous byte range, so the CTA that owns query block 0 of each slice pulls whole
       // tiles into L2 a few tiles ahead with sequential bulk prefetches; the boxes then hit L2.
-      constexpr uint32_t kPrefetchAhead = 4;
+      const uint32_t kPrefetchAhead = p.prefetch_ahead;
       const uint32_t tile_bytes = kBlockN * KB * kBlockK * 2;
       auto prefetch_tile = [&](uint32_t ii) {
         if (m_blk != 0 || ii >= count) return;

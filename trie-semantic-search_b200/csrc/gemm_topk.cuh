@@ -20,6 +20,7 @@ struct GemmParams {
   uint64_t* cand;          // mode 1 out: [mb*128][nslices*split][cand_cap] keys (unscaled by 1/|q|)
   uint32_t* cand_count;    // [mb*128][nslices*split] survivors seen (may exceed cand_cap)
   uint32_t cand_cap;       // per (query, slice, column part) list
+  uint32_t prefetch_ahead; // tiles of contiguous L2 prefetch ahead of the TMA boxes (0 = off)
   uint32_t debug;          // diagnostics: 1 = no epilogue math, 2 = no MMA issue, 4 = no corpus TMA
 };
 

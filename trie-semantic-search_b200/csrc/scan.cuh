@@ -52,7 +52,7 @@ struct ScanParams {
   // group, mapped into this process with CUDA IPC; xchg_nranks == 0 switches it off
   uint8_t* xchg_peer[8];
   uint32_t xchg_nranks, xchg_rank, xchg_seq;
-  unsigned int* xchg_status;  // set to 1 when a peer never showed up (5 s), instead of hanging
+  unsigned int* xchg_status;  // set to 1 when a peer never showed up (20 s), instead of hanging
   // exchanges of consecutive launches must happen in launch order on each GPU (launches
   // overlap under PDL): *xchg_turn is the sequence number of the last finished exchange
   unsigned int* xchg_turn;
@@ -597,7 +597,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_topk_kernel(const __grid_c
       while ((int32_t)(ld_acquire_sys(flag) - p.xchg_seq) < 0) {
         __nanosleep(64);
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
-        if (t1 - t0 > 5000000000ull) {  // a rank died: report, do not spin forever
+        if (t1 - t0 > 20000000000ull) {  // a rank died: report, do not spin forever
           atomicExch(p.xchg_status, 1u);
           break;
         }
