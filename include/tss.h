@@ -214,6 +214,8 @@ int tss_prefix_mask(tss_terms* t, const char* prefix, uint32_t len, int kind, ts
 
 /* ---- plumbing for callers that time or pipeline the device path ------------ */
 void* tss_index_stream(tss_index* ix); /* cudaStream_t the index enqueues on */
+/* waits for the index stream; also reports (TSS_ERR_NCCL) a sharded tss_index_search_device
+ * whose peers never delivered their top-k */
 int tss_index_sync(tss_index* ix);
 int tss_dev_alloc(int device, uint64_t bytes, void** out);
 int tss_dev_free(int device, void* p);

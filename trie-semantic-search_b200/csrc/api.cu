@@ -1519,6 +1519,10 @@ int tss_index_sync(tss_index* ix) {
   if (!ix) return fail(TSS_ERR_INVALID_ARG, "index is NULL");
   DeviceGuard g(ix->device);
   CU(cudaStreamSynchronize(ix->stream));
+  if (ix->h_status && *ix->h_status) {  // a fused sharded search gave up waiting for a peer
+    *ix->h_status = 0;
+    return fail(TSS_ERR_NCCL, "a rank of the shard group did not deliver its top-k within 20 s");
+  }
   return TSS_OK;
 }
 
