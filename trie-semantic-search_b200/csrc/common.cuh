@@ -31,6 +31,17 @@ __device__ __forceinline__ float finish_score(float dot, float sqrt_nq2, float n
   return s;
 }
 
+// ---- packed fp32 FMA (SASS FFMA2): two independent round-to-nearest fmas in one instruction,
+// bit-identical to two __fmaf_rn calls, half the issue slots ------------------------------------
+__device__ __forceinline__ void fma2(float ax, float ay, float bx, float by, float& cx, float& cy) {
+  unsigned long long ra, rb, rc;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(ax), "f"(ay));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(bx), "f"(by));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(cx), "f"(cy));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(rc) : "l"(ra), "l"(rb));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(cx), "=f"(cy) : "l"(rc));
+}
+
 // ---- transposed butterfly over RG rows ------------------------------------------
 // v[r] is this lane's partial for row r.  On return v[0] holds the full 32-lane
 // sum for row (lane >> (5 - log2 RG)); the addition tree per row is exactly

@@ -444,16 +444,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_topk_kernel(const __grid_c
             e = *reinterpret_cast<const float4*>(rp + s * 512 + lane * 16);
           }
 #pragma unroll
-          for (int b = 0; b < BQ; ++b) {
-            d[b][0] = __fmaf_rn(q[b][s].x, e.x, d[b][0]);
-            d[b][1] = __fmaf_rn(q[b][s].y, e.y, d[b][1]);
-            d[b][2] = __fmaf_rn(q[b][s].z, e.z, d[b][2]);
-            d[b][3] = __fmaf_rn(q[b][s].w, e.w, d[b][3]);
+          for (int b = 0; b < BQ; ++b) {  // FFMA2: the same four fmas, two per instruction
+            fma2(q[b][s].x, q[b][s].y, e.x, e.y, d[b][0], d[b][1]);
+            fma2(q[b][s].z, q[b][s].w, e.z, e.w, d[b][2], d[b][3]);
           }
-          n0 = __fmaf_rn(e.x, e.x, n0);
-          n1 = __fmaf_rn(e.y, e.y, n1);
-          n2 = __fmaf_rn(e.z, e.z, n2);
-          n3 = __fmaf_rn(e.w, e.w, n3);
+          fma2(e.x, e.y, e.x, e.y, n0, n1);
+          fma2(e.z, e.w, e.z, e.w, n2, n3);
         }
 #pragma unroll
         for (int b = 0; b < BQ; ++b)
