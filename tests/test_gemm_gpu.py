@@ -120,3 +120,32 @@ def test_other_dimensions(tss, orc, dim):
     wi, ws = _f64_topk(_bf16(rows), _bf16(q), k)
     assert _recall(gr, wi) >= 0.99
     np.testing.assert_allclose(gs[:, 0], ws[:, 0], rtol=3e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("mode", ["include", "exclude"])
+def test_masked_large_batch(tss, orc, mode):
+    """Masks ride along on the tensor-core path: a masked row's 1/|row| is NaN in the epilogue."""
+    n, nq, k, dim = 160_000, 96, 20, 384
+    rows = orc.gen_rows(0, n, dim, SEED)
+    q = orc.gen_rows(0, nq, dim, 0xBEEF)
+    rng = np.random.default_rng(4)
+    bits = rng.random(n) < (0.3 if mode == "include" else 0.6)
+    bits[:2048] = mode == "exclude"  # whole tiles without a live row
+    words = np.zeros((n + 31) // 32, dtype=np.uint32)
+    idx = np.nonzero(bits)[0]
+    np.bitwise_or.at(words, idx >> 5, (np.uint32(1) << (idx & 31).astype(np.uint32)))
+    ix = tss.FlatIndex(dim, tss.TSS_BF16)
+    ix.add(rows)
+    ix.finalize()
+    m = tss.Mask(n)
+    m.upload(words)
+    before = tss.launch_count()
+    gr, gs, gc = ix.search(q, k, m, tss.TSS_MASK_INCLUDE if mode == "include" else tss.TSS_MASK_EXCLUDE)
+    assert tss.launch_count() - before <= 6  # the K2 pipeline (+ the one-off row norms), not nq/4 scans
+    live = bits if mode == "include" else ~bits
+    assert np.all(gc == k) and np.all(live[gr])  # only live rows come back
+    rb, qb = _bf16(rows).astype(np.float64), _bf16(q).astype(np.float64)
+    s = (qb @ rb.T) / (np.linalg.norm(qb, axis=1)[:, None] * np.linalg.norm(rb, axis=1)[None, :])
+    s[:, ~live] = -np.inf
+    wi = np.argsort(-s, axis=1, kind="stable")[:, :k]
+    assert _recall(gr, wi) >= 0.995

@@ -369,8 +369,9 @@ int ensure_gather_ws(tss_index* ix) {
 }
 
 bool gemm_eligible(const tss_index* ix, uint32_t nq, uint32_t k, int mode) {
-  return ix->storage == TSS_BF16 && ix->ns <= 3 && mode == TSS_MASK_NONE &&
-         nq >= ix->gemm_min_nq && ix->n_rows >= 4ull * 256 * k && k <= TSS_MAX_K;
+  (void)mode;  // masks ride along: a masked row's 1/|row| is NaN in the epilogue
+  return ix->storage == TSS_BF16 && ix->ns <= 3 && nq >= ix->gemm_min_nq &&
+         ix->n_rows >= 4ull * 256 * k && k <= TSS_MAX_K;
 }
 
 int ensure_gemm_ws(tss_index* ix) {
@@ -423,7 +424,8 @@ int enqueue_scan_rounds(tss_index* ix, const float* d_queries, uint32_t nq, uint
 // K2: nq <= kWsQueries device-resident fp32 queries -> d_out (nq x k local keys).
 // Synchronises the stream once to check the survivor lists for overflow; queries whose list
 // overflowed (adversarially clustered scores) are redone exactly by the K1 scan.
-int enqueue_gemm(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k, uint64_t* d_out) {
+int enqueue_gemm(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
+                 const tss_mask* mask, int mode, uint64_t* d_out) {
   int rc = ensure_gemm_ws(ix);
   if (rc) return rc;
   tss_index::Gemm& g = ix->gemm;
@@ -455,6 +457,8 @@ int enqueue_gemm(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
   p.row_base = (uint32_t)ix->row_base;
   p.rows_bytes = ix->d_rows;
   p.inv_norm = g.d_inv_norm;
+  p.mask = mode != TSS_MASK_NONE ? mask->d_words : nullptr;
+  p.mask_mode = mode;
   p.mb = mb;
   p.num_tiles = num_tiles;
   p.sample_stride = num_tiles / sample;
@@ -487,10 +491,10 @@ int enqueue_gemm(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
     if (!g.h_cand_count[qi]) continue;
     ix->xchg.suppress = true;
     if (k > TSS_MAX_FUSED_K)
-      rc = enqueue_scan_rounds(ix, d_queries + (size_t)qi * ix->dim, 1, k, nullptr, TSS_MASK_NONE,
+      rc = enqueue_scan_rounds(ix, d_queries + (size_t)qi * ix->dim, 1, k, mask, mode,
                                d_out + (size_t)qi * k);
     else
-      rc = enqueue_scan(ix, d_queries + (size_t)qi * ix->dim, 1, k, nullptr, TSS_MASK_NONE,
+      rc = enqueue_scan(ix, d_queries + (size_t)qi * ix->dim, 1, k, mask, mode,
                         d_out + (size_t)qi * k);
     ix->xchg.suppress = false;
     if (rc) return rc;
@@ -555,7 +559,8 @@ int enqueue_local(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k
   }
   for (uint32_t q0 = 0; q0 < nq; q0 += kWsQueries) {
     uint32_t n = nq - q0 < kWsQueries ? nq - q0 : kWsQueries;
-    int rc = enqueue_gemm(ix, d_queries + (size_t)q0 * ix->dim, n, k, d_out + (size_t)q0 * k);
+    int rc = enqueue_gemm(ix, d_queries + (size_t)q0 * ix->dim, n, k, mask, mode,
+                          d_out + (size_t)q0 * k);
     if (rc) return rc;
   }
   return TSS_OK;
@@ -954,7 +959,7 @@ int tss_index_search(tss_index* ix, const float* queries, uint32_t nq, uint32_t 
     bool merged = false;
     bool direct = false;  // result already lands in h_keys
     if (gemm) {
-      rc = enqueue_gemm(ix, ix->d_queries, n, k, ix->d_keys);
+      rc = enqueue_gemm(ix, ix->d_queries, n, k, mask, mask_mode, ix->d_keys);
     } else if (rounds) {
       rc = enqueue_scan_rounds(ix, ix->d_queries, n, k, mask, mask_mode, ix->d_keys);
     } else {

@@ -304,7 +304,15 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       float* ninv = s_ninv + acc * kBlockN;
       if (et < (uint32_t)kBlockN) {
         uint64_t r = row0 + et;
-        ninv[et] = r < p.n_rows ? __ldg(p.inv_norm + r) : 0.f;
+        float w = r < p.n_rows ? __ldg(p.inv_norm + r) : 0.f;
+        if (p.mask && r < p.n_rows) {
+          uint32_t bit = (__ldg(p.mask + (r >> 5)) >> (uint32_t)(r & 31)) & 1u;
+          if (p.mask_mode == 2) bit ^= 1u;  // TSS_MASK_EXCLUDE
+          // a masked row's score becomes NaN: fmax drops it from every maximum and
+          // `v >= thr` is false, at no cost in the per-element code
+          if (!bit) w = __uint_as_float(0x7FC00000u);
+        }
+        ninv[et] = w;
       }
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       mbar_wait(bar_tfull + 8 * acc, use & 1u);

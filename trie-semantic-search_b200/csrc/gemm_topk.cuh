@@ -11,6 +11,8 @@ struct GemmParams {
   uint32_t row_base;       // global id of local row 0
   const uint8_t* rows_bytes;  // the bf16 matrix itself (for contiguous L2 prefetches)
   const float* inv_norm;   // [n_rows] 1/|row|
+  const uint32_t* mask;    // row mask words (bit r&31 of word r>>5 <-> local row r) or null
+  int mask_mode;           // TSS_MASK_*: masked rows get 1/|row| = NaN, which fmax and >= ignore
   uint32_t mb;             // 128-query blocks in this launch (grid = nslices * mb)
   uint32_t num_tiles;      // ceil(n_rows / 256)
   int mode;                // 0 = per-tile maxima over the sample, 1 = collect survivors
