@@ -18,8 +18,9 @@
 // are bit-identical to oracle/oracle.cpp:canon_dot_norm.
 //
 // Top-k: each warp keeps an unsorted candidate list in shared memory guarded
-// by a running threshold (its current k-th best key); the list is pruned with
-// a warp bitonic sort when full.  Lists are merged per CTA, written as
+// by a running threshold (its current k-th best key); a full list is pruned
+// (k <= 32: k rounds of a REDUX warp max over two keys per lane; else a warp
+// bitonic sort).  Lists are merged per CTA, written as
 // per-CTA partials, and the last CTA to finish (atomic ticket) merges the
 // partials into the final k keys -- one launch per query batch.  Both merges are
 // warp tournaments (k rounds of a 32-lane max) rather than sort networks.
