@@ -12,11 +12,12 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--rows", type=int, default=10_000_000)
 ap.add_argument("--nq", type=int, default=1024)
 ap.add_argument("--k", type=int, default=100)
+ap.add_argument("--dim", type=int, default=384)
 ap.add_argument("--iters", type=int, default=5, help="timed batches (5 = burst clocks; >= 200 "
                 "reaches the 1 kW power cap and sustained clocks)")
 ap.add_argument("--recall-queries", type=int, default=0)
 a = ap.parse_args()
-dim = 384
+dim = a.dim
 ix = tss.FlatIndex(dim, tss.TSS_BF16)
 ix.reserve(a.rows)
 ix.add_synthetic(0, a.rows, 0x5EED)
@@ -39,7 +40,7 @@ ix.sync()
 ms = e0.elapsed_ms(e1) / a.iters
 flops = 2.0 * a.nq * a.rows * dim
 peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
-out = {"rows": a.rows, "nq": a.nq, "k": a.k, "ms_per_batch": ms, "queries_per_s": a.nq / ms * 1e3,
+out = {"rows": a.rows, "dim": dim, "nq": a.nq, "k": a.k, "ms_per_batch": ms, "queries_per_s": a.nq / ms * 1e3,
        "achieved_tflops_algorithmic": flops / ms / 1e9, "peak_tflops_burst": peaks["bf16_tflops"],
        "frac_of_burst": flops / ms / 1e9 / peaks["bf16_tflops"],
        "frac_of_sustained": flops / ms / 1e9 / peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]),

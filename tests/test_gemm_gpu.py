@@ -104,9 +104,10 @@ def test_small_batches_keep_using_the_scan(tss, orc):
     assert np.array_equal(got[1].view(np.uint32), want[1].view(np.uint32))
 
 
-@pytest.mark.parametrize("dim", [64, 100, 256, 300])
+@pytest.mark.parametrize("dim", [64, 100, 256, 300, 512, 768, 1000])
 def test_other_dimensions(tss, orc, dim):
-    """D < 384 pads to 128 / 256 / 384 columns: 2, 4 or 6 k-blocks of the same kernel."""
+    """D pads to 128 ... 1024 columns: 2 ... 16 k-blocks of the same kernel (beyond 384 the query
+    tile streams through the ring instead of staying resident)."""
     n, nq, k = 80_000, 130, 10
     rng = np.random.default_rng(dim)
     rows = rng.standard_normal((n, dim)).astype(np.float32)

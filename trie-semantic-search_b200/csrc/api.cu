@@ -370,8 +370,8 @@ int ensure_gather_ws(tss_index* ix) {
 
 bool gemm_eligible(const tss_index* ix, uint32_t nq, uint32_t k, int mode) {
   (void)mode;  // masks ride along: a masked row's 1/|row| is NaN in the epilogue
-  return ix->storage == TSS_BF16 && ix->ns <= 3 && nq >= ix->gemm_min_nq &&
-         ix->n_rows >= 4ull * 256 * k && k <= TSS_MAX_K;
+  return ix->storage == TSS_BF16 && nq >= ix->gemm_min_nq && ix->n_rows >= 4ull * 256 * k &&
+         k <= TSS_MAX_K;
 }
 
 int ensure_gemm_ws(tss_index* ix) {

@@ -153,6 +153,9 @@ __device__ __forceinline__ void tmem_ld_wait() {
 // CL == 2 the two CTAs of a cluster score different query blocks against the SAME corpus
 // tiles: each loads half of every 256-row stage and multicasts it into both CTAs' shared
 // memory, which halves the L2 -> SM traffic per CTA (the bound of the CL == 1 kernel).
+// KB <= 6 (D <= 384): the 128 queries stay resident in shared memory (KB x 16 KB).  Larger D
+// does not leave room for that next to the corpus ring, so the query tile of each k-block
+// streams through the ring together with the corpus box (16 + 32 KB per stage, L2-resident).
 template <int KB, int CL>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_e,
@@ -163,9 +166,12 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   const uint32_t smem_base = smem_u32(smem_raw);
   if ((smem_base & 1023u) != 0) __trap();
   uint8_t* smem = smem_raw;
-  const uint32_t sA = smem_base;                         // KB tiles of 16 KB
-  const uint32_t sB = sA + KB * kATileBytes;             // kStages tiles of 32 KB
-  uint8_t* tail = smem + KB * kATileBytes + kStages * kBTileBytes;
+  constexpr bool ARES = KB <= 6;                         // queries resident (else streamed)
+  constexpr int kABytes = ARES ? KB * kATileBytes : 0;
+  constexpr int kStageBytes = kBTileBytes + (ARES ? 0 : kATileBytes);
+  const uint32_t sA = smem_base;                         // ARES: KB tiles of 16 KB
+  const uint32_t sB = sA + kABytes;                      // kStages stages: [B 32 KB][A 16 KB if !ARES]
+  uint8_t* tail = smem + kABytes + kStages * kStageBytes;
   float* s_ninv = reinterpret_cast<float*>(tail);        // [2][256] inverse row norms
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail + 2 * kBlockN * sizeof(float));
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 16);
@@ -215,9 +221,11 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      mbar_arrive_expect_tx(bar_a, KB * kATileBytes);
-      for (int kb = 0; kb < KB; ++kb)
-        tma_load_2d(sA + kb * kATileBytes, &tmap_q, bar_a, kb * kBlockK, (int)(m_blk * kBlockM));
+      if (ARES) {
+        mbar_arrive_expect_tx(bar_a, KB * kATileBytes);
+        for (int kb = 0; kb < KB; ++kb)
+          tma_load_2d(sA + kb * kATileBytes, &tmap_q, bar_a, kb * kBlockK, (int)(m_blk * kBlockM));
+      }
       uint32_t s = 0, ph = 0;
       // The 2-D boxes below touch 128 bytes of every 768-byte row, which is a poor DRAM
       // access pattern (a page is re-opened once per k-block).  A tile's rows are one
@@ -242,15 +250,21 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           mbar_wait(bar_empty + 8 * s, ph ^ 1);
           if (p.debug & 4) {
             mbar_arrive(bar_full + 8 * s);
-          } else if (CL == 1) {
-            mbar_arrive_expect_tx(bar_full + 8 * s, kBTileBytes);
-            tma_load_2d(sB + s * kBTileBytes, &tmap_e, bar_full + 8 * s, kb * kBlockK, row0);
           } else {
-            // my barrier counts the whole stage: my slice of the rows plus the peers' multicasts
-            mbar_arrive_expect_tx(bar_full + 8 * s, kBTileBytes);
-            constexpr int kRowsPer = kBlockN / CL;
-            tma_load_2d_mc(sB + s * kBTileBytes + rank * (kBTileBytes / CL), &tmap_e,
-                           bar_full + 8 * s, kb * kBlockK, row0 + (int)rank * kRowsPer, kMask);
+            // my barrier counts the whole stage: (my query tile,) my slice of the corpus rows
+            // plus the peers' multicasts of theirs
+            mbar_arrive_expect_tx(bar_full + 8 * s, kStageBytes);
+            const uint32_t stage = sB + s * kStageBytes;
+            if (!ARES)
+              tma_load_2d(stage + kBTileBytes, &tmap_q, bar_full + 8 * s, kb * kBlockK,
+                          (int)(m_blk * kBlockM));
+            if (CL == 1) {
+              tma_load_2d(stage, &tmap_e, bar_full + 8 * s, kb * kBlockK, row0);
+            } else {
+              constexpr int kRowsPer = kBlockN / CL;
+              tma_load_2d_mc(stage + rank * (kBTileBytes / CL), &tmap_e, bar_full + 8 * s,
+                             kb * kBlockK, row0 + (int)rank * kRowsPer, kMask);
+            }
           }
           if (++s == kStages) s = 0, ph ^= 1;
         }
@@ -259,7 +273,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   } else if (warp == 1) {
     // ===== MMA issuer (one elected lane) =====
     if (lane == 0) {
-      mbar_wait(bar_a, 0);
+      if (ARES) mbar_wait(bar_a, 0);
       uint32_t s = 0, ph = 0, it = 0;
       for (uint32_t i = slice; i < count; i += nslices, ++it) {
         const uint32_t acc = it & 1u, use = it >> 1;
@@ -269,8 +283,9 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(bar_full + 8 * s, ph);
           tc_fence_after();
-          const uint64_t adesc = make_desc(sA + kb * kATileBytes);
-          const uint64_t bdesc = make_desc(sB + s * kBTileBytes);
+          const uint32_t stage = sB + s * kStageBytes;
+          const uint64_t adesc = make_desc(ARES ? sA + kb * kATileBytes : stage + kBTileBytes);
+          const uint64_t bdesc = make_desc(stage);
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k)  // +32 bytes along K per step (>> 4 = 2)
             if (!(p.debug & 2)) umma(tmem_d, adesc + 2 * k, bdesc + 2 * k, (kb | k) != 0 ? 1u : 0u);
@@ -579,7 +594,9 @@ __global__ void select_kernel(const uint64_t* cand, const uint32_t* cand_count, 
 // ---- host side ------------------------------------------------------------------------------
 int gemm_col_split() { return kColSplit; }
 size_t gemm_smem_bytes(int kb) {
-  return (size_t)kb * kATileBytes + (size_t)kStages * kBTileBytes + 2 * kBlockN * 4 + 16 * 8 + 16;
+  const size_t ring = kb <= 6 ? (size_t)kb * kATileBytes + (size_t)kStages * kBTileBytes
+                              : (size_t)kStages * (kBTileBytes + kATileBytes);
+  return ring + 2 * kBlockN * 4 + 16 * 8 + 16;
 }
 
 template <int KB, int CL>
@@ -615,6 +632,9 @@ cudaError_t launch_gemm_topk(int kb, int cluster, const CUtensorMap& tmap_q,
     TSS_GEMM_CASE(2)
     TSS_GEMM_CASE(4)
     TSS_GEMM_CASE(6)
+    TSS_GEMM_CASE(8)
+    TSS_GEMM_CASE(12)
+    TSS_GEMM_CASE(16)
     default: return cudaErrorInvalidValue;
   }
 #undef TSS_GEMM_CASE
