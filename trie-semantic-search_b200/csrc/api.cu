@@ -443,10 +443,15 @@ int enqueue_gemm(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
   if (nslices * (int)tss::gemm_col_split() > 1024) nslices = 1024 / tss::gemm_col_split();
   if (nslices < 1) return fail(TSS_ERR_INVALID_ARG, "batch of %u queries exceeds one K2 launch", nq);
   const int grid = nslices * (int)mb;
-  // CTA pairs that share corpus tiles by TMA multicast need an even number of query blocks
-  int cluster = (mb % 2 == 0) ? 2 : 1;
-  if (const char* cl = getenv("TSS_GEMM_CLUSTER")) cluster = atoi(cl) == 2 && mb % 2 == 0 ? 2 : 1;
-  const CUtensorMap& tmap_e = cluster == 2 ? g.tmap_e_half : g.tmap_e;
+  // CTA pairs (one cta_group::2 MMA over two query blocks) need an even number of query blocks
+  int cluster = (mb % 2 == 0) ? tss::TSS_GEMM_PAIR : tss::TSS_GEMM_SINGLE;
+  if (const char* cl = getenv("TSS_GEMM_CLUSTER")) {  // 1 single, 2 TMA multicast, 3 pair
+    const int want = atoi(cl);
+    cluster = (want == tss::TSS_GEMM_MULTICAST || want == tss::TSS_GEMM_PAIR) && mb % 2 == 0
+                  ? want
+                  : tss::TSS_GEMM_SINGLE;
+  }
+  const CUtensorMap& tmap_e = cluster == tss::TSS_GEMM_SINGLE ? g.tmap_e : g.tmap_e_half;
   cudaError_t e;
   e = tss::launch_prep_queries(d_queries, nq, ix->dim, kpad, nq_pad, g.d_qbf16, g.d_inv_q, ix->stream);
   if (e != cudaSuccess) return cuda_fail(e, "prep_queries launch");

@@ -36,11 +36,12 @@ constexpr int kBlockM = 128;      // queries per CTA (UMMA M)
 constexpr int kBlockN = 256;      // corpus rows per tile (UMMA N)
 constexpr int kBlockK = 64;       // bf16 elements per k-block = 128 bytes = one swizzle atom row
 constexpr int kUmmaK = 16;        // K per tcgen05.mma for 16-bit inputs
-constexpr int kStages = 4;
 constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KB
 constexpr int kBTileBytes = kBlockN * kBlockK * 2;  // 32 KB
 constexpr int kColSplit = 4;      // epilogue warps per TMEM lane quadrant (each takes 256/4 columns)
 constexpr int kEpiThreads = 128 * kColSplit;
+constexpr int kEpiWarps = kEpiThreads / 32;
+constexpr int kBarSlots = 24;     // full[stages] + empty[stages] + queries + 2 tmem full + 2 tmem empty
 constexpr int kThreads = 64 + kEpiThreads;  // warp 0 TMA, warp 1 MMA + TMEM alloc, rest epilogue
 constexpr int kTmemCols = 512;    // two 256-column fp32 accumulators
 
@@ -71,6 +72,35 @@ __device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t cta_mask) 
       "[%0], %1;" ::"r"(bar),
       "h"(cta_mask)
       : "memory");
+}
+// ---- cta_group::2 (a CTA pair drives one M256 MMA; SASS UTCHMMA.2CTA) ----
+// shared::cluster address of `addr` (an address in this CTA's window) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+// TMA box into THIS CTA's shared memory whose bytes are counted on a barrier that may live in
+// the pair's other CTA (the leader's, where the MMA thread waits)
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map,
+                                                 uint32_t cluster_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(cluster_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+      "[%0], %1;" ::"r"(bar),
+      "h"(cta_mask)
+      : "memory");
+}
+// (default .release.cta: what it orders here are TMEM reads, which tcgen05.fence covers; the
+// .release.cluster form costs a MEMBAR.ALL.GPU per arrival -- 30 % of all stall samples)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
@@ -105,6 +135,20 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kBlockN >> 3) << 17) |
                             ((uint32_t)(kBlockM >> 4) << 24);
 
+// the pair's instruction: M = 256 (128 queries from each CTA), N = 256 (128 corpus rows from each)
+constexpr uint32_t kIdescPair = (1u << 4) | (1u << 7) | (1u << 10) |
+                                ((uint32_t)(kBlockN >> 3) << 17) | ((uint32_t)((2 * kBlockM) >> 4) << 24);
+__device__ __forceinline__ void umma_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(kIdescPair), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
                                      uint32_t accumulate) {
   asm volatile(
@@ -156,7 +200,23 @@ __device__ __forceinline__ void tmem_ld_wait() {
 // KB <= 6 (D <= 384): the 128 queries stay resident in shared memory (KB x 16 KB).  Larger D
 // does not leave room for that next to the corpus ring, so the query tile of each k-block
 // streams through the ring together with the corpus box (16 + 32 KB per stage, L2-resident).
-template <int KB, int CL>
+// PAIR (CL == 2 only): the two CTAs are one cta_group::2 pair.  The leader (cluster rank 0)
+// issues M256 N256 K16 MMAs whose A rows are the 128 queries of EACH CTA and whose B rows are
+// the 128 corpus rows EACH CTA staged -- a CTA's shared memory feeds 4 KB (A) + 4 KB (its half
+// of B) per MMA instead of 4 + 8, which is what bounds the cta_group::1 kernel (128 B/clk of
+// shared-memory bandwidth against 192 B/clk of operands at the full MMA rate).  No multicast:
+// every CTA loads only its own half of the tile (16 KB per stage, so the ring is 8 deep) with
+// the cta_group::2 form of the TMA load, which counts its bytes on the leader's barrier.  Each
+// CTA's TMEM receives its own 128 queries x all 256 rows, so the epilogue is unchanged.
+template <int KB, bool PAIR>
+__host__ __device__ constexpr int gemm_stages() { return PAIR ? (KB <= 6 ? 7 : 6) : 4; }
+// floats of staged 1/|row|: a pair's epilogue warps each keep their own 64 columns' worth (no
+// block barrier); otherwise one double-buffered tile's worth shared by all epilogue warps
+__host__ __device__ constexpr int gemm_ninv_floats(bool pair) {
+  return pair ? kEpiWarps * (kBlockN / kColSplit) : 2 * kBlockN;
+}
+
+template <int KB, int CL, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_e,
                  const GemmParams p) {
@@ -166,15 +226,20 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   const uint32_t smem_base = smem_u32(smem_raw);
   if ((smem_base & 1023u) != 0) __trap();
   uint8_t* smem = smem_raw;
+  static_assert(!PAIR || CL == 2, "a cta_group::2 pair is a cluster of two");
   constexpr bool ARES = KB <= 6;                         // queries resident (else streamed)
+  constexpr int kStages = gemm_stages<KB, PAIR>();
+  constexpr int kBBytes = PAIR ? kBTileBytes / 2 : kBTileBytes;  // corpus rows staged per CTA
   constexpr int kABytes = ARES ? KB * kATileBytes : 0;
-  constexpr int kStageBytes = kBTileBytes + (ARES ? 0 : kATileBytes);
+  constexpr int kStageBytes = kBBytes + (ARES ? 0 : kATileBytes);
+  constexpr uint32_t kTxCtas = PAIR ? 2 : 1;             // CTAs whose bytes one full barrier counts
   const uint32_t sA = smem_base;                         // ARES: KB tiles of 16 KB
-  const uint32_t sB = sA + kABytes;                      // kStages stages: [B 32 KB][A 16 KB if !ARES]
+  const uint32_t sB = sA + kABytes;                      // kStages stages: [B][A 16 KB if !ARES]
   uint8_t* tail = smem + kABytes + kStages * kStageBytes;
-  float* s_ninv = reinterpret_cast<float*>(tail);        // [2][256] inverse row norms
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tail + 2 * kBlockN * sizeof(float));
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 16);
+  float* s_ninv = reinterpret_cast<float*>(tail);        // inverse row norms (gemm_ninv_floats)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail + gemm_ninv_floats(PAIR) * sizeof(float));
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + kBarSlots);
+  static_assert(2 * kStages + 5 <= kBarSlots, "barrier slots");
   const uint32_t bar_full = smem_u32(&bars[0]);        // [kStages]
   const uint32_t bar_empty = smem_u32(&bars[kStages]); // [kStages]
   const uint32_t bar_a = smem_u32(&bars[2 * kStages]);
@@ -196,35 +261,55 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     prefetch_tmap(&tmap_e);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_empty + 8 * s, CL);  // every CTA that reads the stage must release it
+      // every MMA thread that reads the stage must release it (a pair has one)
+      mbar_init(bar_empty + 8 * s, PAIR ? 1 : CL);
     }
     mbar_init(bar_a, 1);
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
-      mbar_init(bar_tempty + 8 * a, kEpiThreads);
+      // one arrival per epilogue warp; the leader's MMA thread also waits for the peer's warps
+      mbar_init(bar_tempty + 8 * a, kEpiWarps * kTxCtas);
     }
     fence_barrier_init();
   }
-  if (warp == 1) {  // TMEM allocation is warp-wide
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                     smem_u32(s_tmem)),
-                 "n"(kTmemCols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  if (warp == 1) {  // TMEM allocation is warp-wide (a pair: the same warp of both CTAs)
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                       smem_u32(s_tmem)),
+                   "n"(kTmemCols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                       smem_u32(s_tmem)),
+                   "n"(kTmemCols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
   if (CL > 1) cluster_sync_all();  // peer barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
+  // PAIR: the barriers TMA bytes and drained accumulators are reported to are the leader's
+  const bool leader = !PAIR || rank == 0;
+  const uint32_t lead_full = PAIR ? map_to_rank(bar_full, 0) : bar_full;
+  const uint32_t lead_a = PAIR ? map_to_rank(bar_a, 0) : bar_a;
+  const uint32_t lead_tempty = PAIR ? map_to_rank(bar_tempty, 0) : bar_tempty;
 
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
       if (ARES) {
-        mbar_arrive_expect_tx(bar_a, KB * kATileBytes);
-        for (int kb = 0; kb < KB; ++kb)
-          tma_load_2d(sA + kb * kATileBytes, &tmap_q, bar_a, kb * kBlockK, (int)(m_blk * kBlockM));
+        if (leader) mbar_arrive_expect_tx(bar_a, kTxCtas * KB * kATileBytes);
+        for (int kb = 0; kb < KB; ++kb) {
+          if (PAIR)
+            tma_load_2d_pair(sA + kb * kATileBytes, &tmap_q, lead_a, kb * kBlockK,
+                             (int)(m_blk * kBlockM));
+          else
+            tma_load_2d(sA + kb * kATileBytes, &tmap_q, bar_a, kb * kBlockK, (int)(m_blk * kBlockM));
+        }
       }
       uint32_t s = 0, ph = 0;
       // The 2-D boxes below touch 128 bytes of every 768-byte row, which is a poor DRAM
@@ -249,7 +334,16 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(bar_empty + 8 * s, ph ^ 1);
           if (p.debug & 4) {
-            mbar_arrive(bar_full + 8 * s);
+            if (leader) mbar_arrive(bar_full + 8 * s);
+          } else if (PAIR) {
+            // the leader's barrier counts both CTAs' stages: (query tile,) 128 corpus rows each
+            if (leader) mbar_arrive_expect_tx(bar_full + 8 * s, kTxCtas * kStageBytes);
+            const uint32_t stage = sB + s * kStageBytes;
+            if (!ARES)
+              tma_load_2d_pair(stage + kBBytes, &tmap_q, lead_full + 8 * s, kb * kBlockK,
+                               (int)(m_blk * kBlockM));
+            tma_load_2d_pair(stage, &tmap_e, lead_full + 8 * s, kb * kBlockK,
+                             row0 + (int)rank * (kBlockN / 2));
           } else {
             // my barrier counts the whole stage: (my query tile,) my slice of the corpus rows
             // plus the peers' multicasts of theirs
@@ -271,8 +365,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (one elected lane) =====
-    if (lane == 0) {
+    // ===== MMA issuer (one elected lane; of a pair, the leader's) =====
+    if (lane == 0 && leader) {
       if (ARES) mbar_wait(bar_a, 0);
       uint32_t s = 0, ph = 0, it = 0;
       for (uint32_t i = slice; i < count; i += nslices, ++it) {
@@ -284,17 +378,24 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           mbar_wait(bar_full + 8 * s, ph);
           tc_fence_after();
           const uint32_t stage = sB + s * kStageBytes;
-          const uint64_t adesc = make_desc(ARES ? sA + kb * kATileBytes : stage + kBTileBytes);
+          // (a pair's descriptors name the same offsets in both CTAs' shared memory)
+          const uint64_t adesc = make_desc(ARES ? sA + kb * kATileBytes : stage + kBBytes);
           const uint64_t bdesc = make_desc(stage);
 #pragma unroll
-          for (int k = 0; k < kBlockK / kUmmaK; ++k)  // +32 bytes along K per step (>> 4 = 2)
-            if (!(p.debug & 2)) umma(tmem_d, adesc + 2 * k, bdesc + 2 * k, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {  // +32 bytes along K per step (>> 4 = 2)
+            if (p.debug & 2) continue;
+            if (PAIR) umma_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, (kb | k) != 0 ? 1u : 0u);
+            else umma(tmem_d, adesc + 2 * k, bdesc + 2 * k, (kb | k) != 0 ? 1u : 0u);
+          }
           // smem stage reusable once these MMAs retire (in every CTA of the cluster)
-          if (CL == 1) umma_commit(bar_empty + 8 * s);
+          if (PAIR) umma_commit_pair(bar_empty + 8 * s, kMask);
+          else if (CL == 1) umma_commit(bar_empty + 8 * s);
           else umma_commit_mc(bar_empty + 8 * s, kMask);
           if (++s == kStages) s = 0, ph ^= 1;
         }
-        umma_commit(bar_tfull + 8 * acc);  // accumulator complete
+        // accumulator complete (a pair's: in both CTAs' TMEM)
+        if (PAIR) umma_commit_pair(bar_tfull + 8 * acc, kMask);
+        else umma_commit(bar_tfull + 8 * acc);
       }
     }
   } else {
@@ -313,23 +414,53 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     uint64_t* my_cand = p.cand + ((size_t)q * nsub + sub) * p.cand_cap;
     uint32_t my_count = 0;
     uint32_t it = 0;
+    // 1/|row| of local row r as the epilogue wants it
+    auto row_weight = [&](uint64_t r) -> float {
+      if (r >= p.n_rows) return 0.f;
+      float w = __ldg(p.inv_norm + r);
+      if (p.mask) {
+        uint32_t bit = (__ldg(p.mask + (r >> 5)) >> (uint32_t)(r & 31)) & 1u;
+        if (p.mask_mode == 2) bit ^= 1u;  // TSS_MASK_EXCLUDE
+        // a masked row's score becomes NaN: fmax drops it from every maximum and
+        // `v >= thr` is false, at no cost in the per-element code
+        if (!bit) w = __uint_as_float(0x7FC00000u);
+      }
+      return w;
+    };
+    // The weights of a tile are fetched one tile ahead into registers, so their global-memory
+    // latency never sits between two tiles.  PAIR: lane l of a warp fetches the weights of
+    // columns part*64 + l and + 32 + l, and the warp stages them in its own 64 floats
+    // (warp-level sync only).  Otherwise thread et < 256 fetches column et and all epilogue
+    // warps meet at a named barrier (double-buffered by accumulator).
+    const uint64_t my_col = PAIR ? part * kColsPer + lane : et;
+    auto fetch_weights = [&](uint32_t i, float& a, float& b) {
+      if (i >= count) return;
+      const uint64_t r = (uint64_t)i * stride * kBlockN + my_col;
+      if (PAIR) {
+        a = row_weight(r);
+        b = row_weight(r + 32);
+      } else if (et < (uint32_t)kBlockN) {
+        a = row_weight(r);
+      }
+    };
+    float w_a = 0.f, w_b = 0.f;
+    fetch_weights(slice, w_a, w_b);
+    float* warp_ninv = s_ninv + (warp - 2) * kColsPer;
     for (uint32_t i = slice; i < count; i += nslices, ++it) {
       const uint32_t acc = it & 1u, use = it >> 1;
       const uint64_t row0 = (uint64_t)i * stride * kBlockN;
-      float* ninv = s_ninv + acc * kBlockN;
-      if (et < (uint32_t)kBlockN) {
-        uint64_t r = row0 + et;
-        float w = r < p.n_rows ? __ldg(p.inv_norm + r) : 0.f;
-        if (p.mask && r < p.n_rows) {
-          uint32_t bit = (__ldg(p.mask + (r >> 5)) >> (uint32_t)(r & 31)) & 1u;
-          if (p.mask_mode == 2) bit ^= 1u;  // TSS_MASK_EXCLUDE
-          // a masked row's score becomes NaN: fmax drops it from every maximum and
-          // `v >= thr` is false, at no cost in the per-element code
-          if (!bit) w = __uint_as_float(0x7FC00000u);
-        }
-        ninv[et] = w;
+      // ninv[c] = weight of the tile's column c (for the columns this thread visits)
+      float* ninv = PAIR ? warp_ninv - part * kColsPer : s_ninv + acc * kBlockN;
+      if (PAIR) {
+        __syncwarp();  // the previous tile's reads of the warp's buffer are done
+        warp_ninv[lane] = w_a;
+        warp_ninv[32 + lane] = w_b;
+        __syncwarp();
+      } else {
+        if (et < (uint32_t)kBlockN) ninv[et] = w_a;
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       }
-      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+      fetch_weights(i + nslices, w_a, w_b);
       mbar_wait(bar_tfull + 8 * acc, use & 1u);
       tc_fence_after();
       const uint64_t left = p.n_rows - row0;
@@ -383,7 +514,11 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         }
       }
       tc_fence_before();
-      mbar_arrive(bar_tempty + 8 * acc);
+      __syncwarp();
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_cluster(lead_tempty + 8 * acc);
+        else mbar_arrive(bar_tempty + 8 * acc);
+      }
       // each (tile, part) is its own sample for the threshold: kColsPer distinct rows
       if (p.mode == 0)
         p.tile_max[(size_t)q * (p.sample_count * kColSplit) + (size_t)i * kColSplit + part] = mx;
@@ -396,9 +531,14 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   if (CL > 1) cluster_sync_all();  // no CTA exits while a peer may still write into it
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                 "n"(kTmemCols)
-                 : "memory");
+    if (PAIR)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                   "n"(kTmemCols)
+                   : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                   "n"(kTmemCols)
+                   : "memory");
   }
 }
 
@@ -593,16 +733,18 @@ __global__ void select_kernel(const uint64_t* cand, const uint32_t* cand_count, 
 
 // ---- host side ------------------------------------------------------------------------------
 int gemm_col_split() { return kColSplit; }
-size_t gemm_smem_bytes(int kb) {
-  const size_t ring = kb <= 6 ? (size_t)kb * kATileBytes + (size_t)kStages * kBTileBytes
-                              : (size_t)kStages * (kBTileBytes + kATileBytes);
-  return ring + 2 * kBlockN * 4 + 16 * 8 + 16;
+size_t gemm_smem_bytes(int kb, bool pair) {
+  const size_t stages = pair ? (kb <= 6 ? 7 : 6) : 4;
+  const size_t b = pair ? kBTileBytes / 2 : kBTileBytes;
+  const size_t ring = kb <= 6 ? (size_t)kb * kATileBytes + stages * b : stages * (b + kATileBytes);
+  return ring + gemm_ninv_floats(pair) * sizeof(float) + kBarSlots * 8 + 16;
 }
 
-template <int KB, int CL>
+template <int KB, int CL, bool PAIR>
 static cudaError_t launch_gemm_inst(const CUtensorMap& tmap_q, const CUtensorMap& tmap_e,
                                     const GemmParams& p, int grid, size_t smem, cudaStream_t st) {
-  auto kern = gemm_topk_kernel<KB, CL>;
+  static_assert(gemm_stages<KB, PAIR>() == (PAIR ? (KB <= 6 ? 7 : 6) : 4), "gemm_smem_bytes");
+  auto kern = gemm_topk_kernel<KB, CL, PAIR>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg{};
@@ -623,11 +765,14 @@ static cudaError_t launch_gemm_inst(const CUtensorMap& tmap_q, const CUtensorMap
 cudaError_t launch_gemm_topk(int kb, int cluster, const CUtensorMap& tmap_q,
                              const CUtensorMap& tmap_e, const GemmParams& p, int grid,
                              cudaStream_t st) {
-  const size_t smem = gemm_smem_bytes(kb);
-#define TSS_GEMM_CASE(KBV)                                                               \
-  case KBV:                                                                               \
-    return cluster == 2 ? launch_gemm_inst<KBV, 2>(tmap_q, tmap_e, p, grid, smem, st)     \
-                        : launch_gemm_inst<KBV, 1>(tmap_q, tmap_e, p, grid, smem, st);
+  const size_t smem = gemm_smem_bytes(kb, cluster == TSS_GEMM_PAIR);
+#define TSS_GEMM_CASE(KBV)                                                                      \
+  case KBV:                                                                                      \
+    return cluster == TSS_GEMM_PAIR                                                             \
+               ? launch_gemm_inst<KBV, 2, true>(tmap_q, tmap_e, p, grid, smem, st)              \
+               : cluster == TSS_GEMM_MULTICAST                                                  \
+                     ? launch_gemm_inst<KBV, 2, false>(tmap_q, tmap_e, p, grid, smem, st)       \
+                     : launch_gemm_inst<KBV, 1, false>(tmap_q, tmap_e, p, grid, smem, st);
   switch (kb) {
     TSS_GEMM_CASE(2)
     TSS_GEMM_CASE(4)

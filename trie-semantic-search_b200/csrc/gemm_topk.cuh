@@ -26,9 +26,12 @@ struct GemmParams {
   uint32_t debug;          // diagnostics: 1 = no epilogue math, 2 = no MMA issue, 4 = no corpus TMA
 };
 
-size_t gemm_smem_bytes(int kb);
+// How the CTAs of a launch cooperate.  MULTICAST and PAIR need an even mb and a tmap_e with a
+// 128-row box: two CTAs score different query blocks against the same corpus tiles, either as
+// two cta_group::1 MMAs fed by TMA multicast, or as one cta_group::2 M256 MMA.
+enum GemmCluster { TSS_GEMM_SINGLE = 1, TSS_GEMM_MULTICAST = 2, TSS_GEMM_PAIR = 3 };
+size_t gemm_smem_bytes(int kb, bool pair);
 int gemm_col_split();  // survivor lists / threshold samples per (slice, tile)
-// cluster: 1, or 2 (needs an even mb; tmap_e must then have a 128-row box)
 cudaError_t launch_gemm_topk(int kb, int cluster, const CUtensorMap& tmap_q,
                              const CUtensorMap& tmap_e, const GemmParams& p, int grid,
                              cudaStream_t st);
