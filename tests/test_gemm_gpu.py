@@ -104,11 +104,13 @@ def test_small_batches_keep_using_the_scan(tss, orc):
     assert np.array_equal(got[1].view(np.uint32), want[1].view(np.uint32))
 
 
-@pytest.mark.parametrize("dim", [64, 100, 256, 300, 512, 768, 1000])
-def test_other_dimensions(tss, orc, dim):
+@pytest.mark.parametrize("dim,nq", [(64, 130), (100, 130), (256, 130), (300, 130), (512, 130),
+                                    (768, 130), (1000, 130), (256, 64), (768, 64)])
+def test_other_dimensions(tss, orc, dim, nq):
     """D pads to 128 ... 1024 columns: 2 ... 16 k-blocks of the same kernel (beyond 384 the query
-    tile streams through the ring instead of staying resident)."""
-    n, nq, k = 80_000, 130, 10
+    tile streams through the ring instead of staying resident).  130 queries = two query blocks =
+    one cta_group::2 pair per slice; 64 queries = one block = independent CTAs."""
+    n, k = 80_000, 10
     rng = np.random.default_rng(dim)
     rows = rng.standard_normal((n, dim)).astype(np.float32)
     q = rng.standard_normal((nq, dim)).astype(np.float32)
@@ -123,10 +125,11 @@ def test_other_dimensions(tss, orc, dim):
     np.testing.assert_allclose(gs[:, 0], ws[:, 0], rtol=3e-5, atol=1e-6)
 
 
-@pytest.mark.parametrize("mode", ["include", "exclude"])
-def test_masked_large_batch(tss, orc, mode):
-    """Masks ride along on the tensor-core path: a masked row's 1/|row| is NaN in the epilogue."""
-    n, nq, k, dim = 160_000, 96, 20, 384
+@pytest.mark.parametrize("mode,nq", [("include", 96), ("exclude", 96), ("include", 200)])
+def test_masked_large_batch(tss, orc, mode, nq):
+    """Masks ride along on the tensor-core path: a masked row's 1/|row| is NaN in the epilogue
+    (96 queries: independent CTAs; 200: CTA pairs)."""
+    n, k, dim = 160_000, 20, 384
     rows = orc.gen_rows(0, n, dim, SEED)
     q = orc.gen_rows(0, nq, dim, 0xBEEF)
     rng = np.random.default_rng(4)

@@ -445,12 +445,8 @@ int enqueue_gemm(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
   const int grid = nslices * (int)mb;
   // CTA pairs (one cta_group::2 MMA over two query blocks) need an even number of query blocks
   int cluster = (mb % 2 == 0) ? tss::TSS_GEMM_PAIR : tss::TSS_GEMM_SINGLE;
-  if (const char* cl = getenv("TSS_GEMM_CLUSTER")) {  // 1 single, 2 TMA multicast, 3 pair
-    const int want = atoi(cl);
-    cluster = (want == tss::TSS_GEMM_MULTICAST || want == tss::TSS_GEMM_PAIR) && mb % 2 == 0
-                  ? want
-                  : tss::TSS_GEMM_SINGLE;
-  }
+  if (const char* cl = getenv("TSS_GEMM_CLUSTER"))  // 1 forces independent CTAs
+    if (atoi(cl) == tss::TSS_GEMM_SINGLE) cluster = tss::TSS_GEMM_SINGLE;
   const CUtensorMap& tmap_e = cluster == tss::TSS_GEMM_SINGLE ? g.tmap_e : g.tmap_e_half;
   cudaError_t e;
   e = tss::launch_prep_queries(d_queries, nq, ix->dim, kpad, nq_pad, g.d_qbf16, g.d_inv_q, ix->stream);
@@ -475,6 +471,7 @@ int enqueue_gemm(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
   p.cand_cap = cap_s;
   p.prefetch_ahead = 4;
   if (const char* pf = getenv("TSS_GEMM_PREFETCH")) p.prefetch_ahead = (uint32_t)atoi(pf);
+  if (const char* rs = getenv("TSS_GEMM_STAGES")) p.ring_stages = (uint32_t)atoi(rs);
   if (const char* dbg = getenv("TSS_GEMM_DEBUG")) p.debug = (uint32_t)atoi(dbg);
   const int kb = (int)(kpad / 64);
   p.mode = 0;

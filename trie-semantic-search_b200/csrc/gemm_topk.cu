@@ -57,22 +57,6 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
 __device__ __forceinline__ void prefetch_l2(const void* src, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
-// same, multicast to every CTA of the cluster named in cta_mask (same smem / barrier offsets)
-__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar,
-                                               int c0, int c1, uint16_t cta_mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
-      ".multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
-      "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(cta_mask)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t cta_mask) {
-  asm volatile(
-      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
-      "[%0], %1;" ::"r"(bar),
-      "h"(cta_mask)
-      : "memory");
-}
 // ---- cta_group::2 (a CTA pair drives one M256 MMA; SASS UTCHMMA.2CTA) ----
 // shared::cluster address of `addr` (an address in this CTA's window) in CTA `rank` of the cluster
 __device__ __forceinline__ uint32_t map_to_rank(uint32_t addr, uint32_t rank) {
@@ -81,7 +65,7 @@ __device__ __forceinline__ uint32_t map_to_rank(uint32_t addr, uint32_t rank) {
   return r;
 }
 // TMA box into THIS CTA's shared memory whose bytes are counted on a barrier that may live in
-// the pair's other CTA (the leader's, where the MMA thread waits)
+// the pair's other CTA (the leader's, where the MMA thread waits); SASS UTMALDG.2D.2CTA
 __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map,
                                                  uint32_t cluster_bar, int c0, int c1) {
   asm volatile(
@@ -90,6 +74,7 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap
       "l"(map), "r"(cluster_bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// arrives (once the MMAs issued so far retire) on the barrier at this offset in every CTA of cta_mask
 __device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t cta_mask) {
   asm volatile(
       "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
@@ -193,21 +178,20 @@ __device__ __forceinline__ void tmem_ld_wait() {
 
 }  // namespace
 
-// KB: k-blocks of 64 elements (D padded to KB*64).  CL: CTAs per cluster (1 or 2).  With
-// CL == 2 the two CTAs of a cluster score different query blocks against the SAME corpus
-// tiles: each loads half of every 256-row stage and multicasts it into both CTAs' shared
-// memory, which halves the L2 -> SM traffic per CTA (the bound of the CL == 1 kernel).
+// KB: k-blocks of 64 elements (D padded to KB*64).
 // KB <= 6 (D <= 384): the 128 queries stay resident in shared memory (KB x 16 KB).  Larger D
 // does not leave room for that next to the corpus ring, so the query tile of each k-block
 // streams through the ring together with the corpus box (16 + 32 KB per stage, L2-resident).
-// PAIR (CL == 2 only): the two CTAs are one cta_group::2 pair.  The leader (cluster rank 0)
-// issues M256 N256 K16 MMAs whose A rows are the 128 queries of EACH CTA and whose B rows are
-// the 128 corpus rows EACH CTA staged -- a CTA's shared memory feeds 4 KB (A) + 4 KB (its half
-// of B) per MMA instead of 4 + 8, which is what bounds the cta_group::1 kernel (128 B/clk of
-// shared-memory bandwidth against 192 B/clk of operands at the full MMA rate).  No multicast:
-// every CTA loads only its own half of the tile (16 KB per stage, so the ring is 8 deep) with
-// the cta_group::2 form of the TMA load, which counts its bytes on the leader's barrier.  Each
-// CTA's TMEM receives its own 128 queries x all 256 rows, so the epilogue is unchanged.
+// PAIR: launched as clusters of two CTAs that form one cta_group::2 pair and score two
+// different query blocks against the same corpus tiles.  The leader (cluster rank 0)
+// issues M256 N256 K16 MMAs (128 clocks each) whose A rows are the 128 queries of EACH CTA and
+// whose B rows are the 128 corpus rows EACH CTA staged.  Shared-memory traffic per SM drops
+// from 96 B/clk of operand reads (4 KB A + 8 KB B per MMA) + 64 B/clk of TMA writes (a 32 KB
+// stage per 4 MMAs) -- more than the 128 B/clk an SM has -- to 64 + 32 B/clk, and the L2 -> SM
+// traffic halves without any multicast: every CTA loads only its own half of the tile (16 KB
+// per stage, so the ring is 7 deep) with the cta_group::2 form of the TMA load, which counts
+// its bytes on the leader's barrier.  Each CTA's TMEM receives its own 128 queries x all 256
+// rows, so the epilogue is the same in both modes.
 template <int KB, bool PAIR>
 __host__ __device__ constexpr int gemm_stages() { return PAIR ? (KB <= 6 ? 7 : 6) : 4; }
 // floats of staged 1/|row|: a pair's epilogue warps each keep their own 64 columns' worth (no
@@ -216,7 +200,7 @@ __host__ __device__ constexpr int gemm_ninv_floats(bool pair) {
   return pair ? kEpiWarps * (kBlockN / kColSplit) : 2 * kBlockN;
 }
 
-template <int KB, int CL, bool PAIR>
+template <int KB, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_e,
                  const GemmParams p) {
@@ -226,7 +210,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   const uint32_t smem_base = smem_u32(smem_raw);
   if ((smem_base & 1023u) != 0) __trap();
   uint8_t* smem = smem_raw;
-  static_assert(!PAIR || CL == 2, "a cta_group::2 pair is a cluster of two");
+  constexpr int CL = PAIR ? 2 : 1;                       // CTAs per cluster
   constexpr bool ARES = KB <= 6;                         // queries resident (else streamed)
   constexpr int kStages = gemm_stages<KB, PAIR>();
   constexpr int kBBytes = PAIR ? kBTileBytes / 2 : kBTileBytes;  // corpus rows staged per CTA
@@ -261,8 +245,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     prefetch_tmap(&tmap_e);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(bar_full + 8 * s, 1);
-      // every MMA thread that reads the stage must release it (a pair has one)
-      mbar_init(bar_empty + 8 * s, PAIR ? 1 : CL);
+      mbar_init(bar_empty + 8 * s, 1);
     }
     mbar_init(bar_a, 1);
     for (int a = 0; a < 2; ++a) {
@@ -292,6 +275,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   if (CL > 1) cluster_sync_all();  // peer barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
+  // ring stages in use (diagnostic knob: fewer stages = fewer bytes in flight)
+  const uint32_t nst = p.ring_stages && p.ring_stages < (uint32_t)kStages ? p.ring_stages : kStages;
   // PAIR: the barriers TMA bytes and drained accumulators are reported to are the leader's
   const bool leader = !PAIR || rank == 0;
   const uint32_t lead_full = PAIR ? map_to_rank(bar_full, 0) : bar_full;
@@ -345,22 +330,15 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             tma_load_2d_pair(stage, &tmap_e, lead_full + 8 * s, kb * kBlockK,
                              row0 + (int)rank * (kBlockN / 2));
           } else {
-            // my barrier counts the whole stage: (my query tile,) my slice of the corpus rows
-            // plus the peers' multicasts of theirs
+            // (query tile and) the 256 corpus rows of this k-block
             mbar_arrive_expect_tx(bar_full + 8 * s, kStageBytes);
             const uint32_t stage = sB + s * kStageBytes;
             if (!ARES)
               tma_load_2d(stage + kBTileBytes, &tmap_q, bar_full + 8 * s, kb * kBlockK,
                           (int)(m_blk * kBlockM));
-            if (CL == 1) {
-              tma_load_2d(stage, &tmap_e, bar_full + 8 * s, kb * kBlockK, row0);
-            } else {
-              constexpr int kRowsPer = kBlockN / CL;
-              tma_load_2d_mc(stage + rank * (kBTileBytes / CL), &tmap_e, bar_full + 8 * s,
-                             kb * kBlockK, row0 + (int)rank * kRowsPer, kMask);
-            }
+            tma_load_2d(stage, &tmap_e, bar_full + 8 * s, kb * kBlockK, row0);
           }
-          if (++s == kStages) s = 0, ph ^= 1;
+          if (++s == nst) s = 0, ph ^= 1;
         }
       }
     }
@@ -387,11 +365,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             if (PAIR) umma_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, (kb | k) != 0 ? 1u : 0u);
             else umma(tmem_d, adesc + 2 * k, bdesc + 2 * k, (kb | k) != 0 ? 1u : 0u);
           }
-          // smem stage reusable once these MMAs retire (in every CTA of the cluster)
+          // smem stage reusable once these MMAs retire (a pair's: in both CTAs)
           if (PAIR) umma_commit_pair(bar_empty + 8 * s, kMask);
-          else if (CL == 1) umma_commit(bar_empty + 8 * s);
-          else umma_commit_mc(bar_empty + 8 * s, kMask);
-          if (++s == kStages) s = 0, ph ^= 1;
+          else umma_commit(bar_empty + 8 * s);
+          if (++s == nst) s = 0, ph ^= 1;
         }
         // accumulator complete (a pair's: in both CTAs' TMEM)
         if (PAIR) umma_commit_pair(bar_tfull + 8 * acc, kMask);
@@ -740,11 +717,11 @@ size_t gemm_smem_bytes(int kb, bool pair) {
   return ring + gemm_ninv_floats(pair) * sizeof(float) + kBarSlots * 8 + 16;
 }
 
-template <int KB, int CL, bool PAIR>
+template <int KB, bool PAIR>
 static cudaError_t launch_gemm_inst(const CUtensorMap& tmap_q, const CUtensorMap& tmap_e,
                                     const GemmParams& p, int grid, size_t smem, cudaStream_t st) {
   static_assert(gemm_stages<KB, PAIR>() == (PAIR ? (KB <= 6 ? 7 : 6) : 4), "gemm_smem_bytes");
-  auto kern = gemm_topk_kernel<KB, CL, PAIR>;
+  auto kern = gemm_topk_kernel<KB, PAIR>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg{};
@@ -754,7 +731,7 @@ static cudaError_t launch_gemm_inst(const CUtensorMap& tmap_q, const CUtensorMap
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.x = PAIR ? 2 : 1;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
@@ -766,13 +743,10 @@ cudaError_t launch_gemm_topk(int kb, int cluster, const CUtensorMap& tmap_q,
                              const CUtensorMap& tmap_e, const GemmParams& p, int grid,
                              cudaStream_t st) {
   const size_t smem = gemm_smem_bytes(kb, cluster == TSS_GEMM_PAIR);
-#define TSS_GEMM_CASE(KBV)                                                                      \
-  case KBV:                                                                                      \
-    return cluster == TSS_GEMM_PAIR                                                             \
-               ? launch_gemm_inst<KBV, 2, true>(tmap_q, tmap_e, p, grid, smem, st)              \
-               : cluster == TSS_GEMM_MULTICAST                                                  \
-                     ? launch_gemm_inst<KBV, 2, false>(tmap_q, tmap_e, p, grid, smem, st)       \
-                     : launch_gemm_inst<KBV, 1, false>(tmap_q, tmap_e, p, grid, smem, st);
+#define TSS_GEMM_CASE(KBV)                                                                  \
+  case KBV:                                                                                  \
+    return cluster == TSS_GEMM_PAIR ? launch_gemm_inst<KBV, true>(tmap_q, tmap_e, p, grid, smem, st) \
+                                    : launch_gemm_inst<KBV, false>(tmap_q, tmap_e, p, grid, smem, st);
   switch (kb) {
     TSS_GEMM_CASE(2)
     TSS_GEMM_CASE(4)

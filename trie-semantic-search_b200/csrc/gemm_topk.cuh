@@ -23,13 +23,14 @@ struct GemmParams {
   uint32_t* cand_count;    // [mb*128][nslices*split] survivors seen (may exceed cand_cap)
   uint32_t cand_cap;       // per (query, slice, column part) list
   uint32_t prefetch_ahead; // tiles of contiguous L2 prefetch ahead of the TMA boxes (0 = off)
+  uint32_t ring_stages;    // 0 = all the stages the kernel has; fewer for latency experiments
   uint32_t debug;          // diagnostics: 1 = no epilogue math, 2 = no MMA issue, 4 = no corpus TMA
 };
 
-// How the CTAs of a launch cooperate.  MULTICAST and PAIR need an even mb and a tmap_e with a
-// 128-row box: two CTAs score different query blocks against the same corpus tiles, either as
-// two cta_group::1 MMAs fed by TMA multicast, or as one cta_group::2 M256 MMA.
-enum GemmCluster { TSS_GEMM_SINGLE = 1, TSS_GEMM_MULTICAST = 2, TSS_GEMM_PAIR = 3 };
+// How the CTAs of a launch cooperate.  PAIR needs an even mb and a tmap_e with a 128-row box:
+// two CTAs score different query blocks against the same corpus tiles as one cta_group::2 M256
+// MMA, each staging half of every tile.  SINGLE: independent CTAs, 256-row box.
+enum GemmCluster { TSS_GEMM_SINGLE = 1, TSS_GEMM_PAIR = 2 };
 size_t gemm_smem_bytes(int kb, bool pair);
 int gemm_col_split();  // survivor lists / threshold samples per (slice, tile)
 cudaError_t launch_gemm_topk(int kb, int cluster, const CUtensorMap& tmap_q,
