@@ -430,7 +430,14 @@ int enqueue_gemm(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
   if (rc) return rc;
   tss_index::Gemm& g = ix->gemm;
   const uint32_t kpad = ix->stride_elems;
-  const uint32_t nq_pad = (nq + 127) / 128 * 128, mb = nq_pad / 128;
+  // CTA pairs (one cta_group::2 MMA over two query blocks): the batch is padded to an even
+  // number of 128-query blocks (a padding query is all zeros and its threshold is +inf)
+  // Up to 128 queries every SM streams its own tiles and independent CTAs are faster.
+  int cluster = nq > 128 ? tss::TSS_GEMM_PAIR : tss::TSS_GEMM_SINGLE;
+  if (const char* cl = getenv("TSS_GEMM_CLUSTER"))  // diagnostics: 1 independent CTAs, 2 pairs
+    cluster = atoi(cl) == tss::TSS_GEMM_SINGLE ? tss::TSS_GEMM_SINGLE : tss::TSS_GEMM_PAIR;
+  const uint32_t qblock = cluster == tss::TSS_GEMM_PAIR ? 256 : 128;
+  const uint32_t nq_pad = (nq + qblock - 1) / qblock * qblock, mb = nq_pad / 128;
   const uint32_t num_tiles = (uint32_t)((ix->n_rows + 255) / 256);
   // the threshold pass yields `split` maxima per sampled tile (one per column part)
   const uint32_t split = (uint32_t)tss::gemm_col_split();
@@ -443,10 +450,6 @@ int enqueue_gemm(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
   if (nslices * (int)tss::gemm_col_split() > 1024) nslices = 1024 / tss::gemm_col_split();
   if (nslices < 1) return fail(TSS_ERR_INVALID_ARG, "batch of %u queries exceeds one K2 launch", nq);
   const int grid = nslices * (int)mb;
-  // CTA pairs (one cta_group::2 MMA over two query blocks) need an even number of query blocks
-  int cluster = (mb % 2 == 0) ? tss::TSS_GEMM_PAIR : tss::TSS_GEMM_SINGLE;
-  if (const char* cl = getenv("TSS_GEMM_CLUSTER"))  // 1 forces independent CTAs
-    if (atoi(cl) == tss::TSS_GEMM_SINGLE) cluster = tss::TSS_GEMM_SINGLE;
   const CUtensorMap& tmap_e = cluster == tss::TSS_GEMM_SINGLE ? g.tmap_e : g.tmap_e_half;
   cudaError_t e;
   e = tss::launch_prep_queries(d_queries, nq, ix->dim, kpad, nq_pad, g.d_qbf16, g.d_inv_q, ix->stream);
@@ -456,7 +459,6 @@ int enqueue_gemm(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
   tss::GemmParams p{};
   p.n_rows = ix->n_rows;
   p.row_base = (uint32_t)ix->row_base;
-  p.rows_bytes = ix->d_rows;
   p.inv_norm = g.d_inv_norm;
   p.mask = mode != TSS_MASK_NONE ? mask->d_words : nullptr;
   p.mask_mode = mode;
@@ -469,8 +471,6 @@ int enqueue_gemm(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
   p.cand = g.d_cand;
   p.cand_count = g.d_cand_count;
   p.cand_cap = cap_s;
-  p.prefetch_ahead = 4;
-  if (const char* pf = getenv("TSS_GEMM_PREFETCH")) p.prefetch_ahead = (uint32_t)atoi(pf);
   if (const char* rs = getenv("TSS_GEMM_STAGES")) p.ring_stages = (uint32_t)atoi(rs);
   if (const char* dbg = getenv("TSS_GEMM_DEBUG")) p.debug = (uint32_t)atoi(dbg);
   const int kb = (int)(kpad / 64);

@@ -4,13 +4,15 @@
 // path runs on the 5th-generation tensor cores.  It replaces the body of HnswIndex::search
 // (reference src/vector.rs:195-202, a stub) for nq >= 16 over a bf16 index.
 //
-// Per CTA (one per SM, 576 threads, cta_group::1):
-//   * 128 queries (one UMMA M tile) stay resident in shared memory for the whole kernel as
-//     K/64 swizzle-128B K-major tiles (TMA, 96 KB at D = 384);
-//   * corpus tiles of 256 rows stream through a 3-stage ring of 256 x 64 bf16 boxes
-//     (TMA 2-D tensor map over the row-major matrix, swizzle 128B, 32 KB per stage);
-//   * one elected thread issues tcgen05.mma (M128 N256 K16, fp32 accumulate) into one of two
-//     256-column TMEM accumulators; tcgen05.commit frees the smem stage / publishes the tile;
+// Per CTA (one per SM, 576 threads; above 128 queries two CTAs form a cta_group::2 pair):
+//   * 128 queries (one UMMA M tile per CTA) stay resident in shared memory for the whole kernel
+//     as K/64 swizzle-128B K-major tiles (TMA, 96 KB at D = 384);
+//   * corpus tiles of 256 rows stream through a ring of 64-element k-blocks (TMA 2-D tensor map
+//     over the row-major matrix, swizzle 128B): a pair's CTAs stage 128 rows each (16 KB per
+//     stage, 7 stages), an independent CTA all 256 (32 KB, 4 stages);
+//   * one elected thread (of a pair: the leader's) issues tcgen05.mma -- M256 N256 K16 across
+//     the pair, M128 N256 K16 alone -- with fp32 accumulation into one of two 256-column TMEM
+//     accumulators; tcgen05.commit frees the smem stage / publishes the tile (in both CTAs);
 //   * sixteen epilogue warps read the accumulator with tcgen05.ld (lane = query, column =
 //     corpus row), scale by the row's 1/norm and either
 //       mode 0: keep the per-tile maximum  (threshold pass over a strided tile sample), or
@@ -52,10 +54,6 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "[%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
       "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
-}
-// contiguous global -> L2 prefetch (no shared-memory destination, no completion signal)
-__device__ __forceinline__ void prefetch_l2(const void* src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 // ---- cta_group::2 (a CTA pair drives one M256 MMA; SASS UTCHMMA.2CTA) ----
 // shared::cluster address of `addr` (an address in this CTA's window) in CTA `rank` of the cluster
@@ -297,24 +295,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         }
       }
       uint32_t s = 0, ph = 0;
-      // The 2-D boxes below touch 128 bytes of every 768-byte row, which is a poor DRAM
-      // access pattern (a page is re-opened once per k-block).  A tile's rows are one
-      // contiguous byte range, so the CTA that owns query block 0 of each slice pulls whole
-      // tiles into L2 a few tiles ahead with sequential bulk prefetches; the boxes then hit L2.
-      const uint32_t kPrefetchAhead = p.prefetch_ahead;
-      const uint32_t tile_bytes = kBlockN * KB * kBlockK * 2;
-      auto prefetch_tile = [&](uint32_t ii) {
-        if (m_blk != 0 || ii >= count) return;
-        const uint64_t r0 = (uint64_t)ii * stride * kBlockN;
-        if (r0 >= p.n_rows) return;
-        const uint64_t rows_left = p.n_rows - r0;
-        const uint32_t bytes =
-            rows_left >= (uint64_t)kBlockN ? tile_bytes : (uint32_t)rows_left * (KB * kBlockK * 2);
-        prefetch_l2(p.rows_bytes + r0 * (uint64_t)(KB * kBlockK * 2), bytes);
-      };
-      for (uint32_t a = 0; a < kPrefetchAhead; ++a) prefetch_tile(slice + a * nslices);
+      // (A contiguous L2 prefetch of whole tiles ahead of these strided boxes used to live here;
+      // measured with the 7-deep ring it changes nothing at 512+ queries and costs 25-40 % at
+      // <= 256, where every SM streams its own tiles.)
       for (uint32_t i = slice; i < count; i += nslices) {
-        prefetch_tile(i + kPrefetchAhead * nslices);
         const int row0 = (int)(i * stride * kBlockN);
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(bar_empty + 8 * s, ph ^ 1);

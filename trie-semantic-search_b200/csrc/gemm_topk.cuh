@@ -9,7 +9,6 @@ namespace tss {
 struct GemmParams {
   uint64_t n_rows;         // rows in this shard
   uint32_t row_base;       // global id of local row 0
-  const uint8_t* rows_bytes;  // the bf16 matrix itself (for contiguous L2 prefetches)
   const float* inv_norm;   // [n_rows] 1/|row|
   const uint32_t* mask;    // row mask words (bit r&31 of word r>>5 <-> local row r) or null
   int mask_mode;           // TSS_MASK_*: masked rows get 1/|row| = NaN, which fmax and >= ignore
@@ -22,7 +21,6 @@ struct GemmParams {
   uint64_t* cand;          // mode 1 out: [mb*128][nslices*split][cand_cap] keys (unscaled by 1/|q|)
   uint32_t* cand_count;    // [mb*128][nslices*split] survivors seen (may exceed cand_cap)
   uint32_t cand_cap;       // per (query, slice, column part) list
-  uint32_t prefetch_ahead; // tiles of contiguous L2 prefetch ahead of the TMA boxes (0 = off)
   uint32_t ring_stages;    // 0 = all the stages the kernel has; fewer for latency experiments
   uint32_t debug;          // diagnostics: 1 = no epilogue math, 2 = no MMA issue, 4 = no corpus TMA
 };
