@@ -204,6 +204,7 @@ struct tss_index {
     uint64_t inv_norm_cap = 0;
     uint16_t* d_qbf16 = nullptr;   // [kWsQueries][kpad]
     float* d_inv_q = nullptr;      // [kWsQueries]
+    float* d_margin = nullptr;     // [kWsQueries] rescoring margins
     float* d_thr = nullptr;        // [kWsQueries]
     float* d_tile_max = nullptr;   // [kGemmMaxSample][kWsQueries]
     uint64_t* d_cand = nullptr;    // [kWsQueries][kGemmCandCap]
@@ -382,6 +383,7 @@ int ensure_gemm_ws(tss_index* ix) {
   if (!g.ready) {
     CU(cudaMalloc(&g.d_qbf16, (size_t)kWsQueries * kpad * 2));
     CU(cudaMalloc(&g.d_inv_q, kWsQueries * sizeof(float)));
+    CU(cudaMalloc(&g.d_margin, kWsQueries * sizeof(float)));
     CU(cudaMalloc(&g.d_thr, kWsQueries * sizeof(float)));
     CU(cudaMalloc(&g.d_tile_max, (size_t)kGemmMaxSample * kWsQueries * sizeof(float)));
     CU(cudaMalloc(&g.d_cand, (size_t)kWsQueries * kGemmCandCap * sizeof(uint64_t)));
@@ -452,7 +454,12 @@ int enqueue_gemm(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
   const int grid = nslices * (int)mb;
   const CUtensorMap& tmap_e = cluster == tss::TSS_GEMM_SINGLE ? g.tmap_e : g.tmap_e_half;
   cudaError_t e;
-  e = tss::launch_prep_queries(d_queries, nq, ix->dim, kpad, nq_pad, g.d_qbf16, g.d_inv_q, ix->stream);
+  // survivors are re-scored with the scan's arithmetic unless TSS_GEMM_RESCORE=0 (then the
+  // result is the top-k of the bf16 x bf16 tensor-core scores)
+  bool rescore = true;
+  if (const char* rsc = getenv("TSS_GEMM_RESCORE")) rescore = atoi(rsc) != 0;
+  e = tss::launch_prep_queries(d_queries, nq, ix->dim, kpad, nq_pad, g.d_qbf16, g.d_inv_q,
+                               g.d_margin, ix->stream);
   if (e != cudaSuccess) return cuda_fail(e, "prep_queries launch");
   const uint32_t nsub = (uint32_t)nslices * split;
   const uint32_t cap_s = kGemmCandCap / nsub;
@@ -477,13 +484,15 @@ int enqueue_gemm(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
   p.mode = 0;
   if ((e = tss::launch_gemm_topk(kb, cluster, g.tmap_q, tmap_e, p, grid, ix->stream)) != cudaSuccess)
     return cuda_fail(e, "gemm_topk_kernel (threshold pass) launch");
-  if ((e = tss::launch_threshold(g.d_tile_max, sample * split, nq_pad, nq, k, g.d_thr, ix->stream)) != cudaSuccess)
+  if ((e = tss::launch_threshold(g.d_tile_max, sample * split, nq_pad, nq, k,
+                                  rescore ? g.d_margin : nullptr, g.d_thr, ix->stream)) != cudaSuccess)
     return cuda_fail(e, "threshold_kernel launch");
   p.mode = 1;
   if ((e = tss::launch_gemm_topk(kb, cluster, g.tmap_q, tmap_e, p, grid, ix->stream)) != cudaSuccess)
     return cuda_fail(e, "gemm_topk_kernel (collect pass) launch");
   if ((e = tss::launch_select(g.d_cand, g.d_cand_count, nsub, cap_s, g.d_inv_q, nq, k,
-                              d_out, g.d_overflow, ix->stream)) != cudaSuccess)
+                              rescore ? d_queries : nullptr, g.d_margin, ix->d_rows, ix->dim, kpad,
+                              (uint32_t)ix->row_base, d_out, g.d_overflow, ix->stream)) != cudaSuccess)
     return cuda_fail(e, "select_kernel launch");
   g_launches.fetch_add(5, std::memory_order_relaxed);
   CU(cudaMemcpyAsync(g.h_cand_count, g.d_overflow, nq * sizeof(uint32_t), cudaMemcpyDeviceToHost,
@@ -680,6 +689,7 @@ void tss_index_destroy(tss_index* ix) {
   cudaFree(ix->gemm.d_inv_norm);
   cudaFree(ix->gemm.d_qbf16);
   cudaFree(ix->gemm.d_inv_q);
+  cudaFree(ix->gemm.d_margin);
   cudaFree(ix->gemm.d_thr);
   cudaFree(ix->gemm.d_tile_max);
   cudaFree(ix->gemm.d_cand);

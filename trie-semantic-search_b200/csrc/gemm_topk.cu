@@ -505,11 +505,14 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 
 // ---- small kernels around it ------------------------------------------------------------
 // fp32 queries -> bf16 [mb*128][kpad] (zero padded) + per-query 1/|q| (of the bf16-rounded query)
+// + the rescoring margin (see select_kernel): a bound on 2 * |q_bf16 . e - q . e| / |e| over
+// all rows e, i.e. twice the rounding of the query to bf16 (2^-9 |q| by Cauchy-Schwarz) plus the
+// fp32 accumulation error of either path (a generous D * 2^-22 |q|).
 __global__ void prep_queries_kernel(const float* q, uint32_t nq, uint32_t dim, uint32_t kpad,
-                                    uint32_t nq_pad, uint16_t* out, float* inv_qnorm) {
+                                    uint32_t nq_pad, uint16_t* out, float* inv_qnorm, float* margin) {
   const uint32_t qi = blockIdx.x;
   if (qi >= nq_pad) return;
-  float ss = 0.f;
+  float ss = 0.f, sf = 0.f;
   for (uint32_t j = threadIdx.x; j < kpad; j += blockDim.x) {
     float v = (qi < nq && j < dim) ? q[(size_t)qi * dim + j] : 0.f;
     uint32_t u = __float_as_uint(v);
@@ -518,16 +521,21 @@ __global__ void prep_queries_kernel(const float* q, uint32_t nq, uint32_t dim, u
     out[(size_t)qi * kpad + j] = h;
     float w = __uint_as_float((uint32_t)h << 16);
     ss = fmaf(w, w, ss);
+    sf = fmaf(v, v, sf);
   }
-  __shared__ float red[32];
+  __shared__ float red[2][32];
 #pragma unroll
-  for (int m = 16; m >= 1; m >>= 1) ss += __shfl_xor_sync(FULL_MASK, ss, m);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  for (int m = 16; m >= 1; m >>= 1) {
+    ss += __shfl_xor_sync(FULL_MASK, ss, m);
+    sf += __shfl_xor_sync(FULL_MASK, sf, m);
+  }
+  if ((threadIdx.x & 31) == 0) red[0][threadIdx.x >> 5] = ss, red[1][threadIdx.x >> 5] = sf;
   __syncthreads();
   if (threadIdx.x == 0) {
-    float t = 0.f;
-    for (uint32_t w = 0; w < (blockDim.x + 31) / 32; ++w) t += red[w];
+    float t = 0.f, tf = 0.f;
+    for (uint32_t w = 0; w < (blockDim.x + 31) / 32; ++w) t += red[0][w], tf += red[1][w];
     inv_qnorm[qi] = t > 0.f ? rsqrtf(t) : 0.f;
+    margin[qi] = 2.f * 1.001f * sqrtf(tf) * (0x1p-9f + (float)dim * 0x1p-22f);
   }
 }
 
@@ -601,8 +609,10 @@ __device__ uint32_t block_radix_kth(uint32_t n, uint32_t k, Fetch fetch, uint32_
 
 // thr[q] = k-th largest of the `count` per-tile-part maxima of query q (+inf for padding
 // queries, -inf when there are fewer than k maxima: keep everything).  tile_max is [nq_pad][count].
+// margin (nullable): the survivors will be re-scored, so everything within the margin below the
+// bound is collected too.
 __global__ void threshold_kernel(const float* tile_max, uint32_t count, uint32_t nq, uint32_t k,
-                                 float* thr) {
+                                 const float* margin, float* thr) {
   __shared__ uint32_t hist[256];
   __shared__ uint32_t s_sel[2];
   const uint32_t q = blockIdx.x;
@@ -617,26 +627,45 @@ __global__ void threshold_kernel(const float* tile_max, uint32_t count, uint32_t
         count, k, [&](uint32_t i) { return orderable_bits(__float_as_uint(mine[i])); }, hist, s_sel);
     uint32_t u = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
     t = __uint_as_float(u);
+    if (margin) t -= margin[q];
   }
   if (threadIdx.x == 0) thr[q] = t;
 }
 
 // exact top-k of each query's survivors (nsub private lists of <= cap_s keys each).  A radix
-// select over the score words finds the k-th score; only keys at or above it (about k of the
-// few thousand survivors) are scaled by 1/|q|, sorted and written.  overflow[q] = 1 when some
-// list was too short to hold its survivors, or the ties at the k-th score do not fit the
-// sorter: the query is then redone by the exact scan.
+// select over the score words finds the k-th best tensor-core score t; overflow[q] = 1 when some
+// list was too short to hold its survivors, or the kept keys do not fit the sorter: the query is
+// then redone by the exact scan.
+//   rs.queries == null: the keys at or above t (about k of the few thousand survivors) are scaled
+//     by 1/|q|, sorted and written -- the exact top-k of the bf16 x bf16 tensor-core scores.
+//   rs.queries != null (default): every key within margin[q] below t is RE-SCORED with the scan
+//     kernel's arithmetic (fp32 query x stored bf16 row, canonical summation order, DESIGN.md
+//     section 3) and the top-k of those scores is written.  With A(e) the tensor-core score of row
+//     e and B(e) the scan's, |A - B| <= margin/2 =: eps.  The k rows with A >= t have B >= t - eps,
+//     so the scan's k-th best score is >= t - eps, so every row of the scan's top-k has
+//     A >= t - 2 eps and is among the re-scored keys: the result is bit-identical to the scan's
+//     (and the oracle's) top-k on the same bf16 index, ties included.
 constexpr uint32_t kSelectSort = 2048;
 constexpr uint32_t kSelectMaxLists = 1024;
-__global__ void select_kernel(const uint64_t* cand, const uint32_t* cand_count, uint32_t nsub,
-                              uint32_t cap_s, const float* inv_qnorm, uint32_t k, uint64_t* out,
-                              uint32_t* overflow) {
+constexpr uint32_t kSelectThreads = 256;
+struct Rescore {
+  const float* queries;     // [nq][dim] fp32 as the caller passed them, or null
+  const float* margin;      // [nq] (prep_queries_kernel)
+  const uint16_t* rows;     // the bf16 matrix, stride_elems per row (a multiple of 128)
+  uint32_t dim, stride_elems, row_base;
+};
+__global__ void __launch_bounds__(kSelectThreads)
+select_kernel(const uint64_t* cand, const uint32_t* cand_count, uint32_t nsub, uint32_t cap_s,
+              const float* inv_qnorm, const Rescore rs, uint32_t k, uint64_t* out,
+              uint32_t* overflow) {
   __shared__ uint64_t sk[kSelectSort];
   __shared__ uint32_t s_off[kSelectMaxLists + 1];
+  __shared__ __align__(16) float s_q[1024];  // the fp32 query, zero padded to the row stride
   __shared__ uint32_t hist[256];
   __shared__ uint32_t s_sel[2];
   __shared__ uint32_t s_over, s_n;
   const uint32_t q = blockIdx.x;
+  const bool rescore = rs.queries != nullptr;
   if (threadIdx.x == 0) {
     uint32_t off = 0, over = 0;
     for (uint32_t sl = 0; sl < nsub; ++sl) {
@@ -649,6 +678,9 @@ __global__ void select_kernel(const uint64_t* cand, const uint32_t* cand_count, 
     s_over = over;
     s_n = 0;
   }
+  if (rescore)
+    for (uint32_t j = threadIdx.x; j < rs.stride_elems; j += blockDim.x)
+      s_q[j] = j < rs.dim ? rs.queries[(size_t)q * rs.dim + j] : 0.f;
   __syncthreads();
   const uint32_t cnt = s_off[nsub];
   const uint64_t* base = cand + (size_t)q * nsub * cap_s;
@@ -665,23 +697,71 @@ __global__ void select_kernel(const uint64_t* cand, const uint32_t* cand_count, 
   uint32_t kth = 0;  // orderable score word of the k-th best survivor (0: keep all)
   if (cnt > k)
     kth = block_radix_kth(cnt, k, [&](uint32_t i) { return (uint32_t)(key_at(i) >> 32); }, hist, s_sel);
+  uint32_t keep_from = kth;  // orderable score word from which keys are kept
+  if (rescore && kth) {
+    const uint32_t u = (kth & 0x80000000u) ? (kth & 0x7FFFFFFFu) : ~kth;
+    keep_from = orderable_bits(__float_as_uint(__uint_as_float(u) - rs.margin[q]));
+  }
   const float iq = inv_qnorm[q];
   for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
     const uint64_t key = key_at(i);
     const uint32_t ob = (uint32_t)(key >> 32);
-    if (ob < kth) continue;
+    if (ob < keep_from) continue;
     const uint32_t pos = atomicAdd(&s_n, 1u);
     if (pos < kSelectSort) {
-      uint32_t u = (ob & 0x80000000u) ? (ob & 0x7FFFFFFFu) : ~ob;
-      float sc = __uint_as_float(u) * iq;
-      if (!isfinite(sc)) sc = 0.f;
-      if (sc == 0.f) sc = 0.f;
-      sk[pos] = ((uint64_t)orderable_bits(__float_as_uint(sc)) << 32) | (key & 0xFFFFFFFFull);
+      if (rescore) {
+        sk[pos] = key;
+      } else {
+        uint32_t u = (ob & 0x80000000u) ? (ob & 0x7FFFFFFFu) : ~ob;
+        float sc = __uint_as_float(u) * iq;
+        if (!isfinite(sc)) sc = 0.f;
+        if (sc == 0.f) sc = 0.f;
+        sk[pos] = ((uint64_t)orderable_bits(__float_as_uint(sc)) << 32) | (key & 0xFFFFFFFFull);
+      }
     }
   }
   __syncthreads();
   uint32_t m = s_n;
   if (m > kSelectSort) m = kSelectSort, s_over = 1;  // (benign race: every writer stores 1)
+  if (rescore) {
+    // one warp per kept key; lane l owns elements 4l..4l+3 of every 128-element stripe, four
+    // sub-accumulators, ((a0+a1)+(a2+a3)), xor butterfly -- scan.cuh's order, explicit _rn ops
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t ns = rs.stride_elems / 128;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (uint32_t st = 0; st < ns; ++st) {
+      const float4 qv = *reinterpret_cast<const float4*>(s_q + st * 128 + lane * 4);
+      a0 = __fmaf_rn(qv.x, qv.x, a0);
+      a1 = __fmaf_rn(qv.y, qv.y, a1);
+      a2 = __fmaf_rn(qv.z, qv.z, a2);
+      a3 = __fmaf_rn(qv.w, qv.w, a3);
+    }
+    const float sq_nq = __fsqrt_rn(butterfly_sum(__fadd_rn(__fadd_rn(a0, a1), __fadd_rn(a2, a3))));
+    for (uint32_t i = warp; i < m; i += kSelectThreads / 32) {
+      const uint32_t row_g = 0xFFFFFFFFu - (uint32_t)sk[i];
+      const uint16_t* rp = rs.rows + (size_t)(row_g - rs.row_base) * rs.stride_elems;
+      float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f, n0 = 0.f, n1 = 0.f, n2 = 0.f, n3 = 0.f;
+      for (uint32_t st = 0; st < ns; ++st) {
+        const uint2 u = __ldg(reinterpret_cast<const uint2*>(rp + st * 128 + lane * 4));
+        const float4 qv = *reinterpret_cast<const float4*>(s_q + st * 128 + lane * 4);
+        const float ex = __uint_as_float(u.x << 16), ey = __uint_as_float(u.x & 0xFFFF0000u);
+        const float ez = __uint_as_float(u.y << 16), ew = __uint_as_float(u.y & 0xFFFF0000u);
+        d0 = __fmaf_rn(qv.x, ex, d0);
+        d1 = __fmaf_rn(qv.y, ey, d1);
+        d2 = __fmaf_rn(qv.z, ez, d2);
+        d3 = __fmaf_rn(qv.w, ew, d3);
+        n0 = __fmaf_rn(ex, ex, n0);
+        n1 = __fmaf_rn(ey, ey, n1);
+        n2 = __fmaf_rn(ez, ez, n2);
+        n3 = __fmaf_rn(ew, ew, n3);
+      }
+      const float dot = butterfly_sum(__fadd_rn(__fadd_rn(d0, d1), __fadd_rn(d2, d3)));
+      const float ne2 = butterfly_sum(__fadd_rn(__fadd_rn(n0, n1), __fadd_rn(n2, n3)));
+      __syncwarp();
+      if (lane == 0) sk[i] = pack_key(finish_score(dot, sq_nq, ne2), row_g);
+    }
+    __syncthreads();
+  }
   uint32_t npad = 2;
   while (npad < m) npad <<= 1;
   for (uint32_t i = m + threadIdx.x; i < npad; i += blockDim.x) sk[i] = 0;
@@ -744,8 +824,9 @@ cudaError_t launch_gemm_topk(int kb, int cluster, const CUtensorMap& tmap_q,
 }
 
 cudaError_t launch_prep_queries(const float* q, uint32_t nq, uint32_t dim, uint32_t kpad,
-                                uint32_t nq_pad, uint16_t* out, float* inv_qnorm, cudaStream_t st) {
-  prep_queries_kernel<<<nq_pad, 128, 0, st>>>(q, nq, dim, kpad, nq_pad, out, inv_qnorm);
+                                uint32_t nq_pad, uint16_t* out, float* inv_qnorm, float* margin,
+                                cudaStream_t st) {
+  prep_queries_kernel<<<nq_pad, 128, 0, st>>>(q, nq, dim, kpad, nq_pad, out, inv_qnorm, margin);
   return cudaGetLastError();
 }
 cudaError_t launch_row_inv_norm(const void* rows, uint64_t n_rows, uint32_t stride_elems, float* out,
@@ -757,15 +838,20 @@ cudaError_t launch_row_inv_norm(const void* rows, uint64_t n_rows, uint32_t stri
   return cudaGetLastError();
 }
 cudaError_t launch_threshold(const float* tile_max, uint32_t count, uint32_t nq_pad, uint32_t nq,
-                             uint32_t k, float* thr, cudaStream_t st) {
-  threshold_kernel<<<nq_pad, 256, 0, st>>>(tile_max, count, nq, k, thr);
+                             uint32_t k, const float* margin, float* thr, cudaStream_t st) {
+  threshold_kernel<<<nq_pad, 256, 0, st>>>(tile_max, count, nq, k, margin, thr);
   return cudaGetLastError();
 }
 cudaError_t launch_select(const uint64_t* cand, const uint32_t* cand_count, uint32_t nslices,
                           uint32_t cap_s, const float* inv_qnorm, uint32_t nq, uint32_t k,
-                          uint64_t* out, uint32_t* overflow, cudaStream_t st) {
-  if (nslices > kSelectMaxLists || k > kSelectSort) return cudaErrorInvalidConfiguration;
-  select_kernel<<<nq, 256, 0, st>>>(cand, cand_count, nslices, cap_s, inv_qnorm, k, out, overflow);
+                          const float* queries, const float* margin, const void* rows, uint32_t dim,
+                          uint32_t stride_elems, uint32_t row_base, uint64_t* out,
+                          uint32_t* overflow, cudaStream_t st) {
+  if (nslices > kSelectMaxLists || k > kSelectSort || stride_elems > 1024 || stride_elems % 128)
+    return cudaErrorInvalidConfiguration;
+  Rescore rs{queries, margin, reinterpret_cast<const uint16_t*>(rows), dim, stride_elems, row_base};
+  select_kernel<<<nq, kSelectThreads, 0, st>>>(cand, cand_count, nslices, cap_s, inv_qnorm, rs, k,
+                                               out, overflow);
   return cudaGetLastError();
 }
 
