@@ -575,28 +575,51 @@ __device__ void block_bitonic_desc(uint64_t* sk, uint32_t n) {
   }
 }
 
-// k-th largest (1-based) of the n 32-bit keys fetch(i), i < n, by a 4-pass 8-bit radix select.
-// hist: 256 shared counters; s_sel: 2 shared words.  All threads of the block call it.
-template <class Fetch>
-__device__ uint32_t block_radix_kth(uint32_t n, uint32_t k, Fetch fetch, uint32_t* hist,
-                                    uint32_t* s_sel) {
+// k-th largest (1-based) of a set of 32-bit keys by a 4-pass 8-bit radix select.  for_each(f)
+// must call f(key, valid) in lock-step across each warp (same trip count in every lane; lanes
+// without an element pass valid = false); it is invoked once per pass.  hist: 256 shared counters,
+// s_sel: 2 shared words.  All 256 threads of the block call it.
+constexpr uint32_t kRadixThreads = 256;
+template <class ForEach>
+__device__ uint32_t block_radix_kth(uint32_t k, ForEach for_each, uint32_t* hist, uint32_t* s_sel) {
+  __shared__ uint32_t s_wtot[kRadixThreads / 32];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t prefix = 0, mask = 0, remaining = k;
   for (int shift = 24; shift >= 0; shift -= 8) {
-    for (uint32_t b = threadIdx.x; b < 256; b += blockDim.x) hist[b] = 0;
+    hist[threadIdx.x] = 0;
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-      uint32_t v = fetch(i);
-      if ((v & mask) == prefix) atomicAdd(&hist[(v >> shift) & 255u], 1u);
+    // Sign, exponent and leading mantissa bits are shared by almost all keys, so the first two
+    // passes would hammer one counter: there a warp adds once per distinct bin.  The low bits
+    // spread over the bins and plain atomics are cheaper than the match.
+    if (shift >= 16) {
+      for_each([&](uint32_t v, bool valid) {
+        const bool mine = valid && (v & mask) == prefix;
+        const uint32_t bin = mine ? (v >> shift) & 255u : 256u;
+        const uint32_t peers = __match_any_sync(FULL_MASK, bin);
+        if (mine && lane == (uint32_t)__ffs(peers) - 1u)
+          atomicAdd(&hist[bin], (uint32_t)__popc(peers));
+      });
+    } else {
+      for_each([&](uint32_t v, bool valid) {
+        if (valid && (v & mask) == prefix) atomicAdd(&hist[(v >> shift) & 255u], 1u);
+      });
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-      uint32_t cum = 0, b = 255;
-      for (;; --b) {
-        if (cum + hist[b] >= remaining || b == 0) break;
-        cum += hist[b];
-      }
-      s_sel[0] = b;
-      s_sel[1] = remaining - cum;
+    // one bin per thread: how many keys sit in higher bins (suffix sums by shuffles)
+    const uint32_t h = hist[threadIdx.x];
+    uint32_t incl = h;
+#pragma unroll
+    for (uint32_t d = 1; d < 32; d <<= 1) {
+      const uint32_t o = __shfl_down_sync(FULL_MASK, incl, d);
+      if (lane + d < 32) incl += o;
+    }
+    if (lane == 0) s_wtot[warp] = incl;
+    __syncthreads();
+    uint32_t above = incl - h;
+    for (uint32_t w = warp + 1; w < kRadixThreads / 32; ++w) above += s_wtot[w];
+    if (above < remaining && remaining <= above + h) {  // exactly one bin holds the k-th key
+      s_sel[0] = threadIdx.x;
+      s_sel[1] = remaining - above;
     }
     __syncthreads();
     prefix |= s_sel[0] << shift;
@@ -611,8 +634,9 @@ __device__ uint32_t block_radix_kth(uint32_t n, uint32_t k, Fetch fetch, uint32_
 // queries, -inf when there are fewer than k maxima: keep everything).  tile_max is [nq_pad][count].
 // margin (nullable): the survivors will be re-scored, so everything within the margin below the
 // bound is collected too.
-__global__ void threshold_kernel(const float* tile_max, uint32_t count, uint32_t nq, uint32_t k,
-                                 const float* margin, float* thr) {
+__global__ void __launch_bounds__(kRadixThreads)
+threshold_kernel(const float* tile_max, uint32_t count, uint32_t nq, uint32_t k,
+                 const float* margin, float* thr) {
   __shared__ uint32_t hist[256];
   __shared__ uint32_t s_sel[2];
   const uint32_t q = blockIdx.x;
@@ -623,8 +647,15 @@ __global__ void threshold_kernel(const float* tile_max, uint32_t count, uint32_t
   } else if (k > count) {
     t = -INFINITY;
   } else {
-    uint32_t o = block_radix_kth(
-        count, k, [&](uint32_t i) { return orderable_bits(__float_as_uint(mine[i])); }, hist, s_sel);
+    auto for_each = [&](auto f) {
+#pragma unroll 4
+      for (uint32_t i0 = 0; i0 < count; i0 += kRadixThreads) {
+        const uint32_t i = i0 + threadIdx.x;
+        const bool valid = i < count;
+        f(valid ? orderable_bits(__float_as_uint(mine[i])) : 0u, valid);
+      }
+    };
+    uint32_t o = block_radix_kth(k, for_each, hist, s_sel);
     uint32_t u = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
     t = __uint_as_float(u);
     if (margin) t -= margin[q];
@@ -647,86 +678,114 @@ __global__ void threshold_kernel(const float* tile_max, uint32_t count, uint32_t
 //     (and the oracle's) top-k on the same bf16 index, ties included.
 constexpr uint32_t kSelectSort = 2048;
 constexpr uint32_t kSelectMaxLists = 1024;
-constexpr uint32_t kSelectThreads = 256;
+constexpr uint32_t kSelectThreads = kRadixThreads;
 struct Rescore {
   const float* queries;     // [nq][dim] fp32 as the caller passed them, or null
   const float* margin;      // [nq] (prep_queries_kernel)
   const uint16_t* rows;     // the bf16 matrix, stride_elems per row (a multiple of 128)
   uint32_t dim, stride_elems, row_base;
 };
-__global__ void __launch_bounds__(kSelectThreads)
+// One block per query; the kernel is a single wave of latency-bound blocks (8 per SM), so it is
+// written for few dependent memory round trips: lists are walked by warps (no index search),
+// four keys per lane are in flight, and the re-scoring runs 32 rows at a time.
+__global__ void __launch_bounds__(kSelectThreads, 8)
 select_kernel(const uint64_t* cand, const uint32_t* cand_count, uint32_t nsub, uint32_t cap_s,
               const float* inv_qnorm, const Rescore rs, uint32_t k, uint64_t* out,
               uint32_t* overflow) {
   __shared__ uint64_t sk[kSelectSort];
-  __shared__ uint32_t s_off[kSelectMaxLists + 1];
+  __shared__ uint32_t s_cnt[kSelectMaxLists];
   __shared__ __align__(16) float s_q[1024];  // the fp32 query, zero padded to the row stride
   __shared__ uint32_t hist[256];
   __shared__ uint32_t s_sel[2];
-  __shared__ uint32_t s_over, s_n;
+  __shared__ uint32_t s_over, s_n, s_tot;
   const uint32_t q = blockIdx.x;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr uint32_t kWarps = kSelectThreads / 32;
   const bool rescore = rs.queries != nullptr;
-  if (threadIdx.x == 0) {
-    uint32_t off = 0, over = 0;
-    for (uint32_t sl = 0; sl < nsub; ++sl) {
+  if (threadIdx.x == 0) s_over = 0, s_n = 0, s_tot = 0;
+  __syncthreads();
+  {
+    uint32_t tot = 0, over = 0;
+    for (uint32_t sl = threadIdx.x; sl < nsub; sl += kSelectThreads) {
       uint32_t c = cand_count[(size_t)q * nsub + sl];
       if (c > cap_s) c = cap_s, over = 1;
-      s_off[sl] = off;
-      off += c;
+      s_cnt[sl] = c;
+      tot += c;
     }
-    s_off[nsub] = off;
-    s_over = over;
-    s_n = 0;
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+      tot += __shfl_xor_sync(FULL_MASK, tot, m);
+      over |= __shfl_xor_sync(FULL_MASK, over, m);
+    }
+    if (lane == 0) {
+      atomicAdd(&s_tot, tot);
+      if (over) s_over = 1;
+    }
   }
   if (rescore)
-    for (uint32_t j = threadIdx.x; j < rs.stride_elems; j += blockDim.x)
+    for (uint32_t j = threadIdx.x; j < rs.stride_elems; j += kSelectThreads)
       s_q[j] = j < rs.dim ? rs.queries[(size_t)q * rs.dim + j] : 0.f;
   __syncthreads();
-  const uint32_t cnt = s_off[nsub];
+  const uint32_t cnt = s_tot;
   const uint64_t* base = cand + (size_t)q * nsub * cap_s;
-  // candidate i of the concatenated lists (binary search over the list offsets)
-  auto key_at = [&](uint32_t i) -> uint64_t {
-    uint32_t lo = 0, hi = nsub;
-    while (hi - lo > 1) {
-      uint32_t mid = (lo + hi) >> 1;
-      if (s_off[mid] <= i) lo = mid;
-      else hi = mid;
+  // f(key, valid) over all survivors, warp w walking lists w, w + 8, ...: lock-step per warp
+  auto for_each_key = [&](auto f) {
+    for (uint32_t sl = warp; sl < nsub; sl += kWarps) {
+      const uint32_t c = s_cnt[sl];
+      const uint64_t* lp = base + (size_t)sl * cap_s;
+      for (uint32_t j0 = 0; j0 < c; j0 += 128) {
+        uint64_t key[4];
+#pragma unroll
+        for (uint32_t u = 0; u < 4; ++u) {
+          const uint32_t j = j0 + 32 * u + lane;
+          key[u] = j < c ? lp[j] : 0ull;
+        }
+#pragma unroll
+        for (uint32_t u = 0; u < 4; ++u)
+          if (j0 + 32 * u < c) f(key[u], j0 + 32 * u + lane < c);
+      }
     }
-    return base[(size_t)lo * cap_s + (i - s_off[lo])];
   };
   uint32_t kth = 0;  // orderable score word of the k-th best survivor (0: keep all)
-  if (cnt > k)
-    kth = block_radix_kth(cnt, k, [&](uint32_t i) { return (uint32_t)(key_at(i) >> 32); }, hist, s_sel);
+  if (cnt > k) {
+    auto for_each_score = [&](auto f) {
+      for_each_key([&](uint64_t key, bool valid) { f((uint32_t)(key >> 32), valid); });
+    };
+    kth = block_radix_kth(k, for_each_score, hist, s_sel);
+  }
   uint32_t keep_from = kth;  // orderable score word from which keys are kept
   if (rescore && kth) {
     const uint32_t u = (kth & 0x80000000u) ? (kth & 0x7FFFFFFFu) : ~kth;
     keep_from = orderable_bits(__float_as_uint(__uint_as_float(u) - rs.margin[q]));
   }
   const float iq = inv_qnorm[q];
-  for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
-    const uint64_t key = key_at(i);
+  for_each_key([&](uint64_t key, bool valid) {
     const uint32_t ob = (uint32_t)(key >> 32);
-    if (ob < keep_from) continue;
+    if (!valid || ob < keep_from) return;
     const uint32_t pos = atomicAdd(&s_n, 1u);
-    if (pos < kSelectSort) {
-      if (rescore) {
-        sk[pos] = key;
-      } else {
-        uint32_t u = (ob & 0x80000000u) ? (ob & 0x7FFFFFFFu) : ~ob;
-        float sc = __uint_as_float(u) * iq;
-        if (!isfinite(sc)) sc = 0.f;
-        if (sc == 0.f) sc = 0.f;
-        sk[pos] = ((uint64_t)orderable_bits(__float_as_uint(sc)) << 32) | (key & 0xFFFFFFFFull);
-      }
+    if (pos >= kSelectSort) return;
+    if (rescore) {
+      sk[pos] = key;
+    } else {
+      uint32_t u = (ob & 0x80000000u) ? (ob & 0x7FFFFFFFu) : ~ob;
+      float sc = __uint_as_float(u) * iq;
+      if (!isfinite(sc)) sc = 0.f;
+      if (sc == 0.f) sc = 0.f;
+      sk[pos] = ((uint64_t)orderable_bits(__float_as_uint(sc)) << 32) | (key & 0xFFFFFFFFull);
     }
-  }
+  });
   __syncthreads();
   uint32_t m = s_n;
   if (m > kSelectSort) m = kSelectSort, s_over = 1;  // (benign race: every writer stores 1)
   if (rescore) {
-    // one warp per kept key; lane l owns elements 4l..4l+3 of every 128-element stripe, four
-    // sub-accumulators, ((a0+a1)+(a2+a3)), xor butterfly -- scan.cuh's order, explicit _rn ops
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // The scan's arithmetic (scan.cuh): "lane" l of 32 owns elements
+    // 4l..4l+3 of every 128-element stripe with four sub-accumulators, combines them
+    // ((a0+a1)+(a2+a3)), then an xor butterfly 16, 8, 4, 2, 1 over the 32 lane partials.
+    // The query norm is done that way by a whole warp.  Rows are done FOUR per warp for memory
+    // parallelism: thread t of an 8-thread group plays lanes t, t+8, t+16, t+24 one after the
+    // other; butterfly steps 16 and 8 pair exactly those four partials inside the thread
+    // ((p_t + p_t+16) + (p_t+8 + p_t+24)), steps 4, 2, 1 are shuffles within the group -- the
+    // same additions in the same order, so the same bits.
     const uint32_t ns = rs.stride_elems / 128;
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
     for (uint32_t st = 0; st < ns; ++st) {
@@ -737,28 +796,42 @@ select_kernel(const uint64_t* cand, const uint32_t* cand_count, uint32_t nsub, u
       a3 = __fmaf_rn(qv.w, qv.w, a3);
     }
     const float sq_nq = __fsqrt_rn(butterfly_sum(__fadd_rn(__fadd_rn(a0, a1), __fadd_rn(a2, a3))));
-    for (uint32_t i = warp; i < m; i += kSelectThreads / 32) {
-      const uint32_t row_g = 0xFFFFFFFFu - (uint32_t)sk[i];
+    const uint32_t grp = lane >> 3, t8 = lane & 7;
+    for (uint32_t i0 = warp * 4; i0 < m; i0 += kWarps * 4) {
+      const uint32_t i = i0 + grp;
+      const bool live = i < m;
+      const uint32_t row_g = 0xFFFFFFFFu - (uint32_t)sk[live ? i : i0];
       const uint16_t* rp = rs.rows + (size_t)(row_g - rs.row_base) * rs.stride_elems;
-      float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f, n0 = 0.f, n1 = 0.f, n2 = 0.f, n3 = 0.f;
-      for (uint32_t st = 0; st < ns; ++st) {
-        const uint2 u = __ldg(reinterpret_cast<const uint2*>(rp + st * 128 + lane * 4));
-        const float4 qv = *reinterpret_cast<const float4*>(s_q + st * 128 + lane * 4);
-        const float ex = __uint_as_float(u.x << 16), ey = __uint_as_float(u.x & 0xFFFF0000u);
-        const float ez = __uint_as_float(u.y << 16), ew = __uint_as_float(u.y & 0xFFFF0000u);
-        d0 = __fmaf_rn(qv.x, ex, d0);
-        d1 = __fmaf_rn(qv.y, ey, d1);
-        d2 = __fmaf_rn(qv.z, ez, d2);
-        d3 = __fmaf_rn(qv.w, ew, d3);
-        n0 = __fmaf_rn(ex, ex, n0);
-        n1 = __fmaf_rn(ey, ey, n1);
-        n2 = __fmaf_rn(ez, ez, n2);
-        n3 = __fmaf_rn(ew, ew, n3);
+      float pd[4], pn[4];
+#pragma unroll
+      for (uint32_t j = 0; j < 4; ++j) {
+        const uint32_t l = t8 + 8 * j;  // the lane being played
+        float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f, n0 = 0.f, n1 = 0.f, n2 = 0.f, n3 = 0.f;
+        for (uint32_t st = 0; st < ns; ++st) {
+          const uint2 u = __ldg(reinterpret_cast<const uint2*>(rp + st * 128 + l * 4));
+          const float4 qv = *reinterpret_cast<const float4*>(s_q + st * 128 + l * 4);
+          const float ex = __uint_as_float(u.x << 16), ey = __uint_as_float(u.x & 0xFFFF0000u);
+          const float ez = __uint_as_float(u.y << 16), ew = __uint_as_float(u.y & 0xFFFF0000u);
+          d0 = __fmaf_rn(qv.x, ex, d0);
+          d1 = __fmaf_rn(qv.y, ey, d1);
+          d2 = __fmaf_rn(qv.z, ez, d2);
+          d3 = __fmaf_rn(qv.w, ew, d3);
+          n0 = __fmaf_rn(ex, ex, n0);
+          n1 = __fmaf_rn(ey, ey, n1);
+          n2 = __fmaf_rn(ez, ez, n2);
+          n3 = __fmaf_rn(ew, ew, n3);
+        }
+        pd[j] = __fadd_rn(__fadd_rn(d0, d1), __fadd_rn(d2, d3));
+        pn[j] = __fadd_rn(__fadd_rn(n0, n1), __fadd_rn(n2, n3));
       }
-      const float dot = butterfly_sum(__fadd_rn(__fadd_rn(d0, d1), __fadd_rn(d2, d3)));
-      const float ne2 = butterfly_sum(__fadd_rn(__fadd_rn(n0, n1), __fadd_rn(n2, n3)));
-      __syncwarp();
-      if (lane == 0) sk[i] = pack_key(finish_score(dot, sq_nq, ne2), row_g);
+      float dot = __fadd_rn(__fadd_rn(pd[0], pd[2]), __fadd_rn(pd[1], pd[3]));  // xor 16, then 8
+      float ne2 = __fadd_rn(__fadd_rn(pn[0], pn[2]), __fadd_rn(pn[1], pn[3]));
+#pragma unroll
+      for (int mm = 4; mm >= 1; mm >>= 1) {
+        dot = __fadd_rn(dot, __shfl_xor_sync(FULL_MASK, dot, mm));
+        ne2 = __fadd_rn(ne2, __shfl_xor_sync(FULL_MASK, ne2, mm));
+      }
+      if (live && t8 == 0) sk[i] = pack_key(finish_score(dot, sq_nq, ne2), row_g);
     }
     __syncthreads();
   }
