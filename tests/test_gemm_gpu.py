@@ -183,3 +183,38 @@ def test_masked_large_batch(tss, orc, mode, nq):
                            bf16=True)
     assert np.array_equal(gr, want[0])
     assert np.array_equal(gs.view(np.uint32), want[1].view(np.uint32))
+
+
+@pytest.mark.parametrize("n,nq,k,dim", [(150_000, 256, 100, 384), (120_001, 40, 10, 384),
+                                        (90_000, 130, 10, 200), (60_000, 64, 5, 768)])
+def test_fp32_index_large_batches_are_exact(tss, orc, n, nq, k, dim):
+    """An fp32 index sends large batches through the tensor cores too (a bf16 shadow of the rows
+    picks the candidates), and the survivors are re-scored from the fp32 rows: rows and score bits
+    equal the fp32 oracle -- north_star's bit-exact bar for the fp32 path."""
+    rng = np.random.default_rng(n + nq)
+    rows = rng.standard_normal((n, dim)).astype(np.float32)
+    q = rng.standard_normal((nq, dim)).astype(np.float32)
+    q[1] = rows[31337] + 0.125 * q[1]
+    ix = tss.FlatIndex(dim, tss.TSS_F32)
+    ix.add(rows)
+    ix.finalize()
+    before = tss.launch_count()
+    gr, gs, gc = ix.search(q, k)
+    assert tss.launch_count() - before <= 8  # shadow + norms + the K2 pipeline, not nq/4 scans
+    assert np.all(gc == k) and gr[1][0] == 31337
+    want = orc.cosine_topk(rows, q, k)
+    assert np.array_equal(gr, want[0])
+    assert np.array_equal(gs.view(np.uint32), want[1].view(np.uint32))
+    # a second batch reuses the shadow; a masked one too
+    bits = rng.random(n) < 0.5
+    words = np.zeros((n + 31) // 32, dtype=np.uint32)
+    idx = np.nonzero(bits)[0]
+    np.bitwise_or.at(words, idx >> 5, (np.uint32(1) << (idx & 31).astype(np.uint32)))
+    m = tss.Mask(n)
+    m.upload(words)
+    before = tss.launch_count()
+    gr, gs, gc = ix.search(q, k, m, tss.TSS_MASK_INCLUDE)
+    assert tss.launch_count() - before == 5
+    want = orc.cosine_topk(rows, q, k, mask_words=words, mask_mode=orc.MASK_INCLUDE)
+    assert np.array_equal(gr, want[0])
+    assert np.array_equal(gs.view(np.uint32), want[1].view(np.uint32))

@@ -211,11 +211,17 @@ struct tss_index {
     uint32_t* d_cand_count = nullptr;  // [kWsQueries][nslices]
     uint32_t* d_overflow = nullptr;    // [kWsQueries]
     uint32_t* h_cand_count = nullptr;  // pinned copy of d_overflow
-    CUtensorMap tmap_q, tmap_e, tmap_e_half;  // corpus boxes of 256 rows / 128 rows (cluster 2)
+    CUtensorMap tmap_q, tmap_e, tmap_e_half;  // corpus boxes of 256 rows / 128 rows (CTA pairs)
     uint64_t tmap_rows = 0;
     const void* tmap_base = nullptr;
+    // fp32 index: bf16 (RNE) shadow of the matrix for the tensor-core pass; the survivors are
+    // re-scored from the fp32 rows, so results stay bit-identical to the fp32 scan
+    uint8_t* d_shadow = nullptr;
+    uint64_t shadow_cap = 0, shadow_rows = 0;
+    const void* shadow_base = nullptr;
+    bool shadow_failed = false;    // no memory for it: large batches stay on the scan
   } gemm;
-  uint32_t gemm_min_nq = 16;  // batches at least this large use K2 (bf16 storage, D <= 384)
+  uint32_t gemm_min_nq = 16;  // batches at least this large use K2
   uint32_t* d_round_mask = nullptr;  // scratch mask of the k > 128 scan rounds
   uint64_t round_mask_words = 0;
   // fused sharded merge: exchange buffers of all ranks mapped with CUDA IPC (<= 8 ranks)
@@ -371,8 +377,8 @@ int ensure_gather_ws(tss_index* ix) {
 
 bool gemm_eligible(const tss_index* ix, uint32_t nq, uint32_t k, int mode) {
   (void)mode;  // masks ride along: a masked row's 1/|row| is NaN in the epilogue
-  return ix->storage == TSS_BF16 && nq >= ix->gemm_min_nq && ix->n_rows >= 4ull * 256 * k &&
-         k <= TSS_MAX_K;
+  if (ix->storage == TSS_F32 && ix->gemm.shadow_failed) return false;
+  return nq >= ix->gemm_min_nq && ix->n_rows >= 4ull * 256 * k && k <= TSS_MAX_K;
 }
 
 int ensure_gemm_ws(tss_index* ix) {
@@ -393,6 +399,32 @@ int ensure_gemm_ws(tss_index* ix) {
     if ((rc = make_tmap(&g.tmap_q, g.d_qbf16, kWsQueries, kpad, 128))) return rc;
     g.ready = true;
   }
+  // the bf16 matrix the tensor cores read: the index itself, or the shadow of an fp32 index
+  const uint8_t* e_rows = ix->d_rows;
+  if (ix->storage == TSS_F32) {
+    if (g.shadow_cap < ix->n_rows) {
+      cudaFree(g.d_shadow);
+      g.d_shadow = nullptr;
+      g.shadow_cap = g.shadow_rows = 0;
+      const size_t bytes = (size_t)(ix->capacity + 16) * kpad * 2;
+      if (cudaMalloc(&g.d_shadow, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        g.shadow_failed = true;
+        return fail(TSS_ERR_OOM, "no memory for the %zu-byte bf16 shadow of the fp32 index", bytes);
+      }
+      g.shadow_cap = ix->capacity;
+    }
+    if (g.shadow_rows != ix->n_rows || g.shadow_base != ix->d_rows) {
+      // the stored rows are already padded to the stride: convert them as stride-wide rows
+      cudaError_t e = tss::launch_pack_rows(reinterpret_cast<const float*>(ix->d_rows), g.d_shadow,
+                                            ix->n_rows, kpad, kpad, true, ix->stream);
+      if (e != cudaSuccess) return cuda_fail(e, "bf16 shadow conversion launch");
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+      g.shadow_rows = ix->n_rows;
+      g.shadow_base = ix->d_rows;
+    }
+    e_rows = g.d_shadow;
+  }
   if (g.inv_norm_cap < ix->n_rows) {
     cudaFree(g.d_inv_norm);
     g.d_inv_norm = nullptr;
@@ -402,15 +434,15 @@ int ensure_gemm_ws(tss_index* ix) {
   }
   if (g.norm_rows != ix->n_rows || g.norm_base != ix->d_rows) {
     cudaError_t e =
-        tss::launch_row_inv_norm(ix->d_rows, ix->n_rows, ix->stride_elems, g.d_inv_norm, ix->stream);
+        tss::launch_row_inv_norm(e_rows, ix->n_rows, ix->stride_elems, g.d_inv_norm, ix->stream);
     if (e != cudaSuccess) return cuda_fail(e, "row_inv_norm launch");
     g_launches.fetch_add(1, std::memory_order_relaxed);
     g.norm_rows = ix->n_rows;
     g.norm_base = ix->d_rows;
   }
   if (g.tmap_rows != ix->n_rows || g.tmap_base != ix->d_rows) {
-    if ((rc = make_tmap(&g.tmap_e, ix->d_rows, ix->n_rows, kpad, 256))) return rc;
-    if ((rc = make_tmap(&g.tmap_e_half, ix->d_rows, ix->n_rows, kpad, 128))) return rc;
+    if ((rc = make_tmap(&g.tmap_e, e_rows, ix->n_rows, kpad, 256))) return rc;
+    if ((rc = make_tmap(&g.tmap_e_half, e_rows, ix->n_rows, kpad, 128))) return rc;
     g.tmap_rows = ix->n_rows;
     g.tmap_base = ix->d_rows;
   }
@@ -458,8 +490,9 @@ int enqueue_gemm(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
   // result is the top-k of the bf16 x bf16 tensor-core scores)
   bool rescore = true;
   if (const char* rsc = getenv("TSS_GEMM_RESCORE")) rescore = atoi(rsc) != 0;
+  if (ix->storage == TSS_F32) rescore = true;  // the raw scores would be those of the shadow
   e = tss::launch_prep_queries(d_queries, nq, ix->dim, kpad, nq_pad, g.d_qbf16, g.d_inv_q,
-                               g.d_margin, ix->stream);
+                               g.d_margin, ix->storage == TSS_F32, ix->stream);
   if (e != cudaSuccess) return cuda_fail(e, "prep_queries launch");
   const uint32_t nsub = (uint32_t)nslices * split;
   const uint32_t cap_s = kGemmCandCap / nsub;
@@ -491,8 +524,9 @@ int enqueue_gemm(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
   if ((e = tss::launch_gemm_topk(kb, cluster, g.tmap_q, tmap_e, p, grid, ix->stream)) != cudaSuccess)
     return cuda_fail(e, "gemm_topk_kernel (collect pass) launch");
   if ((e = tss::launch_select(g.d_cand, g.d_cand_count, nsub, cap_s, g.d_inv_q, nq, k,
-                              rescore ? d_queries : nullptr, g.d_margin, ix->d_rows, ix->dim, kpad,
-                              (uint32_t)ix->row_base, d_out, g.d_overflow, ix->stream)) != cudaSuccess)
+                              rescore ? d_queries : nullptr, g.d_margin, ix->d_rows,
+                              ix->storage == TSS_F32, ix->dim, kpad, (uint32_t)ix->row_base, d_out,
+                              g.d_overflow, ix->stream)) != cudaSuccess)
     return cuda_fail(e, "select_kernel launch");
   g_launches.fetch_add(5, std::memory_order_relaxed);
   CU(cudaMemcpyAsync(g.h_cand_count, g.d_overflow, nq * sizeof(uint32_t), cudaMemcpyDeviceToHost,
@@ -563,7 +597,11 @@ int enqueue_scan_rounds(tss_index* ix, const float* d_queries, uint32_t nq, uint
 int enqueue_local(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
                   const tss_mask* mask, int mode, uint64_t* d_out, bool* merged) {
   *merged = false;
-  if (!gemm_eligible(ix, nq, k, mode)) {
+  bool use_gemm = gemm_eligible(ix, nq, k, mode);
+  if (use_gemm && ix->storage == TSS_F32 && ensure_gemm_ws(ix) == TSS_ERR_OOM &&
+      ix->gemm.shadow_failed)
+    use_gemm = false;  // no room for the bf16 shadow: exact all the same, one scan per 4 queries
+  if (!use_gemm) {
     if (k > TSS_MAX_FUSED_K) return enqueue_scan_rounds(ix, d_queries, nq, k, mask, mode, d_out);
     *merged = ix->comm && ix->xchg.ready;
     return enqueue_scan(ix, d_queries, nq, k, mask, mode, d_out);
@@ -687,6 +725,7 @@ void tss_index_destroy(tss_index* ix) {
   cudaFree(ix->xchg.local);
   cudaFree(ix->d_round_mask);
   cudaFree(ix->gemm.d_inv_norm);
+  cudaFree(ix->gemm.d_shadow);
   cudaFree(ix->gemm.d_qbf16);
   cudaFree(ix->gemm.d_inv_q);
   cudaFree(ix->gemm.d_margin);

@@ -505,11 +505,16 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 
 // ---- small kernels around it ------------------------------------------------------------
 // fp32 queries -> bf16 [mb*128][kpad] (zero padded) + per-query 1/|q| (of the bf16-rounded query)
-// + the rescoring margin (see select_kernel): a bound on 2 * |q_bf16 . e - q . e| / |e| over
-// all rows e, i.e. twice the rounding of the query to bf16 (2^-9 |q| by Cauchy-Schwarz) plus the
-// fp32 accumulation error of either path (a generous D * 2^-22 |q|).
+// + the rescoring margin (see select_kernel): a bound on 2 * |A(e) - B(e)| over all rows e, where
+// A = q_bf16 . e_t / |e_t| is what the tensor cores see (e_t: the bf16 row they read) and
+// B = q . e / |e| what the scan computes from the stored row e.  A - B = (q_bf16 - q) . e_t/|e_t|
+// + q . (e_t/|e_t| - e/|e|): the first term is at most 2^-9 |q| (RNE of the query, Cauchy-
+// Schwarz); the second is zero on a bf16 index (e_t = e) and at most 2 |e_t - e| / |e| * |q| <=
+// 2^-8 |q| when e_t is the bf16 shadow of an fp32 row; plus the fp32 accumulation error of either
+// path (a generous D * 2^-22 |q|).
 __global__ void prep_queries_kernel(const float* q, uint32_t nq, uint32_t dim, uint32_t kpad,
-                                    uint32_t nq_pad, uint16_t* out, float* inv_qnorm, float* margin) {
+                                    uint32_t nq_pad, uint16_t* out, float* inv_qnorm, float* margin,
+                                    int shadowed) {
   const uint32_t qi = blockIdx.x;
   if (qi >= nq_pad) return;
   float ss = 0.f, sf = 0.f;
@@ -535,7 +540,8 @@ __global__ void prep_queries_kernel(const float* q, uint32_t nq, uint32_t dim, u
     float t = 0.f, tf = 0.f;
     for (uint32_t w = 0; w < (blockDim.x + 31) / 32; ++w) t += red[0][w], tf += red[1][w];
     inv_qnorm[qi] = t > 0.f ? rsqrtf(t) : 0.f;
-    margin[qi] = 2.f * 1.001f * sqrtf(tf) * (0x1p-9f + (float)dim * 0x1p-22f);
+    margin[qi] = 2.f * 1.001f * sqrtf(tf) *
+                 ((shadowed ? 0x1p-9f + 0x1p-8f : 0x1p-9f) + (float)dim * 0x1p-22f);
   }
 }
 
@@ -682,7 +688,8 @@ constexpr uint32_t kSelectThreads = kRadixThreads;
 struct Rescore {
   const float* queries;     // [nq][dim] fp32 as the caller passed them, or null
   const float* margin;      // [nq] (prep_queries_kernel)
-  const uint16_t* rows;     // the bf16 matrix, stride_elems per row (a multiple of 128)
+  const void* rows;         // the STORED matrix (bf16 or fp32), stride_elems per row (k * 128)
+  int rows_f32;
   uint32_t dim, stride_elems, row_base;
 };
 // One block per query; the kernel is a single wave of latency-bound blocks (8 per SM), so it is
@@ -801,17 +808,25 @@ select_kernel(const uint64_t* cand, const uint32_t* cand_count, uint32_t nsub, u
       const uint32_t i = i0 + grp;
       const bool live = i < m;
       const uint32_t row_g = 0xFFFFFFFFu - (uint32_t)sk[live ? i : i0];
-      const uint16_t* rp = rs.rows + (size_t)(row_g - rs.row_base) * rs.stride_elems;
+      const size_t roff = (size_t)(row_g - rs.row_base) * rs.stride_elems;
+      const uint16_t* rp = reinterpret_cast<const uint16_t*>(rs.rows) + roff;
+      const float* rpf = reinterpret_cast<const float*>(rs.rows) + roff;
       float pd[4], pn[4];
 #pragma unroll
       for (uint32_t j = 0; j < 4; ++j) {
         const uint32_t l = t8 + 8 * j;  // the lane being played
         float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f, n0 = 0.f, n1 = 0.f, n2 = 0.f, n3 = 0.f;
         for (uint32_t st = 0; st < ns; ++st) {
-          const uint2 u = __ldg(reinterpret_cast<const uint2*>(rp + st * 128 + l * 4));
           const float4 qv = *reinterpret_cast<const float4*>(s_q + st * 128 + l * 4);
-          const float ex = __uint_as_float(u.x << 16), ey = __uint_as_float(u.x & 0xFFFF0000u);
-          const float ez = __uint_as_float(u.y << 16), ew = __uint_as_float(u.y & 0xFFFF0000u);
+          float ex, ey, ez, ew;
+          if (rs.rows_f32) {
+            const float4 e = __ldg(reinterpret_cast<const float4*>(rpf + st * 128 + l * 4));
+            ex = e.x, ey = e.y, ez = e.z, ew = e.w;
+          } else {
+            const uint2 u = __ldg(reinterpret_cast<const uint2*>(rp + st * 128 + l * 4));
+            ex = __uint_as_float(u.x << 16), ey = __uint_as_float(u.x & 0xFFFF0000u);
+            ez = __uint_as_float(u.y << 16), ew = __uint_as_float(u.y & 0xFFFF0000u);
+          }
           d0 = __fmaf_rn(qv.x, ex, d0);
           d1 = __fmaf_rn(qv.y, ey, d1);
           d2 = __fmaf_rn(qv.z, ez, d2);
@@ -898,8 +913,9 @@ cudaError_t launch_gemm_topk(int kb, int cluster, const CUtensorMap& tmap_q,
 
 cudaError_t launch_prep_queries(const float* q, uint32_t nq, uint32_t dim, uint32_t kpad,
                                 uint32_t nq_pad, uint16_t* out, float* inv_qnorm, float* margin,
-                                cudaStream_t st) {
-  prep_queries_kernel<<<nq_pad, 128, 0, st>>>(q, nq, dim, kpad, nq_pad, out, inv_qnorm, margin);
+                                bool shadowed, cudaStream_t st) {
+  prep_queries_kernel<<<nq_pad, 128, 0, st>>>(q, nq, dim, kpad, nq_pad, out, inv_qnorm, margin,
+                                              shadowed ? 1 : 0);
   return cudaGetLastError();
 }
 cudaError_t launch_row_inv_norm(const void* rows, uint64_t n_rows, uint32_t stride_elems, float* out,
@@ -917,12 +933,12 @@ cudaError_t launch_threshold(const float* tile_max, uint32_t count, uint32_t nq_
 }
 cudaError_t launch_select(const uint64_t* cand, const uint32_t* cand_count, uint32_t nslices,
                           uint32_t cap_s, const float* inv_qnorm, uint32_t nq, uint32_t k,
-                          const float* queries, const float* margin, const void* rows, uint32_t dim,
-                          uint32_t stride_elems, uint32_t row_base, uint64_t* out,
-                          uint32_t* overflow, cudaStream_t st) {
+                          const float* queries, const float* margin, const void* rows,
+                          bool rows_f32, uint32_t dim, uint32_t stride_elems, uint32_t row_base,
+                          uint64_t* out, uint32_t* overflow, cudaStream_t st) {
   if (nslices > kSelectMaxLists || k > kSelectSort || stride_elems > 1024 || stride_elems % 128)
     return cudaErrorInvalidConfiguration;
-  Rescore rs{queries, margin, reinterpret_cast<const uint16_t*>(rows), dim, stride_elems, row_base};
+  Rescore rs{queries, margin, rows, rows_f32 ? 1 : 0, dim, stride_elems, row_base};
   select_kernel<<<nq, kSelectThreads, 0, st>>>(cand, cand_count, nslices, cap_s, inv_qnorm, rs, k,
                                                out, overflow);
   return cudaGetLastError();

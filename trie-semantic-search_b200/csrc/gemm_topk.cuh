@@ -34,10 +34,11 @@ int gemm_col_split();  // survivor lists / threshold samples per (slice, tile)
 cudaError_t launch_gemm_topk(int kb, int cluster, const CUtensorMap& tmap_q,
                              const CUtensorMap& tmap_e, const GemmParams& p, int grid,
                              cudaStream_t st);
-// margin: [nq_pad] out, the rescoring margin of every query (see select_kernel)
+// margin: [nq_pad] out, the rescoring margin of every query (see select_kernel); shadowed: the
+// tensor cores read a bf16 shadow of fp32 rows (the margin then covers the rows' rounding too)
 cudaError_t launch_prep_queries(const float* q, uint32_t nq, uint32_t dim, uint32_t kpad,
                                 uint32_t nq_pad, uint16_t* out, float* inv_qnorm, float* margin,
-                                cudaStream_t st);
+                                bool shadowed, cudaStream_t st);
 cudaError_t launch_row_inv_norm(const void* rows, uint64_t n_rows, uint32_t stride_elems, float* out,
                                 cudaStream_t st);
 // margin: null, or what to subtract from every threshold (survivors will be re-scored)
@@ -45,11 +46,12 @@ cudaError_t launch_threshold(const float* tile_max, uint32_t sample_count, uint3
                              uint32_t nq, uint32_t k, const float* margin, float* thr,
                              cudaStream_t st);
 // queries != null: re-score the keys within the margin of the k-th best with the scan's arithmetic
-// (fp32 queries [nq][dim], bf16 rows of stride_elems); null: top-k of the tensor-core scores
+// (fp32 queries [nq][dim]; rows = the stored matrix, bf16 or fp32, stride_elems per row); null:
+// top-k of the tensor-core scores
 cudaError_t launch_select(const uint64_t* cand, const uint32_t* cand_count, uint32_t nslices,
                           uint32_t cap_s, const float* inv_qnorm, uint32_t nq, uint32_t k,
-                          const float* queries, const float* margin, const void* rows, uint32_t dim,
-                          uint32_t stride_elems, uint32_t row_base, uint64_t* out,
-                          uint32_t* overflow, cudaStream_t st);
+                          const float* queries, const float* margin, const void* rows,
+                          bool rows_f32, uint32_t dim, uint32_t stride_elems, uint32_t row_base,
+                          uint64_t* out, uint32_t* overflow, cudaStream_t st);
 
 }  // namespace tss
