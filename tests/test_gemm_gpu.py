@@ -218,3 +218,22 @@ def test_fp32_index_large_batches_are_exact(tss, orc, n, nq, k, dim):
     want = orc.cosine_topk(rows, q, k, mask_words=words, mask_mode=orc.MASK_INCLUDE)
     assert np.array_equal(gr, want[0])
     assert np.array_equal(gs.view(np.uint32), want[1].view(np.uint32))
+
+
+@pytest.mark.parametrize("storage", ["bf16", "f32"])
+def test_k_1000_stays_on_the_tensor_cores(tss, orc, storage):
+    """k = 1000: the sorter takes 4k keys, the tile sample and the batch split keep the expected
+    survivors inside the pool -- no fallback scans (which would be 8 rounds per query)."""
+    n, nq, k, dim = 1_100_000, 48, 1000, 384
+    ix = tss.FlatIndex(dim, tss.TSS_BF16 if storage == "bf16" else tss.TSS_F32)
+    ix.add_synthetic(0, n, SEED)
+    ix.finalize()
+    q = orc.gen_rows(0, nq, dim, 0xBEEF)
+    ix.search(q[:16], k)  # builds the one-off workspaces (norms, shadow)
+    before = tss.launch_count()
+    gr, gs, gc = ix.search(q, k)
+    assert tss.launch_count() - before == 5
+    rows = orc.gen_rows(0, n, dim, SEED)
+    want = orc.cosine_topk(rows, q, k, bf16=storage == "bf16")
+    assert np.array_equal(gr, want[0])
+    assert np.array_equal(gs.view(np.uint32), want[1].view(np.uint32))

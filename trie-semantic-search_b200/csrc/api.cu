@@ -87,7 +87,8 @@ constexpr uint32_t kMaxBq = 4;           // queries per scan launch
 constexpr uint32_t kScanSlots = 4;       // scan workspace slots (launches in flight under PDL)
 constexpr uint32_t kWsQueries = 1024;    // device query/result workspace, in queries
 constexpr size_t kStageBytes = 64u << 20;  // upload staging buffer
-constexpr uint32_t kGemmCandCap = 16384;   // survivors kept per query by the K2 epilogue
+constexpr uint32_t kGemmCandCap = 16384;   // K2 survivor keys per query of a FULL workspace batch:
+                                           // the pool (kWsQueries x this) is shared out per batch
 constexpr uint32_t kGemmMaxSample = 8192;  // tiles sampled by the K2 threshold pass
 
 typedef CUresult (*TmapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -381,6 +382,24 @@ bool gemm_eligible(const tss_index* ix, uint32_t nq, uint32_t k, int mode) {
   return nq >= ix->gemm_min_nq && ix->n_rows >= 4ull * 256 * k && k <= TSS_MAX_K;
 }
 
+// survivors a query is expected to leave in the K2 lists when `sample` tiles set its threshold
+uint64_t gemm_expected_survivors(const tss_index* ix, uint32_t k, uint32_t num_tiles, uint32_t sample) {
+  const uint64_t spread = ix->storage == TSS_F32 ? 3 : 2;  // measured 2.7x / 1.4x at k = 100
+  return spread * k * (uint64_t)num_tiles / (sample ? sample : 1);
+}
+// largest batch (a multiple of 256 queries, <= kWsQueries) whose queries' expected survivors fit
+// half their share of the pool with the largest tile sample the threshold pass can take
+uint32_t gemm_batch_limit(const tss_index* ix, uint32_t k) {
+  const uint32_t num_tiles = (uint32_t)((ix->n_rows + 255) / 256);
+  uint32_t max_sample = kGemmMaxSample / (uint32_t)tss::gemm_col_split();
+  if (max_sample > num_tiles) max_sample = num_tiles;
+  const uint64_t need = gemm_expected_survivors(ix, k, num_tiles, max_sample) * 2;
+  uint64_t lim = (uint64_t)kWsQueries * kGemmCandCap / (need ? need : 1);
+  lim = lim / 256 * 256;
+  if (lim < 256) lim = 256;
+  return lim > kWsQueries ? kWsQueries : (uint32_t)lim;
+}
+
 int ensure_gemm_ws(tss_index* ix) {
   tss_index::Gemm& g = ix->gemm;
   int rc = load_tmap_encode();
@@ -449,6 +468,15 @@ int ensure_gemm_ws(tss_index* ix) {
   return TSS_OK;
 }
 
+// gemm_eligible, and (fp32 index) the bf16 shadow could be built.  Without room for the shadow the
+// batch stays on the scan: exact all the same, one launch per 4 queries.
+bool gemm_route(tss_index* ix, uint32_t nq, uint32_t k, int mode) {
+  if (!gemm_eligible(ix, nq, k, mode)) return false;
+  if (ix->storage == TSS_F32 && ensure_gemm_ws(ix) == TSS_ERR_OOM && ix->gemm.shadow_failed)
+    return false;
+  return true;
+}
+
 int enqueue_scan(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
                  const tss_mask* mask, int mode, uint64_t* d_out,
                  const float* h_inline_query = nullptr);
@@ -476,6 +504,12 @@ int enqueue_gemm(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
   // the threshold pass yields `split` maxima per sampled tile (one per column part)
   const uint32_t split = (uint32_t)tss::gemm_col_split();
   uint32_t sample = k * 8 / split > 1024 ? k * 8 / split : 1024;
+  // The survivor pool is shared out among the queries of this batch.  About
+  // spread * k * num_tiles / sample keys of a query pass its threshold (spread: the rescoring
+  // margin lets in more); sample enough tiles for that to stay under half a query's share.
+  const uint64_t share = (uint64_t)kWsQueries * kGemmCandCap / nq_pad;
+  const uint64_t want = gemm_expected_survivors(ix, k, num_tiles, 1) * 2 / share + 1;
+  if (want > sample) sample = (uint32_t)(want < num_tiles ? want : num_tiles);
   if (const char* sm = getenv("TSS_GEMM_SAMPLE")) sample = (uint32_t)atoi(sm);
   if (sample < (k + split - 1) / split) sample = (k + split - 1) / split;
   if (sample > kGemmMaxSample / split) sample = kGemmMaxSample / split;
@@ -495,7 +529,8 @@ int enqueue_gemm(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
                                g.d_margin, ix->storage == TSS_F32, ix->stream);
   if (e != cudaSuccess) return cuda_fail(e, "prep_queries launch");
   const uint32_t nsub = (uint32_t)nslices * split;
-  const uint32_t cap_s = kGemmCandCap / nsub;
+  const uint64_t cap64 = share / nsub;
+  const uint32_t cap_s = cap64 > 4096 ? 4096u : (uint32_t)cap64;
   tss::GemmParams p{};
   p.n_rows = ix->n_rows;
   p.row_base = (uint32_t)ix->row_base;
@@ -597,17 +632,14 @@ int enqueue_scan_rounds(tss_index* ix, const float* d_queries, uint32_t nq, uint
 int enqueue_local(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
                   const tss_mask* mask, int mode, uint64_t* d_out, bool* merged) {
   *merged = false;
-  bool use_gemm = gemm_eligible(ix, nq, k, mode);
-  if (use_gemm && ix->storage == TSS_F32 && ensure_gemm_ws(ix) == TSS_ERR_OOM &&
-      ix->gemm.shadow_failed)
-    use_gemm = false;  // no room for the bf16 shadow: exact all the same, one scan per 4 queries
-  if (!use_gemm) {
+  if (!gemm_route(ix, nq, k, mode)) {
     if (k > TSS_MAX_FUSED_K) return enqueue_scan_rounds(ix, d_queries, nq, k, mask, mode, d_out);
     *merged = ix->comm && ix->xchg.ready;
     return enqueue_scan(ix, d_queries, nq, k, mask, mode, d_out);
   }
-  for (uint32_t q0 = 0; q0 < nq; q0 += kWsQueries) {
-    uint32_t n = nq - q0 < kWsQueries ? nq - q0 : kWsQueries;
+  const uint32_t step = gemm_batch_limit(ix, k);  // large k at large N: smaller batches
+  for (uint32_t q0 = 0; q0 < nq; q0 += step) {
+    uint32_t n = nq - q0 < step ? nq - q0 : step;
     int rc = enqueue_gemm(ix, d_queries + (size_t)q0 * ix->dim, n, k, mask, mode,
                           d_out + (size_t)q0 * k);
     if (rc) return rc;
@@ -949,7 +981,7 @@ int tss_index_search_device(tss_index* ix, const float* d_queries, uint32_t nq, 
   if ((rc = ensure_gather_ws(ix))) return rc;
   for (uint32_t q0 = 0; q0 < nq; q0 += kWsQueries) {
     uint32_t n = nq - q0 < kWsQueries ? nq - q0 : kWsQueries;
-    const bool fused = ix->xchg.ready && !gemm_eligible(ix, nq, k, mask_mode) && k <= TSS_MAX_FUSED_K;
+    const bool fused = ix->xchg.ready && !gemm_route(ix, nq, k, mask_mode) && k <= TSS_MAX_FUSED_K;
     uint64_t* d_local = fused ? d_out_keys + (size_t)q0 * k : ix->d_keys;
     if ((rc = enqueue_local(ix, d_queries + (size_t)q0 * ix->dim, n, k, mask, mask_mode, d_local,
                             &merged)))
@@ -998,7 +1030,7 @@ int tss_index_search(tss_index* ix, const float* queries, uint32_t nq, uint32_t 
     size_t qbytes = (size_t)n * ix->dim * sizeof(float);
     const float* hq = queries + (size_t)q0 * ix->dim;
     // a large batch of a bf16 index takes the tensor-core path as a whole (nq, not n, decides)
-    const bool gemm = gemm_eligible(ix, nq, k, mask_mode);
+    const bool gemm = gemm_route(ix, nq, k, mask_mode);
     const bool rounds = !gemm && k > TSS_MAX_FUSED_K;
     // scan path: a lone query travels in the kernel parameters, and the last CTA writes the
     // result straight into mapped pinned host memory -- no H2D / D2H copy operations at all

@@ -682,7 +682,12 @@ threshold_kernel(const float* tile_max, uint32_t count, uint32_t nq, uint32_t k,
 //     so the scan's k-th best score is >= t - eps, so every row of the scan's top-k has
 //     A >= t - 2 eps and is among the re-scored keys: the result is bit-identical to the scan's
 //     (and the oracle's) top-k on the same bf16 index, ties included.
-constexpr uint32_t kSelectSort = 2048;
+constexpr uint32_t kSelectSortMax = 4096;  // keys the sorter can take (dynamic shared memory)
+__host__ __device__ inline uint32_t select_sort_cap(uint32_t k) {  // power of two >= 4k
+  uint32_t c = 1024;
+  while (c < 4 * k && c < kSelectSortMax) c <<= 1;
+  return c;
+}
 constexpr uint32_t kSelectMaxLists = 1024;
 constexpr uint32_t kSelectThreads = kRadixThreads;
 struct Rescore {
@@ -699,7 +704,8 @@ __global__ void __launch_bounds__(kSelectThreads, 8)
 select_kernel(const uint64_t* cand, const uint32_t* cand_count, uint32_t nsub, uint32_t cap_s,
               const float* inv_qnorm, const Rescore rs, uint32_t k, uint64_t* out,
               uint32_t* overflow) {
-  __shared__ uint64_t sk[kSelectSort];
+  extern __shared__ __align__(16) uint64_t sk[];  // select_sort_cap(k) keys
+  const uint32_t kSelectSort = select_sort_cap(k);
   __shared__ uint32_t s_cnt[kSelectMaxLists];
   __shared__ __align__(16) float s_q[1024];  // the fp32 query, zero padded to the row stride
   __shared__ uint32_t hist[256];
@@ -936,11 +942,12 @@ cudaError_t launch_select(const uint64_t* cand, const uint32_t* cand_count, uint
                           const float* queries, const float* margin, const void* rows,
                           bool rows_f32, uint32_t dim, uint32_t stride_elems, uint32_t row_base,
                           uint64_t* out, uint32_t* overflow, cudaStream_t st) {
-  if (nslices > kSelectMaxLists || k > kSelectSort || stride_elems > 1024 || stride_elems % 128)
+  if (nslices > kSelectMaxLists || k > kSelectSortMax / 2 || stride_elems > 1024 ||
+      stride_elems % 128)
     return cudaErrorInvalidConfiguration;
   Rescore rs{queries, margin, rows, rows_f32 ? 1 : 0, dim, stride_elems, row_base};
-  select_kernel<<<nq, kSelectThreads, 0, st>>>(cand, cand_count, nslices, cap_s, inv_qnorm, rs, k,
-                                               out, overflow);
+  select_kernel<<<nq, kSelectThreads, select_sort_cap(k) * sizeof(uint64_t), st>>>(
+      cand, cand_count, nslices, cap_s, inv_qnorm, rs, k, out, overflow);
   return cudaGetLastError();
 }
 
