@@ -8,6 +8,11 @@ device (queries and result buffers resident in HBM, CUDA events on the index str
 corpus is row-sharded (fixed total size: strong scaling) and each step ends in the
 all-gather + merge of the per-rank top-k.
 
+At N=1 the line also carries `batched`: the same metric for one 1024-query batch on the same
+index (K2: tcgen05 GEMM over a bf16 shadow + exact re-scoring), whose keys must equal the
+batch-1 legs' bit for bit -- a full-size cross-check of the two kernels -- with its own tensor
+roofline.
+
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
   torchrun ... bench.py --gpus N ...       (one rank per GPU)
 
@@ -46,6 +51,8 @@ def parse_args():
     ap.add_argument("--storage", default="f32", choices=["f32", "bf16"])
     ap.add_argument("--cpu-sample-rows", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-batched", action="store_true",
+                    help="skip the extra 1024-query leg (same index, same metric, tensor-core path)")
     return ap.parse_args()
 
 
@@ -377,6 +384,43 @@ def main():
                 ok &= orc.scores(e, queries[i])[0].view(np.uint32) == s.view(np.uint32)
         check = "ok" if ok else "FAILED"
 
+    # ---- extra (N=1): the same metric for a 1024-query batch on the same index -----------------
+    # K2: tcgen05 GEMM picks candidates (from a bf16 shadow of an fp32 index), survivors are
+    # re-scored with the scan's arithmetic -- the keys must equal the batch-1 legs' bit for bit.
+    batched = None
+    if world == 1 and not args.no_batched and args.rows >= 4 * 256 * args.k:
+        nb = 1024
+        qb = orc.gen_rows(0, nb, args.dim, SEED_Q ^ 0x1234)
+        qb[:min(nb, nq_total)] = queries[:min(nb, nq_total)]
+        d_qb = tss.DeviceBuffer(device, qb.nbytes).upload(qb)
+        d_kb = tss.DeviceBuffer(device, nb * args.k * 8)
+        for _ in range(2):
+            ix.search_device(d_qb, nb, args.k, d_kb)
+        ix.sync()
+        iters = 5
+        l0 = tss.launch_count()
+        ev0.record(ix)
+        for _ in range(iters):
+            ix.search_device(d_qb, nb, args.k, d_kb)
+        ev1.record(ix)
+        ix.sync()
+        bms = ev0.elapsed_ms(ev1) / iters
+        kb = d_kb.download(np.uint64, nb * args.k).reshape(nb, args.k)
+        same = bool(np.array_equal(kb[:min(nb, nq_total)], keys_value_leg[:min(nb, nq_total)]))
+        tf = 2.0 * nb * args.rows * args.dim / (bms * 1e-3) / 1e12
+        batched = {
+            "workload": f"{nb}-query batch, same index, exact cosine top-{args.k}", "batch": nb,
+            "value": nb / bms * 1e3, "unit": UNIT, "ms_per_batch": bms,
+            "gpu_launches_per_batch": (tss.launch_count() - l0) / iters,
+            "keys_equal_batch1_leg": same,
+            "roofline": {"bound": "tensor", "kernel": "gemm_topk_kernel", "achieved": tf,
+                         "peak": peaks.get("bf16_tflops"), "unit": "TFLOP/s",
+                         "frac": tf / peaks["bf16_tflops"] if peaks.get("bf16_tflops") else None,
+                         "algorithmic_flops_per_batch": 2.0 * nb * args.rows * args.dim},
+        }
+        if not same:
+            check = "FAILED"
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu, _ = cpu_baseline(orc, args, queries)
@@ -390,6 +434,8 @@ def main():
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "clocks": clocks, "check": check,
         }
+        if batched is not None:
+            line["batched"] = batched
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
