@@ -222,7 +222,13 @@ struct tss_index {
     const void* shadow_base = nullptr;
     bool shadow_failed = false;    // no memory for it: large batches stay on the scan
   } gemm;
-  uint32_t gemm_min_nq = 16;  // batches at least this large use K2
+  // Batches at least this large use K2.  On a big corpus (where its five launches and one host
+  // sync are noise) K2 also takes batches from gemm_small_nq queries when the bf16 matrix it
+  // reads exists already: 3..15 queries cost one 1.3 ms pass over 10M bf16 rows instead of
+  // ceil(nq/4) scans of 1.9 ms (bf16) / 2.3 ms (fp32).  Results are bit-identical either way.
+  uint32_t gemm_min_nq = 16;
+  uint32_t gemm_small_nq = 3;
+  uint64_t gemm_small_rows = 2'000'000;
   uint32_t* d_round_mask = nullptr;  // scratch mask of the k > 128 scan rounds
   uint64_t round_mask_words = 0;
   // fused sharded merge: exchange buffers of all ranks mapped with CUDA IPC (<= 8 ranks)
@@ -379,7 +385,9 @@ int ensure_gather_ws(tss_index* ix) {
 bool gemm_eligible(const tss_index* ix, uint32_t nq, uint32_t k, int mode) {
   (void)mode;  // masks ride along: a masked row's 1/|row| is NaN in the epilogue
   if (ix->storage == TSS_F32 && ix->gemm.shadow_failed) return false;
-  return nq >= ix->gemm_min_nq && ix->n_rows >= 4ull * 256 * k && k <= TSS_MAX_K;
+  const bool have_bf16 = ix->storage == TSS_BF16 || ix->gemm.shadow_rows == ix->n_rows;
+  const bool small_ok = have_bf16 && nq >= ix->gemm_small_nq && ix->n_rows >= ix->gemm_small_rows;
+  return (nq >= ix->gemm_min_nq || small_ok) && ix->n_rows >= 4ull * 256 * k && k <= TSS_MAX_K;
 }
 
 // survivors a query is expected to leave in the K2 lists when `sample` tiles set its threshold
@@ -730,7 +738,10 @@ int tss_index_create(tss_index** out, uint32_t dim, int storage, int device) {
   ALLOC(cudaMallocHost(&ix->h_keys, (size_t)kWsQueries * TSS_MAX_K * sizeof(uint64_t)))
   ALLOC(cudaMallocHost(&ix->h_status, 64))
   *ix->h_status = 0;
-  if (const char* sf = getenv("TSS_GEMM_MIN_NQ")) ix->gemm_min_nq = (uint32_t)atoi(sf);
+  if (const char* sf = getenv("TSS_GEMM_MIN_NQ")) {  // diagnostics: one plain threshold
+    ix->gemm_min_nq = (uint32_t)atoi(sf);
+    ix->gemm_small_nq = 0xFFFFFFFFu;
+  }
 #undef ALLOC
   *out = ix;
   return TSS_OK;
