@@ -421,6 +421,33 @@ def main():
         if not same:
             check = "FAILED"
 
+    # ---- extra (N=1): batch-1 queries answered from the bf16 matrix + exact re-scoring ---------
+    # tss_index_set_batch_policy(1): every query takes the K2 pipeline, which streams 2 bytes per
+    # element (the shadow of an fp32 index) instead of 4 and re-scores the candidates exactly.
+    # Same keys as the scan; NOT the kernel the HBM roofline above is quoted for.
+    prefiltered = None
+    if batched is not None:
+        ix.set_batch_policy(1, True)
+        npf = min(args.steps, 200)
+        device_leg(0, args.warmup)
+        ix.sync()
+        ev0.record(ix)
+        device_leg(args.warmup, npf)
+        ev1.record(ix)
+        ix.sync()
+        pms = ev0.elapsed_ms(ev1) / npf
+        kp = d_out.download(np.uint64, nq_total * args.k).reshape(nq_total, args.k)
+        same = bool(np.array_equal(kp[:args.warmup + npf], keys_value_leg[:args.warmup + npf]))
+        ix.set_batch_policy(0, False)
+        prefiltered = {
+            "workload": "batch-1 queries, tss_index_set_batch_policy(1): bf16 pass + exact re-scoring",
+            "value": 1e3 / pms, "unit": UNIT, "ms_per_step": pms, "steps": npf,
+            "keys_equal_batch1_leg": same,
+            "bytes_streamed_per_query": n_local * args.dim * 2,
+        }
+        if not same:
+            check = "FAILED"
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu, _ = cpu_baseline(orc, args, queries)
@@ -436,6 +463,8 @@ def main():
         }
         if batched is not None:
             line["batched"] = batched
+        if prefiltered is not None:
+            line["prefiltered"] = prefiltered
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)

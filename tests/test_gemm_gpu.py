@@ -237,3 +237,29 @@ def test_k_1000_stays_on_the_tensor_cores(tss, orc, storage):
     want = orc.cosine_topk(rows, q, k, bf16=storage == "bf16")
     assert np.array_equal(gr, want[0])
     assert np.array_equal(gs.view(np.uint32), want[1].view(np.uint32))
+
+
+def test_batch_policy_single_queries_through_the_shadow(tss, orc):
+    """tss_index_set_batch_policy(1, build_shadow_now): an fp32 index answers even single queries
+    from its bf16 shadow + exact re-scoring -- same bits as the fp32 scan, half the bytes."""
+    n, dim, k = 200_000, 384, 10
+    rows = orc.gen_rows(0, n, dim, SEED)
+    q = orc.gen_rows(0, 5, dim, 0xBEEF)
+    q[2] = rows[77] + 0.125 * q[2]
+    ix = tss.FlatIndex(dim, tss.TSS_F32)
+    ix.add(rows)
+    ix.finalize()
+    scan = ix.search(q, k)                      # default policy: K1
+    ix.set_batch_policy(1, build_shadow_now=True)
+    before = tss.launch_count()
+    got = [ix.search(q[i:i + 1], k) for i in range(5)]
+    assert tss.launch_count() - before == 25    # five K2 pipelines
+    for i in range(5):
+        assert np.array_equal(got[i][0][0], scan[0][i])
+        assert np.array_equal(got[i][1][0].view(np.uint32), scan[1][i].view(np.uint32))
+    want = orc.cosine_topk(rows, q, k)
+    assert np.array_equal(scan[0], want[0]) and scan[0][2][0] == 77
+    ix.set_batch_policy(0)                       # default again: single queries scan
+    before = tss.launch_count()
+    ix.search(q[:1], k)
+    assert tss.launch_count() - before == 1

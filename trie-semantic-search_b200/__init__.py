@@ -32,7 +32,7 @@ ABI_SYMBOLS = [
     "tss_index_create", "tss_index_reserve", "tss_index_add", "tss_index_add_synthetic",
     "tss_index_finalize", "tss_index_size", "tss_index_dim", "tss_index_destroy",
     "tss_index_get_rows", "tss_index_search", "tss_index_search_device", "tss_unpack_keys",
-    "tss_comm_unique_id", "tss_comm_create", "tss_comm_destroy", "tss_index_set_shard",
+    "tss_comm_unique_id", "tss_comm_create", "tss_comm_destroy", "tss_index_set_shard", "tss_index_set_batch_policy",
     "tss_mask_create", "tss_mask_clear", "tss_mask_set_rows", "tss_mask_upload",
     "tss_mask_download", "tss_mask_popcount", "tss_mask_nbits", "tss_mask_destroy",
     "tss_terms_create", "tss_terms_size", "tss_terms_destroy", "tss_prefix_mask",
@@ -90,6 +90,7 @@ def lib() -> C.CDLL:
         "tss_comm_create": (i32, [C.POINTER(vp), vp, i32, i32, i32]),
         "tss_comm_destroy": (None, [vp]),
         "tss_index_set_shard": (i32, [vp, u64, vp]),
+        "tss_index_set_batch_policy": (i32, [vp, u32, i32]),
         "tss_mask_create": (i32, [C.POINTER(vp), u64, i32]),
         "tss_mask_clear": (i32, [vp]),
         "tss_mask_set_rows": (i32, [vp, vp, u64, u64]),
@@ -451,6 +452,12 @@ class FlatIndex:
         out = np.empty((nrows, self.dim), dtype=np.float32)
         _check(lib().tss_index_get_rows(self.handle, int(row_begin), int(nrows), out.ctypes.data))
         return out
+
+    def set_batch_policy(self, min_queries: int = 0, build_shadow_now: bool = False) -> None:
+        """Which batches take the tensor-core path (results are bit-identical either way); see
+        tss_index_set_batch_policy in include/tss.h."""
+        _check(lib().tss_index_set_batch_policy(self.handle, int(min_queries),
+                                                1 if build_shadow_now else 0))
 
     def set_shard(self, row_base: int, comm: Optional[Comm]) -> None:
         _check(lib().tss_index_set_shard(self.handle, int(row_base), comm.handle if comm else None))

@@ -1184,6 +1184,27 @@ int setup_xchg(tss_index* ix, tss_comm* comm) {
 }
 }  // namespace
 
+int tss_index_set_batch_policy(tss_index* ix, uint32_t min_queries, int build_shadow_now) {
+  if (!ix) return fail(TSS_ERR_INVALID_ARG, "index is NULL");
+  if (min_queries) {
+    ix->gemm_min_nq = min_queries;
+    ix->gemm_small_nq = 0xFFFFFFFFu;
+  } else {
+    ix->gemm_min_nq = 16;
+    ix->gemm_small_nq = 3;
+  }
+  if (build_shadow_now && ix->storage == TSS_F32) {
+    if (!ix->finalized) return fail(TSS_ERR_STATE, "build the shadow after tss_index_finalize");
+    if (!ix->n_rows) return TSS_OK;
+    DeviceGuard g(ix->device);
+    ix->gemm.shadow_failed = false;
+    int rc = ensure_gemm_ws(ix);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(ix->stream));
+  }
+  return TSS_OK;
+}
+
 int tss_index_set_shard(tss_index* ix, uint64_t row_base, tss_comm* comm) {
   if (!ix) return fail(TSS_ERR_INVALID_ARG, "index is NULL");
   if (row_base + ix->n_rows >= 0xFFFFFFFFull)

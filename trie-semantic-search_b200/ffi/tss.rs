@@ -75,6 +75,7 @@ extern "C" {
     pub fn tss_comm_create(out: *mut *mut tss_comm, id: *const u8, rank: c_int, nranks: c_int, device: c_int) -> c_int;
     pub fn tss_comm_destroy(c: *mut tss_comm);
     pub fn tss_index_set_shard(ix: *mut tss_index, row_base: u64, comm: *mut tss_comm) -> c_int;
+    pub fn tss_index_set_batch_policy(ix: *mut tss_index, min_queries: u32, build_shadow_now: c_int) -> c_int;
 
     pub fn tss_mask_create(out: *mut *mut tss_mask, nbits: u64, device: c_int) -> c_int;
     pub fn tss_mask_clear(m: *mut tss_mask) -> c_int;
