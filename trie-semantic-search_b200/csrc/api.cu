@@ -634,6 +634,19 @@ int enqueue_scan_rounds(tss_index* ix, const float* d_queries, uint32_t nq, uint
   return rc;
 }
 
+// K2 over nq queries in batches the survivor pool can take (large k at large N: smaller batches)
+int enqueue_gemm_batches(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
+                         const tss_mask* mask, int mode, uint64_t* d_out) {
+  const uint32_t step = gemm_batch_limit(ix, k);
+  for (uint32_t q0 = 0; q0 < nq; q0 += step) {
+    uint32_t n = nq - q0 < step ? nq - q0 : step;
+    int rc = enqueue_gemm(ix, d_queries + (size_t)q0 * ix->dim, n, k, mask, mode,
+                          d_out + (size_t)q0 * k);
+    if (rc) return rc;
+  }
+  return TSS_OK;
+}
+
 // local (per-shard) search of nq device-resident queries: picks K2 or K1.  *merged is set
 // when d_out already holds the GLOBAL result (the K1 scan of a sharded index exchanges and
 // merges inside its last CTA; K2 leaves that to NCCL + merge_gathered_kernel).
@@ -645,14 +658,7 @@ int enqueue_local(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k
     *merged = ix->comm && ix->xchg.ready;
     return enqueue_scan(ix, d_queries, nq, k, mask, mode, d_out);
   }
-  const uint32_t step = gemm_batch_limit(ix, k);  // large k at large N: smaller batches
-  for (uint32_t q0 = 0; q0 < nq; q0 += step) {
-    uint32_t n = nq - q0 < step ? nq - q0 : step;
-    int rc = enqueue_gemm(ix, d_queries + (size_t)q0 * ix->dim, n, k, mask, mode,
-                          d_out + (size_t)q0 * k);
-    if (rc) return rc;
-  }
-  return TSS_OK;
+  return enqueue_gemm_batches(ix, d_queries, nq, k, mask, mode, d_out);
 }
 
 int validate_search(const tss_index* ix, const void* queries, uint32_t nq, uint32_t k) {
@@ -1040,7 +1046,7 @@ int tss_index_search(tss_index* ix, const float* queries, uint32_t nq, uint32_t 
     uint32_t n = nq - q0 < kWsQueries ? nq - q0 : kWsQueries;
     size_t qbytes = (size_t)n * ix->dim * sizeof(float);
     const float* hq = queries + (size_t)q0 * ix->dim;
-    // a large batch of a bf16 index takes the tensor-core path as a whole (nq, not n, decides)
+    // a batch takes the tensor-core path as a whole (nq, not n, decides)
     const bool gemm = gemm_route(ix, nq, k, mask_mode);
     const bool rounds = !gemm && k > TSS_MAX_FUSED_K;
     // scan path: a lone query travels in the kernel parameters, and the last CTA writes the
@@ -1053,7 +1059,7 @@ int tss_index_search(tss_index* ix, const float* queries, uint32_t nq, uint32_t 
     bool merged = false;
     bool direct = false;  // result already lands in h_keys
     if (gemm) {
-      rc = enqueue_gemm(ix, ix->d_queries, n, k, mask, mask_mode, ix->d_keys);
+      rc = enqueue_gemm_batches(ix, ix->d_queries, n, k, mask, mask_mode, ix->d_keys);
     } else if (rounds) {
       rc = enqueue_scan_rounds(ix, ix->d_queries, n, k, mask, mask_mode, ix->d_keys);
     } else {
