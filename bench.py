@@ -421,10 +421,11 @@ def main():
         if not same:
             check = "FAILED"
 
-    # ---- extra (N=1): batch-1 queries answered from the bf16 matrix + exact re-scoring ---------
-    # tss_index_set_batch_policy(1): every query takes the K2 pipeline, which streams 2 bytes per
-    # element (the shadow of an fp32 index) instead of 4 and re-scores the candidates exactly.
-    # Same keys as the scan; NOT the kernel the HBM roofline above is quoted for.
+    # ---- extra (N=1): batch-1 queries answered from the bf16 shadow + exact re-scoring ---------
+    # tss_index_set_batch_policy(1): the scan kernel streams the bf16 shadow of the fp32 index
+    # (2 bytes per element instead of 4) for the top-64, a refine kernel proves the fp32 top-k is
+    # among them and re-scores them from the fp32 rows.  Same keys as the fp32 scan; NOT the
+    # configuration the HBM roofline above is quoted for.
     prefiltered = None
     if batched is not None:
         ix.set_batch_policy(1, True)
@@ -440,7 +441,8 @@ def main():
         same = bool(np.array_equal(kp[:args.warmup + npf], keys_value_leg[:args.warmup + npf]))
         ix.set_batch_policy(0, False)
         prefiltered = {
-            "workload": "batch-1 queries, tss_index_set_batch_policy(1): bf16 pass + exact re-scoring",
+            "workload": ("batch-1 queries, tss_index_set_batch_policy(1): scan of the bf16 shadow "
+                         "+ proof + exact re-scoring from the fp32 rows"),
             "value": 1e3 / pms, "unit": UNIT, "ms_per_step": pms, "steps": npf,
             "keys_equal_batch1_leg": same,
             "bytes_streamed_per_query": n_local * args.dim * 2,

@@ -135,9 +135,11 @@ int tss_index_search_device(tss_index* ix, const float* d_queries, uint32_t nq, 
  * scan's arithmetic).  Default: batches of >= 16 queries; and >= 3 queries on a corpus of >= 2M
  * rows once the bf16 matrix K2 reads exists (a bf16 index, or an fp32 index that has built its
  * bf16 shadow, +50 % memory, on its first K2 batch).
- *   min_queries >= 1: every batch of at least that many queries takes K2 (1 = also single
- *     queries: an fp32 index then answers from a 2-byte-per-element stream plus exact
- *     re-scoring, 1.3 ms instead of 2.05 ms over 10M x 384); 0 restores the default.
+ *   min_queries >= 1: every batch of at least that many queries leaves the plain scan (0
+ *     restores the default).  With 1, an fp32 index that has its shadow answers calls of one or
+ *     two queries (k <= 32) by scanning the SHADOW for the top-64/128, proving the fp32 top-k is
+ *     among them, and re-scoring those from the fp32 rows -- 1.17 ms instead of 2.05 ms over
+ *     10M x 384, same bits; a query the proof fails for is redone by the fp32 scan.
  *   build_shadow_now != 0: an fp32 index builds its shadow inside this call
  *     (TSS_ERR_OOM if it does not fit; large batches then stay on the scan).
  * New entry: the reference has no batched or two-stage search (src/vector.rs:195-202). */

@@ -240,26 +240,49 @@ def test_k_1000_stays_on_the_tensor_cores(tss, orc, storage):
 
 
 def test_batch_policy_single_queries_through_the_shadow(tss, orc):
-    """tss_index_set_batch_policy(1, build_shadow_now): an fp32 index answers even single queries
-    from its bf16 shadow + exact re-scoring -- same bits as the fp32 scan, half the bytes."""
+    """tss_index_set_batch_policy(1, build_shadow_now): an fp32 index answers one or two queries
+    per call from its bf16 shadow (K1 streams the shadow for the top-64, refine_kernel proves the
+    fp32 top-k is among them and re-scores from the fp32 rows) -- same bits as the fp32 scan, half
+    the bytes.  Three or more queries per call take K2."""
     n, dim, k = 200_000, 384, 10
     rows = orc.gen_rows(0, n, dim, SEED)
-    q = orc.gen_rows(0, 5, dim, 0xBEEF)
+    rows[150_000:150_300] = rows[9]          # 301 identical rows: no top-64 can be proven complete
+    q = orc.gen_rows(0, 6, dim, 0xBEEF)
     q[2] = rows[77] + 0.125 * q[2]
+    q[4] = rows[9]
     ix = tss.FlatIndex(dim, tss.TSS_F32)
     ix.add(rows)
     ix.finalize()
-    scan = ix.search(q, k)                      # default policy: K1
-    ix.set_batch_policy(1, build_shadow_now=True)
-    before = tss.launch_count()
-    got = [ix.search(q[i:i + 1], k) for i in range(5)]
-    assert tss.launch_count() - before == 25    # five K2 pipelines
-    for i in range(5):
-        assert np.array_equal(got[i][0][0], scan[0][i])
-        assert np.array_equal(got[i][1][0].view(np.uint32), scan[1][i].view(np.uint32))
+    scan = ix.search(q, k)                      # default policy: K1 on the fp32 rows
     want = orc.cosine_topk(rows, q, k)
     assert np.array_equal(scan[0], want[0]) and scan[0][2][0] == 77
-    ix.set_batch_policy(0)                       # default again: single queries scan
+    assert list(scan[0][4][:3]) == [9, 150_000, 150_001]
+    ix.set_batch_policy(1, build_shadow_now=True)
+    for i in range(6):
+        before = tss.launch_count()
+        got = ix.search(q[i:i + 1], k)
+        used = tss.launch_count() - before
+        assert used == (3 if i == 4 else 2), (i, used)   # shadow scan + refine (+ fp32 redo)
+        assert np.array_equal(got[0][0], scan[0][i])
+        assert np.array_equal(got[1][0].view(np.uint32), scan[1][i].view(np.uint32))
+    got = ix.search(q[:2], k)                   # two per call: two shadow scans, one refine
+    assert np.array_equal(got[0], scan[0][:2])
+    before = tss.launch_count()
+    got = ix.search(q[:3], k)                   # three: the K2 pipeline
+    assert tss.launch_count() - before == 5
+    assert np.array_equal(got[0], scan[0][:3])
+    assert np.array_equal(got[1].view(np.uint32), scan[1][:3].view(np.uint32))
+    # masked single query
+    bits = np.random.default_rng(3).random(n) < 0.4
+    words = np.zeros((n + 31) // 32, dtype=np.uint32)
+    idx = np.nonzero(bits)[0]
+    np.bitwise_or.at(words, idx >> 5, (np.uint32(1) << (idx & 31).astype(np.uint32)))
+    m = tss.Mask(n)
+    m.upload(words)
+    got = ix.search(q[:1], k, m, tss.TSS_MASK_INCLUDE)
+    wm = orc.cosine_topk(rows, q[:1], k, mask_words=words, mask_mode=orc.MASK_INCLUDE)
+    assert np.array_equal(got[0], wm[0]) and np.array_equal(got[1].view(np.uint32), wm[1].view(np.uint32))
+    ix.set_batch_policy(0)                       # default again: single queries scan the fp32 rows
     before = tss.launch_count()
     ix.search(q[:1], k)
     assert tss.launch_count() - before == 1

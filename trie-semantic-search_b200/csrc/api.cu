@@ -90,6 +90,7 @@ constexpr size_t kStageBytes = 64u << 20;  // upload staging buffer
 constexpr uint32_t kGemmCandCap = 16384;   // K2 survivor keys per query of a FULL workspace batch:
                                            // the pool (kWsQueries x this) is shared out per batch
 constexpr uint32_t kGemmMaxSample = 8192;  // tiles sampled by the K2 threshold pass
+constexpr uint32_t kPrefilterMaxNq = 2;    // queries per call the shadow prefilter takes (K2 beyond)
 
 typedef CUresult (*TmapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -211,6 +212,7 @@ struct tss_index {
     uint64_t* d_cand = nullptr;    // [kWsQueries][kGemmCandCap]
     uint32_t* d_cand_count = nullptr;  // [kWsQueries][nslices]
     uint32_t* d_overflow = nullptr;    // [kWsQueries]
+    uint64_t* d_pref_keys = nullptr;   // [kPrefilterMaxNq][128] shadow-scan candidates
     uint32_t* h_cand_count = nullptr;  // pinned copy of d_overflow
     CUtensorMap tmap_q, tmap_e, tmap_e_half;  // corpus boxes of 256 rows / 128 rows (CTA pairs)
     uint64_t tmap_rows = 0;
@@ -295,8 +297,13 @@ int check_mask(const tss_index* ix, const tss_mask* mask, int mode) {
 
 // enqueue the scan for nq device-resident queries -> d_out (nq x k local keys).  A single
 // query of <= 384 dims may instead be handed over from host memory inside the kernel parameters.
+// bf16_rows: scan this bf16 matrix of the same geometry (the shadow of an fp32 index) instead
+// of the stored rows.
 int enqueue_scan(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
-                 const tss_mask* mask, int mode, uint64_t* d_out, const float* h_inline_query) {
+                 const tss_mask* mask, int mode, uint64_t* d_out, const float* h_inline_query,
+                 const uint8_t* bf16_rows) {
+  const bool as_bf16 = bf16_rows || ix->storage == TSS_BF16;
+  const size_t row_bytes = bf16_rows ? (size_t)ix->stride_elems * 2 : ix->row_bytes;
   const uint32_t kp = tss::kp_for_k(k), cap = tss::cap_for_k(k);
   const uint32_t bq_max = (uint32_t)tss::max_bq_for_k(k);
   for (uint32_t q0 = 0; q0 < nq;) {
@@ -304,7 +311,7 @@ int enqueue_scan(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
     uint32_t take = left < bq_max ? left : bq_max;
     int bq = take >= 3 ? 4 : (int)take;  // kernel instances: 1, 2, 4
     tss::ScanParams p{};
-    p.rows = ix->d_rows;
+    p.rows = bf16_rows ? bf16_rows : ix->d_rows;
     p.n_rows = ix->n_rows;
     p.row_base = (uint32_t)ix->row_base;
     p.dim = ix->dim;
@@ -330,11 +337,11 @@ int enqueue_scan(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
     p.pdl = ix->pdl ? 1 : 0;
     {
       // tiles per warp-round = num_sms * 16 warps; rows per tile from the storage geometry
-      const uint64_t tile_rows = 12288 / ix->row_bytes >= 16  ? 16
-                                 : 12288 / ix->row_bytes >= 8 ? 8
-                                 : 12288 / ix->row_bytes >= 4 ? 4
-                                 : 12288 / ix->row_bytes >= 2 ? 2
-                                                              : 1;
+      const uint64_t tile_rows = 12288 / row_bytes >= 16  ? 16
+                                 : 12288 / row_bytes >= 8 ? 8
+                                 : 12288 / row_bytes >= 4 ? 4
+                                 : 12288 / row_bytes >= 2 ? 2
+                                                          : 1;
       const uint64_t tiles = (ix->n_rows + tile_rows - 1) / tile_rows;
       const uint64_t gw = (uint64_t)ix->num_sms * 16;
       p.static_rounds = (uint32_t)((double)(tiles / gw) * ix->static_frac);
@@ -352,7 +359,7 @@ int enqueue_scan(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
       p.xchg_status = ix->h_status;  // mapped pinned: the host reads it without a copy
       p.xchg_turn = ix->d_counter + 17;
     }
-    cudaError_t e = tss::launch_scan(ix->ns, p, bq, ix->storage == TSS_BF16, mode != TSS_MASK_NONE,
+    cudaError_t e = tss::launch_scan(ix->ns, p, bq, as_bf16, mode != TSS_MASK_NONE,
                                      ix->num_sms, ix->device, ix->stream);
     if (e != cudaSuccess) return cuda_fail(e, "scan_topk_kernel launch");
     g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -422,6 +429,7 @@ int ensure_gemm_ws(tss_index* ix) {
     CU(cudaMalloc(&g.d_cand, (size_t)kWsQueries * kGemmCandCap * sizeof(uint64_t)));
     CU(cudaMalloc(&g.d_cand_count, (size_t)kWsQueries * 1024 * sizeof(uint32_t)));
     CU(cudaMalloc(&g.d_overflow, kWsQueries * sizeof(uint32_t)));
+    CU(cudaMalloc(&g.d_pref_keys, (size_t)kPrefilterMaxNq * 128 * sizeof(uint64_t)));
     CU(cudaMallocHost(&g.h_cand_count, kWsQueries * sizeof(uint32_t)));
     if ((rc = make_tmap(&g.tmap_q, g.d_qbf16, kWsQueries, kpad, 128))) return rc;
     g.ready = true;
@@ -487,7 +495,7 @@ bool gemm_route(tss_index* ix, uint32_t nq, uint32_t k, int mode) {
 
 int enqueue_scan(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
                  const tss_mask* mask, int mode, uint64_t* d_out,
-                 const float* h_inline_query = nullptr);
+                 const float* h_inline_query = nullptr, const uint8_t* bf16_rows = nullptr);
 int enqueue_scan_rounds(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
                         const tss_mask* mask, int mode, uint64_t* d_out);
 
@@ -634,9 +642,47 @@ int enqueue_scan_rounds(tss_index* ix, const float* d_queries, uint32_t nq, uint
   return rc;
 }
 
+// Shadow prefilter: one or two queries on an fp32 index whose bf16 shadow exists.  K1 streams the
+// shadow (2 bytes per element) for the top-kc, kc = 64 or 128 > 4k; refine_kernel proves the
+// fp32 top-k is among them, re-scores them from the fp32 rows and writes it.  A query it cannot
+// prove (the kc-th shadow score within the error margin of the k-th) is redone by the fp32 scan.
+int enqueue_prefilter(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
+                      const tss_mask* mask, int mode, uint64_t* d_out) {
+  int rc = ensure_gemm_ws(ix);
+  if (rc) return rc;
+  tss_index::Gemm& g = ix->gemm;
+  const uint32_t kc = 4 * k <= 64 ? 64 : 128;
+  const bool saved = ix->xchg.suppress;
+  ix->xchg.suppress = true;  // rank-local candidates; the caller merges across ranks
+  for (uint32_t qi = 0; qi < nq && !rc; ++qi)
+    rc = enqueue_scan(ix, d_queries + (size_t)qi * ix->dim, 1, kc, mask, mode,
+                      g.d_pref_keys + (size_t)qi * kc, nullptr, g.d_shadow);
+  ix->xchg.suppress = saved;
+  if (rc) return rc;
+  cudaError_t e = tss::launch_refine(g.d_pref_keys, kc, d_queries, ix->d_rows, ix->dim,
+                                     ix->stride_elems, (uint32_t)ix->row_base, nq, k, d_out,
+                                     g.d_overflow, ix->stream);
+  if (e != cudaSuccess) return cuda_fail(e, "refine_kernel launch");
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  CU(cudaMemcpyAsync(g.h_cand_count, g.d_overflow, nq * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                     ix->stream));
+  CU(cudaStreamSynchronize(ix->stream));
+  for (uint32_t qi = 0; qi < nq; ++qi) {
+    if (!g.h_cand_count[qi]) continue;
+    ix->xchg.suppress = true;
+    rc = enqueue_scan(ix, d_queries + (size_t)qi * ix->dim, 1, k, mask, mode, d_out + (size_t)qi * k);
+    ix->xchg.suppress = saved;
+    if (rc) return rc;
+  }
+  return TSS_OK;
+}
+
 // K2 over nq queries in batches the survivor pool can take (large k at large N: smaller batches)
 int enqueue_gemm_batches(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
                          const tss_mask* mask, int mode, uint64_t* d_out) {
+  if (ix->storage == TSS_F32 && nq <= kPrefilterMaxNq && k <= 32 &&
+      ix->gemm.shadow_rows == ix->n_rows && ix->gemm.shadow_base == ix->d_rows)
+    return enqueue_prefilter(ix, d_queries, nq, k, mask, mode, d_out);
   const uint32_t step = gemm_batch_limit(ix, k);
   for (uint32_t q0 = 0; q0 < nq; q0 += step) {
     uint32_t n = nq - q0 < step ? nq - q0 : step;
@@ -783,6 +829,7 @@ void tss_index_destroy(tss_index* ix) {
   cudaFree(ix->gemm.d_cand);
   cudaFree(ix->gemm.d_cand_count);
   cudaFree(ix->gemm.d_overflow);
+  cudaFree(ix->gemm.d_pref_keys);
   if (ix->gemm.h_cand_count) cudaFreeHost(ix->gemm.h_cand_count);
   if (ix->stream) cudaStreamDestroy(ix->stream);
   delete ix;

@@ -697,6 +697,77 @@ struct Rescore {
   int rows_f32;
   uint32_t dim, stride_elems, row_base;
 };
+// Re-score the keys sk[0..m) in place (low word = ~global row) with the scan's arithmetic
+// (scan.cuh): "lane" l of 32 owns elements 4l..4l+3 of every 128-element
+// stripe with four sub-accumulators, combines them ((a0+a1)+(a2+a3)), then an xor butterfly
+// 16, 8, 4, 2, 1 over the 32 lane partials.  The query norm is done that way by a whole warp.
+// Rows are done FOUR per warp for memory parallelism: thread t of an 8-thread group plays lanes
+// t, t+8, t+16, t+24 one after the other; butterfly steps 16 and 8 pair exactly those four
+// partials inside the thread ((p_t + p_t+16) + (p_t+8 + p_t+24)), steps 4, 2, 1 are shuffles
+// within the group -- the same additions in the same order, so the same bits.
+// s_q: the fp32 query in shared memory, zero padded to the row stride.  All kSelectThreads
+// threads call it; it ends with a block barrier.
+__device__ void rescore_keys(uint64_t* sk, uint32_t m, const Rescore& rs, const float* s_q) {
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr uint32_t kWarps = kSelectThreads / 32;
+  const uint32_t ns = rs.stride_elems / 128;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  for (uint32_t st = 0; st < ns; ++st) {
+    const float4 qv = *reinterpret_cast<const float4*>(s_q + st * 128 + lane * 4);
+    a0 = __fmaf_rn(qv.x, qv.x, a0);
+    a1 = __fmaf_rn(qv.y, qv.y, a1);
+    a2 = __fmaf_rn(qv.z, qv.z, a2);
+    a3 = __fmaf_rn(qv.w, qv.w, a3);
+  }
+  const float sq_nq = __fsqrt_rn(butterfly_sum(__fadd_rn(__fadd_rn(a0, a1), __fadd_rn(a2, a3))));
+  const uint32_t grp = lane >> 3, t8 = lane & 7;
+  for (uint32_t i0 = warp * 4; i0 < m; i0 += kWarps * 4) {
+    const uint32_t i = i0 + grp;
+    const bool live = i < m;
+    const uint32_t row_g = 0xFFFFFFFFu - (uint32_t)sk[live ? i : i0];
+    const size_t roff = (size_t)(row_g - rs.row_base) * rs.stride_elems;
+    const uint16_t* rp = reinterpret_cast<const uint16_t*>(rs.rows) + roff;
+    const float* rpf = reinterpret_cast<const float*>(rs.rows) + roff;
+    float pd[4], pn[4];
+#pragma unroll
+    for (uint32_t j = 0; j < 4; ++j) {
+      const uint32_t l = t8 + 8 * j;  // the lane being played
+      float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f, n0 = 0.f, n1 = 0.f, n2 = 0.f, n3 = 0.f;
+      for (uint32_t st = 0; st < ns; ++st) {
+        const float4 qv = *reinterpret_cast<const float4*>(s_q + st * 128 + l * 4);
+        float ex, ey, ez, ew;
+        if (rs.rows_f32) {
+          const float4 e = __ldg(reinterpret_cast<const float4*>(rpf + st * 128 + l * 4));
+          ex = e.x, ey = e.y, ez = e.z, ew = e.w;
+        } else {
+          const uint2 u = __ldg(reinterpret_cast<const uint2*>(rp + st * 128 + l * 4));
+          ex = __uint_as_float(u.x << 16), ey = __uint_as_float(u.x & 0xFFFF0000u);
+          ez = __uint_as_float(u.y << 16), ew = __uint_as_float(u.y & 0xFFFF0000u);
+        }
+        d0 = __fmaf_rn(qv.x, ex, d0);
+        d1 = __fmaf_rn(qv.y, ey, d1);
+        d2 = __fmaf_rn(qv.z, ez, d2);
+        d3 = __fmaf_rn(qv.w, ew, d3);
+        n0 = __fmaf_rn(ex, ex, n0);
+        n1 = __fmaf_rn(ey, ey, n1);
+        n2 = __fmaf_rn(ez, ez, n2);
+        n3 = __fmaf_rn(ew, ew, n3);
+      }
+      pd[j] = __fadd_rn(__fadd_rn(d0, d1), __fadd_rn(d2, d3));
+      pn[j] = __fadd_rn(__fadd_rn(n0, n1), __fadd_rn(n2, n3));
+    }
+    float dot = __fadd_rn(__fadd_rn(pd[0], pd[2]), __fadd_rn(pd[1], pd[3]));  // xor 16, then 8
+    float ne2 = __fadd_rn(__fadd_rn(pn[0], pn[2]), __fadd_rn(pn[1], pn[3]));
+#pragma unroll
+    for (int mm = 4; mm >= 1; mm >>= 1) {
+      dot = __fadd_rn(dot, __shfl_xor_sync(FULL_MASK, dot, mm));
+      ne2 = __fadd_rn(ne2, __shfl_xor_sync(FULL_MASK, ne2, mm));
+    }
+    if (live && t8 == 0) sk[i] = pack_key(finish_score(dot, sq_nq, ne2), row_g);
+  }
+  __syncthreads();
+}
+
 // One block per query; the kernel is a single wave of latency-bound blocks (8 per SM), so it is
 // written for few dependent memory round trips: lists are walked by warps (no index search),
 // four keys per lane are in flight, and the re-scoring runs 32 rows at a time.
@@ -790,72 +861,7 @@ select_kernel(const uint64_t* cand, const uint32_t* cand_count, uint32_t nsub, u
   __syncthreads();
   uint32_t m = s_n;
   if (m > kSelectSort) m = kSelectSort, s_over = 1;  // (benign race: every writer stores 1)
-  if (rescore) {
-    // The scan's arithmetic (scan.cuh): "lane" l of 32 owns elements
-    // 4l..4l+3 of every 128-element stripe with four sub-accumulators, combines them
-    // ((a0+a1)+(a2+a3)), then an xor butterfly 16, 8, 4, 2, 1 over the 32 lane partials.
-    // The query norm is done that way by a whole warp.  Rows are done FOUR per warp for memory
-    // parallelism: thread t of an 8-thread group plays lanes t, t+8, t+16, t+24 one after the
-    // other; butterfly steps 16 and 8 pair exactly those four partials inside the thread
-    // ((p_t + p_t+16) + (p_t+8 + p_t+24)), steps 4, 2, 1 are shuffles within the group -- the
-    // same additions in the same order, so the same bits.
-    const uint32_t ns = rs.stride_elems / 128;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    for (uint32_t st = 0; st < ns; ++st) {
-      const float4 qv = *reinterpret_cast<const float4*>(s_q + st * 128 + lane * 4);
-      a0 = __fmaf_rn(qv.x, qv.x, a0);
-      a1 = __fmaf_rn(qv.y, qv.y, a1);
-      a2 = __fmaf_rn(qv.z, qv.z, a2);
-      a3 = __fmaf_rn(qv.w, qv.w, a3);
-    }
-    const float sq_nq = __fsqrt_rn(butterfly_sum(__fadd_rn(__fadd_rn(a0, a1), __fadd_rn(a2, a3))));
-    const uint32_t grp = lane >> 3, t8 = lane & 7;
-    for (uint32_t i0 = warp * 4; i0 < m; i0 += kWarps * 4) {
-      const uint32_t i = i0 + grp;
-      const bool live = i < m;
-      const uint32_t row_g = 0xFFFFFFFFu - (uint32_t)sk[live ? i : i0];
-      const size_t roff = (size_t)(row_g - rs.row_base) * rs.stride_elems;
-      const uint16_t* rp = reinterpret_cast<const uint16_t*>(rs.rows) + roff;
-      const float* rpf = reinterpret_cast<const float*>(rs.rows) + roff;
-      float pd[4], pn[4];
-#pragma unroll
-      for (uint32_t j = 0; j < 4; ++j) {
-        const uint32_t l = t8 + 8 * j;  // the lane being played
-        float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f, n0 = 0.f, n1 = 0.f, n2 = 0.f, n3 = 0.f;
-        for (uint32_t st = 0; st < ns; ++st) {
-          const float4 qv = *reinterpret_cast<const float4*>(s_q + st * 128 + l * 4);
-          float ex, ey, ez, ew;
-          if (rs.rows_f32) {
-            const float4 e = __ldg(reinterpret_cast<const float4*>(rpf + st * 128 + l * 4));
-            ex = e.x, ey = e.y, ez = e.z, ew = e.w;
-          } else {
-            const uint2 u = __ldg(reinterpret_cast<const uint2*>(rp + st * 128 + l * 4));
-            ex = __uint_as_float(u.x << 16), ey = __uint_as_float(u.x & 0xFFFF0000u);
-            ez = __uint_as_float(u.y << 16), ew = __uint_as_float(u.y & 0xFFFF0000u);
-          }
-          d0 = __fmaf_rn(qv.x, ex, d0);
-          d1 = __fmaf_rn(qv.y, ey, d1);
-          d2 = __fmaf_rn(qv.z, ez, d2);
-          d3 = __fmaf_rn(qv.w, ew, d3);
-          n0 = __fmaf_rn(ex, ex, n0);
-          n1 = __fmaf_rn(ey, ey, n1);
-          n2 = __fmaf_rn(ez, ez, n2);
-          n3 = __fmaf_rn(ew, ew, n3);
-        }
-        pd[j] = __fadd_rn(__fadd_rn(d0, d1), __fadd_rn(d2, d3));
-        pn[j] = __fadd_rn(__fadd_rn(n0, n1), __fadd_rn(n2, n3));
-      }
-      float dot = __fadd_rn(__fadd_rn(pd[0], pd[2]), __fadd_rn(pd[1], pd[3]));  // xor 16, then 8
-      float ne2 = __fadd_rn(__fadd_rn(pn[0], pn[2]), __fadd_rn(pn[1], pn[3]));
-#pragma unroll
-      for (int mm = 4; mm >= 1; mm >>= 1) {
-        dot = __fadd_rn(dot, __shfl_xor_sync(FULL_MASK, dot, mm));
-        ne2 = __fadd_rn(ne2, __shfl_xor_sync(FULL_MASK, ne2, mm));
-      }
-      if (live && t8 == 0) sk[i] = pack_key(finish_score(dot, sq_nq, ne2), row_g);
-    }
-    __syncthreads();
-  }
+  if (rescore) rescore_keys(sk, m, rs, s_q);
   uint32_t npad = 2;
   while (npad < m) npad <<= 1;
   for (uint32_t i = m + threadIdx.x; i < npad; i += blockDim.x) sk[i] = 0;
@@ -864,6 +870,46 @@ select_kernel(const uint64_t* cand, const uint32_t* cand_count, uint32_t nsub, u
   for (uint32_t e = threadIdx.x; e < k; e += blockDim.x)
     out[(size_t)q * k + e] = e < npad ? sk[e] : 0;
   if (threadIdx.x == 0) overflow[q] = s_over;
+}
+
+// Shadow prefilter for single queries on an fp32 index (tss_index_set_batch_policy(1)): the scan
+// kernel has streamed the bf16 SHADOW of the matrix and left its top-kc keys (cosine of the fp32
+// query with the bf16 rows, sorted) in cand[q][kc], kc > k.  With A the shadow score and B the
+// score of the stored fp32 row, |A - B| <= eps := 2^-8 + D * 2^-22 (the rows' rounding,
+// |e_t/|e_t| - e/|e|| <= 2 |e_t - e| / |e|, plus both accumulations; cosine units).  If the kc-th
+// shadow score lies more than 2 eps below the k-th, every row of the fp32 top-k is among the kc
+// candidates (the argument of select_kernel); they are re-scored from the fp32 rows and the top-k
+// written.  Otherwise incomplete[q] = 1 and the host redoes the query with the fp32 scan.
+constexpr uint32_t kRefineMax = 128;
+__global__ void __launch_bounds__(kSelectThreads)
+refine_kernel(const uint64_t* cand, uint32_t kc, const Rescore rs, float two_eps, uint32_t k,
+              uint64_t* out, uint32_t* incomplete) {
+  __shared__ uint64_t sk[kRefineMax];
+  __shared__ __align__(16) float s_q[1024];
+  const uint32_t q = blockIdx.x;
+  for (uint32_t j = threadIdx.x; j < rs.stride_elems; j += kSelectThreads)
+    s_q[j] = j < rs.dim ? rs.queries[(size_t)q * rs.dim + j] : 0.f;
+  if (threadIdx.x < kRefineMax) sk[threadIdx.x] = threadIdx.x < kc ? cand[(size_t)q * kc + threadIdx.x] : 0;
+  __syncthreads();
+  const uint32_t m = (uint32_t)__syncthreads_count(threadIdx.x < kc && sk[threadIdx.x] != 0);
+  if (threadIdx.x == 0) {
+    uint32_t bad = 0;
+    if (m == kc && m > k) {  // a full list: rows beyond it exist and must be provably too low
+      auto score = [&](uint64_t key) {
+        const uint32_t o = (uint32_t)(key >> 32);
+        return __uint_as_float((o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o);
+      };
+      bad = !(score(sk[kc - 1]) < score(sk[k - 1]) - two_eps);
+    } else if (m == kc) {
+      bad = 1;  // kc <= k: nothing to spare
+    }
+    incomplete[q] = bad;
+  }
+  __syncthreads();
+  rescore_keys(sk, m, rs, s_q);
+  block_bitonic_desc(sk, kRefineMax);  // unused slots are 0 = lowest key
+  for (uint32_t e = threadIdx.x; e < k; e += kSelectThreads)
+    out[(size_t)q * k + e] = e < kRefineMax ? sk[e] : 0;
 }
 
 // ---- host side ------------------------------------------------------------------------------
@@ -948,6 +994,17 @@ cudaError_t launch_select(const uint64_t* cand, const uint32_t* cand_count, uint
   Rescore rs{queries, margin, rows, rows_f32 ? 1 : 0, dim, stride_elems, row_base};
   select_kernel<<<nq, kSelectThreads, select_sort_cap(k) * sizeof(uint64_t), st>>>(
       cand, cand_count, nslices, cap_s, inv_qnorm, rs, k, out, overflow);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_refine(const uint64_t* cand, uint32_t kc, const float* queries, const void* rows_f32,
+                          uint32_t dim, uint32_t stride_elems, uint32_t row_base, uint32_t nq,
+                          uint32_t k, uint64_t* out, uint32_t* incomplete, cudaStream_t st) {
+  if (kc > kRefineMax || k > kRefineMax || stride_elems > 1024 || stride_elems % 128)
+    return cudaErrorInvalidConfiguration;
+  Rescore rs{queries, nullptr, rows_f32, 1, dim, stride_elems, row_base};
+  const float two_eps = 2.f * (0x1p-8f + (float)dim * 0x1p-22f);
+  refine_kernel<<<nq, kSelectThreads, 0, st>>>(cand, kc, rs, two_eps, k, out, incomplete);
   return cudaGetLastError();
 }
 
