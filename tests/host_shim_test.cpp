@@ -202,6 +202,16 @@ static void hnsw_vs_oracle() {
   CHECK(threw);
   auto batch = h.search_batch({q, synth(2, dim, 9), synth(3, dim, 9)}, 5);
   CHECK(batch.size() == 3 && batch[0][0].first.case_id == cid(99999) && batch[2].size() == 5);
+  // batch policy: single queries through the bf16 shadow answer exactly like the scan
+  {
+    auto plain = h.search(q, 5);
+    h.set_batch_policy(1, true);
+    auto pre = h.search(q, 5);
+    h.set_batch_policy(0, false);
+    CHECK(plain.size() == pre.size());
+    for (size_t i = 0; i < plain.size() && i < pre.size(); ++i)
+      CHECK(plain[i].first == pre[i].first && plain[i].second == pre[i].second);
+  }
   // N1: save -> load -> same answers, DocRefs included
   const std::string path = "/tmp/tss_host_shim_test_index";
   h.save(path);

@@ -9,7 +9,7 @@
 //     as K/64 swizzle-128B K-major tiles (TMA, 96 KB at D = 384);
 //   * corpus tiles of 256 rows stream through a ring of 64-element k-blocks (TMA 2-D tensor map
 //     over the row-major matrix, swizzle 128B): a pair's CTAs stage 128 rows each (16 KB per
-//     stage, 7 stages), an independent CTA all 256 (32 KB, 4 stages);
+//     stage, 8 stages), an independent CTA all 256 (32 KB, 4 stages);
 //   * one elected thread (of a pair: the leader's) issues tcgen05.mma -- M256 N256 K16 across
 //     the pair, M128 N256 K16 alone -- with fp32 accumulation into one of two 256-column TMEM
 //     accumulators; tcgen05.commit frees the smem stage / publishes the tile (in both CTAs);
@@ -187,15 +187,16 @@ __device__ __forceinline__ void tmem_ld_wait() {
 // from 96 B/clk of operand reads (4 KB A + 8 KB B per MMA) + 64 B/clk of TMA writes (a 32 KB
 // stage per 4 MMAs) -- more than the 128 B/clk an SM has -- to 64 + 32 B/clk, and the L2 -> SM
 // traffic halves without any multicast: every CTA loads only its own half of the tile (16 KB
-// per stage, so the ring is 7 deep) with the cta_group::2 form of the TMA load, which counts
+// per stage, so the ring is 8 deep) with the cta_group::2 form of the TMA load, which counts
 // its bytes on the leader's barrier.  Each CTA's TMEM receives its own 128 queries x all 256
 // rows, so the epilogue is the same in both modes.
 template <int KB, bool PAIR>
-__host__ __device__ constexpr int gemm_stages() { return PAIR ? (KB <= 6 ? 7 : 6) : 4; }
-// floats of staged 1/|row|: a pair's epilogue warps each keep their own 64 columns' worth (no
-// block barrier); otherwise one double-buffered tile's worth shared by all epilogue warps
+__host__ __device__ constexpr int gemm_stages() { return PAIR ? (KB <= 6 ? 8 : 6) : 4; }
+// floats of staged 1/|row|: a pair's epilogue warps each keep the 32 columns' worth of the chunk
+// they are on (no block barrier); otherwise one double-buffered tile's worth shared by all
+// epilogue warps
 __host__ __device__ constexpr int gemm_ninv_floats(bool pair) {
-  return pair ? kEpiWarps * (kBlockN / kColSplit) : 2 * kBlockN;
+  return pair ? kEpiWarps * 32 : 2 * kBlockN;
 }
 
 template <int KB, bool PAIR>
@@ -296,7 +297,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       }
       uint32_t s = 0, ph = 0;
       // (A contiguous L2 prefetch of whole tiles ahead of these strided boxes used to live here;
-      // measured with the 7-deep ring it changes nothing at 512+ queries and costs 25-40 % at
+      // measured with a 7- or 8-deep ring it changes nothing at 512+ queries and costs 25-40 % at
       // <= 256, where every SM streams its own tiles.)
       for (uint32_t i = slice; i < count; i += nslices) {
         const int row0 = (int)(i * stride * kBlockN);
@@ -390,8 +391,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     };
     // The weights of a tile are fetched one tile ahead into registers, so their global-memory
     // latency never sits between two tiles.  PAIR: lane l of a warp fetches the weights of
-    // columns part*64 + l and + 32 + l, and the warp stages them in its own 64 floats
-    // (warp-level sync only).  Otherwise thread et < 256 fetches column et and all epilogue
+    // columns part*64 + l and + 32 + l, and the warp stages the 32 of the chunk it is about to
+    // read in its own 128 bytes (warp-level sync only).  Otherwise thread et < 256 fetches column et and all epilogue
     // warps meet at a named barrier (double-buffered by accumulator).
     const uint64_t my_col = PAIR ? part * kColsPer + lane : et;
     auto fetch_weights = [&](uint32_t i, float& a, float& b) {
@@ -406,22 +407,22 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     };
     float w_a = 0.f, w_b = 0.f;
     fetch_weights(slice, w_a, w_b);
-    float* warp_ninv = s_ninv + (warp - 2) * kColsPer;
+    float* warp_ninv = s_ninv + (warp - 2) * 32;
     for (uint32_t i = slice; i < count; i += nslices, ++it) {
       const uint32_t acc = it & 1u, use = it >> 1;
       const uint64_t row0 = (uint64_t)i * stride * kBlockN;
       // ninv[c] = weight of the tile's column c (for the columns this thread visits)
-      float* ninv = PAIR ? warp_ninv - part * kColsPer : s_ninv + acc * kBlockN;
+      float* ninv = s_ninv + acc * kBlockN;
       if (PAIR) {
         __syncwarp();  // the previous tile's reads of the warp's buffer are done
         warp_ninv[lane] = w_a;
-        warp_ninv[32 + lane] = w_b;
         __syncwarp();
       } else {
         if (et < (uint32_t)kBlockN) ninv[et] = w_a;
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       }
-      fetch_weights(i + nslices, w_a, w_b);
+      float n_a = 0.f, n_b = 0.f;  // the next tile's weights, in flight while this one is scored
+      fetch_weights(i + nslices, n_a, n_b);
       mbar_wait(bar_tfull + 8 * acc, use & 1u);
       tc_fence_after();
       const uint64_t left = p.n_rows - row0;
@@ -429,6 +430,11 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       float mx = -INFINITY;
 #pragma unroll 1
       for (uint32_t cb = part * kColsPer; cb < (part + 1) * kColsPer; cb += 32) {
+        if (PAIR && cb != part * kColsPer) {  // second chunk: its weights replace the first's
+          __syncwarp();
+          warp_ninv[lane] = w_b;
+          __syncwarp();
+        }
         uint32_t r[32];
         tmem_ld32(tmem_base + (lane_base << 16) + acc * kBlockN + cb, r);
         tmem_ld_wait();
@@ -436,7 +442,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         // branch-free common case: scale by 1/|row|, maxima of the four groups of 8 and of
         // the chunk; only a chunk (then a group) whose maximum reaches the threshold is walked
         float v[32];
-        const float4* nv = reinterpret_cast<const float4*>(ninv + cb);
+        const float4* nv = reinterpret_cast<const float4*>(PAIR ? warp_ninv : ninv + cb);
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
           const float4 w = nv[j4];
@@ -474,6 +480,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           }
         }
       }
+      w_a = n_a;
+      w_b = n_b;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -915,7 +923,7 @@ refine_kernel(const uint64_t* cand, uint32_t kc, const Rescore rs, float two_eps
 // ---- host side ------------------------------------------------------------------------------
 int gemm_col_split() { return kColSplit; }
 size_t gemm_smem_bytes(int kb, bool pair) {
-  const size_t stages = pair ? (kb <= 6 ? 7 : 6) : 4;
+  const size_t stages = pair ? (kb <= 6 ? 8 : 6) : 4;
   const size_t b = pair ? kBTileBytes / 2 : kBTileBytes;
   const size_t ring = kb <= 6 ? (size_t)kb * kATileBytes + stages * b : stages * (b + kATileBytes);
   return ring + gemm_ninv_floats(pair) * sizeof(float) + kBarSlots * 8 + 16;
@@ -924,7 +932,7 @@ size_t gemm_smem_bytes(int kb, bool pair) {
 template <int KB, bool PAIR>
 static cudaError_t launch_gemm_inst(const CUtensorMap& tmap_q, const CUtensorMap& tmap_e,
                                     const GemmParams& p, int grid, size_t smem, cudaStream_t st) {
-  static_assert(gemm_stages<KB, PAIR>() == (PAIR ? (KB <= 6 ? 7 : 6) : 4), "gemm_smem_bytes");
+  static_assert(gemm_stages<KB, PAIR>() == (PAIR ? (KB <= 6 ? 8 : 6) : 4), "gemm_smem_bytes");
   auto kern = gemm_topk_kernel<KB, PAIR>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;

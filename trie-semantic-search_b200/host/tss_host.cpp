@@ -160,6 +160,12 @@ const std::vector<uint32_t>* HnswIndex::rows_of_case(const CaseId& id) const {
   return it == case_rows_.end() ? nullptr : &it->second;
 }
 
+void HnswIndex::set_batch_policy(uint32_t min_queries, bool build_shadow_now) {
+  if (build_shadow_now) make_searchable();
+  int rc = tss_index_set_batch_policy(ix_, min_queries, build_shadow_now ? 1 : 0);
+  if (rc) raise_tss(SearchError::VectorIndexFailed, "HnswIndex set_batch_policy", rc);
+}
+
 std::vector<std::vector<std::pair<DocRef, float>>> HnswIndex::search_batch(
     const std::vector<std::vector<float>>& queries, size_t top_k) {
   std::vector<std::vector<std::pair<DocRef, float>>> out(queries.size());

@@ -131,6 +131,9 @@ class HnswIndex {
                                                       int mask_mode);
   std::vector<std::vector<std::pair<DocRef, float>>> search_batch(
       const std::vector<std::vector<float>>& queries, size_t top_k);
+  // from how many queries a call leaves the plain scan for the tensor-core path / the shadow
+  // prefilter (results are bit-identical either way; tss_index_set_batch_policy in tss.h)
+  void set_batch_policy(uint32_t min_queries, bool build_shadow_now);
   // on-disk form: <path>.tssidx (tss_index_save) + <path>.docrefs
   void save(const std::string& path);
   static std::unique_ptr<HnswIndex> load(const HnswConfig& config, const std::string& path,
