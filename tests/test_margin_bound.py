@@ -1,0 +1,76 @@
+"""The error bound behind K2's exact re-scoring and the shadow prefilter.
+
+Both paths pick candidates by a cheaper score A and prove the exact top-k (by the scan's score B)
+is among them using |A - B| <= eps.  This checks the bound itself on the CPU, in float64:
+  bf16 index:        A = q_bf16 . e / |e|        B = q . e / |e|       eps = |q| 2^-8
+  fp32 + bf16 shadow: A = q_bf16 . e_t / |e_t|    B = q . e / |e|       eps = |q| 2^-7
+  shadow prefilter:   A = q . e_t / (|q||e_t|)    B = q . e / (|q||e|)  eps = 2^-8 (1 + 2^-8)  (cosine)
+(e_t = bf16(e).  bf16 keeps 8 significant bits, so round-to-nearest moves a vector by at most 2^-8
+of its norm -- NOT 2^-9, which the first version of the kernels assumed and this test caught; the
+(D + 4) * 2^-22 slack the kernels add for fp32 accumulation is not needed in float64) and
+the selection argument: keeping every row with A >= t - 2 eps, t the k-th largest A, keeps the
+whole top-k by B.
+"""
+import numpy as np
+import pytest
+
+
+def _bf16(x):
+    u = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32)
+    return ((u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000).astype(np.uint32).view(np.float32)
+
+
+def _cases():
+    rng = np.random.default_rng(11)
+    for dim in (3, 64, 384, 1000):
+        for scale in (1e-3, 1.0, 250.0):
+            rows = (rng.standard_normal((4000, dim)) * scale).astype(np.float32)
+            rows[::7] *= rng.uniform(0.01, 100.0, size=(len(rows[::7]), 1)).astype(np.float32)
+            rows[5] = rows[4]                      # duplicates
+            rows[6] = -rows[4]
+            q = (rng.standard_normal((16, dim)) * rng.uniform(1e-2, 1e2)).astype(np.float32)
+            q[0] = rows[17] * 3.0                  # a query parallel to a row
+            q[1] = np.abs(q[1])                    # all components one sign: worst case for rounding
+            yield dim, rows, q
+
+
+@pytest.mark.parametrize("dim,rows,q", list(_cases()), ids=lambda v: str(v) if isinstance(v, int) else None)
+def test_score_differences_stay_inside_eps(dim, rows, q):
+    r64, q64 = rows.astype(np.float64), q.astype(np.float64)
+    rt64, qb64 = _bf16(rows).astype(np.float64), _bf16(q).astype(np.float64)
+    rn = np.linalg.norm(r64, axis=1)
+    rtn = np.linalg.norm(rt64, axis=1)
+    qn = np.linalg.norm(q64, axis=1)[:, None]
+    b = (q64 @ r64.T) / rn                                   # unscaled by |q|, like the K2 epilogue
+    a_bf16_index = (qb64 @ r64.T) / rn                       # the index rows ARE bf16 there: e_t = e
+    a_shadow = (qb64 @ rt64.T) / rtn
+    # the rounding itself: at most 2^-8 of the norm, and it does get close to it
+    dq = np.linalg.norm(qb64 - q64, axis=1) / qn[:, 0]
+    de = np.linalg.norm(rt64 - r64, axis=1) / rn
+    assert dq.max() <= 2.0 ** -8 and de.max() <= 2.0 ** -8
+    assert np.all(np.abs(a_bf16_index - b) <= qn * 2.0 ** -8 * (1 + 1e-12))
+    assert np.all(np.abs(a_shadow - b) <= qn * 2.0 ** -7 * (1 + 1e-12))
+    cos_b = b / qn
+    cos_a = (q64 @ rt64.T) / rtn / qn
+    assert np.all(np.abs(cos_a - cos_b) <= 2.0 ** -8 * (1 + 2.0 ** -8))
+
+
+@pytest.mark.parametrize("k", [1, 10, 100])
+def test_margin_keeps_the_whole_topk(k):
+    rng = np.random.default_rng(k)
+    dim, n = 384, 20000
+    rows = rng.standard_normal((n, dim)).astype(np.float32)
+    rows[100:140] = rows[7] + 1e-3 * rng.standard_normal((40, dim)).astype(np.float32)  # a cluster
+    q = rng.standard_normal((8, dim)).astype(np.float32)
+    q[0] = rows[7]
+    r64, q64 = rows.astype(np.float64), q.astype(np.float64)
+    rt64, qb64 = _bf16(rows).astype(np.float64), _bf16(q).astype(np.float64)
+    b = (q64 @ r64.T) / np.linalg.norm(r64, axis=1)
+    a = (qb64 @ rt64.T) / np.linalg.norm(rt64, axis=1)
+    eps = np.linalg.norm(q64, axis=1) * 2.0 ** -7
+    for i in range(len(q)):
+        t = np.sort(a[i])[-k]
+        kept = set(np.nonzero(a[i] >= t - 2 * eps[i])[0].tolist())
+        top_b = set(np.argsort(-b[i], kind="stable")[:k].tolist())
+        assert top_b <= kept
+        assert len(kept) < 60 * k + 400                      # and the margin stays selective

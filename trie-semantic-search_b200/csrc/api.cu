@@ -87,7 +87,7 @@ constexpr uint32_t kMaxBq = 4;           // queries per scan launch
 constexpr uint32_t kScanSlots = 4;       // scan workspace slots (launches in flight under PDL)
 constexpr uint32_t kWsQueries = 1024;    // device query/result workspace, in queries
 constexpr size_t kStageBytes = 64u << 20;  // upload staging buffer
-constexpr uint32_t kGemmCandCap = 16384;   // K2 survivor keys per query of a FULL workspace batch:
+constexpr uint32_t kGemmCandCap = 32768;   // K2 survivor keys per query of a FULL workspace batch:
                                            // the pool (kWsQueries x this) is shared out per batch
 constexpr uint32_t kGemmMaxSample = 8192;  // tiles sampled by the K2 threshold pass
 constexpr uint32_t kPrefilterMaxNq = 2;    // queries per call the shadow prefilter takes (K2 beyond)
@@ -399,7 +399,8 @@ bool gemm_eligible(const tss_index* ix, uint32_t nq, uint32_t k, int mode) {
 
 // survivors a query is expected to leave in the K2 lists when `sample` tiles set its threshold
 uint64_t gemm_expected_survivors(const tss_index* ix, uint32_t k, uint32_t num_tiles, uint32_t sample) {
-  const uint64_t spread = ix->storage == TSS_F32 ? 3 : 2;  // measured 2.7x / 1.4x at k = 100
+  // e^(z * margin / sigma) with the margins of prep_queries_kernel, z ~ 4.3 at k = 100 of 10M
+  const uint64_t spread = ix->storage == TSS_F32 ? 5 : 3;
   return spread * k * (uint64_t)num_tiles / (sample ? sample : 1);
 }
 // largest batch (a multiple of 256 queries, <= kWsQueries) whose queries' expected survivors fit

@@ -515,11 +515,13 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 // fp32 queries -> bf16 [mb*128][kpad] (zero padded) + per-query 1/|q| (of the bf16-rounded query)
 // + the rescoring margin (see select_kernel): a bound on 2 * |A(e) - B(e)| over all rows e, where
 // A = q_bf16 . e_t / |e_t| is what the tensor cores see (e_t: the bf16 row they read) and
-// B = q . e / |e| what the scan computes from the stored row e.  A - B = (q_bf16 - q) . e_t/|e_t|
-// + q . (e_t/|e_t| - e/|e|): the first term is at most 2^-9 |q| (RNE of the query, Cauchy-
-// Schwarz); the second is zero on a bf16 index (e_t = e) and at most 2 |e_t - e| / |e| * |q| <=
-// 2^-8 |q| when e_t is the bf16 shadow of an fp32 row; plus the fp32 accumulation error of either
-// path (a generous D * 2^-22 |q|).
+// B = q . e / |e| what the scan computes from the stored row e.  bf16 keeps 8 significant bits,
+// so round-to-nearest moves a vector by at most 2^-8 of its norm (tests/test_margin_bound.py).
+// A - B = (q_bf16 - q) . e_t/|e_t| + q . (e_t/|e_t| - e/|e|): the first term is at most 2^-8 |q|
+// (Cauchy-Schwarz); the second is zero on a bf16 index (e_t = e), and when e_t is the bf16 shadow
+// of an fp32 row the two unit vectors are a chord 2 sin(theta/2) apart with sin(theta) <= 2^-8,
+// i.e. at most 2^-8 (1 + 2^-17) |q|; plus the fp32 accumulation errors of both paths and the
+// rsqrt behind 1/|e_t| (together under (D + 4) * 2^-22 |q|).
 __global__ void prep_queries_kernel(const float* q, uint32_t nq, uint32_t dim, uint32_t kpad,
                                     uint32_t nq_pad, uint16_t* out, float* inv_qnorm, float* margin,
                                     int shadowed) {
@@ -549,7 +551,7 @@ __global__ void prep_queries_kernel(const float* q, uint32_t nq, uint32_t dim, u
     for (uint32_t w = 0; w < (blockDim.x + 31) / 32; ++w) t += red[0][w], tf += red[1][w];
     inv_qnorm[qi] = t > 0.f ? rsqrtf(t) : 0.f;
     margin[qi] = 2.f * 1.001f * sqrtf(tf) *
-                 ((shadowed ? 0x1p-9f + 0x1p-8f : 0x1p-9f) + (float)dim * 0x1p-22f);
+                 ((shadowed ? 0x1p-7f : 0x1p-8f) + (float)(dim + 4) * 0x1p-22f);
   }
 }
 
@@ -883,8 +885,9 @@ select_kernel(const uint64_t* cand, const uint32_t* cand_count, uint32_t nsub, u
 // Shadow prefilter for single queries on an fp32 index (tss_index_set_batch_policy(1)): the scan
 // kernel has streamed the bf16 SHADOW of the matrix and left its top-kc keys (cosine of the fp32
 // query with the bf16 rows, sorted) in cand[q][kc], kc > k.  With A the shadow score and B the
-// score of the stored fp32 row, |A - B| <= eps := 2^-8 + D * 2^-22 (the rows' rounding,
-// |e_t/|e_t| - e/|e|| <= 2 |e_t - e| / |e|, plus both accumulations; cosine units).  If the kc-th
+// score of the stored fp32 row, |A - B| <= eps := 2^-8 (1 + 2^-8) + (D + 4) * 2^-22 (cosine units:
+// the unit vectors of a row and of its bf16 rounding are at most a 2^-8 chord apart, see
+// prep_queries_kernel; plus both accumulations).  If the kc-th
 // shadow score lies more than 2 eps below the k-th, every row of the fp32 top-k is among the kc
 // candidates (the argument of select_kernel); they are re-scored from the fp32 rows and the top-k
 // written.  Otherwise incomplete[q] = 1 and the host redoes the query with the fp32 scan.
@@ -1011,7 +1014,7 @@ cudaError_t launch_refine(const uint64_t* cand, uint32_t kc, const float* querie
   if (kc > kRefineMax || k > kRefineMax || stride_elems > 1024 || stride_elems % 128)
     return cudaErrorInvalidConfiguration;
   Rescore rs{queries, nullptr, rows_f32, 1, dim, stride_elems, row_base};
-  const float two_eps = 2.f * (0x1p-8f + (float)dim * 0x1p-22f);
+  const float two_eps = 2.f * (0x1.01p-8f + (float)(dim + 4) * 0x1p-22f);
   refine_kernel<<<nq, kSelectThreads, 0, st>>>(cand, kc, rs, two_eps, k, out, incomplete);
   return cudaGetLastError();
 }
