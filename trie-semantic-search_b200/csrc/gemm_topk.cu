@@ -536,7 +536,8 @@ __global__ void prep_queries_kernel(const float* q, uint32_t nq, uint32_t dim, u
     out[(size_t)qi * kpad + j] = h;
     float w = __uint_as_float((uint32_t)h << 16);
     ss = fmaf(w, w, ss);
-    sf = fmaf(v, v, sf);
+    sf = fmaf(v, v, sf);  // (a component that rounds to inf, or a norm that overflows, makes the
+                          // margin inf: every row survives, the list overflows, the scan answers)
   }
   __shared__ float red[2][32];
 #pragma unroll
