@@ -223,6 +223,11 @@ struct tss_index {
     uint64_t shadow_cap = 0, shadow_rows = 0;
     const void* shadow_base = nullptr;
     bool shadow_failed = false;    // no memory for it: large batches stay on the scan
+    // Self-tuning of the survivor estimate: doubled (up to 64x) whenever more than 5 % of a
+    // batch's queries overflowed their lists and had to be redone by the scan -- a corpus whose
+    // scores crowd near the top (near-duplicates, tight clusters) then gets a larger tile
+    // sample and smaller batches instead of one fallback scan per query.
+    uint32_t spread_boost = 1;
   } gemm;
   // Batches at least this large use K2.  On a big corpus (where its five launches and one host
   // sync are noise) K2 also takes batches from gemm_small_nq queries when the bf16 matrix it
@@ -401,7 +406,7 @@ bool gemm_eligible(const tss_index* ix, uint32_t nq, uint32_t k, int mode) {
 uint64_t gemm_expected_survivors(const tss_index* ix, uint32_t k, uint32_t num_tiles, uint32_t sample) {
   // e^(z * margin / sigma) with the margins of prep_queries_kernel, z ~ 4.3 at k = 100 of 10M
   const uint64_t spread = ix->storage == TSS_F32 ? 5 : 3;
-  return spread * k * (uint64_t)num_tiles / (sample ? sample : 1);
+  return spread * ix->gemm.spread_boost * k * (uint64_t)num_tiles / (sample ? sample : 1);
 }
 // largest batch (a multiple of 256 queries, <= kWsQueries) whose queries' expected survivors fit
 // half their share of the pool with the largest tile sample the threshold pass can take
@@ -584,6 +589,9 @@ int enqueue_gemm(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
   CU(cudaMemcpyAsync(g.h_cand_count, g.d_overflow, nq * sizeof(uint32_t), cudaMemcpyDeviceToHost,
                      ix->stream));
   CU(cudaStreamSynchronize(ix->stream));
+  uint32_t redo = 0;
+  for (uint32_t qi = 0; qi < nq; ++qi) redo += g.h_cand_count[qi] != 0;
+  if (redo * 20 > nq && g.spread_boost < 64) g.spread_boost *= 2;
   for (uint32_t qi = 0; qi < nq; ++qi) {
     if (!g.h_cand_count[qi]) continue;
     ix->xchg.suppress = true;
