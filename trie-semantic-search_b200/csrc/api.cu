@@ -396,9 +396,12 @@ int ensure_gather_ws(tss_index* ix) {
 
 bool gemm_eligible(const tss_index* ix, uint32_t nq, uint32_t k, int mode) {
   (void)mode;  // masks ride along: a masked row's 1/|row| is NaN in the epilogue
-  if (ix->storage == TSS_F32 && ix->gemm.shadow_failed) return false;
+  if (ix->storage == TSS_F32 && ix->gemm.shadow_failed && !ix->comm) return false;
+  // (every rank of a sharded index must take the same path, or the exchange deadlocks: the
+  // rank-local conditions -- shard size, shadow built -- only count on an unsharded index)
   const bool have_bf16 = ix->storage == TSS_BF16 || ix->gemm.shadow_rows == ix->n_rows;
-  const bool small_ok = have_bf16 && nq >= ix->gemm_small_nq && ix->n_rows >= ix->gemm_small_rows;
+  const bool small_ok = !ix->comm && have_bf16 && nq >= ix->gemm_small_nq &&
+                        ix->n_rows >= ix->gemm_small_rows;
   return (nq >= ix->gemm_min_nq || small_ok) && ix->n_rows >= 4ull * 256 * k && k <= TSS_MAX_K;
 }
 
@@ -494,7 +497,10 @@ int ensure_gemm_ws(tss_index* ix) {
 // batch stays on the scan: exact all the same, one launch per 4 queries.
 bool gemm_route(tss_index* ix, uint32_t nq, uint32_t k, int mode) {
   if (!gemm_eligible(ix, nq, k, mode)) return false;
-  if (ix->storage == TSS_F32 && ensure_gemm_ws(ix) == TSS_ERR_OOM && ix->gemm.shadow_failed)
+  // a sharded index reports the failure instead (enqueue_gemm returns it): quietly scanning on
+  // one rank while the others run K2 would desynchronise the exchange
+  if (ix->storage == TSS_F32 && !ix->comm && ensure_gemm_ws(ix) == TSS_ERR_OOM &&
+      ix->gemm.shadow_failed)
     return false;
   return true;
 }
