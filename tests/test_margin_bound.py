@@ -74,3 +74,19 @@ def test_margin_keeps_the_whole_topk(k):
         top_b = set(np.argsort(-b[i], kind="stable")[:k].tolist())
         assert top_b <= kept
         assert len(kept) < 60 * k + 400                      # and the margin stays selective
+
+
+@pytest.mark.parametrize("dim", [3, 100, 384, 1024])
+def test_scan_arithmetic_stays_inside_the_accumulation_slack(orc, dim):
+    """The margins reserve (D + 4) * 2^-22 (relative to |q|, i.e. in cosine units) for the fp32
+    accumulation of BOTH paths; the scan's share -- its canonical fp32 order against exact
+    arithmetic -- has to fit in a quarter of that with room to spare."""
+    rng = np.random.default_rng(dim)
+    rows = rng.standard_normal((3000, dim)).astype(np.float32)
+    rows[:500] = np.abs(rows[:500])            # no cancellation: rounding errors all push one way
+    for q in (rng.standard_normal(dim).astype(np.float32), np.abs(rng.standard_normal(dim)).astype(np.float32)):
+        for bf16 in (False, True):
+            got = orc.scores(rows, q, bf16=bf16).astype(np.float64)
+            r64 = (_bf16(rows) if bf16 else rows).astype(np.float64)
+            exact = (r64 @ q.astype(np.float64)) / (np.linalg.norm(r64, axis=1) * np.linalg.norm(q.astype(np.float64)))
+            assert np.max(np.abs(got - exact)) <= (dim + 4) * 2.0 ** -24
