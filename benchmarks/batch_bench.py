@@ -4,8 +4,9 @@ one K2 pass).  --shadow builds the bf16 shadow of an fp32 index first (one 16-qu
 import argparse, json, os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
-import tss_loader, orc
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import tss_loader
+from _common import make_queries
 tss = tss_loader.load()
 ap = argparse.ArgumentParser()
 ap.add_argument("--rows", type=int, default=10_000_000)
@@ -18,10 +19,10 @@ st = tss.TSS_F32 if a.storage == "f32" else tss.TSS_BF16
 ix = tss.FlatIndex(dim, st); ix.reserve(a.rows); ix.add_synthetic(0, a.rows, 0x5EED); ix.finalize()
 elem = 4 if a.storage == "f32" else 2
 if a.shadow:
-    q16 = orc.gen_rows(0, 16, dim, 0xBEEF)
+    q16 = make_queries(16, dim, 0xBEEF)
     ix.search(q16, 10)
 for nq in (1, 2, 3, 4, 8, 12):
-    q = orc.gen_rows(0, nq, dim, 0xBEEF)
+    q = make_queries(nq, dim, 0xBEEF)
     dq = tss.DeviceBuffer(0, q.nbytes).upload(q); dk = tss.DeviceBuffer(0, nq * 10 * 8)
     for _ in range(3): ix.search_device(dq, nq, 10, dk)
     ix.sync()

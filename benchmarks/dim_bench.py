@@ -2,8 +2,9 @@
 import json, os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
-import tss_loader, orc
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import tss_loader
+from _common import make_queries
 tss = tss_loader.load()
 for dim, storage in ((128, "f32"), (256, "f32"), (384, "f32"), (512, "f32"), (768, "f32"), (1024, "f32"),
                      (100, "f32"), (384, "bf16"), (768, "bf16")):
@@ -12,7 +13,7 @@ for dim, storage in ((128, "f32"), (256, "f32"), (384, "f32"), (512, "f32"), (76
     rows = int(7.68e9 // (ns * 128 * elem))
     ix = tss.FlatIndex(dim, tss.TSS_F32 if storage == "f32" else tss.TSS_BF16)
     ix.reserve(rows); ix.add_synthetic(0, rows, 1); ix.finalize()
-    q = orc.gen_rows(0, 1, dim, 2)
+    q = make_queries(1, dim, 2)
     dq = tss.DeviceBuffer(0, q.nbytes).upload(q); dk = tss.DeviceBuffer(0, 80)
     for _ in range(5): ix.search_device(dq, 1, 10, dk)
     ix.sync()

@@ -4,7 +4,7 @@ recall@k vs the fp32 exact oracle on a query subset (CPU, bounded rows if --reca
 import argparse, json, os, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import tss_loader
 tss = tss_loader.load()
 
@@ -26,8 +26,8 @@ ix.reserve(a.rows)
 ix.add_synthetic(0, a.rows, 0x5EED)
 ix.finalize()
 rng = np.random.default_rng(1)
-import orc
-q = orc.gen_rows(0, a.nq, dim, 0xBEEF)
+from _common import make_queries
+q = make_queries(a.nq, dim, 0xBEEF)
 dq = tss.DeviceBuffer(0, q.nbytes).upload(q)
 dk = tss.DeviceBuffer(0, a.nq * a.k * 8)
 for _ in range(2):
@@ -53,6 +53,8 @@ if a.recall_queries:
     keys = dk.download(np.uint64, a.nq * a.k).reshape(a.nq, a.k)
     gr, gs = tss.unpack_keys(keys)
     nqr = a.recall_queries
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import orc  # the checker: the exact fp32 top-k of the same seeded corpus on the CPU
     t = time.time()
     er, es, _ = orc.cosine_topk_synth(0, a.rows, dim, 0x5EED, q[:nqr], a.k)
     out["recall_at_k_vs_fp32_exact"] = float(np.mean([len(set(gr[i].tolist()) & set(er[i].tolist())) / a.k for i in range(nqr)]))

@@ -7,10 +7,10 @@ bit against numpy (the expected row set of the matching term range)."""
 import argparse, json, os, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import tss_loader
 tss = tss_loader.load()
-import orc
+from _common import make_queries
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--rows", type=int, default=10_000_000)
@@ -56,7 +56,7 @@ assert built.size() == T
 ix = tss.FlatIndex(dim)
 ix.reserve(N); ix.add_synthetic(0, N, 0x5EED); ix.finalize()
 mask = tss.Mask(N)
-q = orc.gen_rows(0, 4, dim, 0xBEEF)
+q = make_queries(4, dim, 0xBEEF)
 
 # postings under each first token -> pick prefixes by selectivity
 first = tok[:, 0]
