@@ -16,6 +16,11 @@ roofline.
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
   torchrun ... bench.py --gpus N ...       (one rank per GPU)
 
+The oracle (oracle/, test infrastructure) appears here in three roles only: it synthesises the
+queries (its seeded generator is the one the device uses to fill the corpus, so "planted" queries
+can be built without reading rows back), it CHECKS the timed results (`check`), and it is the
+thing timed in `cpu_baseline` / `--impl reference`.  No timed GPU leg calls it.
+
 --impl reference times the CPU restatement of the reference contract (oracle/, all host
 threads) on a bounded sample of the same workload; the reference itself has no scoring
 implementation to run (reference src/vector.rs:195-202 is a stub).
