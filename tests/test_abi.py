@@ -29,6 +29,15 @@ def test_header_symbols_all_exported(tss):
     assert sorted(tss.ABI_SYMBOLS) == declared
 
 
+def test_rust_binding_source_declares_the_same_symbols():
+    """ffi/tss.rs cannot be compiled here (no rustc), but its extern block must at least name
+    every entry point of the header, no more and no fewer."""
+    rs = open(os.path.join(ROOT, "trie-semantic-search_b200", "ffi", "tss.rs")).read()
+    block = rs[rs.index('extern "C" {'):]
+    block = block[:block.index("\n}")]
+    assert sorted(set(re.findall(r"pub fn (tss_[a-z0-9_]+)\s*\(", block))) == _declared()
+
+
 def test_library_loads_and_reports_version(tss):
     L = tss.lib()
     assert L.tss_abi_version() == 1

@@ -119,6 +119,16 @@ extern "C" {
 
     pub fn tss_index_stream(ix: *mut tss_index) -> *mut c_void;
     pub fn tss_index_sync(ix: *mut tss_index) -> c_int;
+    // measurement / diagnostics helpers (bench harnesses; not needed by vector.rs)
+    pub fn tss_dev_alloc(device: c_int, bytes: u64, out: *mut *mut c_void) -> c_int;
+    pub fn tss_dev_free(device: c_int, p: *mut c_void) -> c_int;
+    pub fn tss_dev_h2d(device: c_int, dst: *mut c_void, src: *const c_void, bytes: u64) -> c_int;
+    pub fn tss_dev_d2h(device: c_int, dst: *mut c_void, src: *const c_void, bytes: u64) -> c_int;
+    pub fn tss_event_create(device: c_int, out: *mut *mut c_void) -> c_int;
+    pub fn tss_event_record(ix: *mut tss_index, ev: *mut c_void) -> c_int;
+    pub fn tss_event_elapsed_ms(ev_a: *mut c_void, ev_b: *mut c_void, out_ms: *mut f32) -> c_int;
+    pub fn tss_event_destroy(ev: *mut c_void) -> c_int;
+    pub fn tss_index_debug_phases(ix: *mut tss_index, d_buf: *mut c_void) -> c_int;
     pub fn tss_launch_count() -> u64;
 }
 
