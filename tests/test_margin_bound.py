@@ -90,3 +90,26 @@ def test_scan_arithmetic_stays_inside_the_accumulation_slack(orc, dim):
             r64 = (_bf16(rows) if bf16 else rows).astype(np.float64)
             exact = (r64 @ q.astype(np.float64)) / (np.linalg.norm(r64, axis=1) * np.linalg.norm(q.astype(np.float64)))
             assert np.max(np.abs(got - exact)) <= (dim + 4) * 2.0 ** -24
+
+
+def test_prefilter_proof_on_the_oracle_scores(orc):
+    """refine_kernel's logic restated with the oracle's own fp32 arithmetic at 400k rows: A = the
+    scan's score over bf16-rounded rows, B = over the fp32 rows.  Whenever the kc-th best A lies
+    more than 2 eps under the k-th, the top-k by (B desc, row asc) is inside the top-kc by A; and
+    for ordinary data the proof goes through almost always (it must, or the prefilter would keep
+    falling back to the fp32 scan)."""
+    n, dim, k, kc = 400_000, 384, 10, 64
+    rows = orc.gen_rows(0, n, dim, 0x5EED)
+    qs = orc.gen_rows(0, 24, dim, 0xBEEF)
+    qs[3] = rows[1234] + 0.125 * qs[3]
+    two_eps = 2 * (2.0 ** -8 * (1 + 2.0 ** -8) + (dim + 4) * 2.0 ** -22)
+    proven = 0
+    for q in qs:
+        a = orc.scores(rows, q, bf16=True)
+        b = orc.scores(rows, q)
+        order_a = np.lexsort((np.arange(n), -a.astype(np.float64)))[:kc]
+        top_b = np.lexsort((np.arange(n), -b.astype(np.float64)))[:k]
+        if a[order_a[kc - 1]] < a[order_a[k - 1]] - np.float32(two_eps):
+            proven += 1
+            assert set(top_b.tolist()) <= set(order_a.tolist())
+    assert proven >= len(qs) - 2
