@@ -694,9 +694,11 @@ threshold_kernel(const float* tile_max, uint32_t count, uint32_t nq, uint32_t k,
 //     A >= t - 2 eps and is among the re-scored keys: the result is bit-identical to the scan's
 //     (and the oracle's) top-k on the same bf16 index, ties included.
 constexpr uint32_t kSelectSortMax = 4096;  // keys the sorter can take (dynamic shared memory)
-__host__ __device__ inline uint32_t select_sort_cap(uint32_t k) {  // power of two >= 4k
+// power of two >= 8k (the keys within the re-scoring margin of the k-th are 2-6x k on ordinary
+// data), at least 1024, at most kSelectSortMax
+__host__ __device__ inline uint32_t select_sort_cap(uint32_t k) {
   uint32_t c = 1024;
-  while (c < 4 * k && c < kSelectSortMax) c <<= 1;
+  while (c < 8 * k && c < kSelectSortMax) c <<= 1;
   return c;
 }
 constexpr uint32_t kSelectMaxLists = 1024;
