@@ -160,7 +160,15 @@ void tss_comm_destroy(tss_comm* c);
  * back to ncclAllGather + a merge kernel).  comm == NULL detaches. */
 int tss_index_set_shard(tss_index* ix, uint64_t row_base, tss_comm* comm /* nullable */);
 
-/* ---- masks ------------------------------------------------------------------*/
+/* ---- masks ------------------------------------------------------------------
+ * Ordering: every call that writes a mask (create, clear, set/clear_rows, upload,
+ * tss_filter_mask, tss_prefix_mask*) and every call that reads one (a search,
+ * download, popcount) is stream-ordered against the others through events the
+ * mask carries -- a search enqueued after tss_prefix_mask sees the finished
+ * mask, a clear enqueued after a search waits for that search -- whatever
+ * streams the handles involved run on, and without host synchronisation
+ * (download / popcount / upload block because they hand data to the host).
+ * One thread mutates a given mask at a time; concurrent searches may read it. */
 /* nbits rows of ONE shard; bit i <-> local row i (global row row_base + i). */
 int tss_mask_create(tss_mask** out, uint64_t nbits, int device);
 int tss_mask_clear(tss_mask* m);
@@ -225,6 +233,17 @@ uint64_t tss_terms_size(const tss_terms* t);
 void tss_terms_destroy(tss_terms* t);
 int tss_prefix_mask(tss_terms* t, const char* prefix, uint32_t len, int kind, tss_mask* out,
                     uint64_t row_base, tss_prefix_stats* stats /* nullable: no host sync */);
+/* tss_mask_clear + tss_prefix_mask as one enqueue: the search kernel's spare CTAs zero the mask
+ * while CTA 0 walks the term array, then the scatter runs -- two launches, no host
+ * synchronisation (stats == NULL), what the hybrid path issues per query
+ * (SearchEngine::execute_hybrid_search, src/search.rs:185-206 builds its seen-set the same way:
+ * from scratch per query). */
+int tss_prefix_mask_fresh(tss_terms* t, const char* prefix, uint32_t len, int kind, tss_mask* out,
+                          uint64_t row_base, tss_prefix_stats* stats /* nullable: no host sync */);
+/* Enqueue this handle's prefix searches on the index's stream (ix == NULL: back on its own):
+ * prefix -> mask -> masked search then run back to back on ONE stream with no cross-stream
+ * event hop.  The index must outlive the binding. */
+int tss_terms_bind_stream(tss_terms* t, tss_index* ix /* nullable */);
 
 /* ---- plumbing for callers that time or pipeline the device path ------------ */
 void* tss_index_stream(tss_index* ix); /* cudaStream_t the index enqueues on */

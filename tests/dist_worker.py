@@ -1,4 +1,8 @@
-"""Run under torchrun on >= 2 GPUs: sharded search (NCCL all-gather + merge) == oracle."""
+"""Run under torchrun on >= 2 GPUs: sharded search (fused peer-memory exchange, or NCCL
+all-gather + merge kernel) == oracle on the unsharded corpus, bit for bit.
+
+run_checks() is also what `bench.py --gpus N` (N > 1) runs as its `selftest`, so the driver's
+multi-GPU lease exercises the equivalence even when the 1-GPU test lease skips test_dist_gpu.py."""
 import os
 import sys
 
@@ -9,25 +13,16 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 
 
-def main():
-    import torch
-    import torch.distributed as dist
-    import tss_loader
-    import orc
-    tss = tss_loader.load()
-    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-    local = int(os.environ.get("LOCAL_RANK", rank))
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
-    if rank == 0:
-        idt.copy_(torch.frombuffer(bytearray(tss.Comm.unique_id()), dtype=torch.uint8))
-    dist.broadcast(idt, 0)
-    comm = tss.Comm(idt.cpu().numpy().tobytes(), rank, world, local)
-
+def run_checks(tss, orc, comm, rank, world, local, quick=False):
+    """-> True when every sharded result on this rank equals the oracle's on the whole corpus"""
     dim, seed = 384, 0x5EED
     ok = True
-    for n, k, nq in [(200_003, 10, 5), (1000, 50, 2), (5, 10, 1), (300_000, 128, 3)]:
+    # every rank runs the oracle at the same time: share the cores (torchrun sets OMP_NUM_THREADS=1)
+    thr = max(1, len(os.sched_getaffinity(0)) // world)
+    cases = [(200_003, 10, 5), (1000, 50, 2), (5, 10, 1), (300_000, 128, 3)]
+    if quick:
+        cases = [(200_003, 10, 5), (5, 10, 1), (100_000, 128, 3)]
+    for n, k, nq in cases:
         per = (n + world - 1) // world
         b = min(rank * per, n)
         cnt = min(per, n - b)
@@ -44,7 +39,7 @@ def main():
         ix.sync()
         r2, s2 = tss.unpack_keys(dk.download(np.uint64, nq * k).reshape(nq, k))
         rows = orc.gen_rows(0, n, dim, seed)
-        want = orc.cosine_topk(rows, q, k)
+        want = orc.cosine_topk(rows, q, k, threads=thr)
         same = (np.array_equal(got[0], want[0]) and
                 np.array_equal(got[1].view(np.uint32), want[1].view(np.uint32)) and
                 np.array_equal(got[2], want[2]) and np.array_equal(r2, want[0]) and
@@ -55,7 +50,7 @@ def main():
         ix.close()
     # stress: hundreds of back-to-back tiny sharded scans.  Launches overlap under programmatic
     # dependent launch, so their peer-memory exchanges must still happen in launch order.
-    n, k, reps = 300, 10, 400
+    n, k, reps = 300, 10, 200 if quick else 400
     per = (n + world - 1) // world
     b = min(rank * per, n)
     cnt = min(per, n - b)
@@ -65,7 +60,7 @@ def main():
     ix.finalize()
     q = orc.gen_rows(0, 4, dim, 0xBEEF)
     rows = orc.gen_rows(0, n, dim, seed)
-    want = orc.cosine_topk(rows, q, k)
+    want = orc.cosine_topk(rows, q, k, threads=thr)
     dq = tss.DeviceBuffer(local, q.nbytes).upload(q)
     dk = tss.DeviceBuffer(local, reps * k * 8)
 
@@ -94,18 +89,48 @@ def main():
     ix.set_shard(b, comm)
     ix.finalize()
     rows = orc.gen_rows(0, n, dim, seed)
-    for nq in (64, 200):
+    for nq in ((200,) if quick else (64, 200, 1030)):  # 1030: a 1024 chunk + a 6-query tail
         q = orc.gen_rows(0, nq, dim, 0xBEEF)
         q[0] = rows[123_456] + 0.125 * q[0]
         gr, gs, gc = ix.search(q, k)
-        want = orc.cosine_topk(rows, q, k, bf16=True)
+        want = orc.cosine_topk(rows, q, k, bf16=True, threads=thr)
         same = (bool(np.all(gc == k)) and gr[0][0] == 123_456 and np.array_equal(gr, want[0])
                 and np.array_equal(gs.view(np.uint32), want[1].view(np.uint32)))
         if not same:
             hits = sum(len(set(g.tolist()) & set(w.tolist())) for g, w in zip(gr, want[0]))
             print(f"rank {rank}: K2 sharded MISMATCH nq {nq} recall {hits / (nq * k):.3f}", flush=True)
         ok &= same
+        # the device-resident entry routes the WHOLE call one way (a short tail chunk
+        # used to take the fused scan and its results never reached the output)
+        dq = tss.DeviceBuffer(local, q.nbytes).upload(q)
+        dk = tss.DeviceBuffer(local, nq * k * 8)
+        ix.search_device(dq, nq, k, dk)
+        ix.sync()
+        r2, s2 = tss.unpack_keys(dk.download(np.uint64, nq * k).reshape(nq, k))
+        same = np.array_equal(r2, want[0]) and np.array_equal(s2.view(np.uint32), want[1].view(np.uint32))
+        if not same:
+            print(f"rank {rank}: K2 sharded search_device MISMATCH nq {nq}", flush=True)
+        ok &= same
     ix.close()
+    return ok
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    import tss_loader
+    import orc
+    tss = tss_loader.load()
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt.copy_(torch.frombuffer(bytearray(tss.Comm.unique_id()), dtype=torch.uint8))
+    dist.broadcast(idt, 0)
+    comm = tss.Comm(idt.cpu().numpy().tobytes(), rank, world, local)
+    ok = run_checks(tss, orc, comm, rank, world, local)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     comm.close()

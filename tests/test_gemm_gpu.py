@@ -286,3 +286,31 @@ def test_batch_policy_single_queries_through_the_shadow(tss, orc):
     before = tss.launch_count()
     ix.search(q[:1], k)
     assert tss.launch_count() - before == 1
+
+
+@pytest.mark.parametrize("storage_f32", [False, True])
+def test_sparse_include_mask_never_returns_rows_past_the_shard(tss, orc, storage_f32):
+    """n % 256 != 0, nq >= 16 and an INCLUDE mask that leaves fewer than k live rows.
+    The threshold degenerates to -inf; the columns of the last partial tile beyond n_rows used to
+    be -inf as well and `-inf >= -inf` pushed row ids that do not exist.  They are NaN now."""
+    n, dim, k, nq = 50_003, 384, 10, 32   # 50_003 % 256 = 83; K2 needs n >= 4*256*k
+    rows = orc.gen_rows(0, n, dim, SEED)
+    q = orc.gen_rows(0, nq, dim, 0xBEEF)
+    ix = tss.FlatIndex(dim, tss.TSS_F32 if storage_f32 else tss.TSS_BF16)
+    ix.add(rows)
+    ix.finalize()
+    for live in ([5, 49_990, 50_002], [50_001], [], [0, 1, 2, 3, 255, 256, 49_919, 49_920, 50_002]):
+        m = tss.Mask(n)
+        m.set_rows(np.asarray(live, dtype=np.uint32))
+        w = np.zeros((n + 31) // 32, dtype=np.uint32)
+        for r in live:
+            w[r >> 5] |= np.uint32(1 << (r & 31))
+        before = tss.launch_count()
+        gr, gs, gc = ix.search(q, k, m, tss.TSS_MASK_INCLUDE)
+        assert tss.launch_count() - before >= 5  # took K2
+        want = orc.cosine_topk(rows, q, k, mask_words=w, mask_mode=orc.MASK_INCLUDE,
+                               bf16=not storage_f32)
+        assert np.all(gc == len(live))
+        assert np.array_equal(gr, want[0]), live
+        assert np.array_equal(gs.view(np.uint32), want[1].view(np.uint32)), live
+        assert np.all((gr < n) | (gr == tss.TSS_ROW_NONE))

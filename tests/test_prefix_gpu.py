@@ -164,3 +164,98 @@ def test_terms_edge_cases(tss):
         tss.Terms([b"b", b"a"], [[], []])  # unsorted
     with pytest.raises(tss.TssError):
         tss.Terms([b"a", b"a"], [[], []])  # duplicate
+
+
+def test_mask_ordering_stress_idle_then_clear_prefix(tss):
+    """Round 1's GPUTEST failure: tss_mask_clear ran on the legacy stream and the scatter on the
+    terms' non-blocking stream, so after the GPU had idled a queued memset could land on top of
+    the scatter's bits.  Masks are now ordered by events across whatever streams touch them:
+    idle the GPU, then clear(); clear(); prefix_mask(built); prefix_mask(uploaded), 200 times,
+    every mask compared with numpy -- never with the other mask."""
+    import time
+    rng = np.random.default_rng(5)
+    n_rows = 300_000
+    vocab = sorted({b"w%04d" % i for i in range(400)})
+    n = 120_000
+    L = 3
+    ntok = rng.integers(1, L + 1, n)
+    ids = (rng.zipf(1.3, size=(n, L)) % len(vocab) + 1).astype(np.uint32)
+    ids[np.arange(L)[None, :] >= ntok[:, None]] = 0
+    rows = rng.integers(0, n_rows, n).astype(np.uint32)
+    built = tss.Terms.build(vocab, ids, rows)
+    terms, posts = built.export()
+    uploaded = tss.Terms(terms, posts)
+    # expectations: term ranges by bisect on the sorted terms, rows by numpy
+    import bisect
+    flat = np.concatenate([np.asarray(p, dtype=np.int64) for p in posts])
+    off = np.zeros(len(terms) + 1, dtype=np.int64)
+    np.cumsum([len(p) for p in posts], out=off[1:])
+
+    def expected(prefix):
+        w = np.zeros((n_rows + 31) // 32, dtype=np.uint32)
+        if prefix == b"":
+            r = flat
+        else:
+            lo = bisect.bisect_left(terms, prefix)
+            hi_exact = lo + (1 if lo < len(terms) and terms[lo] == prefix else 0)
+            slo = bisect.bisect_left(terms, prefix + b" ")
+            shi = bisect.bisect_left(terms, prefix + b"!")
+            r = np.concatenate([flat[off[lo]:off[hi_exact]], flat[off[slo]:off[shi]]])
+        if r.size:
+            np.bitwise_or.at(w, r >> 5, (np.uint32(1) << (r & 31).astype(np.uint32)))
+        return w
+
+    prefixes = [b"", vocab[0], vocab[1], vocab[0] + b" " + vocab[0], vocab[7], b"nope", vocab[3] + b" " + vocab[1]]
+    want = {p: expected(p) for p in prefixes}
+    m1, m2 = tss.Mask(n_rows), tss.Mask(n_rows)
+    full = np.full((n_rows + 31) // 32, 0xFFFFFFFF, dtype=np.uint32)
+    for it in range(200):
+        p = prefixes[it % len(prefixes)]
+        if it % 50 == 0:
+            time.sleep(1.5)  # the GPU idles: queued work from different streams starts together
+        if it % 3 == 0:      # dirty masks, so a lost clear shows as well as a lost bit
+            m1.upload(full)
+            m2.upload(full)
+        m1.clear(); m1.clear()
+        m2.clear(); m2.clear()
+        built.prefix_mask(p, m1, want_stats=False)
+        uploaded.prefix_mask(p, m2, want_stats=False)
+        a, b = m1.download(), m2.download()
+        assert np.array_equal(a, want[p]), (it, p)
+        assert np.array_equal(b, want[p]), (it, p)
+    # the one-enqueue form (clear folded into the search kernel) on dirty masks, no host sync
+    for it in range(100):
+        p = prefixes[it % len(prefixes)]
+        m1.upload(full)
+        built.prefix_mask(p, m1, want_stats=False, fresh=True)
+        assert np.array_equal(m1.download(), want[p]), (it, p)
+        assert m1.popcount() == int(np.unpackbits(want[p].view(np.uint8)).sum())
+
+
+def test_prefix_then_masked_search_is_ordered(tss, orc):
+    """prefix mask on the terms' stream -> masked search on the index stream -> next query's
+    clear: no host synchronisation anywhere in between, results == oracle with the numpy mask."""
+    rng = np.random.default_rng(9)
+    n, dim, k = 60_000, 128, 10
+    rows = orc.gen_rows(0, n, dim, 0x5EED)
+    ix = tss.FlatIndex(dim)
+    ix.add_synthetic(0, n, 0x5EED)
+    ix.finalize()
+    terms = [b"t%03d" % i for i in range(64)]
+    posts = [sorted(set(int(r) for r in rng.integers(0, n, size=int(rng.integers(1, 4000))))) for _ in terms]
+    t = tss.Terms(terms, posts)
+    m = tss.Mask(n)
+    q = orc.gen_rows(0, 40, dim, 0xBEEF)
+    for bound in (False, True):
+        if bound:
+            t.bind_stream(ix)
+        for i in range(40):
+            p = terms[(i * 7) % len(terms)]
+            t.prefix_mask(p, m, want_stats=False, fresh=True)
+            got = ix.search(q[i], k, m, tss.TSS_MASK_INCLUDE)
+            w = np.zeros((n + 31) // 32, dtype=np.uint32)
+            idx = np.asarray(posts[(i * 7) % len(terms)], dtype=np.int64)
+            np.bitwise_or.at(w, idx >> 5, (np.uint32(1) << (idx & 31).astype(np.uint32)))
+            want = orc.cosine_topk(rows, q[i], k, mask_words=w, mask_mode=orc.MASK_INCLUDE)
+            assert np.array_equal(got[0], want[0]) and np.array_equal(got[2], want[2]), (bound, i)
+    t.bind_stream(None)

@@ -15,6 +15,20 @@ def _host_build(vocab, ids, rows):
     return terms, [d[t] for t in terms]
 
 
+def _expected_mask(terms, posts, prefix, n_rows):
+    """numpy/python restatement of the prefix posting set: the term equal to the token prefix and
+    every term below it (trie.rs:223-278 without the limit), as mask words"""
+    rows = []
+    for t, ps in zip(terms, posts):
+        if prefix == b"" or t == prefix or t.startswith(prefix + b" "):
+            rows.extend(ps)
+    w = np.zeros((n_rows + 31) // 32, dtype=np.uint32)
+    idx = np.array(sorted({r for r in rows if r < n_rows}), dtype=np.int64)
+    if idx.size:
+        np.bitwise_or.at(w, idx >> 5, (np.uint32(1) << (idx & 31).astype(np.uint32)))
+    return w
+
+
 def test_device_build_matches_host_build(tss, orc):
     rng = np.random.default_rng(31)
     vocab = sorted({b"w%05d" % i for i in rng.integers(0, 100000, 3000)} |
@@ -39,7 +53,9 @@ def test_device_build_matches_host_build(tss, orc):
         m1.clear(); m2.clear()
         s1 = t.prefix_mask(p, m1)
         s2 = ref.prefix_mask(p, m2)
-        assert np.array_equal(m1.download(), m2.download()), p
+        want = _expected_mask(want_terms, want_posts, p, n_rows)  # host-computed, not each other
+        assert np.array_equal(m1.download(), want), p
+        assert np.array_equal(m2.download(), want), p
         assert (s1.exact_lo, s1.exact_hi, s1.sub_lo, s1.sub_hi, s1.npostings) == \
                (s2.exact_lo, s2.exact_hi, s2.sub_lo, s2.sub_hi, s2.npostings)
     # and like the reference's trie: same prefix posting set as the literal restatement

@@ -42,6 +42,7 @@ ABI_SYMBOLS = [
     "tss_index_save", "tss_index_load",
     "tss_mask_clear_rows", "tss_columns_create", "tss_columns_destroy", "tss_filter_mask",
     "tss_terms_build", "tss_terms_sizes", "tss_terms_export",
+    "tss_prefix_mask_fresh", "tss_terms_bind_stream",
 ]
 
 
@@ -103,6 +104,8 @@ def lib() -> C.CDLL:
         "tss_terms_size": (u64, [vp]),
         "tss_terms_destroy": (None, [vp]),
         "tss_prefix_mask": (i32, [vp, C.c_char_p, u32, i32, vp, u64, C.POINTER(PrefixStats)]),
+        "tss_prefix_mask_fresh": (i32, [vp, C.c_char_p, u32, i32, vp, u64, C.POINTER(PrefixStats)]),
+        "tss_terms_bind_stream": (i32, [vp, vp]),
         "tss_index_stream": (vp, [vp]),
         "tss_index_sync": (i32, [vp]),
         "tss_dev_alloc": (i32, [i32, u64, C.POINTER(vp)]),
@@ -379,11 +382,17 @@ class Terms:
         return int(lib().tss_terms_size(self.handle))
 
     def prefix_mask(self, prefix: bytes, mask: Mask, kind: int = TSS_PREFIX_TOKEN,
-                    row_base: int = 0, want_stats: bool = True) -> Optional[PrefixStats]:
+                    row_base: int = 0, want_stats: bool = True,
+                    fresh: bool = False) -> Optional[PrefixStats]:
+        """fresh=True: clear + prefix mask as one enqueue (tss_prefix_mask_fresh)."""
         st = PrefixStats() if want_stats else None
-        _check(lib().tss_prefix_mask(self.handle, prefix, len(prefix), kind, mask.handle,
-                                     int(row_base), C.byref(st) if st is not None else None))
+        fn = lib().tss_prefix_mask_fresh if fresh else lib().tss_prefix_mask
+        _check(fn(self.handle, prefix, len(prefix), kind, mask.handle,
+                  int(row_base), C.byref(st) if st is not None else None))
         return st
+
+    def bind_stream(self, index: Optional["FlatIndex"]) -> None:
+        _check(lib().tss_terms_bind_stream(self.handle, index.handle if index else None))
 
     def close(self) -> None:
         if self.handle:

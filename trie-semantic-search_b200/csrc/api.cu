@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -129,11 +130,28 @@ struct tss_comm {
   int rank = 0, nranks = 1, device = 0;
 };
 
+// A mask is written and read by kernels on different streams (its own, a terms handle's, a
+// columns handle's, an index's), all cudaStreamNonBlocking: nothing orders them implicitly.
+// Every enqueue that touches d_words is therefore bracketed by mask_begin_write/mask_end_write or
+// mask_begin_read/mask_end_read (below), which chain the streams with events: a write waits for
+// the previous write and for every read enqueued since; a read waits for the last write.  No
+// call relies on the legacy stream or on a host synchronisation for ordering.
 struct tss_mask {
   int device = 0;
   uint64_t nbits = 0, nwords = 0;
   uint32_t* d_words = nullptr;
   unsigned long long* d_scratch = nullptr;
+  cudaStream_t stream = nullptr;   // own stream: clear / upload / set_rows / download / popcount
+  std::mutex mu;                   // guards the ordering state (concurrent readers are legal)
+  bool has_write = false;
+  cudaStream_t wstream = nullptr;  // stream the last write was enqueued on (identity only)
+  cudaEvent_t wev = nullptr;       // recorded behind that write
+  struct Reader {
+    cudaStream_t s;
+    cudaEvent_t ev;
+  };
+  std::vector<Reader> readers;     // reads enqueued since that write, one entry per stream
+  std::vector<cudaEvent_t> spare;  // recycled reader events
 };
 
 struct tss_columns {
@@ -142,6 +160,7 @@ struct tss_columns {
   uint16_t* d_court = nullptr;
   int32_t* d_date = nullptr;
   uint32_t* d_allow = nullptr;  // 65 536-bit allow set of the current call
+  cudaStream_t stream = nullptr;
 };
 
 struct tss_terms {
@@ -155,7 +174,8 @@ struct tss_terms {
   char* h_keys = nullptr;     // pinned
   uint64_t* d_bounds = nullptr;  // 4 bounds + npostings
   uint32_t key_cap = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;      // the stream prefix searches are enqueued on
+  cudaStream_t own_stream = nullptr;  // (stream == own_stream unless bound to an index's)
 };
 
 struct tss_index {
@@ -186,6 +206,7 @@ struct tss_index {
   uint64_t* d_partials = nullptr;
   unsigned int* d_counter = nullptr;
   uint32_t launch_no = 0;
+  uint64_t shard_min_rows = 0;  // rows of the smallest shard of the group (tss_index_set_shard)
   bool pdl = true;
   // tile schedule of the unmasked scan (see scan.cuh): share of tiles walked statically,
   // tiles per dynamic claim, and how many warp-rounds at the very end are claimed one
@@ -260,6 +281,58 @@ struct DeviceGuard {
   }
   ~DeviceGuard() {
     if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+// ---- mask ordering (see struct tss_mask) ----------------------------------------------------
+cudaError_t mask_begin_write(tss_mask* m, cudaStream_t s) {
+  std::lock_guard<std::mutex> lk(m->mu);
+  cudaError_t e = cudaSuccess;
+  if (m->has_write && m->wstream != s) e = cudaStreamWaitEvent(s, m->wev, 0);
+  for (auto& r : m->readers) {
+    if (e == cudaSuccess && r.s != s) e = cudaStreamWaitEvent(s, r.ev, 0);
+    m->spare.push_back(r.ev);
+  }
+  m->readers.clear();
+  return e;
+}
+cudaError_t mask_end_write(tss_mask* m, cudaStream_t s) {
+  std::lock_guard<std::mutex> lk(m->mu);
+  m->has_write = true;
+  m->wstream = s;
+  return cudaEventRecord(m->wev, s);
+}
+cudaError_t mask_begin_read(tss_mask* m, cudaStream_t s) {
+  std::lock_guard<std::mutex> lk(m->mu);
+  if (m->has_write && m->wstream != s) return cudaStreamWaitEvent(s, m->wev, 0);
+  return cudaSuccess;
+}
+cudaError_t mask_end_read(tss_mask* m, cudaStream_t s) {
+  std::lock_guard<std::mutex> lk(m->mu);
+  for (auto& r : m->readers)
+    if (r.s == s) return cudaEventRecord(r.ev, s);
+  cudaEvent_t ev = nullptr;
+  if (!m->spare.empty()) {
+    ev = m->spare.back();
+    m->spare.pop_back();
+  } else {
+    cudaError_t e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    if (e != cudaSuccess) return e;
+  }
+  m->readers.push_back({s, ev});
+  return cudaEventRecord(ev, s);
+}
+// brackets the enqueues of one search that reads `mask` on stream s
+struct MaskReadScope {
+  tss_mask* m;
+  cudaStream_t s;
+  cudaError_t err = cudaSuccess;
+  MaskReadScope(const tss_mask* mask, int mode, cudaStream_t st)
+      : m(mode != TSS_MASK_NONE ? const_cast<tss_mask*>(mask) : nullptr), s(st) {
+    if (m) err = mask_begin_read(m, s);
+  }
+  ~MaskReadScope() {
+    if (m) mask_end_read(m, s);
   }
 };
 
@@ -366,7 +439,13 @@ int enqueue_scan(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
     }
     cudaError_t e = tss::launch_scan(ix->ns, p, bq, as_bf16, mode != TSS_MASK_NONE,
                                      ix->num_sms, ix->device, ix->stream);
-    if (e != cudaSuccess) return cuda_fail(e, "scan_topk_kernel launch");
+    if (e != cudaSuccess) {
+      // nothing will ever publish slot_gen / xchg_turn for this number: give it back, or the
+      // launch that reuses the slot (the next exchange) would wait for it forever
+      --ix->launch_no;
+      if (p.xchg_nranks) --ix->xchg.seq;
+      return cuda_fail(e, "scan_topk_kernel launch");
+    }
     g_launches.fetch_add(1, std::memory_order_relaxed);
     q0 += take;
   }
@@ -402,7 +481,9 @@ bool gemm_eligible(const tss_index* ix, uint32_t nq, uint32_t k, int mode) {
   const bool have_bf16 = ix->storage == TSS_BF16 || ix->gemm.shadow_rows == ix->n_rows;
   const bool small_ok = !ix->comm && have_bf16 && nq >= ix->gemm_small_nq &&
                         ix->n_rows >= ix->gemm_small_rows;
-  return (nq >= ix->gemm_min_nq || small_ok) && ix->n_rows >= 4ull * 256 * k && k <= TSS_MAX_K;
+  // (sharded: the smallest shard of the group decides, so every rank routes alike)
+  const uint64_t rows = ix->comm ? ix->shard_min_rows : ix->n_rows;
+  return (nq >= ix->gemm_min_nq || small_ok) && rows >= 4ull * 256 * k && k <= TSS_MAX_K;
 }
 
 // survivors a query is expected to leave in the K2 lists when `sample` tiles set its threshold
@@ -588,8 +669,8 @@ int enqueue_gemm(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
     return cuda_fail(e, "gemm_topk_kernel (collect pass) launch");
   if ((e = tss::launch_select(g.d_cand, g.d_cand_count, nsub, cap_s, g.d_inv_q, nq, k,
                               rescore ? d_queries : nullptr, g.d_margin, ix->d_rows,
-                              ix->storage == TSS_F32, ix->dim, kpad, (uint32_t)ix->row_base, d_out,
-                              g.d_overflow, ix->stream)) != cudaSuccess)
+                              ix->storage == TSS_F32, ix->dim, kpad, (uint32_t)ix->row_base,
+                              ix->n_rows, d_out, g.d_overflow, ix->stream)) != cudaSuccess)
     return cuda_fail(e, "select_kernel launch");
   g_launches.fetch_add(5, std::memory_order_relaxed);
   CU(cudaMemcpyAsync(g.h_cand_count, g.d_overflow, nq * sizeof(uint32_t), cudaMemcpyDeviceToHost,
@@ -675,8 +756,8 @@ int enqueue_prefilter(tss_index* ix, const float* d_queries, uint32_t nq, uint32
   ix->xchg.suppress = saved;
   if (rc) return rc;
   cudaError_t e = tss::launch_refine(g.d_pref_keys, kc, d_queries, ix->d_rows, ix->dim,
-                                     ix->stride_elems, (uint32_t)ix->row_base, nq, k, d_out,
-                                     g.d_overflow, ix->stream);
+                                     ix->stride_elems, (uint32_t)ix->row_base, nq, ix->n_rows, k,
+                                     d_out, g.d_overflow, ix->stream);
   if (e != cudaSuccess) return cuda_fail(e, "refine_kernel launch");
   g_launches.fetch_add(1, std::memory_order_relaxed);
   CU(cudaMemcpyAsync(g.h_cand_count, g.d_overflow, nq * sizeof(uint32_t), cudaMemcpyDeviceToHost,
@@ -711,10 +792,12 @@ int enqueue_gemm_batches(tss_index* ix, const float* d_queries, uint32_t nq, uin
 // local (per-shard) search of nq device-resident queries: picks K2 or K1.  *merged is set
 // when d_out already holds the GLOBAL result (the K1 scan of a sharded index exchanges and
 // merges inside its last CTA; K2 leaves that to NCCL + merge_gathered_kernel).
+// gemm: the route (gemm_route) decided ONCE for the whole call -- every chunk of a call, and every
+// rank of a shard group, must take the same one.
 int enqueue_local(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
-                  const tss_mask* mask, int mode, uint64_t* d_out, bool* merged) {
+                  const tss_mask* mask, int mode, uint64_t* d_out, bool gemm, bool* merged) {
   *merged = false;
-  if (!gemm_route(ix, nq, k, mode)) {
+  if (!gemm) {
     if (k > TSS_MAX_FUSED_K) return enqueue_scan_rounds(ix, d_queries, nq, k, mask, mode, d_out);
     *merged = ix->comm && ix->xchg.ready;
     return enqueue_scan(ix, d_queries, nq, k, mask, mode, d_out);
@@ -1055,16 +1138,20 @@ int tss_index_search_device(tss_index* ix, const float* d_queries, uint32_t nq, 
   if ((rc = check_k_path(ix, nq, k, mask_mode))) return rc;
   if (!nq) return TSS_OK;
   DeviceGuard g(ix->device);
+  MaskReadScope mrs(mask, mask_mode, ix->stream);
+  if (mrs.err != cudaSuccess) return cuda_fail(mrs.err, "mask ordering");
   bool merged = false;
-  if (!ix->comm) return enqueue_local(ix, d_queries, nq, k, mask, mask_mode, d_out_keys, &merged);
+  const bool gemm = gemm_route(ix, nq, k, mask_mode);  // the whole call takes one route
+  if (!ix->comm) return enqueue_local(ix, d_queries, nq, k, mask, mask_mode, d_out_keys, gemm, &merged);
   if ((rc = ensure_gather_ws(ix))) return rc;
+  const bool fused = ix->xchg.ready && !gemm && k <= TSS_MAX_FUSED_K;
   for (uint32_t q0 = 0; q0 < nq; q0 += kWsQueries) {
     uint32_t n = nq - q0 < kWsQueries ? nq - q0 : kWsQueries;
-    const bool fused = ix->xchg.ready && !gemm_route(ix, nq, k, mask_mode) && k <= TSS_MAX_FUSED_K;
     uint64_t* d_local = fused ? d_out_keys + (size_t)q0 * k : ix->d_keys;
     if ((rc = enqueue_local(ix, d_queries + (size_t)q0 * ix->dim, n, k, mask, mask_mode, d_local,
-                            &merged)))
+                            gemm, &merged)))
       return rc;
+    if (merged != fused) return fail(TSS_ERR_STATE, "sharded search: route and exchange disagree");
     if (!merged && (rc = enqueue_gather_merge(ix, ix->d_keys, n, k, d_out_keys + (size_t)q0 * k)))
       return rc;
   }
@@ -1104,6 +1191,8 @@ int tss_index_search(tss_index* ix, const float* queries, uint32_t nq, uint32_t 
                   (unsigned long long)(i / ix->dim));
   DeviceGuard g(ix->device);
   if ((rc = ensure_gather_ws(ix))) return rc;
+  MaskReadScope mrs(mask, mask_mode, ix->stream);
+  if (mrs.err != cudaSuccess) return cuda_fail(mrs.err, "mask ordering");
   for (uint32_t q0 = 0; q0 < nq; q0 += kWsQueries) {
     uint32_t n = nq - q0 < kWsQueries ? nq - q0 : kWsQueries;
     size_t qbytes = (size_t)n * ix->dim * sizeof(float);
@@ -1200,54 +1289,101 @@ void tss_comm_destroy(tss_comm* c) {
 }
 
 namespace {
-// Map every rank's exchange buffer into this process (CUDA IPC; handles travel over the comm's
-// own all-gather).  Failure is not an error: the sharded search then uses NCCL + a merge kernel.
-int setup_xchg(tss_index* ix, tss_comm* comm) {
-  tss_index::Xchg& x = ix->xchg;
-  if (x.ready && x.comm == comm) return TSS_OK;
-  x.ready = false;
-  const char* env = getenv("TSS_FUSED_XCHG");
-  if ((env && atoi(env) == 0) || comm->nranks < 2 || comm->nranks > (int)tss::kXchgMaxRanks)
-    return TSS_OK;
-  if (!x.local) {
-    CU(cudaMalloc(&x.local, tss::kXchgBytes));
-    CU(cudaMemset(x.local, 0, tss::kXchgBytes));
-  }
-  cudaIpcMemHandle_t mine;
-  CU(cudaIpcGetMemHandle(&mine, x.local));
-  uint8_t* d_h = nullptr;
-  CU(cudaMalloc(&d_h, sizeof(mine) * (size_t)(comm->nranks + 1)));
-  std::vector<cudaIpcMemHandle_t> all(comm->nranks);
-  cudaError_t e = cudaMemcpyAsync(d_h, &mine, sizeof(mine), cudaMemcpyHostToDevice, ix->stream);
+// all-gather `bytes` bytes per rank over the comm through a scratch device buffer
+int comm_allgather_host(tss_index* ix, tss_comm* comm, const void* mine, void* all, size_t bytes) {
+  uint8_t* d = nullptr;
+  CU(cudaMalloc(&d, bytes * (size_t)(comm->nranks + 1)));
+  cudaError_t e = cudaMemcpyAsync(d, mine, bytes, cudaMemcpyHostToDevice, ix->stream);
   int nrc = 0;
   if (e == cudaSuccess)
-    nrc = g_nccl.AllGather(d_h, d_h + sizeof(mine), sizeof(mine), /*ncclUint8*/ 1, comm->comm,
-                           ix->stream);
+    nrc = g_nccl.AllGather(d, d + bytes, bytes, /*ncclUint8*/ 1, comm->comm, ix->stream);
   if (e == cudaSuccess && nrc == 0)
-    e = cudaMemcpyAsync(all.data(), d_h + sizeof(mine), sizeof(mine) * comm->nranks,
-                        cudaMemcpyDeviceToHost, ix->stream);
+    e = cudaMemcpyAsync(all, d + bytes, bytes * comm->nranks, cudaMemcpyDeviceToHost, ix->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ix->stream);
-  cudaFree(d_h);
-  if (nrc != 0) return fail(TSS_ERR_NCCL, "ncclAllGather (IPC handles): %s", g_nccl.GetErrorString(nrc));
-  if (e != cudaSuccess) return cuda_fail(e, "IPC handle exchange");
-  bool ok = true;
-  for (int r = 0; r < comm->nranks; ++r) {
-    if (r == comm->rank) {
-      x.peer[r] = x.local;
-      continue;
+  cudaFree(d);
+  if (nrc != 0) return fail(TSS_ERR_NCCL, "ncclAllGather (shard setup): %s", g_nccl.GetErrorString(nrc));
+  if (e != cudaSuccess) return cuda_fail(e, "shard setup exchange");
+  return TSS_OK;
+}
+
+// Collective over the comm.  (1) Every rank learns every shard's row count: the K1-vs-K2 route
+// of a sharded call must not depend on rank-local state, so it uses the SMALLEST shard.
+// (2) Every rank's exchange buffer is mapped into this process (CUDA IPC) for the fused merge;
+// the fused path is used only if EVERY rank mapped EVERY buffer (agreed by a second all-gather),
+// otherwise all ranks use ncclAllGather + the merge kernel.  A rank with a local failure still
+// takes part in both collectives, so its peers never hang in NCCL.
+struct ShardHello {
+  uint64_t n_rows;
+  uint32_t have_handle;
+  uint32_t pad;
+  cudaIpcMemHandle_t handle;
+};
+int setup_shard_group(tss_index* ix, tss_comm* comm) {
+  tss_index::Xchg& x = ix->xchg;
+  x.ready = false;
+  const char* env = getenv("TSS_FUSED_XCHG");
+  const bool want_fused = !(env && atoi(env) == 0) && comm->nranks >= 2 &&
+                          comm->nranks <= (int)tss::kXchgMaxRanks;
+  if (x.comm != comm) {
+    // another group: sequence numbers restart, so the arrival flags the old group left in this
+    // buffer must go (every rank does this before the first collective below completes)
+    x.seq = 0;
+    for (int r = 0; r < 8; ++r) {
+      if (x.peer[r] && x.peer[r] != x.local) cudaIpcCloseMemHandle(x.peer[r]);
+      x.peer[r] = nullptr;
     }
-    void* ptr = nullptr;
-    if (cudaIpcOpenMemHandle(&ptr, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
-      cudaGetLastError();
-      ok = false;
-      break;
-    }
-    x.peer[r] = static_cast<uint8_t*>(ptr);
+    if (x.local) CU(cudaMemset(x.local, 0, tss::kXchgBytes));
+    CU(cudaMemset(ix->d_counter + 17, 0, sizeof(unsigned int)));
+    CU(cudaDeviceSynchronize());
+    x.comm = nullptr;
   }
+  ShardHello mine{};
+  mine.n_rows = ix->n_rows;
+  if (want_fused) {
+    bool ok = true;
+    if (!x.local) {
+      ok = cudaMalloc(&x.local, tss::kXchgBytes) == cudaSuccess &&
+           cudaMemset(x.local, 0, tss::kXchgBytes) == cudaSuccess &&
+           cudaDeviceSynchronize() == cudaSuccess;
+    }
+    if (ok) ok = cudaIpcGetMemHandle(&mine.handle, x.local) == cudaSuccess;
+    if (!ok) cudaGetLastError();
+    mine.have_handle = ok ? 1u : 0u;
+  }
+  std::vector<ShardHello> all(comm->nranks);
+  int rc = comm_allgather_host(ix, comm, &mine, all.data(), sizeof(ShardHello));
+  if (rc) return rc;
+  uint64_t min_rows = ~0ull;
+  bool all_have = true;
+  for (int r = 0; r < comm->nranks; ++r) {
+    if (all[r].n_rows < min_rows) min_rows = all[r].n_rows;
+    all_have = all_have && all[r].have_handle;
+  }
+  ix->shard_min_rows = min_rows;
+  uint32_t mapped = 0;
+  if (want_fused && all_have) {
+    mapped = 1;
+    for (int r = 0; r < comm->nranks; ++r) {
+      if (r == comm->rank) {
+        x.peer[r] = x.local;
+        continue;
+      }
+      if (x.peer[r]) continue;  // still mapped from the previous attach of this comm
+      void* ptr = nullptr;
+      if (cudaIpcOpenMemHandle(&ptr, all[r].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        mapped = 0;
+        break;
+      }
+      x.peer[r] = static_cast<uint8_t*>(ptr);
+    }
+  }
+  std::vector<uint32_t> oks(comm->nranks);
+  if ((rc = comm_allgather_host(ix, comm, &mapped, oks.data(), sizeof(uint32_t)))) return rc;
+  bool ready = want_fused;
+  for (int r = 0; r < comm->nranks; ++r) ready = ready && oks[r];
   x.comm = comm;
-  x.ready = ok;
-  x.seq = 0;
-  CU(cudaMemset(ix->d_counter + 17, 0, sizeof(unsigned int)));
+  x.ready = ready;
   return TSS_OK;
 }
 }  // namespace
@@ -1283,9 +1419,11 @@ int tss_index_set_shard(tss_index* ix, uint64_t row_base, tss_comm* comm) {
     return fail(TSS_ERR_INVALID_ARG, "at most %d ranks", 48 * 1024 / (TSS_MAX_FUSED_K * 8));
   ix->row_base = row_base;
   ix->comm = comm;
-  if (comm) {  // collective over the comm the first time a given comm is attached
+  ix->shard_min_rows = ix->n_rows;
+  if (comm) {  // collective over the comm: every rank calls it with its own shard
     DeviceGuard g(ix->device);
-    int rc = setup_xchg(ix, comm);
+    int rc = load_nccl();
+    if (!rc) rc = setup_shard_group(ix, comm);
     if (rc) return rc;
   }
   return TSS_OK;
@@ -1305,9 +1443,13 @@ int tss_mask_create(tss_mask** out, uint64_t nbits, int device) {
   m->nbits = nbits;
   m->nwords = (nbits + 31) / 32;
   // the scan reads whole words for the last (partial) tile: pad by one word
-  cudaError_t e = cudaMalloc(&m->d_words, (size_t)(m->nwords + 1) * sizeof(uint32_t));
-  if (e == cudaSuccess) e = cudaMemset(m->d_words, 0, (size_t)(m->nwords + 1) * sizeof(uint32_t));
+  cudaError_t e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->wev, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaMalloc(&m->d_words, (size_t)(m->nwords + 1) * sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaMalloc(&m->d_scratch, sizeof(unsigned long long));
+  if (e == cudaSuccess)
+    e = cudaMemsetAsync(m->d_words, 0, (size_t)(m->nwords + 1) * sizeof(uint32_t), m->stream);
+  if (e == cudaSuccess) e = mask_end_write(m, m->stream);
   if (e != cudaSuccess) {
     tss_mask_destroy(m);
     return cuda_fail(e, "mask allocation");
@@ -1319,8 +1461,18 @@ int tss_mask_create(tss_mask** out, uint64_t nbits, int device) {
 void tss_mask_destroy(tss_mask* m) {
   if (!m) return;
   DeviceGuard g(m->device);
+  // everything that was enqueued against the words must have run before they are freed
+  if (m->has_write) cudaEventSynchronize(m->wev);
+  for (auto& r : m->readers) {
+    cudaEventSynchronize(r.ev);
+    cudaEventDestroy(r.ev);
+  }
+  for (cudaEvent_t ev : m->spare) cudaEventDestroy(ev);
+  if (m->stream) cudaStreamSynchronize(m->stream);
   cudaFree(m->d_words);
   cudaFree(m->d_scratch);
+  if (m->wev) cudaEventDestroy(m->wev);
+  if (m->stream) cudaStreamDestroy(m->stream);
   delete m;
 }
 
@@ -1329,7 +1481,9 @@ uint64_t tss_mask_nbits(const tss_mask* m) { return m ? m->nbits : 0; }
 int tss_mask_clear(tss_mask* m) {
   if (!m) return fail(TSS_ERR_INVALID_ARG, "mask is NULL");
   DeviceGuard g(m->device);
-  CU(cudaMemset(m->d_words, 0, (size_t)(m->nwords + 1) * sizeof(uint32_t)));
+  CU(mask_begin_write(m, m->stream));
+  CU(cudaMemsetAsync(m->d_words, 0, (size_t)(m->nwords + 1) * sizeof(uint32_t), m->stream));
+  CU(mask_end_write(m, m->stream));
   return TSS_OK;
 }
 
@@ -1339,15 +1493,27 @@ int mask_update_rows(tss_mask* m, const uint32_t* rows, uint64_t n, uint64_t row
   if (!n) return TSS_OK;
   if (!rows) return fail(TSS_ERR_INVALID_ARG, "rows is NULL");
   DeviceGuard g(m->device);
-  uint32_t* d_rows = nullptr;
-  CU(cudaMalloc(&d_rows, (size_t)n * sizeof(uint32_t)));
-  cudaError_t e = cudaMemcpy(d_rows, rows, (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice);
-  if (e == cudaSuccess)
-    e = tss::launch_mask_set_rows(m->d_words, m->nbits, d_rows, n, row_base, set, 0);
-  if (e == cudaSuccess) e = cudaDeviceSynchronize();
-  cudaFree(d_rows);
+  CU(mask_begin_write(m, m->stream));
+  cudaError_t e = cudaSuccess;
+  if (n <= tss::kInlineRows) {
+    // a short list (the seen cases of one query) rides in the kernel parameters: no staging
+    // allocation, no copy, no host synchronisation
+    tss::InlineRows ir;
+    ir.n = (uint32_t)n;
+    memcpy(ir.rows, rows, (size_t)n * sizeof(uint32_t));
+    e = tss::launch_mask_set_rows_inline(m->d_words, m->nbits, ir, row_base, set, m->stream);
+  } else {
+    uint32_t* d_rows = nullptr;
+    CU(cudaMalloc(&d_rows, (size_t)n * sizeof(uint32_t)));
+    e = cudaMemcpyAsync(d_rows, rows, (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice, m->stream);
+    if (e == cudaSuccess)
+      e = tss::launch_mask_set_rows(m->d_words, m->nbits, d_rows, n, row_base, set, m->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);  // d_rows is freed below
+    cudaFree(d_rows);
+  }
   if (e != cudaSuccess) return cuda_fail(e, "mask_set_rows");
   g_launches.fetch_add(1, std::memory_order_relaxed);
+  CU(mask_end_write(m, m->stream));
   return TSS_OK;
 }
 }  // namespace
@@ -1373,13 +1539,15 @@ int tss_columns_create(tss_columns** out, const uint16_t* court_ids, const int32
   if (!c) return fail(TSS_ERR_OOM, "host allocation failed");
   c->device = device;
   c->nrows = nrows;
-  cudaError_t e = cudaMalloc(&c->d_court, (nrows + 1) * sizeof(uint16_t));
+  cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaMalloc(&c->d_court, (nrows + 1) * sizeof(uint16_t));
   if (e == cudaSuccess) e = cudaMalloc(&c->d_date, (nrows + 1) * sizeof(int32_t));
   if (e == cudaSuccess) e = cudaMalloc(&c->d_allow, 2048 * sizeof(uint32_t));
   if (e == cudaSuccess && nrows)
     e = cudaMemcpy(c->d_court, court_ids, nrows * sizeof(uint16_t), cudaMemcpyHostToDevice);
   if (e == cudaSuccess && nrows)
     e = cudaMemcpy(c->d_date, dates, nrows * sizeof(int32_t), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();  // pageable H2D: see tss_terms_create
   if (e != cudaSuccess) {
     tss_columns_destroy(c);
     return cuda_fail(e, "columns upload");
@@ -1391,9 +1559,11 @@ int tss_columns_create(tss_columns** out, const uint16_t* court_ids, const int32
 void tss_columns_destroy(tss_columns* c) {
   if (!c) return;
   DeviceGuard g(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
   cudaFree(c->d_court);
   cudaFree(c->d_date);
   cudaFree(c->d_allow);
+  if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
 
@@ -1409,40 +1579,56 @@ int tss_filter_mask(tss_columns* c, const uint16_t* allowed_courts, uint32_t n_a
   if (n_allowed) {
     std::vector<uint32_t> bits(2048, 0);
     for (uint32_t i = 0; i < n_allowed; ++i) bits[allowed_courts[i] >> 5] |= 1u << (allowed_courts[i] & 31);
-    CU(cudaMemcpy(c->d_allow, bits.data(), 2048 * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    // (pageable source: the copy is staged before the call returns; in order on c->stream with
+    // the previous call's kernel, which read d_allow)
+    CU(cudaMemcpyAsync(c->d_allow, bits.data(), 2048 * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                       c->stream));
   }
+  CU(mask_begin_write(mask, c->stream));
   cudaError_t e = tss::launch_filter_mask(c->d_court, c->d_date, c->nrows, c->d_allow, n_allowed == 0,
-                                          date_lo, date_hi, mask->d_words, combine_and != 0, 0);
-  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+                                          date_lo, date_hi, mask->d_words, combine_and != 0, c->stream);
   if (e != cudaSuccess) return cuda_fail(e, "filter_mask");
   g_launches.fetch_add(1, std::memory_order_relaxed);
+  CU(mask_end_write(mask, c->stream));
   return TSS_OK;
 }
 
 int tss_mask_upload(tss_mask* m, const uint32_t* words) {
   if (!m || !words) return fail(TSS_ERR_INVALID_ARG, "NULL argument");
   DeviceGuard g(m->device);
-  CU(cudaMemcpy(m->d_words, words, (size_t)m->nwords * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  CU(mask_begin_write(m, m->stream));
+  CU(cudaMemcpyAsync(m->d_words, words, (size_t)m->nwords * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                     m->stream));
+  CU(mask_end_write(m, m->stream));
+  // the caller may reuse `words` right away
+  CU(cudaStreamSynchronize(m->stream));
   return TSS_OK;
 }
 
 int tss_mask_download(const tss_mask* m, uint32_t* words) {
   if (!m || !words) return fail(TSS_ERR_INVALID_ARG, "NULL argument");
   DeviceGuard g(m->device);
-  CU(cudaDeviceSynchronize());
-  CU(cudaMemcpy(words, m->d_words, (size_t)m->nwords * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  tss_mask* mm = const_cast<tss_mask*>(m);
+  CU(mask_begin_read(mm, mm->stream));
+  CU(cudaMemcpyAsync(words, m->d_words, (size_t)m->nwords * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                     mm->stream));
+  CU(mask_end_read(mm, mm->stream));
+  CU(cudaStreamSynchronize(mm->stream));
   return TSS_OK;
 }
 
 int tss_mask_popcount(const tss_mask* m, uint64_t* out) {
   if (!m || !out) return fail(TSS_ERR_INVALID_ARG, "NULL argument");
   DeviceGuard g(m->device);
-  CU(cudaDeviceSynchronize());
-  cudaError_t e = tss::launch_mask_popcount(m->d_words, m->nwords, m->d_scratch, 0);
+  tss_mask* mm = const_cast<tss_mask*>(m);
+  CU(mask_begin_read(mm, mm->stream));
+  cudaError_t e = tss::launch_mask_popcount(m->d_words, m->nwords, m->d_scratch, mm->stream);
   if (e != cudaSuccess) return cuda_fail(e, "mask_popcount launch");
   g_launches.fetch_add(1, std::memory_order_relaxed);
   unsigned long long v = 0;
-  CU(cudaMemcpy(&v, m->d_scratch, sizeof(v), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpyAsync(&v, m->d_scratch, sizeof(v), cudaMemcpyDeviceToHost, mm->stream));
+  CU(mask_end_read(mm, mm->stream));
+  CU(cudaStreamSynchronize(mm->stream));
   *out = v;
   return TSS_OK;
 }
@@ -1497,7 +1683,11 @@ int tss_terms_create(tss_terms** out, const char* pool, const uint64_t* term_off
   TRY(cudaMemcpy(t->d_term_off, term_off, (nterms + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice))
   TRY(cudaMemcpy(t->d_post_off, post_off, (nterms + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice))
   if (nposts) TRY(cudaMemcpy(t->d_post_rows, post_rows, nposts * sizeof(uint32_t), cudaMemcpyHostToDevice))
+  // (a pageable H2D cudaMemcpy may return before its last DMA lands, and the non-blocking
+  // streams that will read these arrays do not order against the legacy stream)
+  TRY(cudaDeviceSynchronize())
 #undef TRY
+  t->own_stream = t->stream;
   if (e != cudaSuccess) {
     tss_terms_destroy(t);
     return cuda_fail(e, "terms upload");
@@ -1551,6 +1741,7 @@ int tss_terms_build(tss_terms** out, const char* vocab_pool, const uint64_t* voc
   t->device = device;
   t->key_cap = 4096;
   cudaError_t e = cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking);
+  t->own_stream = t->stream;
   if (e == cudaSuccess) e = cudaMalloc(&t->d_keys, t->key_cap);
   if (e == cudaSuccess) e = cudaMallocHost(&t->h_keys, t->key_cap);
   if (e == cudaSuccess) e = cudaMalloc(&t->d_bounds, 8 * sizeof(uint64_t));
@@ -1602,6 +1793,7 @@ void tss_terms_destroy(tss_terms* t) {
   if (!t) return;
   DeviceGuard g(t->device);
   if (t->stream) cudaStreamSynchronize(t->stream);
+  if (t->own_stream && t->own_stream != t->stream) cudaStreamSynchronize(t->own_stream);
   cudaFree(t->d_pool);
   cudaFree(t->d_term_off);
   cudaFree(t->d_post_off);
@@ -1609,12 +1801,15 @@ void tss_terms_destroy(tss_terms* t) {
   cudaFree(t->d_keys);
   cudaFree(t->d_bounds);
   if (t->h_keys) cudaFreeHost(t->h_keys);
-  if (t->stream) cudaStreamDestroy(t->stream);
+  if (t->own_stream) cudaStreamDestroy(t->own_stream);
   delete t;
 }
 
-int tss_prefix_mask(tss_terms* t, const char* prefix, uint32_t len, int kind, tss_mask* out,
-                    uint64_t row_base, tss_prefix_stats* stats) {
+namespace {
+// clear_first: the output mask is zeroed by the search kernel's spare CTAs (one launch less than
+// tss_mask_clear + tss_prefix_mask, and no cross-stream hop)
+int prefix_mask_impl(tss_terms* t, const char* prefix, uint32_t len, int kind, tss_mask* out,
+                     uint64_t row_base, tss_prefix_stats* stats, bool clear_first) {
   if (!t || !out) return fail(TSS_ERR_INVALID_ARG, "NULL argument");
   if (len && !prefix) return fail(TSS_ERR_INVALID_ARG, "prefix is NULL");
   if (kind != TSS_PREFIX_TOKEN && kind != TSS_PREFIX_CHAR)
@@ -1669,29 +1864,57 @@ int tss_prefix_mask(tss_terms* t, const char* prefix, uint32_t len, int kind, ts
       }
     }
   }
-  CU(cudaStreamSynchronize(t->stream));  // h_keys is reused
-  memcpy(t->h_keys, kb.data(), kb.size());
-  if (!kb.empty())
-    CU(cudaMemcpyAsync(t->d_keys, t->h_keys, kb.size(), cudaMemcpyHostToDevice, t->stream));
+  cudaStream_t st = t->stream;
+  const char* d_keybytes = nullptr;
+  if (kb.size() <= tss::kPrefixInlineBytes) {
+    memcpy(keys.bytes, kb.data(), kb.size());  // the keys travel in the kernel parameters
+  } else {
+    CU(cudaStreamSynchronize(st));  // long prefix: the pinned staging buffer is reused
+    memcpy(t->h_keys, kb.data(), kb.size());
+    CU(cudaMemcpyAsync(t->d_keys, t->h_keys, kb.size(), cudaMemcpyHostToDevice, st));
+    d_keybytes = t->d_keys;
+  }
+  CU(mask_begin_write(out, st));
   tss::TermsDev td{t->d_pool, t->d_term_off, t->d_post_off, t->d_post_rows, t->nterms};
-  cudaError_t e = tss::launch_prefix_search(td, t->d_keys, keys, t->d_bounds, t->stream);
+  cudaError_t e = tss::launch_prefix_search(td, d_keybytes, keys, t->d_bounds,
+                                            clear_first ? out->d_words : nullptr, out->nwords + 1, st);
   if (e != cudaSuccess) return cuda_fail(e, "prefix_search launch");
   e = tss::launch_prefix_scatter(td, t->d_bounds, out->d_words, out->nbits, row_base,
-                                 reinterpret_cast<unsigned long long*>(t->d_bounds + 4), 148 * 4,
-                                 t->stream);
+                                 reinterpret_cast<unsigned long long*>(t->d_bounds + 4), 148 * 4, st);
   if (e != cudaSuccess) return cuda_fail(e, "prefix_scatter launch");
   g_launches.fetch_add(2, std::memory_order_relaxed);
-  // the mask is consumed on other streams: make it visible before returning
-  uint64_t h[5];
-  CU(cudaMemcpyAsync(h, t->d_bounds, sizeof(h), cudaMemcpyDeviceToHost, t->stream));
-  CU(cudaStreamSynchronize(t->stream));
+  // consumers on other streams are ordered behind the scatter by the mask's write event:
+  // no host synchronisation unless the caller wants the statistics
+  CU(mask_end_write(out, st));
   if (stats) {
+    uint64_t h[5];
+    CU(cudaMemcpyAsync(h, t->d_bounds, sizeof(h), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
     stats->exact_lo = h[0];
     stats->exact_hi = h[1] > h[0] ? h[1] : h[0];
     stats->sub_lo = h[2];
     stats->sub_hi = h[3] > h[2] ? h[3] : h[2];
     stats->npostings = h[4];
   }
+  return TSS_OK;
+}
+}  // namespace
+
+int tss_prefix_mask(tss_terms* t, const char* prefix, uint32_t len, int kind, tss_mask* out,
+                    uint64_t row_base, tss_prefix_stats* stats) {
+  return prefix_mask_impl(t, prefix, len, kind, out, row_base, stats, false);
+}
+int tss_prefix_mask_fresh(tss_terms* t, const char* prefix, uint32_t len, int kind, tss_mask* out,
+                          uint64_t row_base, tss_prefix_stats* stats) {
+  return prefix_mask_impl(t, prefix, len, kind, out, row_base, stats, true);
+}
+
+int tss_terms_bind_stream(tss_terms* t, tss_index* ix) {
+  if (!t) return fail(TSS_ERR_INVALID_ARG, "terms is NULL");
+  if (ix && ix->device != t->device) return fail(TSS_ERR_INVALID_ARG, "terms and index on different devices");
+  DeviceGuard g(t->device);
+  CU(cudaStreamSynchronize(t->stream));  // d_bounds / d_keys change streams: drain the old one
+  t->stream = ix ? ix->stream : t->own_stream;
   return TSS_OK;
 }
 
@@ -1729,6 +1952,7 @@ int tss_dev_free(int device, void* p) {
 int tss_dev_h2d(int device, void* dst, const void* src, uint64_t bytes) {
   DeviceGuard g(device);
   CU(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+  CU(cudaDeviceSynchronize());  // pageable H2D may return before the last DMA lands
   return TSS_OK;
 }
 int tss_dev_d2h(int device, void* dst, const void* src, uint64_t bytes) {

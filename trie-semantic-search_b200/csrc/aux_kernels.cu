@@ -126,6 +126,24 @@ cudaError_t launch_mask_set_rows(uint32_t* words, uint64_t nbits, const uint32_t
   return cudaGetLastError();
 }
 
+__global__ void mask_set_rows_inline_kernel(uint32_t* words, uint64_t nbits,
+                                            const __grid_constant__ InlineRows rows, uint64_t row_base,
+                                            int set) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows.n) return;
+  uint64_t r = (uint64_t)rows.rows[i] - row_base;
+  if (r >= nbits) return;
+  if (set) atomicOr(words + (r >> 5), 1u << (uint32_t)(r & 31));
+  else atomicAnd(words + (r >> 5), ~(1u << (uint32_t)(r & 31)));
+}
+cudaError_t launch_mask_set_rows_inline(uint32_t* words, uint64_t nbits, const InlineRows& rows,
+                                        uint64_t row_base, bool set, cudaStream_t st) {
+  if (!rows.n) return cudaSuccess;
+  mask_set_rows_inline_kernel<<<(rows.n + 127) / 128, 128, 0, st>>>(words, nbits, rows, row_base,
+                                                                   set ? 1 : 0);
+  return cudaGetLastError();
+}
+
 // set (or clear) the bits of the rows named by packed keys (0 = empty slot)
 __global__ void mask_update_from_keys_kernel(uint32_t* words, uint64_t nbits, const uint64_t* keys,
                                              uint32_t n, uint64_t row_base, int set) {
@@ -243,8 +261,19 @@ __device__ uint64_t warp_lower_bound(const TermsDev& t, const char* key, uint32_
   return lo + __popc(__ballot_sync(FULL_MASK, less));
 }
 
-__global__ void prefix_search_kernel(TermsDev t, const char* keybytes, PrefixKeys keys,
-                                     uint64_t* bounds) {
+__global__ void prefix_search_kernel(TermsDev t, const char* keybytes_dev,
+                                     const __grid_constant__ PrefixKeys keys, uint64_t* bounds,
+                                     uint32_t* clear_words, uint64_t clear_nwords) {
+  if (blockIdx.x != 0) {  // the other CTAs clear the output mask while CTA 0 searches
+    const uint64_t tid = (uint64_t)(blockIdx.x - 1) * blockDim.x + threadIdx.x;
+    const uint64_t nth = (uint64_t)(gridDim.x - 1) * blockDim.x;
+    uint4* w4 = reinterpret_cast<uint4*>(clear_words);  // cudaMalloc'ed: 256-byte aligned
+    const uint64_t n4 = clear_nwords >> 2;
+    for (uint64_t i = tid; i < n4; i += nth) w4[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (uint64_t i = (n4 << 2) + tid; i < clear_nwords; i += nth) clear_words[i] = 0u;
+    return;
+  }
+  const char* keybytes = keybytes_dev ? keybytes_dev : keys.bytes;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;  // 4 warps, one bound each
   uint64_t r;
   if (keys.fixed[warp] >= 0)
@@ -255,9 +284,16 @@ __global__ void prefix_search_kernel(TermsDev t, const char* keybytes, PrefixKey
     r = warp_lower_bound(t, keybytes + keys.off[warp], keys.off[warp + 1] - keys.off[warp], lane);
   if (lane == 0) bounds[warp] = r;
 }
-cudaError_t launch_prefix_search(const TermsDev& t, const char* d_keybytes, PrefixKeys keys,
-                                 uint64_t* d_bounds, cudaStream_t st) {
-  prefix_search_kernel<<<1, 128, 0, st>>>(t, d_keybytes, keys, d_bounds);
+cudaError_t launch_prefix_search(const TermsDev& t, const char* d_keybytes, const PrefixKeys& keys,
+                                 uint64_t* d_bounds, uint32_t* clear_words, uint64_t clear_nwords,
+                                 cudaStream_t st) {
+  unsigned grid = 1;
+  if (clear_words && clear_nwords) {
+    // 128 threads x one 16-byte store per trip; at most two CTAs' worth per SM
+    const uint64_t want = (clear_nwords / 4 + 127) / 128;
+    grid += (unsigned)(want < 295 ? (want ? want : 1) : 295);
+  }
+  prefix_search_kernel<<<grid, 128, 0, st>>>(t, d_keybytes, keys, d_bounds, clear_words, clear_nwords);
   return cudaGetLastError();
 }
 

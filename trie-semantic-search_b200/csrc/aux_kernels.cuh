@@ -21,6 +21,14 @@ cudaError_t launch_unpack_rows(const void* src, float* dst, uint64_t nrows, uint
 // masks
 cudaError_t launch_mask_set_rows(uint32_t* words, uint64_t nbits, const uint32_t* rows, uint64_t n,
                                  uint64_t row_base, bool set, cudaStream_t st);
+// the same for a short list that travels in the kernel parameters (no staging copy, no sync)
+constexpr uint32_t kInlineRows = 896;
+struct InlineRows {
+  uint32_t n;
+  uint32_t rows[kInlineRows];
+};
+cudaError_t launch_mask_set_rows_inline(uint32_t* words, uint64_t nbits, const InlineRows& rows,
+                                        uint64_t row_base, bool set, cudaStream_t st);
 // N3: metadata columns -> mask words (overwrite or AND)
 cudaError_t launch_filter_mask(const uint16_t* court, const int32_t* date, uint64_t nrows,
                                const uint32_t* allow_bits, bool any_court, int32_t lo, int32_t hi,
@@ -38,13 +46,20 @@ struct TermsDev {
   const uint32_t* post_rows;
   uint64_t nterms;
 };
-struct PrefixKeys {  // up to 4 lower-bound probes, keys concatenated in `bytes`
+constexpr uint32_t kPrefixInlineBytes = 1024;
+struct PrefixKeys {  // up to 4 lower-bound probes, keys concatenated
   uint32_t off[5];
   int32_t fixed[4];  // >= 0: bound is this constant (no search); -1: search; -2: nterms
+  // the concatenated key bytes ride in the kernel parameters when they fit (prefixes up to 255
+  // bytes): no staging copy, so nothing on the host has to wait for the previous call
+  char bytes[kPrefixInlineBytes];
 };
-// bounds[4] <- lower bounds; then ranges [b0,b1) and [b2,b3) are scattered.
-cudaError_t launch_prefix_search(const TermsDev& t, const char* d_keybytes, PrefixKeys keys,
-                                 uint64_t* d_bounds, cudaStream_t st);
+// bounds[4] <- lower bounds; then ranges [b0,b1) and [b2,b3) are scattered.  d_keybytes == null:
+// the keys are keys.bytes.  clear_words != null: the kernel's other CTAs zero those words (the
+// output mask) while CTA 0 searches -- clear + search in one launch.
+cudaError_t launch_prefix_search(const TermsDev& t, const char* d_keybytes, const PrefixKeys& keys,
+                                 uint64_t* d_bounds, uint32_t* clear_words, uint64_t clear_nwords,
+                                 cudaStream_t st);
 cudaError_t launch_prefix_scatter(const TermsDev& t, const uint64_t* d_bounds, uint32_t* words,
                                   uint64_t nbits, uint64_t row_base, unsigned long long* d_npost,
                                   int grid, cudaStream_t st);

@@ -450,9 +450,12 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           mul2(r[4 * j4 + 2], r[4 * j4 + 3], w.z, w.w, v[4 * j4 + 2], v[4 * j4 + 3]);
         }
         if (cb + 32 > ncols) {  // last, partial tile of the corpus only
+          // columns past the last row are marked like masked rows: NaN, which fmax drops and
+          // `>= thr` rejects even when thr is -inf (fewer than k live maxima) -- -inf here
+          // would pass `-inf >= -inf` and push row ids that do not exist
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (cb + j >= ncols) v[j] = -INFINITY;
+            if (cb + j >= ncols) v[j] = __uint_as_float(0x7FC00000u);
         }
         float gm[4];
 #pragma unroll
@@ -709,6 +712,7 @@ struct Rescore {
   const void* rows;         // the STORED matrix (bf16 or fp32), stride_elems per row (k * 128)
   int rows_f32;
   uint32_t dim, stride_elems, row_base;
+  uint64_t n_rows;          // rows of the shard: a key naming a row beyond them is dropped
 };
 // Re-score the keys sk[0..m) in place (low word = ~global row) with the scan's arithmetic
 // (scan.cuh): "lane" l of 32 owns elements 4l..4l+3 of every 128-element
@@ -859,6 +863,9 @@ select_kernel(const uint64_t* cand, const uint32_t* cand_count, uint32_t nsub, u
   for_each_key([&](uint64_t key, bool valid) {
     const uint32_t ob = (uint32_t)(key >> 32);
     if (!valid || ob < keep_from) return;
+    // (belt and braces: the collect pass never emits a row beyond the shard, and re-scoring
+    // one would read past the matrix)
+    if ((uint64_t)(0xFFFFFFFFu - (uint32_t)key - rs.row_base) >= rs.n_rows) return;
     const uint32_t pos = atomicAdd(&s_n, 1u);
     if (pos >= kSelectSort) return;
     if (rescore) {
@@ -1001,11 +1008,11 @@ cudaError_t launch_select(const uint64_t* cand, const uint32_t* cand_count, uint
                           uint32_t cap_s, const float* inv_qnorm, uint32_t nq, uint32_t k,
                           const float* queries, const float* margin, const void* rows,
                           bool rows_f32, uint32_t dim, uint32_t stride_elems, uint32_t row_base,
-                          uint64_t* out, uint32_t* overflow, cudaStream_t st) {
+                          uint64_t n_rows, uint64_t* out, uint32_t* overflow, cudaStream_t st) {
   if (nslices > kSelectMaxLists || k > kSelectSortMax / 2 || stride_elems > 1024 ||
       stride_elems % 128)
     return cudaErrorInvalidConfiguration;
-  Rescore rs{queries, margin, rows, rows_f32 ? 1 : 0, dim, stride_elems, row_base};
+  Rescore rs{queries, margin, rows, rows_f32 ? 1 : 0, dim, stride_elems, row_base, n_rows};
   select_kernel<<<nq, kSelectThreads, select_sort_cap(k) * sizeof(uint64_t), st>>>(
       cand, cand_count, nslices, cap_s, inv_qnorm, rs, k, out, overflow);
   return cudaGetLastError();
@@ -1013,10 +1020,11 @@ cudaError_t launch_select(const uint64_t* cand, const uint32_t* cand_count, uint
 
 cudaError_t launch_refine(const uint64_t* cand, uint32_t kc, const float* queries, const void* rows_f32,
                           uint32_t dim, uint32_t stride_elems, uint32_t row_base, uint32_t nq,
-                          uint32_t k, uint64_t* out, uint32_t* incomplete, cudaStream_t st) {
+                          uint64_t n_rows, uint32_t k, uint64_t* out, uint32_t* incomplete,
+                          cudaStream_t st) {
   if (kc > kRefineMax || k > kRefineMax || stride_elems > 1024 || stride_elems % 128)
     return cudaErrorInvalidConfiguration;
-  Rescore rs{queries, nullptr, rows_f32, 1, dim, stride_elems, row_base};
+  Rescore rs{queries, nullptr, rows_f32, 1, dim, stride_elems, row_base, n_rows};
   const float two_eps = 2.f * (0x1.01p-8f + (float)(dim + 4) * 0x1p-22f);
   refine_kernel<<<nq, kSelectThreads, 0, st>>>(cand, kc, rs, two_eps, k, out, incomplete);
   return cudaGetLastError();

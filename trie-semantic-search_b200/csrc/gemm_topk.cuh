@@ -52,13 +52,14 @@ cudaError_t launch_select(const uint64_t* cand, const uint32_t* cand_count, uint
                           uint32_t cap_s, const float* inv_qnorm, uint32_t nq, uint32_t k,
                           const float* queries, const float* margin, const void* rows,
                           bool rows_f32, uint32_t dim, uint32_t stride_elems, uint32_t row_base,
-                          uint64_t* out, uint32_t* overflow, cudaStream_t st);
+                          uint64_t n_rows, uint64_t* out, uint32_t* overflow, cudaStream_t st);
 
 // Shadow prefilter (single queries, fp32 index): cand [nq][kc] = the scan's top-kc over the bf16
 // shadow; re-scores them from the fp32 rows and writes the top-k, or flags the query incomplete
 // (the kc-th shadow score is not provably below the fp32 top-k): see refine_kernel.
 cudaError_t launch_refine(const uint64_t* cand, uint32_t kc, const float* queries, const void* rows_f32,
                           uint32_t dim, uint32_t stride_elems, uint32_t row_base, uint32_t nq,
-                          uint32_t k, uint64_t* out, uint32_t* incomplete, cudaStream_t st);
+                          uint64_t n_rows, uint32_t k, uint64_t* out, uint32_t* incomplete,
+                          cudaStream_t st);
 
 }  // namespace tss

@@ -1,6 +1,8 @@
 // scan_ns.cu -- instantiates the K1 scan kernel for one stripe count.
 // Compiled once per supported NS with -DTSS_NS=<n> (see Makefile) so the
 // instances build in parallel.
+#include <mutex>
+
 #include "scan.cuh"
 #include "scan_launch.h"
 
@@ -28,13 +30,19 @@ static cudaError_t launch_one(const ScanParams& p, int grid, int device, cudaStr
   if (smem < xchg_bytes) smem = xchg_bytes;
   // 227 KB per CTA minus the kernel's static shared memory (ticket word, padded)
   if (smem > 232448 - 256) return cudaErrorInvalidConfiguration;
+  // per-instance cache of the attribute already set on each device; distinct index handles may
+  // launch from distinct threads (include/tss.h), so the cache is guarded
   static size_t attr_bytes[kMaxDevices] = {};
+  static std::mutex attr_mu;
   if (device < 0 || device >= kMaxDevices) return cudaErrorInvalidDevice;
-  if (attr_bytes[device] < smem) {
-    cudaError_t e =
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    attr_bytes[device] = smem;
+  {
+    std::lock_guard<std::mutex> lk(attr_mu);
+    if (attr_bytes[device] < smem) {
+      cudaError_t e =
+          cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      attr_bytes[device] = smem;
+    }
   }
   ScanParams q = p;
   q.smem_bytes = (uint32_t)smem;

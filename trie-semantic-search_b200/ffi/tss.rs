@@ -96,6 +96,11 @@ extern "C" {
         t: *mut tss_terms, prefix: *const c_char, len: u32, kind: c_int, out: *mut tss_mask,
         row_base: u64, stats: *mut tss_prefix_stats,
     ) -> c_int;
+    pub fn tss_prefix_mask_fresh(
+        t: *mut tss_terms, prefix: *const c_char, len: u32, kind: c_int, out: *mut tss_mask,
+        row_base: u64, stats: *mut tss_prefix_stats,
+    ) -> c_int;
+    pub fn tss_terms_bind_stream(t: *mut tss_terms, ix: *mut tss_index) -> c_int;
 
     pub fn tss_terms_build(
         out: *mut *mut tss_terms, vocab_pool: *const c_char, vocab_off: *const u64, vocab_size: u32,

@@ -83,9 +83,22 @@ void HnswIndex::add_vector(const DocRef& doc_ref, const std::vector<float>& embe
 void HnswIndex::flush() {
   if (pending_rows_) {
     int rc = tss_index_add(ix_, pending_.data(), pending_rows_);
-    if (rc) raise_tss(SearchError::VectorIndexFailed, "HnswIndex::add_vector", rc);
     pending_.clear();
     pending_rows_ = 0;
+    if (rc) {
+      // the device refused the batch (tss_index_add leaves the index unchanged): the row ->
+      // DocRef table must not run ahead of it, or later hits would name the wrong documents
+      const size_t have = (size_t)tss_index_size(ix_);
+      while (row_docref_.size() > have) {
+        auto it = case_rows_.find(row_docref_.back().case_id);
+        if (it != case_rows_.end()) {
+          it->second.pop_back();
+          if (it->second.empty()) case_rows_.erase(it);
+        }
+        row_docref_.pop_back();
+      }
+      raise_tss(SearchError::VectorIndexFailed, "HnswIndex::add_vector", rc);
+    }
   }
 }
 
@@ -403,16 +416,17 @@ void TrieIndex::freeze(Which w, int device, const RowsOf& rows_of) {
                             post_rows.data(), term_off.size() - 1, device);
   if (rc) raise_tss(SearchError::VectorIndexFailed, "TrieIndex::freeze", rc);
 }
-void TrieIndex::prefix_mask(Which w, const std::string& query, tss_mask* mask,
-                            uint64_t row_base) const {
+void TrieIndex::prefix_mask(Which w, const std::string& query, tss_mask* mask, uint64_t row_base,
+                            bool fresh) const {
   if (!frozen_[w]) throw SearchError(SearchError::NotSupported, "TrieIndex::prefix_mask before freeze");
   std::string p;
   for (const auto& t : tries_[w].tokenize(query)) {
     if (!p.empty()) p.push_back(' ');
     p += t;
   }
-  int rc = tss_prefix_mask(frozen_[w], p.data(), (uint32_t)p.size(), TSS_PREFIX_TOKEN, mask,
-                           row_base, nullptr);
+  // fresh: the mask is zeroed by the same enqueue (no separate clear, no host synchronisation)
+  int rc = (fresh ? tss_prefix_mask_fresh : tss_prefix_mask)(frozen_[w], p.data(), (uint32_t)p.size(),
+                                                            TSS_PREFIX_TOKEN, mask, row_base, nullptr);
   if (rc) raise_tss(SearchError::HnswSearchError, "TrieIndex::prefix_mask", rc);
 }
 
@@ -597,8 +611,13 @@ std::vector<SearchResult> SearchEngine::execute_hybrid_search(const SearchQuery&
     if (policy_ != MaskPolicy::PostHoc || filtered) {
       if (!mask_ || mask_bits_ != h.size())
         throw SearchError(SearchError::NotSupported, "SearchEngine::freeze() not called after the last insert");
-      int rc = tss_mask_clear(mask_);
-      if (rc) raise_tss(SearchError::HnswSearchError, "mask clear", rc);
+      // every mask operation below is stream-ordered by the library (include/tss.h, masks):
+      // clear -> prefix scatter -> filter -> row edits -> the masked search, no host round trips
+      int rc = TSS_OK;
+      if (policy_ != MaskPolicy::PrefixFilter) {  // (the prefix path clears inside its first enqueue)
+        rc = tss_mask_clear(mask_);
+        if (rc) raise_tss(SearchError::HnswSearchError, "mask clear", rc);
+      }
       std::vector<uint32_t> seen_rows;
       if (policy_ == MaskPolicy::ExcludeOnDevice)
         for (const CaseId& c : seen_cases)
@@ -606,7 +625,7 @@ std::vector<SearchResult> SearchEngine::execute_hybrid_search(const SearchQuery&
       bool have_include = false;
       if (policy_ == MaskPolicy::PrefixFilter) {  // rows at or below the node the query reaches
         for (int w = 0; w < 3; ++w)
-          trie_index_.prefix_mask((TrieIndex::Which)w, query.query, mask_);
+          trie_index_.prefix_mask((TrieIndex::Which)w, query.query, mask_, 0, /*fresh=*/w == 0);
         have_include = true;
       }
       if (filtered) {  // N3: the filter's rows, intersected with the prefix rows if any

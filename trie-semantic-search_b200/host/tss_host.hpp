@@ -274,7 +274,8 @@ class TrieIndex {
   using RowsOf = std::function<const std::vector<uint32_t>*(const CaseId&)>;
   void freeze(Which w, int device, const RowsOf& rows_of);
   // OR the rows of every posting at or below the node `query` reaches into `mask`.
-  void prefix_mask(Which w, const std::string& query, tss_mask* mask, uint64_t row_base = 0) const;
+  void prefix_mask(Which w, const std::string& query, tss_mask* mask, uint64_t row_base = 0,
+                   bool fresh = false) const;
   const TokenTrie& trie(Which w) const { return tries_[w]; }
 
  private:
