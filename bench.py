@@ -243,6 +243,12 @@ def workload_config(args, n_gpus):
     }
 
 
+def _json_default(o):
+    if isinstance(o, np.generic):
+        return o.item()
+    raise TypeError(f"Object of type {o.__class__.__name__} is not JSON serializable")
+
+
 class _Slice:  # a view into a DeviceBuffer (the ABI takes raw pointers)
     def __init__(self, ptr):
         self.ptr = ptr
@@ -864,7 +870,7 @@ def main():
         line.update(extras)
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line, default=_json_default), flush=True)
     if dist is not None:
         dist.barrier()
         if comm is not None:

@@ -225,6 +225,27 @@ int tss_terms_create(tss_terms** out, const char* pool, const uint64_t* term_off
 int tss_terms_build(tss_terms** out, const char* vocab_pool, const uint64_t* vocab_off,
                     uint32_t vocab_size, const uint32_t* token_ids, uint32_t max_tokens,
                     const uint32_t* rows, uint64_t n_postings, int device);
+/* N2 from raw strings: what feeds TrieIndex::insert_case_name / insert_content / insert_citation
+ * (src/trie.rs:97-110) is text; the wrappers tokenise with split_whitespace() and lower-case
+ * case names and content (src/trie.rs:147,158,171,177) but not citations (:190,196).  Here the
+ * n phrases of one trie arrive as one byte buffer (text + phrase_off[n + 1]), phrase i posting
+ * rows[i]; the DEVICE splits them at ASCII whitespace (0x09-0x0D, 0x20), lower-cases A-Z when
+ * lowercase != 0, dictionary-encodes the tokens (string sort by radix passes over 8-byte chunks,
+ * unique -> the byte-sorted vocabulary) and builds the flattened trie as tss_terms_build does.
+ * A phrase without tokens posts on the root term "".  Limits (TSS_ERR_INVALID_ARG): tokens of at
+ * most 128 bytes, at most max_tokens (<= 64) tokens per phrase, no control bytes below 0x20
+ * other than whitespace.  Bytes >= 0x80 pass through unchanged: case folding and whitespace are
+ * ASCII where the reference's are Unicode. */
+int tss_terms_build_text(tss_terms** out, const char* text, const uint64_t* phrase_off,
+                         const uint32_t* rows, uint64_t n_phrases, int lowercase, uint32_t max_tokens,
+                         int device);
+/* On-disk form of the flattened term array (second half): fills in
+ * TrieIndex::save_to_disk / load_from_disk (src/trie.rs:83-94: a no-op and a NotSupported stub;
+ * TrieConfig.index_path, src/config.rs:190).  64-byte header + term_off + post_off + post_rows +
+ * pool exactly as they sit in HBM; the loader checks the sizes against the file and validates
+ * ordering on the device. */
+int tss_terms_save(const tss_terms* t, const char* path);
+int tss_terms_load(tss_terms** out, const char* path, int device);
 int tss_terms_sizes(const tss_terms* t, uint64_t* nterms, uint64_t* pool_bytes, uint64_t* npostings);
 /* copy the flattened arrays back (caller-allocated per tss_terms_sizes) */
 int tss_terms_export(const tss_terms* t, char* pool, uint64_t* term_off, uint64_t* post_off,

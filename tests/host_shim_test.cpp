@@ -8,6 +8,8 @@
 #include <random>
 #include <string>
 #include <thread>
+#include <unistd.h>
+#include <unordered_map>
 
 #include "../include/tss.h"
 #include "../oracle/oracle.h"
@@ -414,11 +416,77 @@ static void engine_hybrid() {
   CHECK(!rs.empty() && rs[0].case_metadata.id == cid(7) && rs[0].match_type == MatchType::Semantic);
 }
 
+// TrieIndex::save_to_disk / load_from_disk (stubs in the reference, src/trie.rs:83-94): the
+// loaded index answers every search like the one that was saved; with a GPU the frozen
+// (flattened, device-resident) form round-trips too and yields the same prefix masks.
+static void trie_disk_round_trip(bool gpu) {
+  TrieIndex t;
+  std::mt19937 rng(7);
+  const char* vocab[] = {"state", "v.", "People", "united", "States", "doe", "Roe", "in", "re", "smith"};
+  std::vector<std::string> names;
+  std::unordered_map<CaseId, std::vector<uint32_t>, CaseIdHash> rows;
+  for (int i = 0; i < 500; ++i) {
+    std::string s;
+    int nt = 1 + rng() % 4;
+    for (int j = 0; j < nt; ++j) s += std::string(j ? " " : "") + vocab[rng() % 10];
+    names.push_back(s);
+    t.insert_case_name(s, cid(i));
+    t.insert_citation(std::to_string(100 + i % 37) + " U.S. " + std::to_string(i), DocRef{cid(i), 1, (size_t)i});
+    t.insert_content({"Equal", vocab[rng() % 10]}, DocRef{cid(i), (size_t)(i % 5), std::nullopt});
+    rows[cid(i)] = {(uint32_t)(2 * i), (uint32_t)(2 * i + 1)};
+  }
+  auto rows_of = [&](const CaseId& c) -> const std::vector<uint32_t>* {
+    auto it = rows.find(c);
+    return it == rows.end() ? nullptr : &it->second;
+  };
+  if (gpu)
+    for (int w = 0; w < 3; ++w) t.freeze((TrieIndex::Which)w, 0, rows_of);
+  char path[] = "/tmp/tss_trie_XXXXXX";
+  int fd = mkstemp(path);
+  CHECK(fd >= 0);
+  if (fd >= 0) close(fd);
+  t.save_to_disk(path);
+  TrieIndex u = TrieIndex::load_from_disk(path, 0);
+  for (int w = 0; w < 3; ++w) {
+    CHECK(u.trie((TrieIndex::Which)w).terms() == t.trie((TrieIndex::Which)w).terms());
+    remove((std::string(path) + "." + std::to_string(w) + ".terms").c_str());
+  }
+  for (const char* q : {"state v.", "People", "100 U.S.", "equal", "equal doe", "nope", ""}) {
+    auto a = t.search(q), b = u.search(q);
+    CHECK(a.exact_matches == b.exact_matches && a.prefix_completions == b.prefix_completions &&
+          a.total_matches == b.total_matches);
+  }
+  if (gpu) {
+    tss_mask *ma = nullptr, *mb = nullptr;
+    CHECK(tss_mask_create(&ma, 1000, 0) == 0 && tss_mask_create(&mb, 1000, 0) == 0);
+    std::vector<uint32_t> wa(32), wb(32);
+    for (int w = 0; w < 3; ++w)
+      for (const char* q : {"state", "state v.", "100 U.S.", "equal", ""}) {
+        t.prefix_mask((TrieIndex::Which)w, q, ma, 0, true);
+        u.prefix_mask((TrieIndex::Which)w, q, mb, 0, true);
+        CHECK(tss_mask_download(ma, wa.data()) == 0 && tss_mask_download(mb, wb.data()) == 0);
+        CHECK(wa == wb);
+      }
+    tss_mask_destroy(ma);
+    tss_mask_destroy(mb);
+  }
+  remove(path);
+  // a foreign file is refused with the error the reference's stub raises
+  bool threw = false;
+  try {
+    TrieIndex::load_from_disk("/proc/self/cmdline");
+  } catch (const SearchError& e) {
+    threw = e.kind == SearchError::NotSupported;
+  }
+  CHECK(threw);
+}
+
 int main(int argc, char** argv) {
   std::string mode = argc > 1 ? argv[1] : "cpu";
   try {
     trie_kats();
     trie_vs_oracle_random();
+    trie_disk_round_trip(mode == "gpu");
     if (mode == "gpu") {
       hnsw_vs_oracle();
       stub_embedding_behaviour();

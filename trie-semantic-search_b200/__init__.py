@@ -43,6 +43,7 @@ ABI_SYMBOLS = [
     "tss_mask_clear_rows", "tss_columns_create", "tss_columns_destroy", "tss_filter_mask",
     "tss_terms_build", "tss_terms_sizes", "tss_terms_export",
     "tss_prefix_mask_fresh", "tss_terms_bind_stream",
+    "tss_terms_build_text", "tss_terms_save", "tss_terms_load",
 ]
 
 
@@ -106,6 +107,9 @@ def lib() -> C.CDLL:
         "tss_prefix_mask": (i32, [vp, C.c_char_p, u32, i32, vp, u64, C.POINTER(PrefixStats)]),
         "tss_prefix_mask_fresh": (i32, [vp, C.c_char_p, u32, i32, vp, u64, C.POINTER(PrefixStats)]),
         "tss_terms_bind_stream": (i32, [vp, vp]),
+        "tss_terms_build_text": (i32, [C.POINTER(vp), vp, vp, vp, u64, i32, u32, i32]),
+        "tss_terms_save": (i32, [vp, C.c_char_p]),
+        "tss_terms_load": (i32, [C.POINTER(vp), C.c_char_p, i32]),
         "tss_index_stream": (vp, [vp]),
         "tss_index_sync": (i32, [vp]),
         "tss_dev_alloc": (i32, [i32, u64, C.POINTER(vp)]),
@@ -360,6 +364,36 @@ class Terms:
         _check(lib().tss_terms_build(C.byref(p), vbuf.ctypes.data, voff.ctypes.data, len(vocab),
                                      ids.ctypes.data if ids.size else None, ids.shape[1],
                                      r.ctypes.data if r.size else None, r.size, device))
+        self.handle, self.device = p.value, device
+        return self
+
+    @classmethod
+    def build_text(cls, phrases: Sequence[bytes], rows, lowercase: bool = True,
+                   max_tokens: int = 16, device: int = 0) -> "Terms":
+        """N2 from raw strings: the device tokenises (ASCII whitespace), lower-cases (optional),
+        dictionary-encodes and builds; phrase i posts rows[i]."""
+        self = cls.__new__(cls)
+        text = b"".join(phrases)
+        off = np.zeros(len(phrases) + 1, dtype=np.uint64)
+        np.cumsum([len(p) for p in phrases], out=off[1:])
+        r = np.ascontiguousarray(rows, dtype=np.uint32)
+        assert r.size == len(phrases)
+        tbuf = np.frombuffer(text, dtype=np.uint8) if text else np.zeros(1, dtype=np.uint8)
+        p = C.c_void_p()
+        _check(lib().tss_terms_build_text(C.byref(p), tbuf.ctypes.data, off.ctypes.data,
+                                          r.ctypes.data if r.size else None, len(phrases),
+                                          1 if lowercase else 0, int(max_tokens), device))
+        self.handle, self.device = p.value, device
+        return self
+
+    def save(self, path: str) -> None:
+        _check(lib().tss_terms_save(self.handle, path.encode()))
+
+    @classmethod
+    def load(cls, path: str, device: int = 0) -> "Terms":
+        p = C.c_void_p()
+        _check(lib().tss_terms_load(C.byref(p), path.encode(), device))
+        self = cls.__new__(cls)
         self.handle, self.device = p.value, device
         return self
 

@@ -1765,6 +1765,205 @@ int tss_terms_build(tss_terms** out, const char* vocab_pool, const uint64_t* voc
   return TSS_OK;
 }
 
+int tss_terms_build_text(tss_terms** out, const char* text, const uint64_t* phrase_off,
+                         const uint32_t* rows, uint64_t n_phrases, int lowercase, uint32_t max_tokens,
+                         int device) {
+  if (!out) return fail(TSS_ERR_INVALID_ARG, "out is NULL");
+  *out = nullptr;
+  if (!phrase_off) return fail(TSS_ERR_INVALID_ARG, "phrase_off is NULL");
+  if (phrase_off[0] != 0) return fail(TSS_ERR_INVALID_ARG, "phrase_off must start at 0");
+  if (n_phrases && !rows) return fail(TSS_ERR_INVALID_ARG, "rows is NULL");
+  if (!max_tokens || max_tokens > 64) return fail(TSS_ERR_INVALID_ARG, "max_tokens must be in [1,64]");
+  for (uint64_t i = 0; i < n_phrases; ++i)
+    if (phrase_off[i + 1] < phrase_off[i])
+      return fail(TSS_ERR_INVALID_ARG, "phrase_off decreases at phrase %llu", (unsigned long long)i);
+  const uint64_t total = phrase_off[n_phrases];
+  if (total && !text) return fail(TSS_ERR_INVALID_ARG, "text is NULL");
+  if (total >= 0x7FFFFFFFull || n_phrases >= 0x7FFFFFFFull || n_phrases * max_tokens >= 0xFFFFFFFFull)
+    return fail(TSS_ERR_INVALID_ARG, "at most 2^31-1 text bytes / phrases (2^32-1 id slots) per build");
+  int ndev = tss_device_count();
+  if (ndev == 0) return fail(TSS_ERR_CUDA, "no CUDA device visible (libtss has no CPU path)");
+  if (device < 0 || device >= ndev) return fail(TSS_ERR_INVALID_ARG, "device %d of %d", device, ndev);
+  DeviceGuard g(device);
+  tss_terms* t = new (std::nothrow) tss_terms();
+  if (!t) return fail(TSS_ERR_OOM, "host allocation failed");
+  t->device = device;
+  t->key_cap = 4096;
+  cudaError_t e = cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking);
+  t->own_stream = t->stream;
+  if (e == cudaSuccess) e = cudaMalloc(&t->d_keys, t->key_cap);
+  if (e == cudaSuccess) e = cudaMallocHost(&t->h_keys, t->key_cap);
+  if (e == cudaSuccess) e = cudaMalloc(&t->d_bounds, 8 * sizeof(uint64_t));
+  tss::BuiltTerms b;
+  uint32_t err_bits = 0, vocab = 0;
+  uint64_t ntok = 0;
+  if (e == cudaSuccess)
+    e = tss::build_terms_from_text(text, phrase_off, rows, n_phrases, lowercase != 0, max_tokens,
+                                   t->stream, &b, &err_bits, &ntok, &vocab);
+  if (e != cudaSuccess) {
+    tss_terms_destroy(t);
+    return cuda_fail(e, "terms build from text");
+  }
+  if (err_bits) {
+    tss_terms_destroy(t);
+    return fail(TSS_ERR_INVALID_ARG, "text rejected:%s%s%s",
+                (err_bits & 1) ? " a control byte below 0x20 that is not whitespace;" : "",
+                (err_bits & 2) ? " a token longer than 128 bytes;" : "",
+                (err_bits & 4) ? " a phrase with more than max_tokens tokens;" : "");
+  }
+  // tokenise + 2 scans, ceil(longest/8) chunk passes, dictionary, then the tuple build
+  g_launches.fetch_add(12 + 2 * max_tokens + 6, std::memory_order_relaxed);
+  t->d_pool = b.d_pool;
+  t->d_term_off = b.d_term_off;
+  t->d_post_off = b.d_post_off;
+  t->d_post_rows = b.d_post_rows;
+  t->nterms = b.nterms;
+  t->pool_bytes = b.pool_bytes;
+  t->nposts = b.nposts;
+  *out = t;
+  return TSS_OK;
+}
+
+// ---- N1, second half: the flattened term array on disk ------------------------------------------
+// TrieIndex::save_to_disk / load_from_disk (reference src/trie.rs:83-94) are a no-op and a
+// NotSupported stub; TrieConfig.index_path (src/config.rs:190) has nowhere to point.  The file is
+// the four arrays exactly as they sit in HBM behind a 64-byte header, so loading is file ->
+// pinned buffer -> HBM with no parsing: [header][term_off (T+1) u64][post_off (T+1) u64]
+// [post_rows P u32][pool bytes], each section padded to 8 bytes.
+namespace {
+struct TermsFileHeader {
+  char magic[8];  // "TSSTRM01"
+  uint64_t nterms, pool_bytes, nposts;
+  uint8_t pad[32];
+};
+static_assert(sizeof(TermsFileHeader) == 64, "header is 64 bytes");
+inline uint64_t pad8(uint64_t n) { return (n + 7) & ~7ull; }
+
+// device -> file / file -> device through one pinned bounce buffer
+bool write_section(FILE* f, void* hbuf, const void* d_src, uint64_t bytes, uint64_t padded) {
+  const uint8_t* src = static_cast<const uint8_t*>(d_src);
+  for (uint64_t off = 0; off < bytes; off += kIoChunk) {
+    size_t n = bytes - off < kIoChunk ? bytes - off : kIoChunk;
+    if (cudaMemcpy(hbuf, src + off, n, cudaMemcpyDeviceToHost) != cudaSuccess) return false;
+    if (fwrite(hbuf, 1, n, f) != n) return false;
+  }
+  const uint8_t zeros[8] = {};
+  return padded == bytes || fwrite(zeros, 1, padded - bytes, f) == padded - bytes;
+}
+bool read_section(FILE* f, void* hbuf, void* d_dst, uint64_t bytes, uint64_t padded) {
+  uint8_t* dst = static_cast<uint8_t*>(d_dst);
+  for (uint64_t off = 0; off < bytes; off += kIoChunk) {
+    size_t n = bytes - off < kIoChunk ? bytes - off : kIoChunk;
+    if (fread(hbuf, 1, n, f) != n) return false;
+    if (cudaMemcpy(dst + off, hbuf, n, cudaMemcpyHostToDevice) != cudaSuccess) return false;
+  }
+  uint8_t skip[8];
+  return padded == bytes || fread(skip, 1, padded - bytes, f) == padded - bytes;
+}
+}  // namespace
+
+int tss_terms_save(const tss_terms* t, const char* path) {
+  if (!t || !path) return fail(TSS_ERR_INVALID_ARG, "NULL argument");
+  DeviceGuard g(t->device);
+  CU(cudaStreamSynchronize(t->stream));
+  FILE* f = fopen(path, "wb");
+  if (!f) return fail(TSS_ERR_INVALID_ARG, "cannot open %s for writing", path);
+  TermsFileHeader h{};
+  memcpy(h.magic, "TSSTRM01", 8);
+  h.nterms = t->nterms;
+  h.pool_bytes = t->pool_bytes;
+  h.nposts = t->nposts;
+  bool ok = fwrite(&h, sizeof(h), 1, f) == 1;
+  void* hbuf = nullptr;
+  if (ok && cudaMallocHost(&hbuf, kIoChunk) != cudaSuccess) ok = false;
+  const uint64_t ob = (t->nterms + 1) * 8;
+  ok = ok && write_section(f, hbuf, t->d_term_off, ob, ob);
+  ok = ok && write_section(f, hbuf, t->d_post_off, ob, ob);
+  ok = ok && write_section(f, hbuf, t->d_post_rows, t->nposts * 4, pad8(t->nposts * 4));
+  ok = ok && write_section(f, hbuf, t->d_pool, t->pool_bytes, pad8(t->pool_bytes));
+  if (hbuf) cudaFreeHost(hbuf);
+  ok = (fclose(f) == 0) && ok;
+  if (!ok) return fail(TSS_ERR_STATE, "writing %s failed", path);
+  return TSS_OK;
+}
+
+int tss_terms_load(tss_terms** out, const char* path, int device) {
+  if (!out || !path) return fail(TSS_ERR_INVALID_ARG, "NULL argument");
+  *out = nullptr;
+  int ndev = tss_device_count();
+  if (ndev == 0) return fail(TSS_ERR_CUDA, "no CUDA device visible (libtss has no CPU path)");
+  if (device < 0 || device >= ndev) return fail(TSS_ERR_INVALID_ARG, "device %d of %d", device, ndev);
+  FILE* f = fopen(path, "rb");
+  if (!f) return fail(TSS_ERR_INVALID_ARG, "cannot open %s", path);
+  TermsFileHeader h{};
+  if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, "TSSTRM01", 8) != 0) {
+    fclose(f);
+    return fail(TSS_ERR_INVALID_ARG, "%s is not a TSSTRM01 file", path);
+  }
+  // the sizes must add up to the file before anything is allocated from them
+  const uint64_t ob = (h.nterms + 1) * 8;
+  const uint64_t want = 64 + 2 * ob + pad8(h.nposts * 4) + pad8(h.pool_bytes);
+  bool sane = h.nterms < (1ull << 40) && h.nposts < (1ull << 40) && h.pool_bytes < (1ull << 44) &&
+              fseek(f, 0, SEEK_END) == 0 && (uint64_t)ftell(f) == want &&
+              fseek(f, 64, SEEK_SET) == 0;
+  if (!sane) {
+    fclose(f);
+    return fail(TSS_ERR_INVALID_ARG, "%s: header and file size disagree (truncated or corrupt)", path);
+  }
+  DeviceGuard g(device);
+  tss_terms* t = new (std::nothrow) tss_terms();
+  if (!t) {
+    fclose(f);
+    return fail(TSS_ERR_OOM, "host allocation failed");
+  }
+  t->device = device;
+  t->nterms = h.nterms;
+  t->pool_bytes = h.pool_bytes;
+  t->nposts = h.nposts;
+  t->key_cap = 4096;
+  cudaError_t e = cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking);
+  t->own_stream = t->stream;
+  void* hbuf = nullptr;
+  if (e == cudaSuccess) e = cudaMalloc(&t->d_pool, h.pool_bytes + 16);
+  if (e == cudaSuccess) e = cudaMalloc(&t->d_term_off, ob);
+  if (e == cudaSuccess) e = cudaMalloc(&t->d_post_off, ob);
+  if (e == cudaSuccess) e = cudaMalloc(&t->d_post_rows, (h.nposts + 1) * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&t->d_keys, t->key_cap);
+  if (e == cudaSuccess) e = cudaMallocHost(&t->h_keys, t->key_cap);
+  if (e == cudaSuccess) e = cudaMalloc(&t->d_bounds, 8 * sizeof(uint64_t));
+  if (e == cudaSuccess) e = cudaMallocHost(&hbuf, kIoChunk);
+  if (e != cudaSuccess) {
+    fclose(f);
+    if (hbuf) cudaFreeHost(hbuf);
+    tss_terms_destroy(t);
+    return cuda_fail(e, "terms load allocation");
+  }
+  bool ok = read_section(f, hbuf, t->d_term_off, ob, ob) && read_section(f, hbuf, t->d_post_off, ob, ob) &&
+            read_section(f, hbuf, t->d_post_rows, h.nposts * 4, pad8(h.nposts * 4)) &&
+            read_section(f, hbuf, t->d_pool, h.pool_bytes, pad8(h.pool_bytes));
+  cudaFreeHost(hbuf);
+  fclose(f);
+  // what tss_terms_create validates on the host is validated here on the device: offsets
+  // monotone and closing on the header's totals, terms strictly byte-sorted
+  unsigned int bad = 1;
+  if (ok) {
+    unsigned int* d_bad = reinterpret_cast<unsigned int*>(t->d_bounds);
+    ok = cudaMemsetAsync(d_bad, 0, sizeof(unsigned int), t->stream) == cudaSuccess;
+    tss::TermsDev td{t->d_pool, t->d_term_off, t->d_post_off, t->d_post_rows, t->nterms};
+    ok = ok && tss::launch_terms_validate(td, h.pool_bytes, h.nposts, d_bad, t->stream) == cudaSuccess;
+    ok = ok && cudaMemcpyAsync(&bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost, t->stream) == cudaSuccess;
+    ok = ok && cudaStreamSynchronize(t->stream) == cudaSuccess;
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+  }
+  if (!ok || bad) {
+    tss_terms_destroy(t);
+    return fail(TSS_ERR_INVALID_ARG, "%s: %s", path,
+                ok ? "offsets not monotone or terms not strictly byte-sorted" : "read failed");
+  }
+  *out = t;
+  return TSS_OK;
+}
+
 int tss_terms_sizes(const tss_terms* t, uint64_t* nterms, uint64_t* pool_bytes, uint64_t* npostings) {
   if (!t) return fail(TSS_ERR_INVALID_ARG, "terms is NULL");
   if (nterms) *nterms = t->nterms;

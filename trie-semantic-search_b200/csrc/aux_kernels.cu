@@ -323,6 +323,39 @@ cudaError_t launch_prefix_scatter(const TermsDev& t, const uint64_t* d_bounds, u
   return cudaGetLastError();
 }
 
+__global__ void terms_validate_kernel(TermsDev t, uint64_t pool_bytes, uint64_t nposts,
+                                      unsigned int* bad) {
+  const uint64_t tid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (tid == 0) {
+    if (t.term_off[0] != 0 || t.post_off[0] != 0 || t.term_off[t.nterms] != pool_bytes ||
+        t.post_off[t.nterms] != nposts)
+      atomicOr(bad, 1u);
+  }
+  for (uint64_t i = tid; i < t.nterms; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t b = t.term_off[i], e = t.term_off[i + 1];
+    bool ok = e >= b && e <= pool_bytes && t.post_off[i + 1] >= t.post_off[i] &&
+              t.post_off[i + 1] <= nposts;
+    if (ok && i) {  // term[i-1] < term[i]
+      const uint64_t pb = t.term_off[i - 1];
+      ok = pb <= b;
+      if (ok) {
+        const uint64_t la = b - pb, lb = e - b, n = la < lb ? la : lb;
+        const unsigned char* pa = reinterpret_cast<const unsigned char*>(t.pool) + pb;
+        const unsigned char* pc = reinterpret_cast<const unsigned char*>(t.pool) + b;
+        int c = 0;
+        for (uint64_t j = 0; j < n && !c; ++j) c = (int)pa[j] - (int)pc[j];
+        ok = c < 0 || (c == 0 && la < lb);
+      }
+    }
+    if (!ok) atomicOr(bad, 1u);
+  }
+}
+cudaError_t launch_terms_validate(const TermsDev& t, uint64_t pool_bytes, uint64_t nposts,
+                                  unsigned int* d_bad, cudaStream_t st) {
+  terms_validate_kernel<<<148 * 4, 256, 0, st>>>(t, pool_bytes, nposts, d_bad);
+  return cudaGetLastError();
+}
+
 // ---- K5: merge of all-gathered per-rank top-k lists ---------------------------------------
 // one warp per query: stage the P sorted lists of k keys in shared memory, then a warp
 // tournament (scan.cuh) picks the k best.  in [P][nq][k] -> out [nq][k].

@@ -64,6 +64,11 @@ cudaError_t launch_prefix_scatter(const TermsDev& t, const uint64_t* d_bounds, u
                                   uint64_t nbits, uint64_t row_base, unsigned long long* d_npost,
                                   int grid, cudaStream_t st);
 
+// *bad |= 1 unless: offsets start at 0, are monotone and end on pool_bytes / nposts, and the terms
+// are strictly increasing in byte order (what the prefix search relies on).  For loaded files.
+cudaError_t launch_terms_validate(const TermsDev& t, uint64_t pool_bytes, uint64_t nposts,
+                                  unsigned int* d_bad, cudaStream_t st);
+
 // K5: merge P gathered lists of k keys per query: in [P][nq][k] -> out [nq][k]
 cudaError_t launch_merge_gathered(const uint64_t* in, uint64_t* out, uint32_t P, uint32_t nq,
                                   uint32_t k, cudaStream_t st);

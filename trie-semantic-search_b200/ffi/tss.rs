@@ -101,6 +101,12 @@ extern "C" {
         row_base: u64, stats: *mut tss_prefix_stats,
     ) -> c_int;
     pub fn tss_terms_bind_stream(t: *mut tss_terms, ix: *mut tss_index) -> c_int;
+    pub fn tss_terms_build_text(
+        out: *mut *mut tss_terms, text: *const c_char, phrase_off: *const u64, rows: *const u32,
+        n_phrases: u64, lowercase: c_int, max_tokens: u32, device: c_int,
+    ) -> c_int;
+    pub fn tss_terms_save(t: *const tss_terms, path: *const c_char) -> c_int;
+    pub fn tss_terms_load(out: *mut *mut tss_terms, path: *const c_char, device: c_int) -> c_int;
 
     pub fn tss_terms_build(
         out: *mut *mut tss_terms, vocab_pool: *const c_char, vocab_off: *const u64, vocab_size: u32,

@@ -393,10 +393,105 @@ TrieSearchResult TrieIndex::search(const std::string& query) const {
 std::vector<std::string> TrieIndex::get_completions(const std::string&, size_t) const {
   return {};  // TODO in the reference too, :133-136
 }
-TrieIndex TrieIndex::load_from_disk(const std::string&) {
-  throw SearchError(SearchError::NotSupported, "Loading trie from disk");  // :85-87
+TrieIndex::TrieIndex(TrieIndex&& o) noexcept
+    : config_(std::move(o.config_)),
+      tries_{std::move(o.tries_[0]), std::move(o.tries_[1]), std::move(o.tries_[2])} {
+  for (int w = 0; w < 3; ++w) frozen_[w] = o.frozen_[w], o.frozen_[w] = nullptr;
 }
-void TrieIndex::save_to_disk(const std::string&) const {}  // :91-94
+TrieIndex& TrieIndex::operator=(TrieIndex&& o) noexcept {
+  if (this != &o) {
+    for (auto* t : frozen_) tss_terms_destroy(t);
+    config_ = std::move(o.config_);
+    for (int w = 0; w < 3; ++w) {
+      tries_[w] = std::move(o.tries_[w]);
+      frozen_[w] = o.frozen_[w];
+      o.frozen_[w] = nullptr;
+    }
+  }
+  return *this;
+}
+
+namespace {
+constexpr char kTrieMagic[8] = {'T', 'S', 'S', 'T', 'R', 'I', 'E', '1'};
+struct FileCloser {
+  void operator()(FILE* f) const {
+    if (f) fclose(f);
+  }
+};
+template <class T>
+bool put(FILE* f, const T& v) { return fwrite(&v, sizeof(T), 1, f) == 1; }
+template <class T>
+bool get(FILE* f, T& v) { return fread(&v, sizeof(T), 1, f) == 1; }
+std::string frozen_path(const std::string& path, int w) { return path + "." + std::to_string(w) + ".terms"; }
+}  // namespace
+
+void TrieIndex::save_to_disk(const std::string& path) const {
+  std::unique_ptr<FILE, FileCloser> f(fopen(path.c_str(), "wb"));
+  if (!f) throw SearchError(SearchError::NotSupported, "Saving trie to disk: cannot open " + path);
+  bool ok = fwrite(kTrieMagic, 8, 1, f.get()) == 1;
+  for (int w = 0; w < 3 && ok; ++w) {
+    ok = put<uint8_t>(f.get(), frozen_[w] ? 1 : 0) && put<uint64_t>(f.get(), tries_[w].terms().size());
+    for (const auto& kv : tries_[w].terms()) {
+      ok = ok && put<uint32_t>(f.get(), (uint32_t)kv.first.size()) &&
+           (kv.first.empty() || fwrite(kv.first.data(), kv.first.size(), 1, f.get()) == 1) &&
+           put<uint64_t>(f.get(), kv.second.size());
+      for (const DocRef& d : kv.second) {
+        const int64_t off = d.char_offset ? (int64_t)*d.char_offset : -1;
+        ok = ok && fwrite(d.case_id.bytes.data(), 16, 1, f.get()) == 1 &&
+             put<uint64_t>(f.get(), d.paragraph_index) && put<int64_t>(f.get(), off);
+      }
+      if (!ok) break;
+    }
+  }
+  if (!ok) throw SearchError(SearchError::NotSupported, "Saving trie to disk: write to " + path + " failed");
+  for (int w = 0; w < 3; ++w) {
+    if (!frozen_[w]) continue;
+    int rc = tss_terms_save(frozen_[w], frozen_path(path, w).c_str());
+    if (rc) raise_tss(SearchError::VectorIndexFailed, "TrieIndex::save_to_disk", rc);
+  }
+}
+
+TrieIndex TrieIndex::load_from_disk(const std::string& path, int device) {
+  std::unique_ptr<FILE, FileCloser> f(fopen(path.c_str(), "rb"));
+  char magic[8];
+  if (!f || fread(magic, 8, 1, f.get()) != 1 || memcmp(magic, kTrieMagic, 8) != 0)
+    throw SearchError(SearchError::NotSupported, "Loading trie from disk: " + path + " is not a saved TrieIndex");
+  TrieIndex t;
+  bool had_frozen[3] = {false, false, false};
+  for (int w = 0; w < 3; ++w) {
+    uint8_t fr = 0;
+    uint64_t nterms = 0;
+    bool ok = get(f.get(), fr) && get(f.get(), nterms);
+    had_frozen[w] = fr != 0;
+    auto& terms = t.tries_[w].mutable_terms();
+    for (uint64_t i = 0; ok && i < nterms; ++i) {
+      uint32_t len = 0;
+      uint64_t nposts = 0;
+      ok = get(f.get(), len) && len < (1u << 24);
+      std::string term(len, '\0');
+      ok = ok && (len == 0 || fread(&term[0], len, 1, f.get()) == 1) && get(f.get(), nposts) &&
+           nposts < (1ull << 40);
+      std::vector<DocRef> posts;
+      for (uint64_t j = 0; ok && j < nposts; ++j) {
+        DocRef d;
+        uint64_t para = 0;
+        int64_t off = -1;
+        ok = fread(d.case_id.bytes.data(), 16, 1, f.get()) == 1 && get(f.get(), para) && get(f.get(), off);
+        d.paragraph_index = (size_t)para;
+        if (off >= 0) d.char_offset = (size_t)off;
+        posts.push_back(d);
+      }
+      if (ok) terms.emplace_hint(terms.end(), std::move(term), std::move(posts));
+    }
+    if (!ok) throw SearchError(SearchError::NotSupported, "Loading trie from disk: " + path + " is truncated");
+  }
+  for (int w = 0; w < 3; ++w) {
+    if (!had_frozen[w]) continue;
+    int rc = tss_terms_load(&t.frozen_[w], frozen_path(path, w).c_str(), device);
+    if (rc) raise_tss(SearchError::VectorIndexFailed, "TrieIndex::load_from_disk", rc);
+  }
+  return t;
+}
 
 void TrieIndex::freeze(Which w, int device, const RowsOf& rows_of) {
   std::string pool;

@@ -247,6 +247,7 @@ class TokenTrie {
   size_t num_terms() const { return terms_.size(); }
   uint32_t frequency(const std::vector<std::string>& tokens) const;  // :56,220
   const std::map<std::string, std::vector<DocRef>>& terms() const { return terms_; }
+  std::map<std::string, std::vector<DocRef>>& mutable_terms() { return terms_; }  // load_from_disk
 
  private:
   std::string normalise_join(const std::vector<std::string>& tokens) const;
@@ -259,14 +260,22 @@ class TrieIndex {
   enum Which { CaseName = 0, Content = 1, Citation = 2 };
   explicit TrieIndex(const TrieConfig& config = TrieConfig());
   ~TrieIndex();
+  TrieIndex(TrieIndex&& o) noexcept;
+  TrieIndex& operator=(TrieIndex&& o) noexcept;
+  TrieIndex(const TrieIndex&) = delete;
+  TrieIndex& operator=(const TrieIndex&) = delete;
   void insert_case_name(const std::string& case_name, const CaseId& case_id);      // :97-99,146-155
   void insert_content(const std::vector<std::string>& tokens, const DocRef& ref);  // :102-104
   void insert_citation(const std::string& citation, const DocRef& ref);            // :107-109
   TrieSearchResult search(const std::string& query) const;  // cascade :112-130
   TrieSearchResult search_one(Which w, const std::string& query) const;
   std::vector<std::string> get_completions(const std::string& prefix, size_t limit) const;  // :133-136
-  static TrieIndex load_from_disk(const std::string& path);  // -> NotSupported, :83-88
-  void save_to_disk(const std::string& path) const;          // no-op, :91-94
+  // The reference's pair is a NotSupported stub and a no-op (:83-94).  Here `path` holds the
+  // three tries (terms + DocRef postings) and, for every frozen trie, `path.<w>.terms` holds its
+  // flattened device form (tss_terms_save); loading restores both without a re-freeze.  A
+  // missing or foreign file raises NotSupported, the error the stub always raised.
+  static TrieIndex load_from_disk(const std::string& path, int device = 0);
+  void save_to_disk(const std::string& path) const;
 
   // --- device side (K4) ---
   // export trie `w` as a flattened term array on `device`; postings become the rows
