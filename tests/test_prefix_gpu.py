@@ -259,3 +259,78 @@ def test_prefix_then_masked_search_is_ordered(tss, orc):
             want = orc.cosine_topk(rows, q[i], k, mask_words=w, mask_mode=orc.MASK_INCLUDE)
             assert np.array_equal(got[0], want[0]) and np.array_equal(got[2], want[2]), (bound, i)
     t.bind_stream(None)
+
+
+def test_list_driven_scan_and_its_invalidation(tss, orc):
+    """tss_prefix_mask_fresh also leaves the list of its unique rows; the masked scan then fetches
+    exactly those rows.  Whatever path runs -- list, mask walk after the list overflowed, mask walk
+    after another call edited the mask -- the result equals the oracle under the numpy mask."""
+    rng = np.random.default_rng(21)
+    n, dim, k = 200_000, 384, 10
+    rows = orc.gen_rows(0, n, dim, 0x5EED)
+    ix = tss.FlatIndex(dim)
+    ix.add_synthetic(0, n, 0x5EED)
+    ix.finalize()
+    sizes = [1, 7, 8, 9, 100, 5_000, 16_384, 16_385, 40_000]   # postings; the list holds 16 384
+    terms = [b"p%02d" % i for i in range(len(sizes))]
+    posts = [[int(r) for r in rng.integers(0, n, size=s)] for s in sizes]  # duplicates included
+    t = tss.Terms(terms, posts)
+    t.bind_stream(ix)
+    m = tss.Mask(n)
+    q = orc.gen_rows(0, 4, dim, 0xBEEF)
+
+    def words(rs):
+        w = np.zeros((n + 31) // 32, dtype=np.uint32)
+        idx = np.asarray(sorted(set(rs)), dtype=np.int64)
+        if idx.size:
+            np.bitwise_or.at(w, idx >> 5, np.uint32(1) << (idx & 31).astype(np.uint32))
+        return w
+
+    def check(w, tag):
+        got = ix.search(q, k, m, tss.TSS_MASK_INCLUDE)
+        want = orc.cosine_topk(rows, q, k, mask_words=w, mask_mode=orc.MASK_INCLUDE)
+        assert np.array_equal(got[0], want[0]) and np.array_equal(got[2], want[2]), tag
+        assert np.array_equal(got[1].view(np.uint32), want[1].view(np.uint32)), tag
+        assert np.array_equal(m.download(), w), tag
+
+    for term, ps in zip(terms, posts):
+        t.prefix_mask(term, m, want_stats=False, fresh=True)
+        check(words(ps), term)
+        # an edit after the scatter: the list no longer describes the mask
+        extra = [int(r) for r in rng.integers(0, n, size=5)]
+        m.set_rows(np.asarray(extra, dtype=np.uint32))
+        check(words(ps + extra), (term, "set_rows"))
+        m.clear_rows(np.asarray(ps[:1], dtype=np.uint32))
+        check(words([r for r in ps + extra if r != ps[0]]), (term, "clear_rows"))
+        # OR-ing a second prefix into the mask
+        t.prefix_mask(term, m, want_stats=False, fresh=True)
+        t.prefix_mask(terms[2], m, want_stats=False)
+        check(words(ps + posts[2]), (term, "or"))
+    # the root prefix: every posting
+    t.prefix_mask(b"", m, want_stats=False, fresh=True)
+    check(words([r for ps in posts for r in ps]), "root")
+    # EXCLUDE never uses the list
+    t.prefix_mask(terms[4], m, want_stats=False, fresh=True)
+    got = ix.search(q, k, m, tss.TSS_MASK_EXCLUDE)
+    want = orc.cosine_topk(rows, q, k, mask_words=words(posts[4]), mask_mode=orc.MASK_EXCLUDE)
+    assert np.array_equal(got[0], want[0])
+    # bf16 storage and a shard offset
+    ixb = tss.FlatIndex(dim, tss.TSS_BF16)
+    ixb.add_synthetic(50_000, 100_000, 0x5EED)
+    ixb.set_shard(50_000, None)
+    ixb.finalize()
+    t.bind_stream(ixb)
+    mb = tss.Mask(100_000)
+    for term, ps in zip(terms[3:7], posts[3:7]):
+        t.prefix_mask(term, mb, want_stats=False, fresh=True, row_base=50_000)
+        local = [r - 50_000 for r in ps if 50_000 <= r < 150_000]
+        w = np.zeros((100_000 + 31) // 32, dtype=np.uint32)
+        idx = np.asarray(sorted(set(local)), dtype=np.int64)
+        if idx.size:
+            np.bitwise_or.at(w, idx >> 5, np.uint32(1) << (idx & 31).astype(np.uint32))
+        got = ixb.search(q, k, mb, tss.TSS_MASK_INCLUDE)
+        want = orc.cosine_topk(rows[50_000:150_000], q, k, mask_words=w, mask_mode=orc.MASK_INCLUDE,
+                               row_base=50_000, bf16=True)
+        assert np.array_equal(got[0], want[0]) and np.array_equal(got[2], want[2]), term
+        assert np.array_equal(got[1].view(np.uint32), want[1].view(np.uint32)), term
+    t.bind_stream(None)

@@ -91,6 +91,7 @@ constexpr size_t kStageBytes = 64u << 20;  // upload staging buffer
 constexpr uint32_t kGemmCandCap = 32768;   // K2 survivor keys per query of a FULL workspace batch:
                                            // the pool (kWsQueries x this) is shared out per batch
 constexpr uint32_t kGemmMaxSample = 8192;  // tiles sampled by the K2 threshold pass
+constexpr uint32_t kMaskListCap = 16384;   // rows a prefix scatter may list for the list-driven scan
 constexpr uint32_t kPrefilterMaxNq = 2;    // queries per call the shadow prefilter takes (K2 beyond)
 
 typedef CUresult (*TmapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -152,6 +153,12 @@ struct tss_mask {
   };
   std::vector<Reader> readers;     // reads enqueued since that write, one entry per stream
   std::vector<cudaEvent_t> spare;  // recycled reader events
+  // Row list of the last tss_prefix_mask_fresh (see ScanParams::row_list): valid on the host
+  // side while nothing else has touched the mask since; the device-side count says whether the
+  // scatter actually produced one (few enough postings).
+  uint32_t* d_list = nullptr;        // [kMaskListCap] unique local rows
+  uint32_t* d_list_count = nullptr;
+  bool list_valid = false;
 };
 
 struct tss_columns {
@@ -172,7 +179,8 @@ struct tss_terms {
   uint32_t* d_post_rows = nullptr;
   char* d_keys = nullptr;     // probe key bytes
   char* h_keys = nullptr;     // pinned
-  uint64_t* d_bounds = nullptr;  // 4 bounds + npostings
+  uint64_t* d_bounds = nullptr;  // 4 bounds + npostings, then two u32 grid-barrier words at [6]
+  int num_sms = 0;
   uint32_t key_cap = 0;
   cudaStream_t stream = nullptr;      // the stream prefix searches are enqueued on
   cudaStream_t own_stream = nullptr;  // (stream == own_stream unless bound to an index's)
@@ -287,6 +295,7 @@ struct DeviceGuard {
 // ---- mask ordering (see struct tss_mask) ----------------------------------------------------
 cudaError_t mask_begin_write(tss_mask* m, cudaStream_t s) {
   std::lock_guard<std::mutex> lk(m->mu);
+  m->list_valid = false;  // (tss_prefix_mask_fresh sets it again after its enqueue)
   cudaError_t e = cudaSuccess;
   if (m->has_write && m->wstream != s) e = cudaStreamWaitEvent(s, m->wev, 0);
   for (auto& r : m->readers) {
@@ -404,6 +413,11 @@ int enqueue_scan(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
     p.cap = cap;
     p.mask = mode != TSS_MASK_NONE ? mask->d_words : nullptr;
     p.mask_mode = mode;
+    if (mode == TSS_MASK_INCLUDE && mask->list_valid && mask->d_list) {
+      p.row_list = mask->d_list;
+      p.row_list_count = mask->d_list_count;
+      p.row_list_cap = kMaskListCap;
+    }
     const uint32_t no = ++ix->launch_no;  // 1, 2, ...
     const uint32_t slot = no % kScanSlots;
     p.partials = ix->d_partials + (size_t)slot * kMaxBq * ix->num_sms * 128;
@@ -1447,6 +1461,8 @@ int tss_mask_create(tss_mask** out, uint64_t nbits, int device) {
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->wev, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaMalloc(&m->d_words, (size_t)(m->nwords + 1) * sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaMalloc(&m->d_scratch, sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMalloc(&m->d_list, (size_t)kMaskListCap * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&m->d_list_count, sizeof(uint32_t));
   if (e == cudaSuccess)
     e = cudaMemsetAsync(m->d_words, 0, (size_t)(m->nwords + 1) * sizeof(uint32_t), m->stream);
   if (e == cudaSuccess) e = mask_end_write(m, m->stream);
@@ -1471,6 +1487,8 @@ void tss_mask_destroy(tss_mask* m) {
   if (m->stream) cudaStreamSynchronize(m->stream);
   cudaFree(m->d_words);
   cudaFree(m->d_scratch);
+  cudaFree(m->d_list);
+  cudaFree(m->d_list_count);
   if (m->wev) cudaEventDestroy(m->wev);
   if (m->stream) cudaStreamDestroy(m->stream);
   delete m;
@@ -2074,17 +2092,32 @@ int prefix_mask_impl(tss_terms* t, const char* prefix, uint32_t len, int kind, t
     d_keybytes = t->d_keys;
   }
   CU(mask_begin_write(out, st));
-  tss::TermsDev td{t->d_pool, t->d_term_off, t->d_post_off, t->d_post_rows, t->nterms};
-  cudaError_t e = tss::launch_prefix_search(td, d_keybytes, keys, t->d_bounds,
-                                            clear_first ? out->d_words : nullptr, out->nwords + 1, st);
-  if (e != cudaSuccess) return cuda_fail(e, "prefix_search launch");
-  e = tss::launch_prefix_scatter(td, t->d_bounds, out->d_words, out->nbits, row_base,
-                                 reinterpret_cast<unsigned long long*>(t->d_bounds + 4), 148 * 4, st);
-  if (e != cudaSuccess) return cuda_fail(e, "prefix_scatter launch");
-  g_launches.fetch_add(2, std::memory_order_relaxed);
+  if (!t->num_sms) {
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, t->device));
+    t->num_sms = prop.multiProcessorCount;
+    CU(cudaMemsetAsync(t->d_bounds, 0, 8 * sizeof(uint64_t), st));  // incl. the barrier words
+  }
+  tss::PrefixMaskArgs pa{};
+  pa.t = tss::TermsDev{t->d_pool, t->d_term_off, t->d_post_off, t->d_post_rows, t->nterms};
+  pa.d_keybytes = d_keybytes;
+  pa.bounds = t->d_bounds;
+  pa.words = out->d_words;
+  pa.clear_nwords = clear_first ? out->nwords + 1 : 0;
+  pa.nbits = out->nbits;
+  pa.row_base = row_base;
+  // only a scatter into a freshly cleared mask knows the mask's complete row set
+  pa.list = clear_first ? out->d_list : nullptr;
+  pa.list_count = clear_first ? out->d_list_count : nullptr;
+  pa.list_cap = kMaskListCap;
+  pa.sync = reinterpret_cast<unsigned int*>(t->d_bounds + 6);
+  cudaError_t e = tss::launch_prefix_mask(pa, keys, t->num_sms, st);
+  if (e != cudaSuccess) return cuda_fail(e, "prefix_mask_kernel launch");
+  g_launches.fetch_add(1, std::memory_order_relaxed);
   // consumers on other streams are ordered behind the scatter by the mask's write event:
   // no host synchronisation unless the caller wants the statistics
   CU(mask_end_write(out, st));
+  out->list_valid = clear_first;
   if (stats) {
     uint64_t h[5];
     CU(cudaMemcpyAsync(h, t->d_bounds, sizeof(h), cudaMemcpyDeviceToHost, st));

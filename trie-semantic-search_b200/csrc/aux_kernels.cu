@@ -239,87 +239,128 @@ __device__ __forceinline__ bool term_less(const TermsDev& t, uint64_t i, const c
   return tlen < klen;
 }
 
-// warp-cooperative 32-ary lower bound: first i in [0,T) with term[i] >= key.
-// Invariant: every term < lo is < key, every term >= hi is >= key.
-__device__ uint64_t warp_lower_bound(const TermsDev& t, const char* key, uint32_t klen, int lane) {
+// ---- K4 fused: search + clear, grid barrier, scatter (+ unique-row list) -----------------------
+// 256-ary cooperative lower bound: every round each thread probes one pivot and the CTA counts
+// the pivots below the key (the predicate is monotone over sorted terms): ceil(log256 T) rounds
+// of two dependent loads instead of log2 T.
+__device__ uint64_t cta_lower_bound(const TermsDev& t, const char* key, uint32_t klen) {
   uint64_t lo = 0, hi = t.nterms;
-  while (hi - lo > 32) {
-    uint64_t step = (hi - lo + 31) / 32;
-    uint64_t pv = lo + (uint64_t)lane * step;
-    bool less = pv < hi && term_less(t, pv, key, klen);
-    unsigned m = __ballot_sync(FULL_MASK, less);
-    int c = __popc(m);  // sorted terms -> the predicate is monotone over lanes
+  const uint32_t nt = blockDim.x;
+  while (hi - lo > nt) {
+    const uint64_t step = (hi - lo + nt - 1) / nt;
+    const uint64_t pv = lo + (uint64_t)threadIdx.x * step;
+    const bool less = pv < hi && term_less(t, pv, key, klen);
+    const int c = __syncthreads_count(less);
     if (c == 0) return lo;
-    uint64_t nlo = lo + (uint64_t)(c - 1) * step + 1;
+    const uint64_t nlo = lo + (uint64_t)(c - 1) * step + 1;
     uint64_t nhi = lo + (uint64_t)c * step;
     if (nhi > hi) nhi = hi;
     lo = nlo;
     hi = nhi;
   }
-  uint64_t pv = lo + lane;
-  bool less = pv < hi && term_less(t, pv, key, klen);
-  return lo + __popc(__ballot_sync(FULL_MASK, less));
+  const uint64_t pv = lo + threadIdx.x;
+  const bool less = pv < hi && term_less(t, pv, key, klen);
+  return lo + (uint64_t)__syncthreads_count(less);
 }
 
-__global__ void prefix_search_kernel(TermsDev t, const char* keybytes_dev,
-                                     const __grid_constant__ PrefixKeys keys, uint64_t* bounds,
-                                     uint32_t* clear_words, uint64_t clear_nwords) {
-  if (blockIdx.x != 0) {  // the other CTAs clear the output mask while CTA 0 searches
-    const uint64_t tid = (uint64_t)(blockIdx.x - 1) * blockDim.x + threadIdx.x;
-    const uint64_t nth = (uint64_t)(gridDim.x - 1) * blockDim.x;
-    uint4* w4 = reinterpret_cast<uint4*>(clear_words);  // cudaMalloc'ed: 256-byte aligned
-    const uint64_t n4 = clear_nwords >> 2;
+constexpr int kPrefixThreads = 256;
+__global__ void __launch_bounds__(kPrefixThreads)
+prefix_mask_kernel(const PrefixMaskArgs a, const __grid_constant__ PrefixKeys keys) {
+  const uint32_t G = gridDim.x;
+  // ---- phase A: bounds (CTAs 0..3) | clear (the rest) ----
+  if (blockIdx.x < 4) {
+    const int b = blockIdx.x;
+    const char* kb = a.d_keybytes ? a.d_keybytes : keys.bytes;
+    uint64_t r;
+    if (keys.fixed[b] >= 0) r = (uint64_t)keys.fixed[b];
+    else if (keys.fixed[b] == -2) r = a.t.nterms;
+    else r = cta_lower_bound(a.t, kb + keys.off[b], keys.off[b + 1] - keys.off[b]);
+    if (threadIdx.x == 0) {
+      a.bounds[b] = r;
+      if (b == 0 && a.list_count) *a.list_count = 0u;
+    }
+  }
+  if (a.clear_nwords) {
+    // every CTA clears a share (search CTAs after their search: they are a small minority and
+    // the barrier below waits for them anyway)
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t nth = (uint64_t)G * blockDim.x;
+    uint4* w4 = reinterpret_cast<uint4*>(a.words);  // cudaMalloc'ed: 256-byte aligned
+    const uint64_t n4 = a.clear_nwords >> 2;
     for (uint64_t i = tid; i < n4; i += nth) w4[i] = make_uint4(0u, 0u, 0u, 0u);
-    for (uint64_t i = (n4 << 2) + tid; i < clear_nwords; i += nth) clear_words[i] = 0u;
-    return;
+    for (uint64_t i = (n4 << 2) + tid; i < a.clear_nwords; i += nth) a.words[i] = 0u;
   }
-  const char* keybytes = keybytes_dev ? keybytes_dev : keys.bytes;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;  // 4 warps, one bound each
-  uint64_t r;
-  if (keys.fixed[warp] >= 0)
-    r = (uint64_t)keys.fixed[warp];
-  else if (keys.fixed[warp] == -2)
-    r = t.nterms;
-  else
-    r = warp_lower_bound(t, keybytes + keys.off[warp], keys.off[warp + 1] - keys.off[warp], lane);
-  if (lane == 0) bounds[warp] = r;
-}
-cudaError_t launch_prefix_search(const TermsDev& t, const char* d_keybytes, const PrefixKeys& keys,
-                                 uint64_t* d_bounds, uint32_t* clear_words, uint64_t clear_nwords,
-                                 cudaStream_t st) {
-  unsigned grid = 1;
-  if (clear_words && clear_nwords) {
-    // 128 threads x one 16-byte store per trip; at most two CTAs' worth per SM
-    const uint64_t want = (clear_nwords / 4 + 127) / 128;
-    grid += (unsigned)(want < 295 ? (want ? want : 1) : 295);
+  // ---- grid barrier (all G <= #SMs CTAs are co-resident; the words are left zeroed) ----
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    atomicAdd(&a.sync[0], 1u);
+    while (*reinterpret_cast<volatile unsigned int*>(&a.sync[0]) < G) __nanosleep(20);
+    __threadfence();
+    if (atomicAdd(&a.sync[1], 1u) == G - 1) {  // last one through: reset for the next launch
+      a.sync[1] = 0u;
+      __threadfence();
+      a.sync[0] = 0u;
+    }
   }
-  prefix_search_kernel<<<grid, 128, 0, st>>>(t, d_keybytes, keys, d_bounds, clear_words, clear_nwords);
-  return cudaGetLastError();
-}
-
-__global__ void prefix_scatter_kernel(TermsDev t, const uint64_t* bounds, uint32_t* words,
-                                      uint64_t nbits, uint64_t row_base,
-                                      unsigned long long* npost) {
-  const uint64_t tid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  const uint64_t nth = (uint64_t)gridDim.x * blockDim.x;
-  uint64_t visited = 0;
+  __syncthreads();
+  // ---- phase B: scatter the two posting ranges ----
+  uint64_t pb[2], pe[2], total = 0;
 #pragma unroll
   for (int rng = 0; rng < 2; ++rng) {
-    uint64_t tlo = bounds[2 * rng], thi = bounds[2 * rng + 1];
-    if (thi <= tlo) continue;
-    uint64_t pb = t.post_off[tlo], pe = t.post_off[thi];
-    for (uint64_t i = pb + tid; i < pe; i += nth) {
-      uint64_t r = (uint64_t)t.post_rows[i] - row_base;
-      if (r < nbits) atomicOr(words + (r >> 5), 1u << (uint32_t)(r & 31));
+    const uint64_t tlo = __ldcg(a.bounds + 2 * rng), thi = __ldcg(a.bounds + 2 * rng + 1);
+    pb[rng] = pe[rng] = 0;
+    if (thi > tlo) {
+      pb[rng] = a.t.post_off[tlo];
+      pe[rng] = a.t.post_off[thi];
     }
-    if (tid == 0) visited += pe - pb;
+    total += pe[rng] - pb[rng];
   }
-  if (tid == 0 && npost) *npost = visited;
+  const bool use_list = a.list && total <= a.list_cap;
+  const uint64_t gtid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t nth = (uint64_t)G * blockDim.x;
+  if (gtid == 0) {
+    a.bounds[4] = total;
+    if (a.list_count && !use_list) *a.list_count = 0xFFFFFFFFu;
+  }
+  const uint32_t lane = threadIdx.x & 31;
+#pragma unroll
+  for (int rng = 0; rng < 2; ++rng) {
+    // whole warps iterate together (the list append uses warp collectives)
+    for (uint64_t i0 = pb[rng] + (gtid - lane); i0 < pe[rng]; i0 += nth) {
+      const uint64_t i = i0 + lane;
+      const bool in = i < pe[rng];
+      const uint64_t r = in ? (uint64_t)a.t.post_rows[i] - a.row_base : ~0ull;
+      const bool ok = in && r < a.nbits;
+      const uint32_t bit = 1u << (uint32_t)(r & 31);
+      uint32_t old = 0xFFFFFFFFu;
+      if (ok) old = atomicOr(a.words + (r >> 5), bit);
+      if (use_list) {
+        const bool win = ok && !(old & bit);  // this thread set the bit: the row is new
+        const unsigned m = __ballot_sync(FULL_MASK, win);
+        if (m) {
+          uint32_t base = 0;
+          if (lane == (uint32_t)__ffs(m) - 1u) base = atomicAdd(a.list_count, (uint32_t)__popc(m));
+          base = __shfl_sync(FULL_MASK, base, __ffs(m) - 1);
+          if (win) {
+            const uint32_t pos = base + __popc(m & ((1u << lane) - 1u));
+            if (pos < a.list_cap) a.list[pos] = (uint32_t)r;
+          }
+        }
+      }
+    }
+  }
 }
-cudaError_t launch_prefix_scatter(const TermsDev& t, const uint64_t* d_bounds, uint32_t* words,
-                                  uint64_t nbits, uint64_t row_base, unsigned long long* d_npost,
-                                  int grid, cudaStream_t st) {
-  prefix_scatter_kernel<<<grid, 256, 0, st>>>(t, d_bounds, words, nbits, row_base, d_npost);
+cudaError_t launch_prefix_mask(const PrefixMaskArgs& a, const PrefixKeys& keys, int num_sms,
+                               cudaStream_t st) {
+  // one CTA per SM at most (the grid barrier needs every CTA resident); a small mask does not
+  // need them all
+  int grid = num_sms > 0 ? num_sms : 148;
+  const uint64_t want = 4 + (a.clear_nwords / 4 + kPrefixThreads - 1) / kPrefixThreads;
+  if (a.clear_nwords && want < (uint64_t)grid && want >= 8) grid = (int)want;
+  if (grid < 8) grid = 8;
+  if (grid > num_sms && num_sms > 0) grid = num_sms;
+  prefix_mask_kernel<<<grid, kPrefixThreads, 0, st>>>(a, keys);
   return cudaGetLastError();
 }
 

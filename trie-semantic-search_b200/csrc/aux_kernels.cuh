@@ -54,20 +54,32 @@ struct PrefixKeys {  // up to 4 lower-bound probes, keys concatenated
   // bytes): no staging copy, so nothing on the host has to wait for the previous call
   char bytes[kPrefixInlineBytes];
 };
-// bounds[4] <- lower bounds; then ranges [b0,b1) and [b2,b3) are scattered.  d_keybytes == null:
-// the keys are keys.bytes.  clear_words != null: the kernel's other CTAs zero those words (the
-// output mask) while CTA 0 searches -- clear + search in one launch.
-cudaError_t launch_prefix_search(const TermsDev& t, const char* d_keybytes, const PrefixKeys& keys,
-                                 uint64_t* d_bounds, uint32_t* clear_words, uint64_t clear_nwords,
-                                 cudaStream_t st);
-cudaError_t launch_prefix_scatter(const TermsDev& t, const uint64_t* d_bounds, uint32_t* words,
-                                  uint64_t nbits, uint64_t row_base, unsigned long long* d_npost,
-                                  int grid, cudaStream_t st);
-
 // *bad |= 1 unless: offsets start at 0, are monotone and end on pool_bytes / nposts, and the terms
 // are strictly increasing in byte order (what the prefix search relies on).  For loaded files.
 cudaError_t launch_terms_validate(const TermsDev& t, uint64_t pool_bytes, uint64_t nposts,
                                   unsigned int* d_bad, cudaStream_t st);
+
+// K4 as ONE launch (what tss_prefix_mask / tss_prefix_mask_fresh enqueue): CTAs 0..3 each find
+// one lower bound with a 256-ary cooperative search while the other CTAs clear the mask
+// (clear_nwords > 0); a grid barrier; then every CTA scatters the posting ranges.  When `list`
+// is given and the ranges hold at most list_cap postings, the threads whose atomicOr flipped a
+// bit also append the row to `list` (unique local rows, *list_count of them): the masked scan
+// then fetches exactly those rows instead of walking the mask.  *list_count = 0xFFFFFFFF
+// otherwise.  sync: two zeroed words used by the grid barrier (left zeroed).
+struct PrefixMaskArgs {
+  TermsDev t;
+  const char* d_keybytes;   // null: keys.bytes
+  uint64_t* bounds;         // [4] out (+ [4] = postings visited)
+  uint32_t* words;          // the mask
+  uint64_t clear_nwords;    // 0: OR into the mask as it is
+  uint64_t nbits, row_base;
+  uint32_t* list;           // nullable
+  uint32_t* list_count;
+  uint32_t list_cap;
+  unsigned int* sync;
+};
+cudaError_t launch_prefix_mask(const PrefixMaskArgs& a, const PrefixKeys& keys, int num_sms,
+                               cudaStream_t st);
 
 // K5: merge P gathered lists of k keys per query: in [P][nq][k] -> out [nq][k]
 cudaError_t launch_merge_gathered(const uint64_t* in, uint64_t* out, uint32_t P, uint32_t nq,

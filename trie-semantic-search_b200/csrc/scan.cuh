@@ -66,6 +66,14 @@ struct ScanParams {
   // a single query of <= 384 dims can ride in the kernel parameters (no H2D copy before the
   // launch): use_inline != 0 -> query 0 is q_inline, `queries` is not read
   uint32_t use_inline;
+  // masked scan, INCLUDE mode: when the mask was produced by one fresh prefix scatter that also
+  // left the list of its (unique, local) rows -- *row_list_count <= row_list_cap of them -- the
+  // warps fetch exactly those rows, 8 per buffer fill, and never read the mask: the cost of a
+  // selective prefix query is then proportional to its live rows.  *row_list_count >
+  // row_list_cap (the scatter found too many postings): the mask is walked as usual.
+  const uint32_t* row_list;        // null: no list
+  const uint32_t* row_list_count;
+  uint32_t row_list_cap;
   float q_inline[384];
 };
 
@@ -316,7 +324,33 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_topk_kernel(const __grid_c
   // A sparse mask therefore still keeps a whole buffer of bytes in flight per warp.
   uint32_t* slot_rows = reinterpret_cast<uint32_t*>(bars + WARPS) + warp * 16;
   uint64_t m_next = (uint64_t)blockIdx.x * WARPS + warp;
+  uint32_t list_n = 0xFFFFFFFFu;  // rows in the list when the scan is list-driven
+  if constexpr (MASKED) {
+    if (p.row_list) {
+      const uint32_t c = __ldcg(p.row_list_count);
+      if (c <= p.row_list_cap) {
+        list_n = c;
+        m_next = (uint64_t)warp * gridDim.x + blockIdx.x;  // chunks spread over the SMs first
+      }
+    }
+  }
   auto gather = [&]() -> uint32_t {
+    if (list_n != 0xFFFFFFFFu) {
+      // list-driven: chunk m_next = rows list[m_next*R .. +R), one bulk copy per row
+      const uint64_t c0 = m_next * (uint64_t)R;
+      if (c0 >= list_n) return 0u;
+      m_next += GW;
+      const uint32_t cnt = list_n - c0 < (uint64_t)R ? (uint32_t)(list_n - c0) : (uint32_t)R;
+      if (lane == 0) mbar_arrive_expect_tx(bar, cnt * ROW_BYTES);
+      __syncwarp();
+      if ((uint32_t)lane < cnt) {
+        const uint32_t r = __ldcg(p.row_list + c0 + lane);
+        bulk_g2s(tile_s + lane * ROW_BYTES, rows_b + (uint64_t)r * ROW_BYTES, ROW_BYTES, bar, policy);
+        slot_rows[lane] = r;
+      }
+      __syncwarp();
+      return cnt;
+    }
     while (m_next < total_tiles) {
       const uint64_t tc = m_next + (uint64_t)lane * GW;
       const uint32_t b = tc < total_tiles ? tile_bits(tc) : 0u;
