@@ -16,9 +16,17 @@
  * There is NO CPU fallback: without a CUDA device every call that would
  * touch one returns TSS_ERR_CUDA.
  *
- * Threading: a handle is externally synchronised (the reference serialises
- * vector searches behind a tokio write lock, src/search.rs:249-252).  Distinct
- * handles may be used from distinct threads.
+ * Threading: every tss_index entry point takes the handle's own lock, so any
+ * number of host threads may call into one index (searches included) with
+ * distinct output buffers; the calls are serialised inside the library instead
+ * of behind the caller's process-wide write lock (the reference:
+ * src/search.rs:249-252).  One scan already saturates HBM, so concurrency is
+ * turned into throughput by BATCHING (nq > 1: the corpus is streamed once per
+ * 4 queries, or once per batch on the tensor-core path; host/tss_host.hpp
+ * QueryBatcher does that for concurrent callers), not by overlapping scans.
+ * tss_mask / tss_terms / tss_columns handles: one thread mutates a given
+ * handle at a time; concurrent searches may read the same mask.  Distinct
+ * handles may always be used from distinct threads.
  */
 #ifndef TSS_H
 #define TSS_H

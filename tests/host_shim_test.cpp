@@ -272,7 +272,10 @@ static void engine_hybrid() {
 
   SearchQuery q;
   q.query = "Miranda v. Arizona";
+  const size_t gets0 = store->gets(), mg0 = store->multi_gets();
   auto r = eng.search_with_params(q);
+  // N4: the merge hydrates with two multi-gets (trie hits, vector hits), never per hit
+  CHECK(store->gets() == gets0 && store->multi_gets() == mg0 + 2);
   // M1 shape: trie exact hit first with weight 2.0, then semantic hits >= 0.5, de-duped by case
   CHECK(r.size() >= 2 && r[0].case_metadata.id == cid(1) && r[0].score == 2.0f &&
         r[0].match_type == MatchType::Exact);
@@ -346,8 +349,10 @@ static void engine_hybrid() {
     qs[3].court_filter = std::vector<std::string>{"ca9"};
     qs[5].config.enable_semantic = false;
     qs[6].max_results = 1;
+    const size_t g0 = store->gets(), m0 = store->multi_gets();
     auto batch = eng.search_batch(qs);
     CHECK(batch.size() == 7);
+    CHECK(store->gets() == g0 && store->multi_gets() == m0 + 2);  // the WHOLE batch: two multi-gets
     for (int i = 0; i < 7; ++i) {
       auto one = eng.search_with_params(qs[i]);
       CHECK(one.size() == batch[i].size());

@@ -324,3 +324,50 @@ def test_back_to_back_launches_overlap_safely(tss, orc):
         for i in range(reps):
             assert np.array_equal(r[i], want[0][i % 6]), (n, i)
             assert np.array_equal(s[i].view(np.uint32), want[1][i % 6].view(np.uint32))
+
+
+def test_concurrent_searches_on_one_handle(tss, orc):
+    """Several host threads search ONE index handle at the same time (ctypes drops the GIL for
+    the call): the handle's lock serialises them, every thread gets the oracle's answer."""
+    import threading
+    n, dim, k = 120_000, 384, 10
+    rows = orc.gen_rows(0, n, dim, 0x5EED)
+    ix = tss.FlatIndex(dim)
+    ix.add_synthetic(0, n, 0x5EED)
+    ix.finalize()
+    q = orc.gen_rows(0, 64, dim, 0xBEEF)
+    want = orc.cosine_topk(rows, q, k)
+    m = tss.Mask(n)
+    m.set_rows(np.arange(0, n, 3, dtype=np.uint32))
+    w = np.zeros((n + 31) // 32, dtype=np.uint32)
+    idx = np.arange(0, n, 3, dtype=np.int64)
+    np.bitwise_or.at(w, idx >> 5, np.uint32(1) << (idx & 31).astype(np.uint32))
+    want_m = orc.cosine_topk(rows, q, k, mask_words=w, mask_mode=orc.MASK_EXCLUDE)
+    errors = []
+
+    def worker(t):
+        try:
+            for i in range(40):
+                j = (t * 7 + i) % 60
+                if (t + i) % 3 == 0:   # a masked search reads the shared mask concurrently
+                    got = ix.search(q[j], k, m, tss.TSS_MASK_EXCLUDE)
+                    ref = want_m
+                    sl = slice(j, j + 1)
+                elif (t + i) % 3 == 1:  # a small batch
+                    got = ix.search(q[j:j + 4], k)
+                    ref, sl = want, slice(j, j + 4)
+                else:
+                    got = ix.search(q[j], k)
+                    ref, sl = want, slice(j, j + 1)
+                if not (np.array_equal(got[0], ref[0][sl]) and
+                        np.array_equal(got[1].view(np.uint32), ref[1][sl].view(np.uint32))):
+                    errors.append((t, i))
+        except Exception as e:  # noqa: BLE001
+            errors.append((t, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(6)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors[:5]

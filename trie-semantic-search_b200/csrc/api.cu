@@ -187,6 +187,9 @@ struct tss_terms {
 };
 
 struct tss_index {
+  // every entry point that touches the handle's stream or workspaces holds this: two host threads
+  // may call into one handle (searches included); the calls are serialised inside, not racing
+  std::mutex mu;
   int device = 0;
   uint32_t dim = 0;
   int storage = TSS_F32;
@@ -949,6 +952,7 @@ void tss_index_destroy(tss_index* ix) {
 
 int tss_index_reserve(tss_index* ix, uint64_t nrows) {
   if (!ix) return fail(TSS_ERR_INVALID_ARG, "index is NULL");
+  std::lock_guard<std::mutex> lock(ix->mu);
   if (nrows >= 0xFFFFFFFFull) return fail(TSS_ERR_INVALID_ARG, "row ids are 32-bit");
   DeviceGuard g(ix->device);
   return ensure_capacity(ix, nrows);
@@ -956,6 +960,7 @@ int tss_index_reserve(tss_index* ix, uint64_t nrows) {
 
 int tss_index_add(tss_index* ix, const float* rows, uint64_t nrows) {
   if (!ix) return fail(TSS_ERR_INVALID_ARG, "index is NULL");
+  std::lock_guard<std::mutex> lock(ix->mu);
   if (!nrows) return TSS_OK;
   if (!rows) return fail(TSS_ERR_INVALID_ARG, "rows is NULL");
   if (ix->row_base + ix->n_rows + nrows >= 0xFFFFFFFFull)
@@ -993,6 +998,7 @@ int tss_index_add(tss_index* ix, const float* rows, uint64_t nrows) {
 
 int tss_index_add_synthetic(tss_index* ix, uint64_t row_begin, uint64_t nrows, uint64_t seed) {
   if (!ix) return fail(TSS_ERR_INVALID_ARG, "index is NULL");
+  std::lock_guard<std::mutex> lock(ix->mu);
   if (!nrows) return TSS_OK;
   if (ix->row_base + ix->n_rows + nrows >= 0xFFFFFFFFull)
     return fail(TSS_ERR_INVALID_ARG, "row ids are 32-bit");
@@ -1011,6 +1017,7 @@ int tss_index_add_synthetic(tss_index* ix, uint64_t row_begin, uint64_t nrows, u
 
 int tss_index_finalize(tss_index* ix) {
   if (!ix) return fail(TSS_ERR_INVALID_ARG, "index is NULL");
+  std::lock_guard<std::mutex> lock(ix->mu);
   DeviceGuard g(ix->device);
   if (!ix->d_rows) {
     int rc = ensure_capacity(ix, 1);  // an empty index still scans (and finds nothing)
@@ -1030,6 +1037,7 @@ uint32_t tss_index_dim(const tss_index* ix) { return ix ? ix->dim : 0; }
 
 int tss_index_get_rows(tss_index* ix, uint64_t row_begin, uint64_t nrows, float* out) {
   if (!ix || !out) return fail(TSS_ERR_INVALID_ARG, "NULL argument");
+  std::lock_guard<std::mutex> lock(ix->mu);
   if (row_begin + nrows > ix->n_rows) return fail(TSS_ERR_INVALID_ARG, "row range out of bounds");
   if (!nrows) return TSS_OK;
   DeviceGuard g(ix->device);
@@ -1065,6 +1073,7 @@ constexpr size_t kIoChunk = 32u << 20;
 
 int tss_index_save(tss_index* ix, const char* path) {
   if (!ix || !path) return fail(TSS_ERR_INVALID_ARG, "NULL argument");
+  std::lock_guard<std::mutex> lock(ix->mu);
   DeviceGuard g(ix->device);
   CU(cudaStreamSynchronize(ix->stream));
   FILE* f = fopen(path, "wb");
@@ -1145,6 +1154,8 @@ int tss_index_load(tss_index** out, const char* path, int device) {
 // ---- search ---------------------------------------------------------------------------
 int tss_index_search_device(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
                             const tss_mask* mask, int mask_mode, uint64_t* d_out_keys) {
+  if (!ix) return fail(TSS_ERR_INVALID_ARG, "index is NULL");
+  std::lock_guard<std::mutex> lock(ix->mu);
   int rc = validate_search(ix, d_queries, nq, k);
   if (rc) return rc;
   if (!d_out_keys) return fail(TSS_ERR_INVALID_ARG, "d_out_keys is NULL");
@@ -1192,6 +1203,8 @@ void tss_unpack_keys(const uint64_t* keys, uint64_t n, uint32_t* out_rows, float
 int tss_index_search(tss_index* ix, const float* queries, uint32_t nq, uint32_t k,
                      const tss_mask* mask, int mask_mode, uint32_t* out_rows, float* out_scores,
                      uint32_t* out_counts) {
+  if (!ix) return fail(TSS_ERR_INVALID_ARG, "index is NULL");
+  std::lock_guard<std::mutex> lock(ix->mu);
   int rc = validate_search(ix, queries, nq, k);
   if (rc) return rc;
   if (!out_rows || !out_scores || !out_counts)
@@ -1404,6 +1417,7 @@ int setup_shard_group(tss_index* ix, tss_comm* comm) {
 
 int tss_index_set_batch_policy(tss_index* ix, uint32_t min_queries, int build_shadow_now) {
   if (!ix) return fail(TSS_ERR_INVALID_ARG, "index is NULL");
+  std::lock_guard<std::mutex> lock(ix->mu);
   if (min_queries) {
     ix->gemm_min_nq = min_queries;
     ix->gemm_small_nq = 0xFFFFFFFFu;
@@ -1425,6 +1439,7 @@ int tss_index_set_batch_policy(tss_index* ix, uint32_t min_queries, int build_sh
 
 int tss_index_set_shard(tss_index* ix, uint64_t row_base, tss_comm* comm) {
   if (!ix) return fail(TSS_ERR_INVALID_ARG, "index is NULL");
+  std::lock_guard<std::mutex> lock(ix->mu);
   if (row_base + ix->n_rows >= 0xFFFFFFFFull)
     return fail(TSS_ERR_INVALID_ARG, "row ids are 32-bit");
   if (comm && comm->device != ix->device)
@@ -2160,6 +2175,7 @@ void* tss_index_stream(tss_index* ix) { return ix ? (void*)ix->stream : nullptr;
 
 int tss_index_sync(tss_index* ix) {
   if (!ix) return fail(TSS_ERR_INVALID_ARG, "index is NULL");
+  std::lock_guard<std::mutex> lock(ix->mu);
   DeviceGuard g(ix->device);
   CU(cudaStreamSynchronize(ix->stream));
   if (ix->h_status && *ix->h_status) {  // a fused sharded search gave up waiting for a peer

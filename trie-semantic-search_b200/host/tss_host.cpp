@@ -527,9 +527,20 @@ void TrieIndex::prefix_mask(Which w, const std::string& query, tss_mask* mask, u
 
 // ---- SearchEngine ----------------------------------------------------------------------------
 std::optional<CaseMetadata> MetadataStore::get_case_metadata(const CaseId& id) const {
+  ++gets_;
   auto it = map_.find(id);
   if (it == map_.end()) return std::nullopt;
   return it->second;
+}
+std::vector<std::optional<CaseMetadata>> MetadataStore::multi_get(const std::vector<CaseId>& ids) const {
+  ++multi_gets_;
+  std::vector<std::optional<CaseMetadata>> out;
+  out.reserve(ids.size());
+  for (const CaseId& id : ids) {
+    auto it = map_.find(id);
+    out.push_back(it == map_.end() ? std::nullopt : std::optional<CaseMetadata>(it->second));
+  }
+  return out;
 }
 
 SearchEngine::SearchEngine(const VectorConfig& vc, const TrieConfig& tc,
@@ -617,15 +628,25 @@ std::vector<std::vector<SearchResult>> SearchEngine::search_batch(
   std::vector<std::unordered_set<CaseId, CaseIdHash>> seen(n);
   std::vector<size_t> need;  // queries that run the semantic pass
   std::vector<std::vector<float>> embeddings;
+  // trie pass of every query first, then ONE multi-get hydrates all their exact hits
+  std::vector<std::vector<DocRef>> exact(n);
+  std::vector<CaseId> ids;
   for (size_t i = 0; i < n; ++i) {
     const SearchQuery& q = queries[i];
     validate_query(q);
     if (q.config.enable_prefix) {  // :190-206
-      for (const DocRef& d : trie_index_.search(q.query).exact_matches) {
-        auto meta = storage_->get_case_metadata(d.case_id);
-        if (meta && seen[i].insert(d.case_id).second)
-          all[i].push_back(SearchResult{*meta, q.config.exact_match_weight, MatchType::Exact, snippet(d)});
-      }
+      exact[i] = trie_index_.search(q.query).exact_matches;
+      for (const DocRef& d : exact[i]) ids.push_back(d.case_id);
+    }
+  }
+  auto metas = storage_->multi_get(ids);
+  size_t at = 0;
+  for (size_t i = 0; i < n; ++i) {
+    const SearchQuery& q = queries[i];
+    for (const DocRef& d : exact[i]) {
+      const auto& meta = metas[at++];
+      if (meta && seen[i].insert(d.case_id).second)
+        all[i].push_back(SearchResult{*meta, q.config.exact_match_weight, MatchType::Exact, snippet(d)});
     }
     if (q.config.enable_semantic && all[i].size() < q.config.max_results) {  // :209
       need.push_back(i);
@@ -633,13 +654,20 @@ std::vector<std::vector<SearchResult>> SearchEngine::search_batch(
     }
   }
   auto hits = vector_index_.hnsw().search_batch(embeddings, kVectorTopK);  // one device call
+  // ... and ONE multi-get for every vector hit of the batch that passes its query's threshold
+  ids.clear();
+  for (size_t j = 0; j < need.size(); ++j)
+    for (const auto& h : hits[j])
+      if (1.0f - h.second >= queries[need[j]].config.min_similarity) ids.push_back(h.first.case_id);
+  metas = storage_->multi_get(ids);
+  at = 0;
   for (size_t j = 0; j < need.size(); ++j) {
     const size_t i = need[j];
     const SearchQuery& q = queries[i];
     for (const auto& h : hits[j]) {
       const float sim = 1.0f - h.second;  // :144
       if (sim < q.config.min_similarity) continue;  // :212
-      auto meta = storage_->get_case_metadata(h.first.case_id);
+      const auto& meta = metas[at++];
       if (meta && seen[i].insert(h.first.case_id).second)
         all[i].push_back(SearchResult{*meta, sim, MatchType::Semantic, snippet(h.first)});
     }
@@ -688,8 +716,12 @@ std::vector<SearchResult> SearchEngine::execute_hybrid_search(const SearchQuery&
   // 1. trie search for exact matches, :190-206
   if (query.config.enable_prefix) {
     TrieSearchResult tr = trie_index_.search(query.query);
+    std::vector<CaseId> ids;
+    for (const DocRef& d : tr.exact_matches) ids.push_back(d.case_id);
+    auto metas = storage_->multi_get(ids);  // N4: one lookup for all of them (:193 is per hit)
+    size_t at = 0;
     for (const DocRef& d : tr.exact_matches) {
-      auto meta = storage_->get_case_metadata(d.case_id);  // :193
+      const auto& meta = metas[at++];
       if (!meta) continue;
       if (seen_cases.insert(d.case_id).second)  // :194
         all_results.push_back(
@@ -754,9 +786,14 @@ std::vector<SearchResult> SearchEngine::execute_hybrid_search(const SearchQuery&
       }
     }
     auto vector_results = vector_index_.search_masked(query.query, kVectorTopK, mask, mode);  // :251
+    std::vector<CaseId> ids;
+    for (const VectorSearchResult& v : vector_results)
+      if (v.similarity_score >= query.config.min_similarity) ids.push_back(v.doc_ref.case_id);
+    auto metas = storage_->multi_get(ids);  // N4: one lookup for the <= 50 hits (:213 is per hit)
+    size_t at = 0;
     for (const VectorSearchResult& v : vector_results) {
       if (v.similarity_score >= query.config.min_similarity) {       // :212
-        auto meta = storage_->get_case_metadata(v.doc_ref.case_id);  // :213
+        const auto& meta = metas[at++];
         if (!meta) continue;
         if (seen_cases.insert(v.doc_ref.case_id).second)             // :214
           all_results.push_back(

@@ -11,6 +11,7 @@
 #pragma once
 
 #include <array>
+#include <atomic>
 #include <condition_variable>
 #include <cstdint>
 #include <deque>
@@ -316,9 +317,18 @@ class MetadataStore {
  public:
   void put(const CaseMetadata& m) { map_[m.id] = m; }
   std::optional<CaseMetadata> get_case_metadata(const CaseId& id) const;
+  // N4: one call for all the cases a query (or a whole batch of queries) has to hydrate, in the
+  // order asked, nullopt where the reference's `if let Ok(Some(..))` would skip (:193,213).  The
+  // reference does one sled lookup + bincode decode per hit (src/storage.rs:118-132), up to ~60
+  // per query, which dominates once scoring takes microseconds.
+  std::vector<std::optional<CaseMetadata>> multi_get(const std::vector<CaseId>& ids) const;
+  // calls served so far (tests: the merge issues two multi-gets per query or batch, no gets)
+  size_t gets() const { return gets_; }
+  size_t multi_gets() const { return multi_gets_; }
 
  private:
   std::unordered_map<CaseId, CaseMetadata, CaseIdHash> map_;
+  mutable std::atomic<size_t> gets_{0}, multi_gets_{0};
 };
 
 class SearchEngine {
