@@ -135,7 +135,14 @@ int tss_index_search(tss_index* ix, const float* queries, uint32_t nq, uint32_t 
 /* Same work with every buffer already in HBM and no host synchronisation:
  * d_queries nq x dim fp32, d_out_keys nq x k packed keys
  * ((orderable(score) << 32) | ~row, 0 = unused slot), enqueued on the index
- * stream.  This is what `value` in bench.py times. */
+ * stream.  This is what `value` in bench.py times.
+ * The tensor-core path redoes a query whose survivor list overflowed with the
+ * exact scan; here that happens ON THE DEVICE: a few guarded scan launches
+ * are enqueued behind every batch and each serves one flagged query if there
+ * is one (none on ordinary data).  Should a batch flag more queries than
+ * launches were enqueued, tss_index_sync reports TSS_ERR_STATE (those queries'
+ * slots are not final) and later batches get twice as many.  One exception:
+ * k > TSS_MAX_FUSED_K, whose redo runs by rounds from the host, synchronises. */
 int tss_index_search_device(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
                             const tss_mask* mask, int mask_mode, uint64_t* d_out_keys);
 /* Which batches take the tensor-core path (K2), whose results are bit-identical to the scan's

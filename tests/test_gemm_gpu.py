@@ -314,3 +314,48 @@ def test_sparse_include_mask_never_returns_rows_past_the_shard(tss, orc, storage
         assert np.array_equal(gr, want[0]), live
         assert np.array_equal(gs.view(np.uint32), want[1].view(np.uint32)), live
         assert np.all((gr < n) | (gr == tss.TSS_ROW_NONE))
+
+
+def test_device_resident_batches_fix_up_on_the_device(tss, orc):
+    """tss_index_search_device never synchronises the host (include/tss.h): queries whose survivor
+    list overflows are redone by guarded scan launches enqueued behind the batch.  One flagged
+    query: exact without any host involvement.  More flagged queries than fix-up launches: the
+    condition is reported by tss_index_sync and the next call has twice the launches."""
+    n, dim, k = 200_000, 384, 10
+    rows = orc.gen_rows(0, n, dim, SEED)
+    rows[100_000:150_000] = rows[7]   # 50k copies: every list of a query near row 7 overflows
+    ix = tss.FlatIndex(dim, tss.TSS_BF16)
+    ix.add(rows)
+    ix.finalize()
+    nq = 64
+    q = orc.gen_rows(0, nq, dim, 0xBEEF)
+    q[3] = rows[7]
+    want = orc.cosine_topk(rows, q, k, bf16=True)
+    dq = tss.DeviceBuffer(0, q.nbytes).upload(q)
+    dk = tss.DeviceBuffer(0, nq * k * 8)
+    before = tss.launch_count()
+    ix.search_device(dq, nq, k, dk)
+    assert tss.launch_count() - before >= 5 + 1 + 4  # K2 pipeline + compaction + guarded fix-ups
+    ix.sync()
+    gr, gs = tss.unpack_keys(dk.download(np.uint64, nq * k).reshape(nq, k))
+    assert np.array_equal(gr, want[0]) and np.array_equal(gs.view(np.uint32), want[1].view(np.uint32))
+    # ten hostile queries > four fix-up launches
+    for j in range(10):
+        q[20 + j] = rows[7] * (1.0 + 0.01 * j)
+    want = orc.cosine_topk(rows, q, k, bf16=True)
+    dq.upload(q)
+    for attempt in range(4):
+        ix.search_device(dq, nq, k, dk)
+        try:
+            ix.sync()
+            break
+        except tss.TssError as e:
+            assert e.code == tss.TSS_ERR_STATE
+    else:
+        raise AssertionError("the fix-up launches never caught up")
+    assert attempt >= 1  # the first try could not cover eleven flagged queries with four launches
+    gr, gs = tss.unpack_keys(dk.download(np.uint64, nq * k).reshape(nq, k))
+    assert np.array_equal(gr, want[0]) and np.array_equal(gs.view(np.uint32), want[1].view(np.uint32))
+    # the host entry covers any number of them in one call
+    got = ix.search(q, k)
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1].view(np.uint32), want[1].view(np.uint32))

@@ -217,6 +217,7 @@ struct tss_index {
   uint64_t* d_partials = nullptr;
   unsigned int* d_counter = nullptr;
   uint32_t launch_no = 0;
+  bool no_host_sync = false;  // inside tss_index_search_device: fix-ups must stay on the device
   uint64_t shard_min_rows = 0;  // rows of the smallest shard of the group (tss_index_set_shard)
   bool pdl = true;
   // tile schedule of the unmasked scan (see scan.cuh): share of tiles walked statically,
@@ -246,7 +247,14 @@ struct tss_index {
     uint32_t* d_overflow = nullptr;    // [kWsQueries]
     uint64_t* d_pref_keys = nullptr;   // [kPrefilterMaxNq][128] shadow-scan candidates
     uint32_t* h_cand_count = nullptr;  // pinned copy of d_overflow
-    CUtensorMap tmap_q, tmap_e, tmap_e_half;  // corpus boxes of 256 rows / 128 rows (CTA pairs)
+    // device-side fix-up of a batch (queries whose survivor list overflowed, or whose shadow
+    // proof failed): [0] = count, [1..] = query indices; the mapped pinned mirror is read by
+    // the host only where it synchronises anyway
+    uint32_t* d_redo = nullptr;
+    uint32_t* h_redo = nullptr;
+    uint32_t fixups = 4;               // guarded fix-up scans enqueued behind every batch
+    CUtensorMap tmap_q, tmap_e, tmap_e_half, tmap_e_quarter;  // corpus boxes of 256 / 128 (CTA
+                                                              // pairs) / 64 rows (quads)
     uint64_t tmap_rows = 0;
     const void* tmap_base = nullptr;
     // fp32 index: bf16 (RNE) shadow of the matrix for the tensor-core pass; the survivors are
@@ -389,9 +397,16 @@ int check_mask(const tss_index* ix, const tss_mask* mask, int mode) {
 // query of <= 384 dims may instead be handed over from host memory inside the kernel parameters.
 // bf16_rows: scan this bf16 matrix of the same geometry (the shadow of an fp32 index) instead
 // of the stored rows.
+// guard != null: ONE guarded launch (see ScanParams::guard_list): d_queries / d_out are the
+// bases of the batch, the query it serves (if any) is picked on the device.
+struct ScanGuard {
+  const uint32_t* list;
+  const uint32_t* count;
+  uint32_t index;
+};
 int enqueue_scan(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
                  const tss_mask* mask, int mode, uint64_t* d_out, const float* h_inline_query,
-                 const uint8_t* bf16_rows) {
+                 const uint8_t* bf16_rows, const ScanGuard* guard) {
   const bool as_bf16 = bf16_rows || ix->storage == TSS_BF16;
   const size_t row_bytes = bf16_rows ? (size_t)ix->stride_elems * 2 : ix->row_bytes;
   const uint32_t kp = tss::kp_for_k(k), cap = tss::cap_for_k(k);
@@ -416,6 +431,11 @@ int enqueue_scan(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
     p.cap = cap;
     p.mask = mode != TSS_MASK_NONE ? mask->d_words : nullptr;
     p.mask_mode = mode;
+    if (guard) {
+      p.guard_list = guard->list;
+      p.guard_count = guard->count;
+      p.guard_index = guard->index;
+    }
     if (mode == TSS_MASK_INCLUDE && mask->list_valid && mask->d_list) {
       p.row_list = mask->d_list;
       p.row_list_count = mask->d_list_count;
@@ -538,6 +558,9 @@ int ensure_gemm_ws(tss_index* ix) {
     CU(cudaMalloc(&g.d_overflow, kWsQueries * sizeof(uint32_t)));
     CU(cudaMalloc(&g.d_pref_keys, (size_t)kPrefilterMaxNq * 128 * sizeof(uint64_t)));
     CU(cudaMallocHost(&g.h_cand_count, kWsQueries * sizeof(uint32_t)));
+    CU(cudaMalloc(&g.d_redo, (kWsQueries + 1) * sizeof(uint32_t)));
+    CU(cudaMallocHost(&g.h_redo, (kWsQueries + 1) * sizeof(uint32_t)));
+    memset(g.h_redo, 0, (kWsQueries + 1) * sizeof(uint32_t));
     if ((rc = make_tmap(&g.tmap_q, g.d_qbf16, kWsQueries, kpad, 128))) return rc;
     g.ready = true;
   }
@@ -585,6 +608,7 @@ int ensure_gemm_ws(tss_index* ix) {
   if (g.tmap_rows != ix->n_rows || g.tmap_base != ix->d_rows) {
     if ((rc = make_tmap(&g.tmap_e, e_rows, ix->n_rows, kpad, 256))) return rc;
     if ((rc = make_tmap(&g.tmap_e_half, e_rows, ix->n_rows, kpad, 128))) return rc;
+    if ((rc = make_tmap(&g.tmap_e_quarter, e_rows, ix->n_rows, kpad, 64))) return rc;
     g.tmap_rows = ix->n_rows;
     g.tmap_base = ix->d_rows;
   }
@@ -603,9 +627,13 @@ bool gemm_route(tss_index* ix, uint32_t nq, uint32_t k, int mode) {
   return true;
 }
 
+struct ScanGuard;
 int enqueue_scan(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
                  const tss_mask* mask, int mode, uint64_t* d_out,
-                 const float* h_inline_query = nullptr, const uint8_t* bf16_rows = nullptr);
+                 const float* h_inline_query = nullptr, const uint8_t* bf16_rows = nullptr,
+                 const ScanGuard* guard = nullptr);
+int enqueue_fixups(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
+                   const tss_mask* mask, int mode, uint64_t* d_out);
 int enqueue_scan_rounds(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
                         const tss_mask* mask, int mode, uint64_t* d_out);
 
@@ -622,9 +650,22 @@ int enqueue_gemm(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
   // number of 128-query blocks (a padding query is all zeros and its threshold is +inf)
   // Up to 128 queries every SM streams its own tiles and independent CTAs are faster.
   int cluster = nq > 128 ? tss::TSS_GEMM_PAIR : tss::TSS_GEMM_SINGLE;
-  if (const char* cl = getenv("TSS_GEMM_CLUSTER"))  // diagnostics: 1 independent CTAs, 2 pairs
-    cluster = atoi(cl) == tss::TSS_GEMM_SINGLE ? tss::TSS_GEMM_SINGLE : tss::TSS_GEMM_PAIR;
-  const uint32_t qblock = cluster == tss::TSS_GEMM_PAIR ? 256 : 128;
+  // Quads (two pairs sharing corpus tiles by multicast) halve the L2 -> SM feed, the resource
+  // the pair kernel runs out of; they need a multiple of four query blocks (no extra padding
+  // beyond the pairs') and enough resident clusters for at least as many SMs as ... see below
+  const int kb = (int)(ix->stride_elems / 64);
+  int max_quads = 0;
+  if (nq > 256 && ((nq + 255) / 256) % 2 == 0) {
+    max_quads = tss::gemm_max_quads(kb);
+    const int groups4 = (int)((nq + 511) / 512);
+    if (max_quads >= groups4) cluster = tss::TSS_GEMM_QUAD;
+  }
+  if (const char* cl = getenv("TSS_GEMM_CLUSTER")) {  // diagnostics: 1 independent CTAs, 2 pairs, 4 quads
+    const int want = atoi(cl);
+    if (want == tss::TSS_GEMM_SINGLE) cluster = tss::TSS_GEMM_SINGLE;
+    else if (want == tss::TSS_GEMM_PAIR || cluster != tss::TSS_GEMM_QUAD) cluster = tss::TSS_GEMM_PAIR;
+  }
+  const uint32_t qblock = cluster == tss::TSS_GEMM_QUAD ? 512 : cluster == tss::TSS_GEMM_PAIR ? 256 : 128;
   const uint32_t nq_pad = (nq + qblock - 1) / qblock * qblock, mb = nq_pad / 128;
   const uint32_t num_tiles = (uint32_t)((ix->n_rows + 255) / 256);
   // the threshold pass yields `split` maxima per sampled tile (one per column part)
@@ -640,11 +681,24 @@ int enqueue_gemm(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
   if (sample < (k + split - 1) / split) sample = (k + split - 1) / split;
   if (sample > kGemmMaxSample / split) sample = kGemmMaxSample / split;
   if (sample > num_tiles) sample = num_tiles;
-  int nslices = ix->num_sms / (int)mb;
-  if (nslices * (int)tss::gemm_col_split() > 1024) nslices = 1024 / tss::gemm_col_split();
-  if (nslices < 1) return fail(TSS_ERR_INVALID_ARG, "batch of %u queries exceeds one K2 launch", nq);
-  const int grid = nslices * (int)mb;
-  const CUtensorMap& tmap_e = cluster == tss::TSS_GEMM_SINGLE ? g.tmap_e : g.tmap_e_half;
+  // every cluster the device can hold is launched; the kernel spreads the (query group, tile)
+  // work over all of them (gemm_topk.cu "work assignment"), so no SM idles because the SM count
+  // is not a multiple of the query blocks.  Lists per query: one per (slice of its group, part).
+  const int cl = cluster == tss::TSS_GEMM_QUAD ? 4 : cluster == tss::TSS_GEMM_PAIR ? 2 : 1;
+  int nclusters = cluster == tss::TSS_GEMM_QUAD ? max_quads : ix->num_sms / cl;
+  if (const char* nc = getenv("TSS_GEMM_CLUSTERS"))  // diagnostics: fewer clusters
+    if (atoi(nc) > 0 && atoi(nc) < nclusters) nclusters = atoi(nc);
+  const int ngroups = (int)mb / cl;
+  if (nclusters < ngroups) return fail(TSS_ERR_INVALID_ARG, "batch of %u queries exceeds one K2 launch", nq);
+  int nslices = nclusters / ngroups + nclusters % ngroups;
+  while (nslices * (int)tss::gemm_col_split() > 1024) {  // (select_kernel's list limit)
+    --nclusters;
+    nslices = nclusters / ngroups + nclusters % ngroups;
+  }
+  const int grid = nclusters * cl;
+  const CUtensorMap& tmap_e = cluster == tss::TSS_GEMM_SINGLE ? g.tmap_e
+                              : cluster == tss::TSS_GEMM_PAIR ? g.tmap_e_half
+                                                              : g.tmap_e_quarter;
   cudaError_t e;
   // survivors are re-scored with the scan's arithmetic unless TSS_GEMM_RESCORE=0 (then the
   // result is the top-k of the bf16 x bf16 tensor-core scores)
@@ -674,7 +728,6 @@ int enqueue_gemm(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
   p.cand_cap = cap_s;
   if (const char* rs = getenv("TSS_GEMM_STAGES")) p.ring_stages = (uint32_t)atoi(rs);
   if (const char* dbg = getenv("TSS_GEMM_DEBUG")) p.debug = (uint32_t)atoi(dbg);
-  const int kb = (int)(kpad / 64);
   p.mode = 0;
   if ((e = tss::launch_gemm_topk(kb, cluster, g.tmap_q, tmap_e, p, grid, ix->stream)) != cudaSuccess)
     return cuda_fail(e, "gemm_topk_kernel (threshold pass) launch");
@@ -690,25 +743,56 @@ int enqueue_gemm(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
                               ix->n_rows, d_out, g.d_overflow, ix->stream)) != cudaSuccess)
     return cuda_fail(e, "select_kernel launch");
   g_launches.fetch_add(5, std::memory_order_relaxed);
-  CU(cudaMemcpyAsync(g.h_cand_count, g.d_overflow, nq * sizeof(uint32_t), cudaMemcpyDeviceToHost,
-                     ix->stream));
+  return enqueue_fixups(ix, d_queries, nq, k, mask, mode, d_out);
+}
+
+// Queries flagged in g.d_overflow (a K2 survivor list overflowed, or the shadow prefilter could
+// not prove completeness) are redone exactly by the scan.  On the device: the flags are compacted
+// into a list and `fixups` GUARDED scans are enqueued behind the batch -- launch j serves the
+// j-th flagged query if there is one, else it is a few microseconds of nothing -- so the common
+// case (no flag, or a handful) needs no host synchronisation.  tss_index_search, which
+// synchronises anyway, then finishes what the guarded launches did not cover;
+// tss_index_search_device leaves a sticky status for tss_index_sync instead and the number of
+// fix-up launches doubles.  k > 128 (scan by rounds) is redone from the host in either entry.
+int enqueue_fixups(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
+                   const tss_mask* mask, int mode, uint64_t* d_out) {
+  tss_index::Gemm& g = ix->gemm;
+  const bool on_device = k <= TSS_MAX_FUSED_K;
+  // what the previous batch needed (its mirror has landed by now or will be read next time)
+  const uint32_t seen = g.h_redo[0];
+  if (seen > g.fixups && g.fixups < 64) g.fixups *= 2;
+  if (seen * 20 > kWsQueries / 4 && g.spread_boost < 64) g.spread_boost *= 2;
+  const uint32_t fixups = on_device ? (g.fixups < nq ? g.fixups : nq) : 0;
+  cudaError_t e = tss::launch_redo_compact(g.d_overflow, nq, g.d_redo + 1, g.d_redo, g.h_redo + 1,
+                                           g.h_redo, on_device && ix->no_host_sync ? fixups : nq,
+                                           ix->h_status + 1, ix->stream);
+  if (e != cudaSuccess) return cuda_fail(e, "redo_compact launch");
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  int rc = TSS_OK;
+  const bool saved = ix->xchg.suppress;
+  ix->xchg.suppress = true;  // a redo is rank-local; the caller merges across ranks
+  for (uint32_t j = 0; j < fixups && !rc; ++j) {
+    ScanGuard guard{g.d_redo + 1, g.d_redo, j};
+    rc = enqueue_scan(ix, d_queries, 1, k, mask, mode, d_out, nullptr, nullptr, &guard);
+  }
+  ix->xchg.suppress = saved;
+  if (rc) return rc;
+  if (on_device && ix->no_host_sync) return TSS_OK;
   CU(cudaStreamSynchronize(ix->stream));
-  uint32_t redo = 0;
-  for (uint32_t qi = 0; qi < nq; ++qi) redo += g.h_cand_count[qi] != 0;
-  if (redo * 20 > nq && g.spread_boost < 64) g.spread_boost *= 2;
-  for (uint32_t qi = 0; qi < nq; ++qi) {
-    if (!g.h_cand_count[qi]) continue;
-    ix->xchg.suppress = true;
+  const uint32_t count = g.h_redo[0];
+  if (count * 20 > nq && g.spread_boost < 64) g.spread_boost *= 2;
+  ix->xchg.suppress = true;
+  for (uint32_t j = fixups; j < count && !rc; ++j) {
+    const uint32_t qi = g.h_redo[1 + j];
     if (k > TSS_MAX_FUSED_K)
       rc = enqueue_scan_rounds(ix, d_queries + (size_t)qi * ix->dim, 1, k, mask, mode,
                                d_out + (size_t)qi * k);
     else
       rc = enqueue_scan(ix, d_queries + (size_t)qi * ix->dim, 1, k, mask, mode,
                         d_out + (size_t)qi * k);
-    ix->xchg.suppress = false;
-    if (rc) return rc;
   }
-  return TSS_OK;
+  ix->xchg.suppress = saved;
+  return rc;
 }
 
 // k > TSS_MAX_FUSED_K on the scan path: rounds of 128, each excluding what the previous rounds
@@ -777,17 +861,9 @@ int enqueue_prefilter(tss_index* ix, const float* d_queries, uint32_t nq, uint32
                                      d_out, g.d_overflow, ix->stream);
   if (e != cudaSuccess) return cuda_fail(e, "refine_kernel launch");
   g_launches.fetch_add(1, std::memory_order_relaxed);
-  CU(cudaMemcpyAsync(g.h_cand_count, g.d_overflow, nq * sizeof(uint32_t), cudaMemcpyDeviceToHost,
-                     ix->stream));
-  CU(cudaStreamSynchronize(ix->stream));
-  for (uint32_t qi = 0; qi < nq; ++qi) {
-    if (!g.h_cand_count[qi]) continue;
-    ix->xchg.suppress = true;
-    rc = enqueue_scan(ix, d_queries + (size_t)qi * ix->dim, 1, k, mask, mode, d_out + (size_t)qi * k);
-    ix->xchg.suppress = saved;
-    if (rc) return rc;
-  }
-  return TSS_OK;
+  // a query the proof failed for is redone by the fp32 scan: guarded launches (nq <= 2 of
+  // them always suffice), no host synchronisation
+  return enqueue_fixups(ix, d_queries, nq, k, mask, mode, d_out);
 }
 
 // K2 over nq queries in batches the survivor pool can take (large k at large N: smaller batches)
@@ -904,7 +980,7 @@ int tss_index_create(tss_index** out, uint32_t dim, int storage, int device) {
   ALLOC(cudaMallocHost(&ix->h_queries, (size_t)kWsQueries * dim * sizeof(float)))
   ALLOC(cudaMallocHost(&ix->h_keys, (size_t)kWsQueries * TSS_MAX_K * sizeof(uint64_t)))
   ALLOC(cudaMallocHost(&ix->h_status, 64))
-  *ix->h_status = 0;
+  memset(ix->h_status, 0, 64);
   if (const char* sf = getenv("TSS_GEMM_MIN_NQ")) {  // diagnostics: one plain threshold
     ix->gemm_min_nq = (uint32_t)atoi(sf);
     ix->gemm_small_nq = 0xFFFFFFFFu;
@@ -946,6 +1022,8 @@ void tss_index_destroy(tss_index* ix) {
   cudaFree(ix->gemm.d_overflow);
   cudaFree(ix->gemm.d_pref_keys);
   if (ix->gemm.h_cand_count) cudaFreeHost(ix->gemm.h_cand_count);
+  cudaFree(ix->gemm.d_redo);
+  if (ix->gemm.h_redo) cudaFreeHost(ix->gemm.h_redo);
   if (ix->stream) cudaStreamDestroy(ix->stream);
   delete ix;
 }
@@ -1167,6 +1245,11 @@ int tss_index_search_device(tss_index* ix, const float* d_queries, uint32_t nq, 
   if (mrs.err != cudaSuccess) return cuda_fail(mrs.err, "mask ordering");
   bool merged = false;
   const bool gemm = gemm_route(ix, nq, k, mask_mode);  // the whole call takes one route
+  struct NoSync {  // K2 fix-ups stay on the device for the duration of this call
+    tss_index* ix;
+    explicit NoSync(tss_index* i) : ix(i) { ix->no_host_sync = true; }
+    ~NoSync() { ix->no_host_sync = false; }
+  } no_sync(ix);
   if (!ix->comm) return enqueue_local(ix, d_queries, nq, k, mask, mask_mode, d_out_keys, gemm, &merged);
   if ((rc = ensure_gather_ws(ix))) return rc;
   const bool fused = ix->xchg.ready && !gemm && k <= TSS_MAX_FUSED_K;
@@ -2181,6 +2264,16 @@ int tss_index_sync(tss_index* ix) {
   if (ix->h_status && *ix->h_status) {  // a fused sharded search gave up waiting for a peer
     *ix->h_status = 0;
     return fail(TSS_ERR_NCCL, "a rank of the shard group did not deliver its top-k within 20 s");
+  }
+  if (ix->h_status && ix->h_status[1]) {
+    // a device-resident tensor-core batch had more overflowing queries than fix-up launches
+    ix->h_status[1] = 0;
+    if (ix->gemm.fixups < 64) ix->gemm.fixups *= 2;
+    return fail(TSS_ERR_STATE,
+                "a tss_index_search_device batch flagged more queries for an exact redo than its "
+                "device-side fix-up launches cover: repeat the call (the number of fix-ups has "
+                "been raised to %u) or use tss_index_search",
+                ix->gemm.fixups);
   }
   return TSS_OK;
 }

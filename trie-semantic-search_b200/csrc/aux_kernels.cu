@@ -397,6 +397,40 @@ cudaError_t launch_terms_validate(const TermsDev& t, uint64_t pool_bytes, uint64
   return cudaGetLastError();
 }
 
+__global__ void __launch_bounds__(1024)
+redo_compact_kernel(const uint32_t* flags, uint32_t nq, uint32_t* d_list, uint32_t* d_count,
+                    uint32_t* h_list, uint32_t* h_count, uint32_t fixups, unsigned int* h_sticky) {
+  __shared__ uint32_t s_warp[32];
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool f = tid < nq && flags[tid] != 0;  // nq <= 1024: one thread per query
+  const unsigned m = __ballot_sync(FULL_MASK, f);
+  if (lane == 0) s_warp[warp] = __popc(m);
+  __syncthreads();
+  uint32_t before = 0, total = 0;
+  for (uint32_t w = 0; w < 32; ++w) {
+    if (w < warp) before += s_warp[w];
+    total += s_warp[w];
+  }
+  if (f) {
+    const uint32_t pos = before + __popc(m & ((1u << lane) - 1u));
+    d_list[pos] = tid;
+    h_list[pos] = tid;
+  }
+  if (tid == 0) {
+    *d_count = total;
+    *h_count = total;
+    if (total > fixups) atomicOr(h_sticky, 2u);
+  }
+}
+cudaError_t launch_redo_compact(const uint32_t* flags, uint32_t nq, uint32_t* d_list,
+                                uint32_t* d_count, uint32_t* h_list, uint32_t* h_count,
+                                uint32_t fixups, unsigned int* h_sticky, cudaStream_t st) {
+  if (nq > 1024) return cudaErrorInvalidValue;
+  redo_compact_kernel<<<1, 1024, 0, st>>>(flags, nq, d_list, d_count, h_list, h_count, fixups,
+                                          h_sticky);
+  return cudaGetLastError();
+}
+
 // ---- K5: merge of all-gathered per-rank top-k lists ---------------------------------------
 // one warp per query: stage the P sorted lists of k keys in shared memory, then a warp
 // tournament (scan.cuh) picks the k best.  in [P][nq][k] -> out [nq][k].

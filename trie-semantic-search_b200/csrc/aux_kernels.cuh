@@ -81,6 +81,14 @@ struct PrefixMaskArgs {
 cudaError_t launch_prefix_mask(const PrefixMaskArgs& a, const PrefixKeys& keys, int num_sms,
                                cudaStream_t st);
 
+// Device-side fix-up list of a K2 batch: the indices of the queries whose flag is set, compacted
+// (ascending) into d_list / *d_count for the guarded scans that follow, mirrored into mapped
+// host memory (h_list / *h_count: read by the host only when it synchronises anyway), and
+// *h_sticky |= 2 when there are more of them than `fixups` guarded launches will serve.
+cudaError_t launch_redo_compact(const uint32_t* flags, uint32_t nq, uint32_t* d_list,
+                                uint32_t* d_count, uint32_t* h_list, uint32_t* h_count,
+                                uint32_t fixups, unsigned int* h_sticky, cudaStream_t st);
+
 // K5: merge P gathered lists of k keys per query: in [P][nq][k] -> out [nq][k]
 cudaError_t launch_merge_gathered(const uint64_t* in, uint64_t* out, uint32_t P, uint32_t nq,
                                   uint32_t k, cudaStream_t st);

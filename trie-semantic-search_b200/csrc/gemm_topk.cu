@@ -72,6 +72,19 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap
       "l"(map), "r"(cluster_bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// the same, delivered to every CTA of cta_mask at the same CTA-relative offset (a quad = two
+// pairs sharing corpus tiles: the CTAs of equal parity in both pairs need the same half tile);
+// each destination's bytes are counted on the leader barrier of ITS OWN pair.
+// SASS UTMALDG.2D.2CTA.MULTICAST
+__device__ __forceinline__ void tma_load_2d_pair_mc(uint32_t dst, const CUtensorMap* map,
+                                                    uint32_t cluster_bar, int c0, int c1,
+                                                    uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      ".multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+      "l"(map), "r"(cluster_bar), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
 // arrives (once the MMAs issued so far retire) on the barrier at this offset in every CTA of cta_mask
 __device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t cta_mask) {
   asm volatile(
@@ -190,8 +203,12 @@ __device__ __forceinline__ void tmem_ld_wait() {
 // per stage, so the ring is 8 deep) with the cta_group::2 form of the TMA load, which counts
 // its bytes on the leader's barrier.  Each CTA's TMEM receives its own 128 queries x all 256
 // rows, so the epilogue is the same in both modes.
-template <int KB, bool PAIR>
-__host__ __device__ constexpr int gemm_stages() { return PAIR ? (KB <= 6 ? 8 : 6) : 4; }
+// CL: CTAs per cluster -- 1 independent CTAs, 2 one cta_group::2 pair, 4 a QUAD = two pairs that
+// score four query blocks against the same corpus tiles: every CTA fetches a QUARTER of each
+// tile (64 rows) and multicasts it to the CTA of its parity in the other pair, so each corpus
+// byte crosses L2 -> SM twice per 512 queries instead of four times.
+template <int KB, int CL>
+__host__ __device__ constexpr int gemm_stages() { return CL >= 2 ? (KB <= 6 ? 8 : 6) : 4; }
 // floats of staged 1/|row|: a pair's epilogue warps each keep the 32 columns' worth of the chunk
 // they are on (no block barrier); otherwise one double-buffered tile's worth shared by all
 // epilogue warps
@@ -199,19 +216,20 @@ __host__ __device__ constexpr int gemm_ninv_floats(bool pair) {
   return pair ? kEpiWarps * 32 : 2 * kBlockN;
 }
 
-template <int KB, bool PAIR>
+template <int KB, int CL>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_e,
                  const GemmParams p) {
+  constexpr bool PAIR = CL >= 2;
+  constexpr bool QUAD = CL == 4;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // swizzle-128B tiles need 1024-byte alignment; the kernel has no static shared memory, so
   // the dynamic window starts on its own allocation boundary (checked, not assumed)
   const uint32_t smem_base = smem_u32(smem_raw);
   if ((smem_base & 1023u) != 0) __trap();
   uint8_t* smem = smem_raw;
-  constexpr int CL = PAIR ? 2 : 1;                       // CTAs per cluster
   constexpr bool ARES = KB <= 6;                         // queries resident (else streamed)
-  constexpr int kStages = gemm_stages<KB, PAIR>();
+  constexpr int kStages = gemm_stages<KB, CL>();
   constexpr int kBBytes = PAIR ? kBTileBytes / 2 : kBTileBytes;  // corpus rows staged per CTA
   constexpr int kABytes = ARES ? KB * kATileBytes : 0;
   constexpr int kStageBytes = kBBytes + (ARES ? 0 : kATileBytes);
@@ -222,20 +240,42 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   float* s_ninv = reinterpret_cast<float*>(tail);        // inverse row norms (gemm_ninv_floats)
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail + gemm_ninv_floats(PAIR) * sizeof(float));
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + kBarSlots);
-  static_assert(2 * kStages + 5 <= kBarSlots, "barrier slots");
+  static_assert(2 * kStages + 6 <= kBarSlots, "barrier slots");
   const uint32_t bar_full = smem_u32(&bars[0]);        // [kStages]
   const uint32_t bar_empty = smem_u32(&bars[kStages]); // [kStages]
   const uint32_t bar_a = smem_u32(&bars[2 * kStages]);
   const uint32_t bar_tfull = smem_u32(&bars[2 * kStages + 1]);   // [2]
   const uint32_t bar_tempty = smem_u32(&bars[2 * kStages + 3]);  // [2]
+  const uint32_t bar_afree = smem_u32(&bars[2 * kStages + 5]);   // resident queries may be replaced
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = CL > 1 ? cluster_rank() : 0u;
-  const uint32_t cluster_id = blockIdx.x / CL, groups = p.mb / CL;  // clusters per slice
-  const uint32_t m_blk = (cluster_id % groups) * CL + rank;
-  const uint32_t slice = cluster_id / groups, nslices = (gridDim.x / CL) / groups;
-  constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
-  // this CTA's tile list: i = slice, slice + nslices, ... < count; tile = i * stride
+  // ---- work assignment, balanced over ALL clusters of the launch --------------------------
+  // C clusters serve G query groups of CL blocks (G = mb / CL).  F = C / G clusters belong to
+  // one group each; the R = C % G left over serve EVERY group in turn (G segments, reloading
+  // their queries in between).  Inside each period of C consecutive items (tiles, or sampled
+  // tiles) a group's own cluster i takes items [i*G, (i+1)*G) and left-over cluster j takes
+  // item F*G + j: every cluster does G items per period -- no SM idles because 148 is not a
+  // multiple of the query blocks -- and all clusters sweep the corpus together, so L2 sees
+  // each tile once per period.  Survivor lists are indexed by (query, slice of its group).
+  const uint32_t cluster_id = blockIdx.x / CL;
+  const uint32_t C = gridDim.x / CL, G = p.mb / CL, F = C / G, R = C - F * G;
+  if (F == 0) __trap();  // the host launches at least one cluster per query group
+  const bool left_over = cluster_id >= F * G;
+  const uint32_t nseg = left_over ? G : 1u;
+  const uint32_t run = left_over ? 1u : G;
+  const uint32_t item_base = left_over ? F * G + (cluster_id - F * G) : (cluster_id % F) * G;
+  const uint32_t slice = left_over ? F + (cluster_id - F * G) : cluster_id % F;
+  const uint32_t nslices = F + R;
+  auto item = [&](uint32_t n) -> uint32_t { return (n / run) * C + item_base + (n % run); };
+  auto seg_m_blk = [&](uint32_t seg) -> uint32_t {
+    return (left_over ? seg : cluster_id / F) * CL + rank;
+  };
+  constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);   // every CTA of the cluster
+  const uint32_t pair_rank = rank & 1u, pair_id = rank >> 1;  // (QUAD: which pair, which half)
+  const uint32_t lead_rank = rank & ~1u;                      // this CTA's pair leader
+  const uint16_t pair_mask = (uint16_t)(3u << lead_rank);     // the two CTAs of this pair
+  // this cluster's items: item(0), item(1), ... < count; tile = item * stride
   const uint32_t count = p.mode == 0 ? p.sample_count : p.num_tiles;
   const uint32_t stride = p.mode == 0 ? p.sample_stride : 1u;
 
@@ -244,9 +284,12 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     prefetch_tmap(&tmap_e);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_empty + 8 * s, 1);
+      // a stage is refilled by loads that land in BOTH pairs of a quad: it is free only when
+      // both leaders' MMAs have read it
+      mbar_init(bar_empty + 8 * s, QUAD ? 2 : 1);
     }
     mbar_init(bar_a, 1);
+    mbar_init(bar_afree, 1);
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
       // one arrival per epilogue warp; the leader's MMA thread also waits for the peer's warps
@@ -277,15 +320,23 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   // ring stages in use (diagnostic knob: fewer stages = fewer bytes in flight)
   const uint32_t nst = p.ring_stages && p.ring_stages < (uint32_t)kStages ? p.ring_stages : kStages;
   // PAIR: the barriers TMA bytes and drained accumulators are reported to are the leader's
-  const bool leader = !PAIR || rank == 0;
-  const uint32_t lead_full = PAIR ? map_to_rank(bar_full, 0) : bar_full;
-  const uint32_t lead_a = PAIR ? map_to_rank(bar_a, 0) : bar_a;
-  const uint32_t lead_tempty = PAIR ? map_to_rank(bar_tempty, 0) : bar_tempty;
+  const bool leader = !PAIR || pair_rank == 0;
+  const uint32_t lead_full = PAIR ? map_to_rank(bar_full, lead_rank) : bar_full;
+  const uint32_t lead_a = PAIR ? map_to_rank(bar_a, lead_rank) : bar_a;
+  const uint32_t lead_tempty = PAIR ? map_to_rank(bar_tempty, lead_rank) : bar_tempty;
 
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
+      uint32_t s = 0, ph = 0;
+      // (A contiguous L2 prefetch of whole tiles ahead of these strided boxes used to live here;
+      // measured with a 7- or 8-deep ring it changes nothing at 512+ queries and costs 25-40 % at
+      // <= 256, where every SM streams its own tiles.)
+      for (uint32_t seg = 0; seg < nseg; ++seg) {
+      const uint32_t m_blk = seg_m_blk(seg);
       if (ARES) {
+        // (a left-over cluster's next group: the MMAs that read the old queries have retired)
+        if (seg) mbar_wait(bar_afree, (seg - 1) & 1u);
         if (leader) mbar_arrive_expect_tx(bar_a, kTxCtas * KB * kATileBytes);
         for (int kb = 0; kb < KB; ++kb) {
           if (PAIR)
@@ -295,11 +346,9 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             tma_load_2d(sA + kb * kATileBytes, &tmap_q, bar_a, kb * kBlockK, (int)(m_blk * kBlockM));
         }
       }
-      uint32_t s = 0, ph = 0;
-      // (A contiguous L2 prefetch of whole tiles ahead of these strided boxes used to live here;
-      // measured with a 7- or 8-deep ring it changes nothing at 512+ queries and costs 25-40 % at
-      // <= 256, where every SM streams its own tiles.)
-      for (uint32_t i = slice; i < count; i += nslices) {
+      for (uint32_t n = 0;; ++n) {
+        const uint32_t i = item(n);
+        if (i >= count) break;
         const int row0 = (int)(i * stride * kBlockN);
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(bar_empty + 8 * s, ph ^ 1);
@@ -312,8 +361,14 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             if (!ARES)
               tma_load_2d_pair(stage + kBBytes, &tmap_q, lead_full + 8 * s, kb * kBlockK,
                                (int)(m_blk * kBlockM));
-            tma_load_2d_pair(stage, &tmap_e, lead_full + 8 * s, kb * kBlockK,
-                             row0 + (int)rank * (kBlockN / 2));
+            if (QUAD)  // my quarter of the tile, into my pair AND the other pair's CTA of my parity
+              tma_load_2d_pair_mc(stage + pair_id * (kBBytes / 2), &tmap_e, lead_full + 8 * s,
+                                  kb * kBlockK,
+                                  row0 + (int)pair_rank * (kBlockN / 2) + (int)pair_id * (kBlockN / 4),
+                                  (uint16_t)(5u << pair_rank));
+            else
+              tma_load_2d_pair(stage, &tmap_e, lead_full + 8 * s, kb * kBlockK,
+                               row0 + (int)rank * (kBlockN / 2));
           } else {
             // (query tile and) the 256 corpus rows of this k-block
             mbar_arrive_expect_tx(bar_full + 8 * s, kStageBytes);
@@ -326,13 +381,15 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           if (++s == nst) s = 0, ph ^= 1;
         }
       }
+      }
     }
   } else if (warp == 1) {
     // ===== MMA issuer (one elected lane; of a pair, the leader's) =====
     if (lane == 0 && leader) {
-      if (ARES) mbar_wait(bar_a, 0);
       uint32_t s = 0, ph = 0, it = 0;
-      for (uint32_t i = slice; i < count; i += nslices, ++it) {
+      for (uint32_t seg = 0; seg < nseg; ++seg) {
+      if (ARES) mbar_wait(bar_a, seg & 1u);
+      for (uint32_t n = 0; item(n) < count; ++n, ++it) {
         const uint32_t acc = it & 1u, use = it >> 1;
         mbar_wait(bar_tempty + 8 * acc, (use & 1u) ^ 1u);  // epilogue drained this accumulator
         tc_fence_after();
@@ -350,14 +407,20 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             if (PAIR) umma_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, (kb | k) != 0 ? 1u : 0u);
             else umma(tmem_d, adesc + 2 * k, bdesc + 2 * k, (kb | k) != 0 ? 1u : 0u);
           }
-          // smem stage reusable once these MMAs retire (a pair's: in both CTAs)
+          // smem stage reusable once these MMAs retire (a pair's: in both CTAs; a quad's: every
+          // CTA hears from both leaders)
           if (PAIR) umma_commit_pair(bar_empty + 8 * s, kMask);
           else umma_commit(bar_empty + 8 * s);
           if (++s == nst) s = 0, ph ^= 1;
         }
         // accumulator complete (a pair's: in both CTAs' TMEM)
-        if (PAIR) umma_commit_pair(bar_tfull + 8 * acc, kMask);
+        if (PAIR) umma_commit_pair(bar_tfull + 8 * acc, pair_mask);
         else umma_commit(bar_tfull + 8 * acc);
+      }
+      if (ARES && seg + 1 < nseg) {  // the resident queries may be replaced once these retire
+        if (PAIR) umma_commit_pair(bar_afree, pair_mask);
+        else umma_commit(bar_afree);
+      }
       }
     }
   } else {
@@ -368,13 +431,9 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const uint32_t lane_base = 32u * (warp & 3);
     const uint32_t part = (uint32_t)(warp - 2) >> 2;      // which kColsPer-column part
     const uint32_t q_local = lane_base + lane;            // query within the block
-    const uint32_t q = m_blk * kBlockM + q_local;         // query within the batch (may be >= nq)
     const uint32_t et = threadIdx.x - 64;                 // 0..kEpiThreads-1
-    const float thr = (p.mode == 1) ? p.thr[q] : 0.f;
     // survivors of (query, slice, part) go to a list only this thread writes: no atomics
     const uint32_t sub = slice * kColSplit + part, nsub = nslices * kColSplit;
-    uint64_t* my_cand = p.cand + ((size_t)q * nsub + sub) * p.cand_cap;
-    uint32_t my_count = 0;
     uint32_t it = 0;
     // 1/|row| of local row r as the epilogue wants it
     auto row_weight = [&](uint64_t r) -> float {
@@ -405,10 +464,17 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         a = row_weight(r);
       }
     };
-    float w_a = 0.f, w_b = 0.f;
-    fetch_weights(slice, w_a, w_b);
     float* warp_ninv = s_ninv + (warp - 2) * 32;
-    for (uint32_t i = slice; i < count; i += nslices, ++it) {
+    for (uint32_t seg = 0; seg < nseg; ++seg) {
+    const uint32_t q = seg_m_blk(seg) * kBlockM + q_local;  // query within the batch (may be >= nq)
+    const float thr = (p.mode == 1) ? p.thr[q] : 0.f;
+    uint64_t* my_cand = p.cand + ((size_t)q * nsub + sub) * p.cand_cap;
+    uint32_t my_count = 0;
+    float w_a = 0.f, w_b = 0.f;
+    fetch_weights(item(0), w_a, w_b);
+    for (uint32_t n = 0;; ++n, ++it) {
+      const uint32_t i = item(n);
+      if (i >= count) break;
       const uint32_t acc = it & 1u, use = it >> 1;
       const uint64_t row0 = (uint64_t)i * stride * kBlockN;
       // ninv[c] = weight of the tile's column c (for the columns this thread visits)
@@ -422,7 +488,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       }
       float n_a = 0.f, n_b = 0.f;  // the next tile's weights, in flight while this one is scored
-      fetch_weights(i + nslices, n_a, n_b);
+      fetch_weights(item(n + 1), n_a, n_b);
       mbar_wait(bar_tfull + 8 * acc, use & 1u);
       tc_fence_after();
       const uint64_t left = p.n_rows - row0;
@@ -496,6 +562,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         p.tile_max[(size_t)q * (p.sample_count * kColSplit) + (size_t)i * kColSplit + part] = mx;
     }
     if (p.mode == 1) p.cand_count[(size_t)q * nsub + sub] = my_count;
+    }
   }
 
   tc_fence_before();
@@ -935,6 +1002,47 @@ refine_kernel(const uint64_t* cand, uint32_t kc, const Rescore rs, float two_eps
 
 // ---- host side ------------------------------------------------------------------------------
 int gemm_col_split() { return kColSplit; }
+int gemm_max_quads(int kb) {
+  // clusters of four 1-CTA/SM blocks the device can keep resident at once (GPC shapes decide)
+  static int cached[17] = {};
+  if (kb < 0 || kb > 16) return 0;
+  if (cached[kb]) return cached[kb] < 0 ? 0 : cached[kb];
+  int n = 0;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(4 * 64);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = gemm_smem_bytes(kb, true);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 4;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaErrorInvalidValue;
+#define TSS_QUAD_OCC(KBV)                                                                        \
+  case KBV:                                                                                       \
+    e = cudaFuncSetAttribute(gemm_topk_kernel<KBV, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                             (int)cfg.dynamicSmemBytes);                                          \
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveClusters(&n, gemm_topk_kernel<KBV, 4>, &cfg); \
+    break;
+  switch (kb) {
+    TSS_QUAD_OCC(2)
+    TSS_QUAD_OCC(4)
+    TSS_QUAD_OCC(6)
+    TSS_QUAD_OCC(8)
+    TSS_QUAD_OCC(12)
+    TSS_QUAD_OCC(16)
+    default: break;
+  }
+#undef TSS_QUAD_OCC
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    n = 0;
+  }
+  cached[kb] = n > 0 ? n : -1;
+  return n;
+}
 size_t gemm_smem_bytes(int kb, bool pair) {
   const size_t stages = pair ? (kb <= 6 ? 8 : 6) : 4;
   const size_t b = pair ? kBTileBytes / 2 : kBTileBytes;
@@ -942,11 +1050,11 @@ size_t gemm_smem_bytes(int kb, bool pair) {
   return ring + gemm_ninv_floats(pair) * sizeof(float) + kBarSlots * 8 + 16;
 }
 
-template <int KB, bool PAIR>
+template <int KB, int CL>
 static cudaError_t launch_gemm_inst(const CUtensorMap& tmap_q, const CUtensorMap& tmap_e,
                                     const GemmParams& p, int grid, size_t smem, cudaStream_t st) {
-  static_assert(gemm_stages<KB, PAIR>() == (PAIR ? (KB <= 6 ? 8 : 6) : 4), "gemm_smem_bytes");
-  auto kern = gemm_topk_kernel<KB, PAIR>;
+  static_assert(gemm_stages<KB, CL>() == (CL >= 2 ? (KB <= 6 ? 8 : 6) : 4), "gemm_smem_bytes");
+  auto kern = gemm_topk_kernel<KB, CL>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg{};
@@ -956,7 +1064,7 @@ static cudaError_t launch_gemm_inst(const CUtensorMap& tmap_q, const CUtensorMap
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = PAIR ? 2 : 1;
+  attr[0].val.clusterDim.x = CL;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
@@ -967,11 +1075,12 @@ static cudaError_t launch_gemm_inst(const CUtensorMap& tmap_q, const CUtensorMap
 cudaError_t launch_gemm_topk(int kb, int cluster, const CUtensorMap& tmap_q,
                              const CUtensorMap& tmap_e, const GemmParams& p, int grid,
                              cudaStream_t st) {
-  const size_t smem = gemm_smem_bytes(kb, cluster == TSS_GEMM_PAIR);
-#define TSS_GEMM_CASE(KBV)                                                                  \
-  case KBV:                                                                                  \
-    return cluster == TSS_GEMM_PAIR ? launch_gemm_inst<KBV, true>(tmap_q, tmap_e, p, grid, smem, st) \
-                                    : launch_gemm_inst<KBV, false>(tmap_q, tmap_e, p, grid, smem, st);
+  const size_t smem = gemm_smem_bytes(kb, cluster != TSS_GEMM_SINGLE);
+#define TSS_GEMM_CASE(KBV)                                                                   \
+  case KBV:                                                                                   \
+    return cluster == TSS_GEMM_QUAD   ? launch_gemm_inst<KBV, 4>(tmap_q, tmap_e, p, grid, smem, st) \
+           : cluster == TSS_GEMM_PAIR ? launch_gemm_inst<KBV, 2>(tmap_q, tmap_e, p, grid, smem, st) \
+                                      : launch_gemm_inst<KBV, 1>(tmap_q, tmap_e, p, grid, smem, st);
   switch (kb) {
     TSS_GEMM_CASE(2)
     TSS_GEMM_CASE(4)

@@ -28,8 +28,11 @@ struct GemmParams {
 // How the CTAs of a launch cooperate.  PAIR needs an even mb and a tmap_e with a 128-row box:
 // two CTAs score different query blocks against the same corpus tiles as one cta_group::2 M256
 // MMA, each staging half of every tile.  SINGLE: independent CTAs, 256-row box.
-enum GemmCluster { TSS_GEMM_SINGLE = 1, TSS_GEMM_PAIR = 2 };
+// QUAD: clusters of four = two pairs sharing corpus tiles by TMA multicast (mb a multiple of 4,
+// tmap_e with a 64-row box); at most gemm_max_quads(kb) clusters are resident at once.
+enum GemmCluster { TSS_GEMM_SINGLE = 1, TSS_GEMM_PAIR = 2, TSS_GEMM_QUAD = 4 };
 size_t gemm_smem_bytes(int kb, bool pair);
+int gemm_max_quads(int kb);
 int gemm_col_split();  // survivor lists / threshold samples per (slice, tile)
 cudaError_t launch_gemm_topk(int kb, int cluster, const CUtensorMap& tmap_q,
                              const CUtensorMap& tmap_e, const GemmParams& p, int grid,

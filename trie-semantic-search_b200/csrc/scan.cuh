@@ -74,6 +74,14 @@ struct ScanParams {
   const uint32_t* row_list;        // null: no list
   const uint32_t* row_list_count;
   uint32_t row_list_cap;
+  // guarded launch (the device-side fix-up of a K2 batch, enqueued before anyone knows whether
+  // it is needed): live only if guard_index < *guard_count, and then it answers query
+  // guard_list[guard_index] of the batch (`queries` / `out_keys` are the batch's bases, one
+  // query per launch).  Otherwise every CTA goes straight to the workspace hand-over and
+  // nothing is written.
+  const uint32_t* guard_list;      // null: an ordinary launch
+  const uint32_t* guard_count;
+  uint32_t guard_index;
   float q_inline[384];
 };
 
@@ -251,6 +259,17 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_topk_kernel(const __grid_c
     fence_barrier_init();
   }
   __syncwarp();
+  bool active = true;  // (grid-uniform)
+  const float* q_base = p.queries;
+  uint64_t* out_base = p.out_keys;
+  if (p.guard_list) {
+    active = p.guard_index < __ldcg(p.guard_count);
+    if (active) {
+      const uint32_t qi = __ldcg(p.guard_list + p.guard_index);
+      q_base += (size_t)qi * p.dim;
+      out_base += (size_t)qi * p.k;
+    }
+  }
 
   // ---- queries -> registers; canonical self norm -----------------------------------
   float4 q[BQ][NS];
@@ -261,7 +280,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_topk_kernel(const __grid_c
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
       uint32_t j = 128u * s + 4u * lane;
-      const float* qb = p.queries + (size_t)b * p.dim;
+      const float* qb = q_base + (size_t)b * p.dim;
       bool live = (uint32_t)b < p.nq_valid;
       float4 v;
       if (p.use_inline) {  // (b == 0 only: nq_valid == 1)
@@ -292,7 +311,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_topk_kernel(const __grid_c
 #pragma unroll
   for (int b = 0; b < BQ; ++b) cnt[b] = 0, thresh[b] = 0;
 
-  const uint64_t total_tiles = (p.n_rows + R - 1) / R;
+  const uint64_t total_tiles = active ? (p.n_rows + R - 1) / R : 0;
   const uint64_t GW = (uint64_t)gridDim.x * WARPS;
   const uint64_t policy = policy_evict_first();
   const uint8_t* rows_b = reinterpret_cast<const uint8_t*>(p.rows);
@@ -329,7 +348,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_topk_kernel(const __grid_c
     if (p.row_list) {
       const uint32_t c = __ldcg(p.row_list_count);
       if (c <= p.row_list_cap) {
-        list_n = c;
+        list_n = active ? c : 0u;
         m_next = (uint64_t)warp * gridDim.x + blockIdx.x;  // chunks spread over the SMs first
       }
     }
@@ -351,7 +370,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_topk_kernel(const __grid_c
       __syncwarp();
       return cnt;
     }
-    while (m_next < total_tiles) {
+    // mask walk: windows of 32 tiles (one per lane) are examined until the buffer's R slots are
+    // full, so a sparse mask still puts a whole buffer of bytes in flight per fill.  The bytes
+    // of each window are announced with expect_tx; the one arrival of the phase comes last.
+    uint32_t filled = 0;
+    while (m_next < total_tiles && filled < (uint32_t)R) {
       const uint64_t tc = m_next + (uint64_t)lane * GW;
       const uint32_t b = tc < total_tiles ? tile_bits(tc) : 0u;
       const uint32_t pc = __popc(b);
@@ -361,16 +384,18 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_topk_kernel(const __grid_c
         uint32_t v = __shfl_up_sync(FULL_MASK, inc, d);
         if (lane >= d) inc += v;
       }
-      // whole tiles only: the lanes whose running total still fits form a prefix (lane 0 always)
-      const unsigned takem = __ballot_sync(FULL_MASK, inc <= (uint32_t)R);
+      // whole tiles only: the lanes whose running total still fits form a prefix (with an empty
+      // buffer lane 0 always fits)
+      const unsigned takem = __ballot_sync(FULL_MASK, inc <= (uint32_t)R - filled);
       const int ntake = takem == FULL_MASK ? 32 : __ffs(~takem) - 1;
+      if (ntake == 0) break;  // the next tile needs more room than is left: ship what we have
       const uint32_t total = __shfl_sync(FULL_MASK, inc, ntake - 1);
       m_next += (uint64_t)ntake * GW;
       if (total == 0) continue;  // nothing live in these tiles
-      if (lane == 0) mbar_arrive_expect_tx(bar, total * ROW_BYTES);
+      if (lane == 0) mbar_expect_tx(bar, total * ROW_BYTES);
       __syncwarp();
       if (lane < ntake && pc) {
-        uint32_t slot = inc - pc;
+        uint32_t slot = filled + inc - pc;
         const uint8_t* src = rows_b + tc * (uint64_t)TILE_BYTES;
         if (b == (1u << pc) - 1u) {  // rows 0..pc-1: contiguous in HBM and in the buffer
           bulk_g2s(tile_s + slot * ROW_BYTES, src, pc * ROW_BYTES, bar, policy);
@@ -383,10 +408,14 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_topk_kernel(const __grid_c
           }
         }
       }
-      __syncwarp();
-      return total;
+      filled += total;
     }
-    return 0u;
+    if (filled) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar);
+    }
+    __syncwarp();
+    return filled;
   };
 
   // the previous user of this workspace slot must have finished (normally long ago)
@@ -542,18 +571,20 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_topk_kernel(const __grid_c
   // its prologue and first tiles overlap our merges and the last CTA's exchange.
   if (p.pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   // ---- per-warp final prune: sorted, zero padded ---------------------------------
-#pragma unroll
-  for (int b = 0; b < BQ; ++b)
-    warp_prune(lists + (size_t)b * p.cap, cnt[b], p.k, p.cap, thresh[b], lane);
-  __syncthreads();
-  dbg_stamp(p, 3);
-
-  // ---- CTA merge: tournament over the WARPS sorted lists, one warp per query -------------
   const int tid = threadIdx.x, nthreads = WARPS * 32;
-  if ((uint32_t)warp < p.nq_valid) {
-    uint64_t* dst = p.partials + ((size_t)warp * gridDim.x + blockIdx.x) * p.kp;
-    warp_tournament<(WARPS + 31) / 32>(cands_base + (size_t)warp * p.cap, BQ * p.cap, WARPS, p.k,
-                                       p.k, dst, lane);
+  if (active) {
+#pragma unroll
+    for (int b = 0; b < BQ; ++b)
+      warp_prune(lists + (size_t)b * p.cap, cnt[b], p.k, p.cap, thresh[b], lane);
+    __syncthreads();
+    dbg_stamp(p, 3);
+
+    // ---- CTA merge: tournament over the WARPS sorted lists, one warp per query -------------
+    if ((uint32_t)warp < p.nq_valid) {
+      uint64_t* dst = p.partials + ((size_t)warp * gridDim.x + blockIdx.x) * p.kp;
+      warp_tournament<(WARPS + 31) / 32>(cands_base + (size_t)warp * p.cap, BQ * p.cap, WARPS, p.k,
+                                         p.k, dst, lane);
+    }
   }
 
   // ---- last CTA merges the per-CTA partials --------------------------------------------
@@ -574,7 +605,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_topk_kernel(const __grid_c
   // stage every partial in shared memory (the launcher sized it for gridDim.x * kp keys
   // per query pass), then one warp per query runs the tournament
   uint64_t* ws = reinterpret_cast<uint64_t*>(smem);
-  for (uint32_t b = 0; b < p.nq_valid; ++b) {
+  for (uint32_t b = 0; active && b < p.nq_valid; ++b) {
     const uint64_t* part = p.partials + (size_t)b * gridDim.x * p.kp;
     const uint32_t total_keys = gridDim.x * p.k;
     for (uint32_t i0 = tid; i0 < total_keys; i0 += 4 * nthreads) {
@@ -594,7 +625,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_topk_kernel(const __grid_c
     __syncthreads();
     // sharded + fused: the local result goes to a staging row in shared memory instead
     uint64_t* fin = ws + (size_t)gridDim.x * p.k + (size_t)b * kXchgMaxK;
-    uint64_t* dst = p.xchg_nranks ? fin : p.out_keys + (size_t)b * p.k;
+    uint64_t* dst = p.xchg_nranks ? fin : out_base + (size_t)b * p.k;
     if (warp == 0) {
       if (gridDim.x <= 160)
         warp_tournament<5>(ws, p.k, gridDim.x, p.k, p.k, dst, lane);
@@ -647,7 +678,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_topk_kernel(const __grid_c
     __syncthreads();
     if ((uint32_t)warp < p.nq_valid)
       warp_tournament<1>(ws + (size_t)warp * p.xchg_nranks * p.k, p.k, p.xchg_nranks, p.k, p.k,
-                         p.out_keys + (size_t)warp * p.k, lane);
+                         out_base + (size_t)warp * p.k, lane);
   }
   dbg_stamp(p, 5);
   if (tid == 0) {
