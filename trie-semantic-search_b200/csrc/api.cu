@@ -87,7 +87,7 @@ constexpr int kNcclUint64 = 5;
 constexpr uint32_t kMaxBq = 4;           // queries per scan launch
 constexpr uint32_t kScanSlots = 4;       // scan workspace slots (launches in flight under PDL)
 constexpr uint32_t kWsQueries = 1024;    // device query/result workspace, in queries
-constexpr size_t kStageBytes = 64u << 20;  // upload staging buffer
+constexpr size_t kStageBytes = 32u << 20;  // one of the two upload staging buffers
 constexpr uint32_t kGemmCandCap = 32768;   // K2 survivor keys per query of a FULL workspace batch:
                                            // the pool (kWsQueries x this) is shared out per batch
 constexpr uint32_t kGemmMaxSample = 8192;  // tiles sampled by the K2 threshold pass
@@ -204,7 +204,11 @@ struct tss_index {
   uint64_t row_base = 0;
   tss_comm* comm = nullptr;
   // workspaces
-  float* d_stage = nullptr;  // kStageBytes upload staging (lazy)
+  // upload pipeline (lazy): two pinned host buffers + two device staging buffers, so the host's
+  // copy of chunk i+1 out of the caller's (pageable) memory overlaps the DMA + packing of chunk i
+  float* d_stage = nullptr;        // 2 x kStageBytes
+  float* h_stage = nullptr;        // 2 x kStageBytes, pinned
+  cudaEvent_t stage_ev[2] = {nullptr, nullptr};
   int* d_flag = nullptr;
   float* d_queries = nullptr;      // kWsQueries x dim
   uint64_t* d_keys = nullptr;      // kWsQueries x TSS_MAX_FUSED_K local results
@@ -749,11 +753,11 @@ int enqueue_gemm(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
 // Queries flagged in g.d_overflow (a K2 survivor list overflowed, or the shadow prefilter could
 // not prove completeness) are redone exactly by the scan.  On the device: the flags are compacted
 // into a list and `fixups` GUARDED scans are enqueued behind the batch -- launch j serves the
-// j-th flagged query if there is one, else it is a few microseconds of nothing -- so the common
-// case (no flag, or a handful) needs no host synchronisation.  tss_index_search, which
-// synchronises anyway, then finishes what the guarded launches did not cover;
-// tss_index_search_device leaves a sticky status for tss_index_sync instead and the number of
-// fix-up launches doubles.  k > 128 (scan by rounds) is redone from the host in either entry.
+// j-th flagged query if there is one, else it is a few microseconds of nothing -- so
+// tss_index_search_device needs no host synchronisation; more flagged queries than launches
+// leave a sticky status for tss_index_sync and the number of fix-up launches doubles.
+// tss_index_search, which synchronises anyway, reads the list and redoes them from the host.
+// k > 128 (scan by rounds) is redone from the host in either entry.
 int enqueue_fixups(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
                    const tss_mask* mask, int mode, uint64_t* d_out) {
   tss_index::Gemm& g = ix->gemm;
@@ -762,7 +766,9 @@ int enqueue_fixups(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t 
   const uint32_t seen = g.h_redo[0];
   if (seen > g.fixups && g.fixups < 64) g.fixups *= 2;
   if (seen * 20 > kWsQueries / 4 && g.spread_boost < 64) g.spread_boost *= 2;
-  const uint32_t fixups = on_device ? (g.fixups < nq ? g.fixups : nq) : 0;
+  // (tss_index_search synchronises anyway and redoes flagged queries from the host: it does not
+  // pay for guarded launches that almost never have work)
+  const uint32_t fixups = on_device && ix->no_host_sync ? (g.fixups < nq ? g.fixups : nq) : 0;
   cudaError_t e = tss::launch_redo_compact(g.d_overflow, nq, g.d_redo + 1, g.d_redo, g.h_redo + 1,
                                            g.h_redo, on_device && ix->no_host_sync ? fixups : nq,
                                            ix->h_status + 1, ix->stream);
@@ -996,6 +1002,9 @@ void tss_index_destroy(tss_index* ix) {
   if (ix->stream) cudaStreamSynchronize(ix->stream);
   cudaFree(ix->d_rows);
   cudaFree(ix->d_stage);
+  if (ix->h_stage) cudaFreeHost(ix->h_stage);
+  for (cudaEvent_t ev : ix->stage_ev)
+    if (ev) cudaEventDestroy(ev);
   cudaFree(ix->d_flag);
   cudaFree(ix->d_queries);
   cudaFree(ix->d_keys);
@@ -1046,22 +1055,32 @@ int tss_index_add(tss_index* ix, const float* rows, uint64_t nrows) {
   DeviceGuard g(ix->device);
   int rc = ensure_capacity(ix, ix->n_rows + nrows);
   if (rc) return rc;
-  if (!ix->d_stage) CU(cudaMalloc(&ix->d_stage, kStageBytes));
+  if (!ix->d_stage) {
+    CU(cudaMalloc(&ix->d_stage, 2 * kStageBytes));
+    CU(cudaMallocHost(&ix->h_stage, 2 * kStageBytes));
+    for (cudaEvent_t& ev : ix->stage_ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  }
   CU(cudaMemsetAsync(ix->d_flag, 0, sizeof(int), ix->stream));
   const uint64_t chunk_rows = kStageBytes / ((size_t)ix->dim * sizeof(float));
   if (!chunk_rows) return fail(TSS_ERR_INVALID_ARG, "dim too large for the staging buffer");
-  for (uint64_t r0 = 0; r0 < nrows; r0 += chunk_rows) {
-    uint64_t n = nrows - r0 < chunk_rows ? nrows - r0 : chunk_rows;
-    CU(cudaMemcpyAsync(ix->d_stage, rows + (size_t)r0 * ix->dim, (size_t)n * ix->dim * sizeof(float),
-                       cudaMemcpyHostToDevice, ix->stream));
-    cudaError_t e = tss::launch_check_finite(ix->d_stage, n * ix->dim, ix->d_flag, ix->stream);
+  uint32_t ci = 0;
+  for (uint64_t r0 = 0; r0 < nrows; r0 += chunk_rows, ++ci) {
+    const uint64_t n = nrows - r0 < chunk_rows ? nrows - r0 : chunk_rows;
+    const size_t bytes = (size_t)n * ix->dim * sizeof(float);
+    const uint32_t b = ci & 1u;
+    float* hs = ix->h_stage + b * (kStageBytes / sizeof(float));
+    float* ds = ix->d_stage + b * (kStageBytes / sizeof(float));
+    // buffer b was last used by chunk ci - 2: its DMA and packing must be done
+    if (ci >= 2) CU(cudaEventSynchronize(ix->stage_ev[b]));
+    memcpy(hs, rows + (size_t)r0 * ix->dim, bytes);  // overlaps chunk ci - 1 on the device
+    CU(cudaMemcpyAsync(ds, hs, bytes, cudaMemcpyHostToDevice, ix->stream));
+    cudaError_t e = tss::launch_check_finite(ds, n * ix->dim, ix->d_flag, ix->stream);
     if (e != cudaSuccess) return cuda_fail(e, "check_finite launch");
-    e = tss::launch_pack_rows(ix->d_stage, ix->d_rows + (size_t)(ix->n_rows + r0) * ix->row_bytes, n,
+    e = tss::launch_pack_rows(ds, ix->d_rows + (size_t)(ix->n_rows + r0) * ix->row_bytes, n,
                               ix->dim, ix->stride_elems, ix->storage == TSS_BF16, ix->stream);
     if (e != cudaSuccess) return cuda_fail(e, "pack_rows launch");
     g_launches.fetch_add(2, std::memory_order_relaxed);
-    // the staging buffer is reused by the next chunk
-    CU(cudaStreamSynchronize(ix->stream));
+    CU(cudaEventRecord(ix->stage_ev[b], ix->stream));
   }
   int flag = 0;
   CU(cudaMemcpyAsync(&flag, ix->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ix->stream));
@@ -1102,9 +1121,15 @@ int tss_index_finalize(tss_index* ix) {
     if (rc) return rc;
   }
   CU(cudaStreamSynchronize(ix->stream));
-  if (ix->d_stage) {
+  if (ix->d_stage) {  // the upload pipeline is only needed while rows arrive
     cudaFree(ix->d_stage);
     ix->d_stage = nullptr;
+    cudaFreeHost(ix->h_stage);
+    ix->h_stage = nullptr;
+    for (cudaEvent_t& ev : ix->stage_ev) {
+      cudaEventDestroy(ev);
+      ev = nullptr;
+    }
   }
   ix->finalized = true;
   return TSS_OK;
@@ -1204,17 +1229,31 @@ int tss_index_load(tss_index** out, const char* path, int device) {
   }
   DeviceGuard g(device);
   rc = ensure_capacity(ix, h.n_rows ? h.n_rows : 1);
-  void* hbuf = nullptr;
-  if (!rc && cudaMallocHost(&hbuf, kIoChunk) != cudaSuccess) rc = fail(TSS_ERR_OOM, "pinned buffer");
+  // two pinned buffers: the read of chunk i+1 from the file overlaps the DMA of chunk i
+  uint8_t* hbuf = nullptr;
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  if (!rc && (cudaMallocHost(&hbuf, 2 * kIoChunk) != cudaSuccess ||
+              cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming) != cudaSuccess ||
+              cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming) != cudaSuccess))
+    rc = fail(TSS_ERR_OOM, "pinned buffer");
   const size_t total = (size_t)h.n_rows * h.row_bytes;
-  for (size_t off = 0; !rc && off < total; off += kIoChunk) {
+  uint32_t ci = 0;
+  for (size_t off = 0; !rc && off < total; off += kIoChunk, ++ci) {
     size_t n = total - off < kIoChunk ? total - off : kIoChunk;
-    if (fread(hbuf, 1, n, f) != n)
+    uint8_t* hb = hbuf + (ci & 1u) * kIoChunk;
+    if (ci >= 2 && cudaEventSynchronize(ev[ci & 1u]) != cudaSuccess)
+      rc = fail(TSS_ERR_CUDA, "upload of %s failed", path);
+    else if (fread(hb, 1, n, f) != n)
       rc = fail(TSS_ERR_INVALID_ARG, "%s is truncated", path);
-    else if (cudaMemcpy(ix->d_rows + off, hbuf, n, cudaMemcpyHostToDevice) != cudaSuccess)
+    else if (cudaMemcpyAsync(ix->d_rows + off, hb, n, cudaMemcpyHostToDevice, ix->stream) != cudaSuccess ||
+             cudaEventRecord(ev[ci & 1u], ix->stream) != cudaSuccess)
       rc = fail(TSS_ERR_CUDA, "upload of %s failed", path);
   }
+  if (cudaStreamSynchronize(ix->stream) != cudaSuccess && !rc)
+    rc = fail(TSS_ERR_CUDA, "upload of %s failed", path);
   if (hbuf) cudaFreeHost(hbuf);
+  for (cudaEvent_t e2 : ev)
+    if (e2) cudaEventDestroy(e2);
   fclose(f);
   if (rc) {
     tss_index_destroy(ix);
