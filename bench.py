@@ -825,7 +825,58 @@ def main():
         if world == 1 and args.rows >= 4 * 256 * 100:
             extras["config3"] = config3_leg(tss, orc, args, ix, device, peaks)
             extras["config4"] = config4_leg(tss, orc, args, ix, device)
+        if world == 1:
+            # how fast rows arrive through tss_index_add (host fp32 -> pinned staging -> HBM, checked
+            # for NaN/Inf and packed on the device; the host copy of chunk i+1 overlaps chunk i)
+            nup = 262_144
+            up_rows = orc.gen_rows(0, nup, args.dim, SEED_ROWS)
+            ixu = tss.FlatIndex(args.dim, storage, device)
+            ixu.reserve(2 * nup)
+            ixu.add(up_rows)  # warm-up: allocates the staging buffers
+            t0 = time.perf_counter()
+            ixu.add(up_rows)
+            ixu.finalize()
+            up_s = time.perf_counter() - t0
+            back = ixu.get_rows(nup + 12345, 2)
+            extras["upload"] = {
+                "what": "tss_index_add of host fp32 rows (pageable numpy memory) + finalize",
+                "rows": nup, "bytes": int(up_rows.nbytes), "seconds": up_s,
+                "gbs": up_rows.nbytes / up_s / 1e9,
+                "check": "ok" if np.array_equal(back, up_rows[12345:12347]) else "FAILED"}
+            ixu.close()
         if world > 1:
+            # a 1024-query batch on the SHARDED index: local K2 (bf16 shadow + exact re-scoring),
+            # NCCL all-gather of the keys, merge kernel
+            nb = 1024
+            if rank == 0:
+                qb = orc.gen_rows(0, nb, args.dim, SEED_Q ^ 0x1234)
+                qb[:min(nb, nq_total)] = queries[:min(nb, nq_total)]
+            else:
+                qb = np.empty((nb, args.dim), np.float32)
+            qbt = torch.from_numpy(qb).cuda()
+            dist.broadcast(qbt, 0)
+            qb = qbt.cpu().numpy()
+            d_qb = tss.DeviceBuffer(device, qb.nbytes).upload(qb)
+            d_kb = tss.DeviceBuffer(device, nb * args.k * 8)
+            for _ in range(2):
+                ix.search_device(d_qb, nb, args.k, d_kb)
+            barrier()
+            iters = 5
+            ev0.record(ix)
+            for _ in range(iters):
+                ix.search_device(d_qb, nb, args.k, d_kb)
+            ev1.record(ix)
+            barrier()
+            bms = max_over_ranks(ev0.elapsed_ms(ev1)) / iters
+            same = True
+            if rank == 0:
+                kb = d_kb.download(np.uint64, nb * args.k).reshape(nb, args.k)
+                same = bool(np.array_equal(kb[:min(nb, nq_total)], keys_value_leg[:min(nb, nq_total)]))
+            extras["batched_sharded"] = {
+                "workload": (f"{nb}-query batch on the index sharded over {world} GPUs: local tcgen05 "
+                             "GEMM top-k, ncclAllGather of the keys, merge kernel"),
+                "value": nb / bms * 1e3, "unit": UNIT, "ms_per_batch": bms,
+                "keys_equal_batch1_leg": same, "check": "ok" if same else "FAILED"}
             sys.path.insert(0, os.path.join(ROOT, "tests"))
             import dist_worker
             t0 = time.perf_counter()

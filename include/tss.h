@@ -155,8 +155,12 @@ int tss_index_search_device(tss_index* ix, const float* d_queries, uint32_t nq, 
  *     two queries (k <= 32) by scanning the SHADOW for the top-64/128, proving the fp32 top-k is
  *     among them, and re-scoring those from the fp32 rows -- 1.17 ms instead of 2.05 ms over
  *     10M x 384, same bits; a query the proof fails for is redone by the fp32 scan.
- *   build_shadow_now != 0: an fp32 index builds its shadow inside this call
- *     (TSS_ERR_OOM if it does not fit; large batches then stay on the scan).
+ *   build_shadow_now != 0: the index builds its shadow inside this call (TSS_ERR_OOM if it does
+ *     not fit; large batches of an fp32 index then stay on the scan).  The shadow is a bf16 copy
+ *     of the matrix with every row scaled to unit length: the tensor cores read it, the
+ *     accumulator is the score and the GEMM epilogue needs no per-row weight.  A bf16 index
+ *     (+100 % memory) builds one on its own at its first large batch only when that leaves plenty
+ *     of memory free; otherwise its stored rows are read and weighted by 1/|row|.
  * New entry: the reference has no batched or two-stage search (src/vector.rs:195-202). */
 int tss_index_set_batch_policy(tss_index* ix, uint32_t min_queries, int build_shadow_now);
 /* unpack keys produced by tss_index_search_device (host side, pure function). */

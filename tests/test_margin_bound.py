@@ -113,3 +113,33 @@ def test_prefilter_proof_on_the_oracle_scores(orc):
             proven += 1
             assert set(top_b.tolist()) <= set(order_a.tolist())
     assert proven >= len(qs) - 2
+
+
+@pytest.mark.parametrize("dim,rows,q", list(_cases()), ids=lambda v: str(v) if isinstance(v, int) else None)
+@pytest.mark.parametrize("stored_bf16", [False, True])
+def test_unit_row_shadow_stays_inside_eps(dim, rows, q, stored_bf16):
+    """The shadow the tensor cores read holds UNIT rows: e_n = bf16(e * rsqrt(sum e^2)), computed
+    in fp32 as launch_normalize_rows does.  Unmasked batches use the raw dot product
+    A' = q_bf16 . e_n as the score (no per-row weight), masked ones A = q_bf16 . e_n / |e_n|;
+    both stay within eps = |q| 2^-7 of B = q . e / |e| (the margin prep_queries_kernel uses for
+    a shadow, minus its accumulation slack), for fp32 and for bf16 stored rows; and the cosine the
+    shadow prefilter scans, cos(q, e_n), within 2^-8 (1 + 2^-8) of cos(q, e)."""
+    stored = _bf16(rows) if stored_bf16 else rows
+    ss = np.einsum("ij,ij->i", stored, stored, dtype=np.float32)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        inv = np.where(ss > 0, np.float32(1.0) / np.sqrt(ss, dtype=np.float32), np.float32(0)).astype(np.float32)
+    unit = _bf16((stored * inv[:, None]).astype(np.float32))
+    r64, q64 = stored.astype(np.float64), q.astype(np.float64)
+    u64, qb64 = unit.astype(np.float64), _bf16(q).astype(np.float64)
+    rn = np.linalg.norm(r64, axis=1)
+    un = np.linalg.norm(u64, axis=1)
+    qn = np.linalg.norm(q64, axis=1)[:, None]
+    b = (q64 @ r64.T) / rn
+    slack = qn * (dim + 4) * 2.0 ** -22            # fp32 rsqrt / multiply of the normalisation
+    assert np.all(np.abs(un - 1.0) <= 2.0 ** -8 + 1e-6)
+    a_raw = qb64 @ u64.T
+    a_weighted = a_raw / un
+    assert np.all(np.abs(a_raw - b) <= qn * 2.0 ** -7 + slack)
+    assert np.all(np.abs(a_weighted - b) <= qn * 2.0 ** -7 + slack)
+    cos_a = (q64 @ u64.T) / un / qn
+    assert np.all(np.abs(cos_a - b / qn) <= 2.0 ** -8 * (1 + 2.0 ** -8) + (dim + 4) * 2.0 ** -22)

@@ -261,9 +261,15 @@ struct tss_index {
                                                               // pairs) / 64 rows (quads)
     uint64_t tmap_rows = 0;
     const void* tmap_base = nullptr;
-    // fp32 index: bf16 (RNE) shadow of the matrix for the tensor-core pass; the survivors are
-    // re-scored from the fp32 rows, so results stay bit-identical to the fp32 scan
+    // The shadow: a bf16 copy of the matrix with every row scaled to UNIT length, which is what
+    // the tensor cores read when it exists -- the accumulator then is the score and the epilogue
+    // needs no per-row weight.  An fp32 index always gets one (+50 % memory; the survivors are
+    // re-scored from the fp32 rows, so results stay bit-identical to the fp32 scan); a bf16 index
+    // gets one (+100 %) when memory is plentiful or tss_index_set_batch_policy asks for it, and
+    // otherwise the tensor cores read the stored rows and the epilogue weights by 1/|row|.
     uint8_t* d_shadow = nullptr;
+    int unit_policy = -1;          // bf16 index: -1 decide at the first batch, 0 stored rows, 1 shadow
+    bool reading_shadow = false;   // what tmap_e / d_inv_norm currently describe
     uint64_t shadow_cap = 0, shadow_rows = 0;
     const void* shadow_base = nullptr;
     bool shadow_failed = false;    // no memory for it: large batches stay on the scan
@@ -530,7 +536,7 @@ bool gemm_eligible(const tss_index* ix, uint32_t nq, uint32_t k, int mode) {
 // survivors a query is expected to leave in the K2 lists when `sample` tiles set its threshold
 uint64_t gemm_expected_survivors(const tss_index* ix, uint32_t k, uint32_t num_tiles, uint32_t sample) {
   // e^(z * margin / sigma) with the margins of prep_queries_kernel, z ~ 4.3 at k = 100 of 10M
-  const uint64_t spread = ix->storage == TSS_F32 ? 5 : 3;
+  const uint64_t spread = ix->storage == TSS_F32 || ix->gemm.reading_shadow ? 5 : 3;
   return spread * ix->gemm.spread_boost * k * (uint64_t)num_tiles / (sample ? sample : 1);
 }
 // largest batch (a multiple of 256 queries, <= kWsQueries) whose queries' expected survivors fit
@@ -546,7 +552,9 @@ uint32_t gemm_batch_limit(const tss_index* ix, uint32_t k) {
   return lim > kWsQueries ? kWsQueries : (uint32_t)lim;
 }
 
-int ensure_gemm_ws(tss_index* ix) {
+// want_shadow: (bf16 index) read the unit-row shadow rather than the stored rows.  An fp32 index
+// always reads its shadow.
+int ensure_gemm_ws(tss_index* ix, bool want_shadow) {
   tss_index::Gemm& g = ix->gemm;
   int rc = load_tmap_encode();
   if (rc) return rc;
@@ -568,9 +576,9 @@ int ensure_gemm_ws(tss_index* ix) {
     if ((rc = make_tmap(&g.tmap_q, g.d_qbf16, kWsQueries, kpad, 128))) return rc;
     g.ready = true;
   }
-  // the bf16 matrix the tensor cores read: the index itself, or the shadow of an fp32 index
+  // the bf16 matrix the tensor cores read: the unit-row shadow, or a bf16 index's own rows
   const uint8_t* e_rows = ix->d_rows;
-  if (ix->storage == TSS_F32) {
+  if (ix->storage == TSS_F32 || want_shadow) {
     if (g.shadow_cap < ix->n_rows) {
       cudaFree(g.d_shadow);
       g.d_shadow = nullptr;
@@ -579,21 +587,22 @@ int ensure_gemm_ws(tss_index* ix) {
       if (cudaMalloc(&g.d_shadow, bytes) != cudaSuccess) {
         cudaGetLastError();
         g.shadow_failed = true;
-        return fail(TSS_ERR_OOM, "no memory for the %zu-byte bf16 shadow of the fp32 index", bytes);
+        return fail(TSS_ERR_OOM, "no memory for the %zu-byte bf16 shadow of the index", bytes);
       }
       g.shadow_cap = ix->capacity;
     }
     if (g.shadow_rows != ix->n_rows || g.shadow_base != ix->d_rows) {
-      // the stored rows are already padded to the stride: convert them as stride-wide rows
-      cudaError_t e = tss::launch_pack_rows(reinterpret_cast<const float*>(ix->d_rows), g.d_shadow,
-                                            ix->n_rows, kpad, kpad, true, ix->stream);
-      if (e != cudaSuccess) return cuda_fail(e, "bf16 shadow conversion launch");
+      // (the stored rows are already padded to the stride)
+      cudaError_t e = tss::launch_normalize_rows(ix->d_rows, ix->storage == TSS_BF16, g.d_shadow,
+                                                 ix->n_rows, kpad, ix->stream);
+      if (e != cudaSuccess) return cuda_fail(e, "unit-row shadow launch");
       g_launches.fetch_add(1, std::memory_order_relaxed);
       g.shadow_rows = ix->n_rows;
       g.shadow_base = ix->d_rows;
     }
     e_rows = g.d_shadow;
   }
+  g.reading_shadow = e_rows == g.d_shadow;
   if (g.inv_norm_cap < ix->n_rows) {
     cudaFree(g.d_inv_norm);
     g.d_inv_norm = nullptr;
@@ -601,22 +610,42 @@ int ensure_gemm_ws(tss_index* ix) {
     g.inv_norm_cap = ix->capacity;
     g.norm_rows = 0;
   }
-  if (g.norm_rows != ix->n_rows || g.norm_base != ix->d_rows) {
+  if (g.norm_rows != ix->n_rows || g.norm_base != e_rows) {
     cudaError_t e =
         tss::launch_row_inv_norm(e_rows, ix->n_rows, ix->stride_elems, g.d_inv_norm, ix->stream);
     if (e != cudaSuccess) return cuda_fail(e, "row_inv_norm launch");
     g_launches.fetch_add(1, std::memory_order_relaxed);
     g.norm_rows = ix->n_rows;
-    g.norm_base = ix->d_rows;
+    g.norm_base = e_rows;
   }
-  if (g.tmap_rows != ix->n_rows || g.tmap_base != ix->d_rows) {
+  if (g.tmap_rows != ix->n_rows || g.tmap_base != e_rows) {
     if ((rc = make_tmap(&g.tmap_e, e_rows, ix->n_rows, kpad, 256))) return rc;
     if ((rc = make_tmap(&g.tmap_e_half, e_rows, ix->n_rows, kpad, 128))) return rc;
     if ((rc = make_tmap(&g.tmap_e_quarter, e_rows, ix->n_rows, kpad, 64))) return rc;
     g.tmap_rows = ix->n_rows;
-    g.tmap_base = ix->d_rows;
+    g.tmap_base = e_rows;
   }
   return TSS_OK;
+}
+
+// bf16 index: should the tensor cores read a unit-row shadow?  Decided once, at the first batch:
+// yes when the copy leaves at least as much memory free again (TSS_GEMM_UNIT_SHADOW=0/1 forces).
+bool unit_shadow_wanted(tss_index* ix) {
+  tss_index::Gemm& g = ix->gemm;
+  if (ix->storage != TSS_BF16) return true;
+  if (g.unit_policy < 0) {
+    g.unit_policy = 0;
+    if (const char* env = getenv("TSS_GEMM_UNIT_SHADOW")) {
+      g.unit_policy = atoi(env) != 0;
+    } else {
+      size_t free_b = 0, total_b = 0;
+      const size_t bytes = (size_t)(ix->capacity + 16) * ix->stride_elems * 2;
+      if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && free_b > 2 * bytes + (4ull << 30))
+        g.unit_policy = 1;
+    }
+  }
+  if (g.unit_policy == 1 && g.shadow_failed) return false;
+  return g.unit_policy == 1;
 }
 
 // gemm_eligible, and (fp32 index) the bf16 shadow could be built.  Without room for the shadow the
@@ -625,7 +654,7 @@ bool gemm_route(tss_index* ix, uint32_t nq, uint32_t k, int mode) {
   if (!gemm_eligible(ix, nq, k, mode)) return false;
   // a sharded index reports the failure instead (enqueue_gemm returns it): quietly scanning on
   // one rank while the others run K2 would desynchronise the exchange
-  if (ix->storage == TSS_F32 && !ix->comm && ensure_gemm_ws(ix) == TSS_ERR_OOM &&
+  if (ix->storage == TSS_F32 && !ix->comm && ensure_gemm_ws(ix, true) == TSS_ERR_OOM &&
       ix->gemm.shadow_failed)
     return false;
   return true;
@@ -646,9 +675,16 @@ int enqueue_scan_rounds(tss_index* ix, const float* d_queries, uint32_t nq, uint
 // overflowed (adversarially clustered scores) are redone exactly by the K1 scan.
 int enqueue_gemm(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
                  const tss_mask* mask, int mode, uint64_t* d_out) {
-  int rc = ensure_gemm_ws(ix);
-  if (rc) return rc;
+  // survivors are re-scored with the scan's arithmetic unless TSS_GEMM_RESCORE=0 (then the
+  // result is the top-k of the bf16 x bf16 tensor-core scores over the STORED bf16 rows)
+  bool rescore = true;
+  if (const char* rsc = getenv("TSS_GEMM_RESCORE")) rescore = atoi(rsc) != 0;
+  if (ix->storage == TSS_F32) rescore = true;  // the raw scores would be those of the shadow
   tss_index::Gemm& g = ix->gemm;
+  int rc = ensure_gemm_ws(ix, rescore && unit_shadow_wanted(ix));
+  if (rc == TSS_ERR_OOM && ix->storage == TSS_BF16 && g.shadow_failed)
+    rc = ensure_gemm_ws(ix, false);  // no room for the unit copy: weight the stored rows instead
+  if (rc) return rc;
   const uint32_t kpad = ix->stride_elems;
   // CTA pairs (one cta_group::2 MMA over two query blocks): the batch is padded to an even
   // number of 128-query blocks (a padding query is all zeros and its threshold is +inf)
@@ -704,13 +740,8 @@ int enqueue_gemm(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
                               : cluster == tss::TSS_GEMM_PAIR ? g.tmap_e_half
                                                               : g.tmap_e_quarter;
   cudaError_t e;
-  // survivors are re-scored with the scan's arithmetic unless TSS_GEMM_RESCORE=0 (then the
-  // result is the top-k of the bf16 x bf16 tensor-core scores)
-  bool rescore = true;
-  if (const char* rsc = getenv("TSS_GEMM_RESCORE")) rescore = atoi(rsc) != 0;
-  if (ix->storage == TSS_F32) rescore = true;  // the raw scores would be those of the shadow
   e = tss::launch_prep_queries(d_queries, nq, ix->dim, kpad, nq_pad, g.d_qbf16, g.d_inv_q,
-                               g.d_margin, ix->storage == TSS_F32, ix->stream);
+                               g.d_margin, g.reading_shadow, ix->stream);
   if (e != cudaSuccess) return cuda_fail(e, "prep_queries launch");
   const uint32_t nsub = (uint32_t)nslices * split;
   const uint64_t cap64 = share / nsub;
@@ -718,7 +749,10 @@ int enqueue_gemm(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
   tss::GemmParams p{};
   p.n_rows = ix->n_rows;
   p.row_base = (uint32_t)ix->row_base;
-  p.inv_norm = g.d_inv_norm;
+  // unit rows and no mask: the accumulator is the score, the epilogue applies no weight
+  p.inv_norm = g.reading_shadow && mode == TSS_MASK_NONE ? nullptr : g.d_inv_norm;
+  if (const char* wt = getenv("TSS_GEMM_WEIGHTS"))  // diagnostics: 1 = always weight
+    if (atoi(wt) != 0) p.inv_norm = g.d_inv_norm;
   p.mask = mode != TSS_MASK_NONE ? mask->d_words : nullptr;
   p.mask_mode = mode;
   p.mb = mb;
@@ -851,7 +885,7 @@ int enqueue_scan_rounds(tss_index* ix, const float* d_queries, uint32_t nq, uint
 // prove (the kc-th shadow score within the error margin of the k-th) is redone by the fp32 scan.
 int enqueue_prefilter(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
                       const tss_mask* mask, int mode, uint64_t* d_out) {
-  int rc = ensure_gemm_ws(ix);
+  int rc = ensure_gemm_ws(ix, true);
   if (rc) return rc;
   tss_index::Gemm& g = ix->gemm;
   const uint32_t kc = 4 * k <= 64 ? 64 : 128;
@@ -1547,12 +1581,13 @@ int tss_index_set_batch_policy(tss_index* ix, uint32_t min_queries, int build_sh
     ix->gemm_min_nq = 16;
     ix->gemm_small_nq = 3;
   }
-  if (build_shadow_now && ix->storage == TSS_F32) {
+  if (build_shadow_now) {  // fp32: the shadow it needs anyway; bf16: opt in to the unit-row copy
     if (!ix->finalized) return fail(TSS_ERR_STATE, "build the shadow after tss_index_finalize");
     if (!ix->n_rows) return TSS_OK;
     DeviceGuard g(ix->device);
     ix->gemm.shadow_failed = false;
-    int rc = ensure_gemm_ws(ix);
+    ix->gemm.unit_policy = 1;
+    int rc = ensure_gemm_ws(ix, true);
     if (rc) return rc;
     CU(cudaStreamSynchronize(ix->stream));
   }

@@ -88,6 +88,38 @@ cudaError_t launch_pack_rows(const float* src, void* dst, uint64_t nrows, uint32
   return cudaGetLastError();
 }
 
+// one warp per row; the row is read twice (the second read hits L1/L2)
+__global__ void normalize_rows_kernel(const void* src, int src_bf16, uint16_t* dst, uint64_t nrows,
+                                      uint32_t stride_elems) {
+  const uint64_t r = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= nrows) return;
+  const float* sf = reinterpret_cast<const float*>(src) + r * stride_elems;
+  const uint16_t* sh = reinterpret_cast<const uint16_t*>(src) + r * stride_elems;
+  auto at = [&](uint32_t j) -> float {
+    return src_bf16 ? __uint_as_float((uint32_t)sh[j] << 16) : sf[j];
+  };
+  float ss = 0.f;
+  for (uint32_t j = lane; j < stride_elems; j += 32) {
+    const float v = at(j);
+    ss = fmaf(v, v, ss);
+  }
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) ss += __shfl_xor_sync(FULL_MASK, ss, m);
+  const float inv = ss > 0.f && isfinite(ss) ? rsqrtf(ss) : 0.f;
+  uint16_t* d = dst + r * stride_elems;
+  for (uint32_t j = lane; j < stride_elems; j += 32) d[j] = f32_to_bf16_rne(at(j) * inv);
+}
+cudaError_t launch_normalize_rows(const void* src, bool src_bf16, void* dst_bf16, uint64_t nrows,
+                                  uint32_t stride_elems, cudaStream_t st) {
+  if (!nrows) return cudaSuccess;
+  const uint64_t blocks = (nrows * 32 + 255) / 256;
+  normalize_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, src_bf16 ? 1 : 0,
+                                                         reinterpret_cast<uint16_t*>(dst_bf16), nrows,
+                                                         stride_elems);
+  return cudaGetLastError();
+}
+
 __global__ void unpack_rows_kernel(const void* src, float* dst, uint64_t nrows, uint32_t dim,
                                    uint32_t stride_elems, int bf16) {
   const uint64_t total = nrows * dim;
@@ -360,8 +392,11 @@ cudaError_t launch_prefix_mask(const PrefixMaskArgs& a, const PrefixKeys& keys, 
   if (a.clear_nwords && want < (uint64_t)grid && want >= 8) grid = (int)want;
   if (grid < 8) grid = 8;
   if (grid > num_sms && num_sms > 0) grid = num_sms;
-  prefix_mask_kernel<<<grid, kPrefixThreads, 0, st>>>(a, keys);
-  return cudaGetLastError();
+  // a cooperative launch: the grid barrier needs every CTA resident at once, and this is the
+  // launch form that guarantees it (or fails instead of hanging)
+  void* args[] = {const_cast<PrefixMaskArgs*>(&a), const_cast<PrefixKeys*>(&keys)};
+  return cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(prefix_mask_kernel), dim3((unsigned)grid),
+                                     dim3(kPrefixThreads), args, 0, st);
 }
 
 __global__ void terms_validate_kernel(TermsDev t, uint64_t pool_bytes, uint64_t nposts,

@@ -14,6 +14,12 @@ cudaError_t launch_check_finite(const float* src, uint64_t count, int* flag, cud
 // unpadded fp32 [nrows][dim] -> padded storage rows (fp32 or bf16 RNE)
 cudaError_t launch_pack_rows(const float* src, void* dst, uint64_t nrows, uint32_t dim,
                              uint32_t stride_elems, bool bf16, cudaStream_t st);
+// padded storage rows (fp32 or bf16) -> bf16 rows of the same stride, each scaled to unit length
+// first (fp32 sum of squares, rsqrt, fp32 multiply, RNE): the matrix the tensor cores read, so
+// that a raw dot product IS the cosine numerator and the epilogue needs no per-row weight.  A
+// zero row stays zero.
+cudaError_t launch_normalize_rows(const void* src, bool src_bf16, void* dst_bf16, uint64_t nrows,
+                                  uint32_t stride_elems, cudaStream_t st);
 // padded storage -> unpadded fp32
 cudaError_t launch_unpack_rows(const void* src, float* dst, uint64_t nrows, uint32_t dim,
                                uint32_t stride_elems, bool bf16, cudaStream_t st);

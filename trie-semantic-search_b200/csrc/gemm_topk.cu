@@ -216,7 +216,12 @@ __host__ __device__ constexpr int gemm_ninv_floats(bool pair) {
   return pair ? kEpiWarps * 32 : 2 * kBlockN;
 }
 
-template <int KB, int CL>
+// W: the epilogue scales every score by a per-row weight (1/|row|, or NaN for a masked row).
+// W = false: the matrix the tensor cores read holds UNIT rows (launch_normalize_rows) and there
+// is no mask, so the accumulator already is the score: the epilogue is a bare maximum + compare
+// -- no weight fetch, no staging, no multiply (the multiplies and their shared-memory loads were
+// half of the epilogue's instructions, and the epilogue math 15 % of a power-capped batch).
+template <int KB, int CL, bool W>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_e,
                  const GemmParams p) {
@@ -455,7 +460,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     // warps meet at a named barrier (double-buffered by accumulator).
     const uint64_t my_col = PAIR ? part * kColsPer + lane : et;
     auto fetch_weights = [&](uint32_t i, float& a, float& b) {
-      if (i >= count) return;
+      if (!W || i >= count) return;
       const uint64_t r = (uint64_t)i * stride * kBlockN + my_col;
       if (PAIR) {
         a = row_weight(r);
@@ -479,7 +484,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       const uint64_t row0 = (uint64_t)i * stride * kBlockN;
       // ninv[c] = weight of the tile's column c (for the columns this thread visits)
       float* ninv = s_ninv + acc * kBlockN;
-      if (PAIR) {
+      if (!W) {
+      } else if (PAIR) {
         __syncwarp();  // the previous tile's reads of the warp's buffer are done
         warp_ninv[lane] = w_a;
         __syncwarp();
@@ -496,7 +502,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       float mx = -INFINITY;
 #pragma unroll 1
       for (uint32_t cb = part * kColsPer; cb < (part + 1) * kColsPer; cb += 32) {
-        if (PAIR && cb != part * kColsPer) {  // second chunk: its weights replace the first's
+        if (W && PAIR && cb != part * kColsPer) {  // second chunk: its weights replace the first's
           __syncwarp();
           warp_ninv[lane] = w_b;
           __syncwarp();
@@ -508,12 +514,17 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         // branch-free common case: scale by 1/|row|, maxima of the four groups of 8 and of
         // the chunk; only a chunk (then a group) whose maximum reaches the threshold is walked
         float v[32];
-        const float4* nv = reinterpret_cast<const float4*>(PAIR ? warp_ninv : ninv + cb);
+        if (W) {
+          const float4* nv = reinterpret_cast<const float4*>(PAIR ? warp_ninv : ninv + cb);
 #pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 w = nv[j4];
-          mul2(r[4 * j4 + 0], r[4 * j4 + 1], w.x, w.y, v[4 * j4 + 0], v[4 * j4 + 1]);
-          mul2(r[4 * j4 + 2], r[4 * j4 + 3], w.z, w.w, v[4 * j4 + 2], v[4 * j4 + 3]);
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 w = nv[j4];
+            mul2(r[4 * j4 + 0], r[4 * j4 + 1], w.x, w.y, v[4 * j4 + 0], v[4 * j4 + 1]);
+            mul2(r[4 * j4 + 2], r[4 * j4 + 3], w.z, w.w, v[4 * j4 + 2], v[4 * j4 + 3]);
+          }
+        } else {  // unit rows: the accumulator is the score
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
         }
         if (cb + 32 > ncols) {  // last, partial tile of the corpus only
           // columns past the last row are marked like masked rows: NaN, which fmax drops and
@@ -1022,9 +1033,10 @@ int gemm_max_quads(int kb) {
   cudaError_t e = cudaErrorInvalidValue;
 #define TSS_QUAD_OCC(KBV)                                                                        \
   case KBV:                                                                                       \
-    e = cudaFuncSetAttribute(gemm_topk_kernel<KBV, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                             (int)cfg.dynamicSmemBytes);                                          \
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveClusters(&n, gemm_topk_kernel<KBV, 4>, &cfg); \
+    e = cudaFuncSetAttribute(gemm_topk_kernel<KBV, 4, true>,                                      \
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes); \
+    if (e == cudaSuccess)                                                                         \
+      e = cudaOccupancyMaxActiveClusters(&n, gemm_topk_kernel<KBV, 4, true>, &cfg);               \
     break;
   switch (kb) {
     TSS_QUAD_OCC(2)
@@ -1050,11 +1062,11 @@ size_t gemm_smem_bytes(int kb, bool pair) {
   return ring + gemm_ninv_floats(pair) * sizeof(float) + kBarSlots * 8 + 16;
 }
 
-template <int KB, int CL>
-static cudaError_t launch_gemm_inst(const CUtensorMap& tmap_q, const CUtensorMap& tmap_e,
-                                    const GemmParams& p, int grid, size_t smem, cudaStream_t st) {
+template <int KB, int CL, bool W>
+static cudaError_t launch_gemm_w(const CUtensorMap& tmap_q, const CUtensorMap& tmap_e,
+                                 const GemmParams& p, int grid, size_t smem, cudaStream_t st) {
   static_assert(gemm_stages<KB, CL>() == (CL >= 2 ? (KB <= 6 ? 8 : 6) : 4), "gemm_smem_bytes");
-  auto kern = gemm_topk_kernel<KB, CL>;
+  auto kern = gemm_topk_kernel<KB, CL, W>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg{};
@@ -1070,6 +1082,14 @@ static cudaError_t launch_gemm_inst(const CUtensorMap& tmap_q, const CUtensorMap
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kern, tmap_q, tmap_e, p);
+}
+
+template <int KB, int CL>
+static cudaError_t launch_gemm_inst(const CUtensorMap& tmap_q, const CUtensorMap& tmap_e,
+                                    const GemmParams& p, int grid, size_t smem, cudaStream_t st) {
+  // no weights <=> unit rows and no mask (GemmParams::inv_norm == null)
+  return p.inv_norm ? launch_gemm_w<KB, CL, true>(tmap_q, tmap_e, p, grid, smem, st)
+                    : launch_gemm_w<KB, CL, false>(tmap_q, tmap_e, p, grid, smem, st);
 }
 
 cudaError_t launch_gemm_topk(int kb, int cluster, const CUtensorMap& tmap_q,

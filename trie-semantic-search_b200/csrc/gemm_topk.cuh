@@ -9,7 +9,8 @@ namespace tss {
 struct GemmParams {
   uint64_t n_rows;         // rows in this shard
   uint32_t row_base;       // global id of local row 0
-  const float* inv_norm;   // [n_rows] 1/|row|
+  const float* inv_norm;   // [n_rows] 1/|row|; null: the rows the tensor cores read are unit
+                           // vectors and there is no mask -- the epilogue applies no weight
   const uint32_t* mask;    // row mask words (bit r&31 of word r>>5 <-> local row r) or null
   int mask_mode;           // TSS_MASK_*: masked rows get 1/|row| = NaN, which fmax and >= ignore
   uint32_t mb;             // 128-query blocks in this launch (grid = nslices * mb)
