@@ -643,8 +643,7 @@ def main():
 
     # ---- value: device-resident, CUDA events on the index stream ------------------------------
     ev0, ev1 = tss.Event(device), tss.Event(device)
-    device_leg(0, args.warmup)
-    time.sleep(0.15)  # (the sampler has been running since before the warm-up)
+    device_leg(0, args.warmup)  # (the clock sampler has been running since before this warm-up)
     launches0 = tss.launch_count()
     barrier()  # immediately before the first event: every rank starts its timed steps together
     ev0.record(ix)

@@ -38,6 +38,63 @@ def test_rust_binding_source_declares_the_same_symbols():
     assert sorted(set(re.findall(r"pub fn (tss_[a-z0-9_]+)\s*\(", block))) == _declared()
 
 
+_C2RS = {"int": "c_int", "char": "c_char", "void": "c_void", "float": "f32", "uint8_t": "u8",
+         "uint16_t": "u16", "uint32_t": "u32", "uint64_t": "u64", "int32_t": "i32", "int64_t": "i64"}
+
+
+def _c_signatures():
+    """name -> (return, [params]) from tss.h, each type as (rust base name, pointer depth)"""
+    src = open(os.path.join(ROOT, "include", "tss.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+
+    def norm(t):
+        t = t.strip()
+        depth = t.count("*") + (1 if re.search(r"\[\d*\]", t) else 0)
+        t = re.sub(r"\[\d*\]", "", t.replace("*", " "))
+        words = [w for w in t.split() if w not in ("const", "struct")]
+        base = words[0] if len(words) == 1 or words[0] in _C2RS or words[0].startswith("tss_") else None
+        assert base, t
+        return (_C2RS.get(base, base), depth)
+
+    out = {}
+    for ret, name, params in re.findall(r"^\s*([A-Za-z_][\w\s\*]*?)\b(tss_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src,
+                                        flags=re.M | re.S):
+        ps = [] if params.strip() in ("", "void") else [norm(x) for x in params.split(",")]
+        out[name] = (norm(ret), ps)
+    return out
+
+
+def _rs_signatures():
+    rs = open(os.path.join(ROOT, "trie-semantic-search_b200", "ffi", "tss.rs")).read()
+    block = rs[rs.index('extern "C" {'):]
+    block = block[:block.index("\n}")]
+
+    def norm(t):
+        t = t.strip()
+        depth = t.count("*")
+        t = re.sub(r"\*\s*(const|mut)\s*", "", t).strip()
+        return (t, depth)
+
+    out = {}
+    for name, params, ret in re.findall(r"pub fn (tss_[a-z0-9_]+)\s*\(([^)]*)\)\s*(?:->\s*([^;]+))?;", block, flags=re.S):
+        ps = [norm(x.split(":", 1)[1]) for x in params.split(",") if ":" in x]
+        out[name] = (norm(ret) if ret else ("c_void", 0), ps)
+    return out
+
+
+def test_rust_binding_signatures_match_the_header():
+    """Beyond the names: every extern fn of ffi/tss.rs has the header's arity, and each parameter
+    and return value the header's base type and pointer depth (u32 <-> uint32_t, *mut *mut tss_index
+    <-> tss_index**, ...).  rustc is not available here, so this is the type check the binding gets."""
+    c, rs = _c_signatures(), _rs_signatures()
+    assert sorted(c) == sorted(rs) == _declared()
+    for name in c:
+        (cret, cps), (rret, rps) = c[name], rs[name]
+        assert len(cps) == len(rps), (name, cps, rps)
+        assert cps == rps, (name, cps, rps)
+        assert cret == rret, (name, cret, rret)
+
+
 def test_library_loads_and_reports_version(tss):
     L = tss.lib()
     assert L.tss_abi_version() == 1

@@ -269,12 +269,16 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   const bool left_over = cluster_id >= F * G;
   const uint32_t nseg = left_over ? G : 1u;
   const uint32_t run = left_over ? 1u : G;
-  const uint32_t item_base = left_over ? F * G + (cluster_id - F * G) : (cluster_id % F) * G;
-  const uint32_t slice = left_over ? F + (cluster_id - F * G) : cluster_id % F;
+  // (own clusters are numbered group-fastest: the G clusters that read the SAME tiles for the
+  // G query groups have consecutive ids, so they are scheduled side by side and the second
+  // reader of a tile finds it in L2 -- numbered group-slowest, 1.5x the corpus came from DRAM)
+  const uint32_t own_i = cluster_id / G, own_g = cluster_id % G;
+  const uint32_t item_base = left_over ? F * G + (cluster_id - F * G) : own_i * G;
+  const uint32_t slice = left_over ? F + (cluster_id - F * G) : own_i;
   const uint32_t nslices = F + R;
   auto item = [&](uint32_t n) -> uint32_t { return (n / run) * C + item_base + (n % run); };
   auto seg_m_blk = [&](uint32_t seg) -> uint32_t {
-    return (left_over ? seg : cluster_id / F) * CL + rank;
+    return (left_over ? seg : own_g) * CL + rank;
   };
   constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);   // every CTA of the cluster
   const uint32_t pair_rank = rank & 1u, pair_id = rank >> 1;  // (QUAD: which pair, which half)

@@ -353,6 +353,14 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_topk_kernel(const __grid_c
       }
     }
   }
+  // mask words of the window starting at tile m_next, one per lane, requested ahead of use
+  uint32_t pre_word = 0;
+  uint64_t pre_for = ~0ull;
+  auto prefetch_mask = [&]() {
+    const uint64_t tc = m_next + (uint64_t)lane * GW;
+    pre_word = (MASKED && tc < total_tiles) ? __ldg(p.mask + ((tc * R) >> 5)) : 0u;
+    pre_for = m_next;
+  };
   auto gather = [&]() -> uint32_t {
     if (list_n != 0xFFFFFFFFu) {
       // list-driven: chunk m_next = rows list[m_next*R .. +R), one bulk copy per row
@@ -376,7 +384,19 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_topk_kernel(const __grid_c
     uint32_t filled = 0;
     while (m_next < total_tiles && filled < (uint32_t)R) {
       const uint64_t tc = m_next + (uint64_t)lane * GW;
-      const uint32_t b = tc < total_tiles ? tile_bits(tc) : 0u;
+      // (the window's mask words were requested when the previous window was consumed: their
+      // latency hides behind the tile of work in between -- ncu had the mask load as the top
+      // stall of the 11 % case)
+      if (pre_for != m_next) prefetch_mask();
+      uint32_t b = 0u;
+      if (tc < total_tiles) {
+        const uint64_t row0 = tc * R;
+        const uint64_t left = p.n_rows - row0;
+        b = left >= (uint64_t)R ? ALL_ROWS : ((1u << (uint32_t)left) - 1u);
+        uint32_t mb = (pre_word >> (uint32_t)(row0 & 31)) & ALL_ROWS;
+        if (p.mask_mode == 2) mb = ~mb;  // TSS_MASK_EXCLUDE
+        b &= mb;
+      }
       const uint32_t pc = __popc(b);
       uint32_t inc = pc;  // inclusive prefix sum of the live-row counts over the lanes
 #pragma unroll
@@ -391,6 +411,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_topk_kernel(const __grid_c
       if (ntake == 0) break;  // the next tile needs more room than is left: ship what we have
       const uint32_t total = __shfl_sync(FULL_MASK, inc, ntake - 1);
       m_next += (uint64_t)ntake * GW;
+      prefetch_mask();
       if (total == 0) continue;  // nothing live in these tiles
       if (lane == 0) mbar_expect_tx(bar, total * ROW_BYTES);
       __syncwarp();
