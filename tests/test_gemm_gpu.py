@@ -359,3 +359,38 @@ def test_device_resident_batches_fix_up_on_the_device(tss, orc):
     # the host entry covers any number of them in one call
     got = ix.search(q, k)
     assert np.array_equal(got[0], want[0]) and np.array_equal(got[1].view(np.uint32), want[1].view(np.uint32))
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_shapes_and_routes(tss, orc, seed):
+    """Random corpus size / dimension / batch / k / storage / mask: whichever route the library
+    picks (scan, pairs, quads, a left-over cluster serving several query groups, weights or the
+    weight-free epilogue), rows, scores and counts equal the oracle's."""
+    rng = np.random.default_rng(1000 + seed)
+    dim = int(rng.choice([64, 128, 200, 384, 768]))
+    n = int(rng.integers(30_000, 260_000))
+    nq = int(rng.choice([16, 100, 129, 256, 300, 512, 600, 1024]))
+    k = int(rng.choice([1, 10, 37, 100]))
+    f32 = bool(rng.integers(0, 2))
+    rows = rng.standard_normal((n, dim)).astype(np.float32)
+    rows[::977] *= 50.0
+    rows[5] = 0.0                                   # a zero row scores 0
+    q = rng.standard_normal((nq, dim)).astype(np.float32)
+    q[1] = rows[n // 2] * 0.5
+    ix = tss.FlatIndex(dim, tss.TSS_F32 if f32 else tss.TSS_BF16)
+    ix.add(rows)
+    ix.finalize()
+    mode = int(rng.integers(0, 3))
+    m = w = None
+    if mode:
+        bits = rng.random(n) < rng.choice([0.02, 0.5, 0.97])
+        w = np.zeros((n + 31) // 32, dtype=np.uint32)
+        idx = np.nonzero(bits)[0]
+        np.bitwise_or.at(w, idx >> 5, np.uint32(1) << (idx & 31).astype(np.uint32))
+        m = tss.Mask(n)
+        m.upload(w)
+    got = ix.search(q, k, m, mode)
+    want = orc.cosine_topk(rows, q, k, mask_words=w, mask_mode=mode, bf16=not f32)
+    assert np.array_equal(got[2], want[2]), (dim, n, nq, k, f32, mode)
+    assert np.array_equal(got[0], want[0]), (dim, n, nq, k, f32, mode)
+    assert np.array_equal(got[1].view(np.uint32), want[1].view(np.uint32)), (dim, n, nq, k, f32, mode)

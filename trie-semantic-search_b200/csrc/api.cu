@@ -796,10 +796,14 @@ int enqueue_fixups(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t 
                    const tss_mask* mask, int mode, uint64_t* d_out) {
   tss_index::Gemm& g = ix->gemm;
   const bool on_device = k <= TSS_MAX_FUSED_K;
-  // what the previous batch needed (its mirror has landed by now or will be read next time)
-  const uint32_t seen = g.h_redo[0];
-  if (seen > g.fixups && g.fixups < 64) g.fixups *= 2;
-  if (seen * 20 > kWsQueries / 4 && g.spread_boost < 64) g.spread_boost *= 2;
+  if (on_device && ix->no_host_sync) {
+    // nobody waits for this batch's flags: tune on what an earlier batch needed (its mirror has
+    // landed in mapped host memory by now, or will be seen by a later call)
+    const uint32_t seen = g.h_redo[0];
+    g.h_redo[0] = 0;
+    if (seen > g.fixups && g.fixups < 64) g.fixups *= 2;
+    if (seen * 20 > nq && g.spread_boost < 64) g.spread_boost *= 2;
+  }
   // (tss_index_search synchronises anyway and redoes flagged queries from the host: it does not
   // pay for guarded launches that almost never have work)
   const uint32_t fixups = on_device && ix->no_host_sync ? (g.fixups < nq ? g.fixups : nq) : 0;
