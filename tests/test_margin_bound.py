@@ -143,3 +143,41 @@ def test_unit_row_shadow_stays_inside_eps(dim, rows, q, stored_bf16):
     assert np.all(np.abs(a_weighted - b) <= qn * 2.0 ** -7 + slack)
     cos_a = (q64 @ u64.T) / un / qn
     assert np.all(np.abs(cos_a - b / qn) <= 2.0 ** -8 * (1 + 2.0 ** -8) + (dim + 4) * 2.0 ** -22)
+
+
+@pytest.mark.parametrize("dim,rows,q", list(_cases()), ids=lambda v: str(v) if isinstance(v, int) else None)
+@pytest.mark.parametrize("stored_bf16", [False, True])
+def test_measured_margins_bound_the_difference(dim, rows, q, stored_bf16):
+    """Round 2 builds the margins from MEASURED rounding distances instead of their worst case:
+    dq = |q_bf16 - q| of the query at hand (prep_queries_kernel) and de = max over rows of
+    |e_n - e/|e|| recorded when the unit-row shadow was built (normalize_rows_kernel):
+        |A - B| <= dq (1 + de) + |q| de (1 + de)      (raw dot and weighted, both)
+        |cos(q, e_n) - cos(q, e)| <= de (1 + de)      (shadow prefilter)
+    and without a shadow (a bf16 index's own rows) |A - B| <= dq.  On ordinary data both
+    distances are ~0.4-0.5 x 2^-8, so the margin is less than half its worst case."""
+    stored = _bf16(rows) if stored_bf16 else rows
+    ss = np.einsum("ij,ij->i", stored, stored, dtype=np.float32)
+    inv = (np.float32(1.0) / np.sqrt(ss, dtype=np.float32)).astype(np.float32)
+    x = (stored * inv[:, None]).astype(np.float32)
+    unit = _bf16(x)
+    de = float(np.max(np.linalg.norm(unit.astype(np.float64) - x.astype(np.float64), axis=1))) * 1.002
+    assert de <= 2.0 ** -8 * 1.002
+    r64, q64 = stored.astype(np.float64), q.astype(np.float64)
+    u64, qb64 = unit.astype(np.float64), _bf16(q).astype(np.float64)
+    rn, un = np.linalg.norm(r64, axis=1), np.linalg.norm(u64, axis=1)
+    qn = np.linalg.norm(q64, axis=1)[:, None]
+    dq = np.linalg.norm(qb64 - q64, axis=1)[:, None]
+    assert np.all(dq <= qn * 2.0 ** -8)
+    b = (q64 @ r64.T) / rn
+    slack = qn * (dim + 4) * 2.0 ** -22
+    eps = dq * (1 + de) + qn * de * (1 + de) + slack
+    a_raw = qb64 @ u64.T
+    assert np.all(np.abs(a_raw - b) <= eps)
+    assert np.all(np.abs(a_raw / un - b) <= eps)
+    cos_a = (q64 @ u64.T) / un / qn
+    assert np.all(np.abs(cos_a - b / qn) <= de * (1 + de) + (dim + 4) * 2.0 ** -22)
+    # a bf16 index read directly (stored rows ARE what the tensor cores see): only the query moves
+    if stored_bf16:
+        assert np.all(np.abs((qb64 @ r64.T) / rn - b) <= dq * (1 + 1e-12))
+    if dim >= 64:  # the point of measuring: well under the worst case on ordinary data
+        assert de < 0.7 * 2.0 ** -8 and np.median(dq / qn) < 0.7 * 2.0 ** -8

@@ -16,7 +16,8 @@ from typing import Optional, Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtss.so")
+# (TSS_LIB_PATH: diagnostics only -- A/B of two builds of the same library in one GPU session)
+LIB_PATH = os.environ.get("TSS_LIB_PATH") or os.path.join(_HERE, "libtss.so")
 
 TSS_OK, TSS_ERR_INVALID_ARG, TSS_ERR_CUDA, TSS_ERR_NCCL, TSS_ERR_OOM, TSS_ERR_STATE = range(6)
 TSS_F32, TSS_BF16 = 0, 1

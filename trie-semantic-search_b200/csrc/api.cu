@@ -268,6 +268,7 @@ struct tss_index {
     // gets one (+100 %) when memory is plentiful or tss_index_set_batch_policy asks for it, and
     // otherwise the tensor cores read the stored rows and the epilogue weights by 1/|row|.
     uint8_t* d_shadow = nullptr;
+    unsigned int* d_shadow_err = nullptr;  // float bits: max over rows of |e_n - e/|e|| (margins)
     int unit_policy = -1;          // bf16 index: -1 decide at the first batch, 0 stored rows, 1 shadow
     bool reading_shadow = false;   // what tmap_e / d_inv_norm currently describe
     uint64_t shadow_cap = 0, shadow_rows = 0;
@@ -593,8 +594,9 @@ int ensure_gemm_ws(tss_index* ix, bool want_shadow) {
     }
     if (g.shadow_rows != ix->n_rows || g.shadow_base != ix->d_rows) {
       // (the stored rows are already padded to the stride)
+      if (!g.d_shadow_err) CU(cudaMalloc(&g.d_shadow_err, sizeof(unsigned int)));
       cudaError_t e = tss::launch_normalize_rows(ix->d_rows, ix->storage == TSS_BF16, g.d_shadow,
-                                                 ix->n_rows, kpad, ix->stream);
+                                                 ix->n_rows, kpad, g.d_shadow_err, ix->stream);
       if (e != cudaSuccess) return cuda_fail(e, "unit-row shadow launch");
       g_launches.fetch_add(1, std::memory_order_relaxed);
       g.shadow_rows = ix->n_rows;
@@ -741,7 +743,7 @@ int enqueue_gemm(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
                                                               : g.tmap_e_quarter;
   cudaError_t e;
   e = tss::launch_prep_queries(d_queries, nq, ix->dim, kpad, nq_pad, g.d_qbf16, g.d_inv_q,
-                               g.d_margin, g.reading_shadow, ix->stream);
+                               g.d_margin, g.reading_shadow ? g.d_shadow_err : nullptr, ix->stream);
   if (e != cudaSuccess) return cuda_fail(e, "prep_queries launch");
   const uint32_t nsub = (uint32_t)nslices * split;
   const uint64_t cap64 = share / nsub;
@@ -901,8 +903,8 @@ int enqueue_prefilter(tss_index* ix, const float* d_queries, uint32_t nq, uint32
   ix->xchg.suppress = saved;
   if (rc) return rc;
   cudaError_t e = tss::launch_refine(g.d_pref_keys, kc, d_queries, ix->d_rows, ix->dim,
-                                     ix->stride_elems, (uint32_t)ix->row_base, nq, ix->n_rows, k,
-                                     d_out, g.d_overflow, ix->stream);
+                                     ix->stride_elems, (uint32_t)ix->row_base, nq, ix->n_rows,
+                                     g.d_shadow_err, k, d_out, g.d_overflow, ix->stream);
   if (e != cudaSuccess) return cuda_fail(e, "refine_kernel launch");
   g_launches.fetch_add(1, std::memory_order_relaxed);
   // a query the proof failed for is redone by the fp32 scan: guarded launches (nq <= 2 of
@@ -1059,6 +1061,7 @@ void tss_index_destroy(tss_index* ix) {
   cudaFree(ix->d_round_mask);
   cudaFree(ix->gemm.d_inv_norm);
   cudaFree(ix->gemm.d_shadow);
+  cudaFree(ix->gemm.d_shadow_err);
   cudaFree(ix->gemm.d_qbf16);
   cudaFree(ix->gemm.d_inv_q);
   cudaFree(ix->gemm.d_margin);

@@ -88,9 +88,12 @@ cudaError_t launch_pack_rows(const float* src, void* dst, uint64_t nrows, uint32
   return cudaGetLastError();
 }
 
-// one warp per row; the row is read twice (the second read hits L1/L2)
+// one warp per row; the row is read twice (the second read hits L1/L2).  *max_err (float bits,
+// >= 0 so unsigned order == float order) ends up holding an upper bound of
+// max over rows of | e_n - e / |e| |: how far bf16 rounding moved any unit row -- the quantity the
+// re-scoring margins are built from (about 0.43 * 2^-8 on ordinary data, 2^-8 in the worst case).
 __global__ void normalize_rows_kernel(const void* src, int src_bf16, uint16_t* dst, uint64_t nrows,
-                                      uint32_t stride_elems) {
+                                      uint32_t stride_elems, unsigned int* max_err) {
   const uint64_t r = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (r >= nrows) return;
@@ -108,15 +111,30 @@ __global__ void normalize_rows_kernel(const void* src, int src_bf16, uint16_t* d
   for (int m = 16; m >= 1; m >>= 1) ss += __shfl_xor_sync(FULL_MASK, ss, m);
   const float inv = ss > 0.f && isfinite(ss) ? rsqrtf(ss) : 0.f;
   uint16_t* d = dst + r * stride_elems;
-  for (uint32_t j = lane; j < stride_elems; j += 32) d[j] = f32_to_bf16_rne(at(j) * inv);
+  float err2 = 0.f;
+  for (uint32_t j = lane; j < stride_elems; j += 32) {
+    const float x = at(j) * inv;
+    const uint16_t h = f32_to_bf16_rne(x);
+    d[j] = h;
+    const float dx = __uint_as_float((uint32_t)h << 16) - x;
+    err2 = fmaf(dx, dx, err2);
+  }
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) err2 += __shfl_xor_sync(FULL_MASK, err2, m);
+  // (+2^-9 relative: the fp32 sums above and rsqrtf's 2 ulp are far inside that)
+  if (lane == 0 && max_err) atomicMax(max_err, __float_as_uint(sqrtf(err2) * 1.002f));
 }
 cudaError_t launch_normalize_rows(const void* src, bool src_bf16, void* dst_bf16, uint64_t nrows,
-                                  uint32_t stride_elems, cudaStream_t st) {
+                                  uint32_t stride_elems, unsigned int* d_max_err, cudaStream_t st) {
+  if (d_max_err) {
+    cudaError_t e = cudaMemsetAsync(d_max_err, 0, sizeof(unsigned int), st);
+    if (e != cudaSuccess) return e;
+  }
   if (!nrows) return cudaSuccess;
   const uint64_t blocks = (nrows * 32 + 255) / 256;
   normalize_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, src_bf16 ? 1 : 0,
                                                          reinterpret_cast<uint16_t*>(dst_bf16), nrows,
-                                                         stride_elems);
+                                                         stride_elems, d_max_err);
   return cudaGetLastError();
 }
 

@@ -18,8 +18,9 @@ cudaError_t launch_pack_rows(const float* src, void* dst, uint64_t nrows, uint32
 // first (fp32 sum of squares, rsqrt, fp32 multiply, RNE): the matrix the tensor cores read, so
 // that a raw dot product IS the cosine numerator and the epilogue needs no per-row weight.  A
 // zero row stays zero.
+// *d_max_err (nullable) <- an upper bound of max over rows of |e_n - e/|e|| (float bits).
 cudaError_t launch_normalize_rows(const void* src, bool src_bf16, void* dst_bf16, uint64_t nrows,
-                                  uint32_t stride_elems, cudaStream_t st);
+                                  uint32_t stride_elems, unsigned int* d_max_err, cudaStream_t st);
 // padded storage -> unpadded fp32
 cudaError_t launch_unpack_rows(const void* src, float* dst, uint64_t nrows, uint32_t dim,
                                uint32_t stride_elems, bool bf16, cudaStream_t st);

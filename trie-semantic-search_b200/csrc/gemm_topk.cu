@@ -504,7 +504,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       const uint64_t left = p.n_rows - row0;
       const uint32_t ncols = left >= (uint64_t)kBlockN ? kBlockN : (uint32_t)left;
       float mx = -INFINITY;
-#pragma unroll 1
+#pragma unroll 1  // (fully unrolled the two chunks cost 20 %: 7.25 vs 6.0 ms per batch)
       for (uint32_t cb = part * kColsPer; cb < (part + 1) * kColsPer; cb += 32) {
         if (W && PAIR && cb != part * kColsPer) {  // second chunk: its weights replace the first's
           __syncwarp();
@@ -538,20 +538,23 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           for (int j = 0; j < 32; ++j)
             if (cb + j >= ncols) v[j] = __uint_as_float(0x7FC00000u);
         }
-        float gm[4];
+        // chunk maximum as a tree of 3-input maxima (16 FMNMX3 for 32 values); the per-group
+        // maxima are only formed on the rare path that found a survivor
+        float t1[11];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float a = fmaxf(fmaxf(v[8 * g + 0], v[8 * g + 1]), fmaxf(v[8 * g + 2], v[8 * g + 3]));
-          float b = fmaxf(fmaxf(v[8 * g + 4], v[8 * g + 5]), fmaxf(v[8 * g + 6], v[8 * g + 7]));
-          gm[g] = fmaxf(a, b);
-        }
-        const float m = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
+        for (int i = 0; i < 10; ++i) t1[i] = fmaxf(fmaxf(v[3 * i], v[3 * i + 1]), v[3 * i + 2]);
+        t1[10] = fmaxf(v[30], v[31]);
+        const float t2a = fmaxf(fmaxf(t1[0], t1[1]), t1[2]), t2b = fmaxf(fmaxf(t1[3], t1[4]), t1[5]);
+        const float t2c = fmaxf(fmaxf(t1[6], t1[7]), t1[8]), t2d = fmaxf(t1[9], t1[10]);
+        const float m = fmaxf(fmaxf(fmaxf(t2a, t2b), t2c), t2d);
         if (p.mode == 0) {
           mx = fmaxf(mx, m);
         } else if (m >= thr) {
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            if (gm[g] >= thr) {
+            const float a = fmaxf(fmaxf(v[8 * g + 0], v[8 * g + 1]), fmaxf(v[8 * g + 2], v[8 * g + 3]));
+            const float b = fmaxf(fmaxf(v[8 * g + 4], v[8 * g + 5]), fmaxf(v[8 * g + 6], v[8 * g + 7]));
+            if (fmaxf(a, b) >= thr) {
 #pragma unroll
               for (int j = 8 * g; j < 8 * g + 8; ++j) {
                 if (v[j] >= thr) {
@@ -599,20 +602,24 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 // ---- small kernels around it ------------------------------------------------------------
 // fp32 queries -> bf16 [mb*128][kpad] (zero padded) + per-query 1/|q| (of the bf16-rounded query)
 // + the rescoring margin (see select_kernel): a bound on 2 * |A(e) - B(e)| over all rows e, where
-// A = q_bf16 . e_t / |e_t| is what the tensor cores see (e_t: the bf16 row they read) and
-// B = q . e / |e| what the scan computes from the stored row e.  bf16 keeps 8 significant bits,
-// so round-to-nearest moves a vector by at most 2^-8 of its norm (tests/test_margin_bound.py).
-// A - B = (q_bf16 - q) . e_t/|e_t| + q . (e_t/|e_t| - e/|e|): the first term is at most 2^-8 |q|
-// (Cauchy-Schwarz); the second is zero on a bf16 index (e_t = e), and when e_t is the bf16 shadow
-// of an fp32 row the two unit vectors are a chord 2 sin(theta/2) apart with sin(theta) <= 2^-8,
-// i.e. at most 2^-8 (1 + 2^-17) |q|; plus the fp32 accumulation errors of both paths and the
-// rsqrt behind 1/|e_t| (together under (D + 4) * 2^-22 |q|).
+// A is what the tensor cores see and B = q . e / |e| what the scan computes from the stored row.
+//   A = q_bf16 . e_t [/ |e_t|], e_t the bf16 row the tensor cores read.  Then
+//   A - B = (q_bf16 - q) . u  +  q . (u - e/|e|),  u = e_t [/ |e_t|],
+//   |A - B| <= dq * |u| + |q| * de,   dq = |q_bf16 - q|,  de = |u - e/|e||.
+// dq is computed HERE, exactly, for this query (Cauchy-Schwarz needs nothing more) instead of its
+// worst case 2^-8 |q| -- on ordinary data it is ~0.41 * 2^-8 |q|.  de: zero when the tensor cores
+// read a bf16 index's own rows (u = e/|e|); for the unit-row shadow the largest rounding distance
+// over all rows was recorded when the shadow was built (*shadow_err, launch_normalize_rows;
+// ~0.45 * 2^-8, at most 2^-8): |u| <= 1 + de, and dividing by |e_t| moves u by at most de more
+// (chord <= de (1 + de)).  Plus the fp32 accumulation errors of both paths and the rsqrt behind
+// the weights (together under (D + 4) * 2^-22 |q|).  tests/test_margin_bound.py checks the bound
+// in float64.
 __global__ void prep_queries_kernel(const float* q, uint32_t nq, uint32_t dim, uint32_t kpad,
                                     uint32_t nq_pad, uint16_t* out, float* inv_qnorm, float* margin,
-                                    int shadowed) {
+                                    const unsigned int* shadow_err) {
   const uint32_t qi = blockIdx.x;
   if (qi >= nq_pad) return;
-  float ss = 0.f, sf = 0.f;
+  float ss = 0.f, sf = 0.f, sd = 0.f;
   for (uint32_t j = threadIdx.x; j < kpad; j += blockDim.x) {
     float v = (qi < nq && j < dim) ? q[(size_t)qi * dim + j] : 0.f;
     uint32_t u = __float_as_uint(v);
@@ -623,21 +630,29 @@ __global__ void prep_queries_kernel(const float* q, uint32_t nq, uint32_t dim, u
     ss = fmaf(w, w, ss);
     sf = fmaf(v, v, sf);  // (a component that rounds to inf, or a norm that overflows, makes the
                           // margin inf: every row survives, the list overflows, the scan answers)
+    const float d = w - v;  // exact: both are fp32 and w is v with low mantissa bits rounded
+    sd = fmaf(d, d, sd);
   }
-  __shared__ float red[2][32];
+  __shared__ float red[3][32];
 #pragma unroll
   for (int m = 16; m >= 1; m >>= 1) {
     ss += __shfl_xor_sync(FULL_MASK, ss, m);
     sf += __shfl_xor_sync(FULL_MASK, sf, m);
+    sd += __shfl_xor_sync(FULL_MASK, sd, m);
   }
-  if ((threadIdx.x & 31) == 0) red[0][threadIdx.x >> 5] = ss, red[1][threadIdx.x >> 5] = sf;
+  if ((threadIdx.x & 31) == 0)
+    red[0][threadIdx.x >> 5] = ss, red[1][threadIdx.x >> 5] = sf, red[2][threadIdx.x >> 5] = sd;
   __syncthreads();
   if (threadIdx.x == 0) {
-    float t = 0.f, tf = 0.f;
-    for (uint32_t w = 0; w < (blockDim.x + 31) / 32; ++w) t += red[0][w], tf += red[1][w];
+    float t = 0.f, tf = 0.f, td = 0.f;
+    for (uint32_t w = 0; w < (blockDim.x + 31) / 32; ++w) t += red[0][w], tf += red[1][w], td += red[2][w];
     inv_qnorm[qi] = t > 0.f ? rsqrtf(t) : 0.f;
-    margin[qi] = 2.f * 1.001f * sqrtf(tf) *
-                 ((shadowed ? 0x1p-7f : 0x1p-8f) + (float)(dim + 4) * 0x1p-22f);
+    const float de = shadow_err ? __uint_as_float(*shadow_err) : 0.f;
+    const float qn = sqrtf(tf), dq = sqrtf(td);
+    // 1.002: the fp32 sums of squares above; inf/NaN inputs propagate to an infinite margin
+    margin[qi] = 2.f * 1.002f *
+                 (dq * (1.f + de) + qn * (de * (1.f + de) + (float)(dim + 4) * 0x1p-22f));
+    if (!(tf < INFINITY)) margin[qi] = INFINITY;
   }
 }
 
@@ -985,8 +1000,13 @@ select_kernel(const uint64_t* cand, const uint32_t* cand_count, uint32_t nsub, u
 // written.  Otherwise incomplete[q] = 1 and the host redoes the query with the fp32 scan.
 constexpr uint32_t kRefineMax = 128;
 __global__ void __launch_bounds__(kSelectThreads)
-refine_kernel(const uint64_t* cand, uint32_t kc, const Rescore rs, float two_eps, uint32_t k,
-              uint64_t* out, uint32_t* incomplete) {
+refine_kernel(const uint64_t* cand, uint32_t kc, const Rescore rs, const unsigned int* shadow_err,
+              uint32_t k, uint64_t* out, uint32_t* incomplete) {
+  // |A - B| <= eps: A = cos(q, e_n) over the unit-row shadow, B = cos(q, e); the two unit
+  // vectors are a chord <= de (1 + de) apart, de the shadow's recorded rounding distance, plus
+  // both fp32 accumulations
+  const float de = __uint_as_float(*shadow_err);
+  const float two_eps = 2.f * 1.002f * (de * (1.f + de) + (float)(rs.dim + 4) * 0x1p-22f);
   __shared__ uint64_t sk[kRefineMax];
   __shared__ __align__(16) float s_q[1024];
   const uint32_t q = blockIdx.x;
@@ -1119,9 +1139,9 @@ cudaError_t launch_gemm_topk(int kb, int cluster, const CUtensorMap& tmap_q,
 
 cudaError_t launch_prep_queries(const float* q, uint32_t nq, uint32_t dim, uint32_t kpad,
                                 uint32_t nq_pad, uint16_t* out, float* inv_qnorm, float* margin,
-                                bool shadowed, cudaStream_t st) {
+                                const unsigned int* shadow_err, cudaStream_t st) {
   prep_queries_kernel<<<nq_pad, 128, 0, st>>>(q, nq, dim, kpad, nq_pad, out, inv_qnorm, margin,
-                                              shadowed ? 1 : 0);
+                                              shadow_err);
   return cudaGetLastError();
 }
 cudaError_t launch_row_inv_norm(const void* rows, uint64_t n_rows, uint32_t stride_elems, float* out,
@@ -1153,13 +1173,13 @@ cudaError_t launch_select(const uint64_t* cand, const uint32_t* cand_count, uint
 
 cudaError_t launch_refine(const uint64_t* cand, uint32_t kc, const float* queries, const void* rows_f32,
                           uint32_t dim, uint32_t stride_elems, uint32_t row_base, uint32_t nq,
-                          uint64_t n_rows, uint32_t k, uint64_t* out, uint32_t* incomplete,
-                          cudaStream_t st) {
+                          uint64_t n_rows, const unsigned int* shadow_err, uint32_t k, uint64_t* out,
+                          uint32_t* incomplete, cudaStream_t st) {
+  if (!shadow_err) return cudaErrorInvalidValue;
   if (kc > kRefineMax || k > kRefineMax || stride_elems > 1024 || stride_elems % 128)
     return cudaErrorInvalidConfiguration;
   Rescore rs{queries, nullptr, rows_f32, 1, dim, stride_elems, row_base, n_rows};
-  const float two_eps = 2.f * (0x1.01p-8f + (float)(dim + 4) * 0x1p-22f);
-  refine_kernel<<<nq, kSelectThreads, 0, st>>>(cand, kc, rs, two_eps, k, out, incomplete);
+  refine_kernel<<<nq, kSelectThreads, 0, st>>>(cand, kc, rs, shadow_err, k, out, incomplete);
   return cudaGetLastError();
 }
 

@@ -38,11 +38,12 @@ int gemm_col_split();  // survivor lists / threshold samples per (slice, tile)
 cudaError_t launch_gemm_topk(int kb, int cluster, const CUtensorMap& tmap_q,
                              const CUtensorMap& tmap_e, const GemmParams& p, int grid,
                              cudaStream_t st);
-// margin: [nq_pad] out, the rescoring margin of every query (see select_kernel); shadowed: the
-// tensor cores read a bf16 shadow of fp32 rows (the margin then covers the rows' rounding too)
+// margin: [nq_pad] out, the rescoring margin of every query (see prep_queries_kernel);
+// shadow_err: null when the tensor cores read a bf16 index's own rows, else the device word
+// launch_normalize_rows left (how far rounding moved any unit row of the shadow)
 cudaError_t launch_prep_queries(const float* q, uint32_t nq, uint32_t dim, uint32_t kpad,
                                 uint32_t nq_pad, uint16_t* out, float* inv_qnorm, float* margin,
-                                bool shadowed, cudaStream_t st);
+                                const unsigned int* shadow_err, cudaStream_t st);
 cudaError_t launch_row_inv_norm(const void* rows, uint64_t n_rows, uint32_t stride_elems, float* out,
                                 cudaStream_t st);
 // margin: null, or what to subtract from every threshold (survivors will be re-scored)
@@ -63,7 +64,7 @@ cudaError_t launch_select(const uint64_t* cand, const uint32_t* cand_count, uint
 // (the kc-th shadow score is not provably below the fp32 top-k): see refine_kernel.
 cudaError_t launch_refine(const uint64_t* cand, uint32_t kc, const float* queries, const void* rows_f32,
                           uint32_t dim, uint32_t stride_elems, uint32_t row_base, uint32_t nq,
-                          uint64_t n_rows, uint32_t k, uint64_t* out, uint32_t* incomplete,
-                          cudaStream_t st);
+                          uint64_t n_rows, const unsigned int* shadow_err, uint32_t k, uint64_t* out,
+                          uint32_t* incomplete, cudaStream_t st);
 
 }  // namespace tss
