@@ -335,16 +335,16 @@ def test_device_resident_batches_fix_up_on_the_device(tss, orc):
     dk = tss.DeviceBuffer(0, nq * k * 8)
     before = tss.launch_count()
     ix.search_device(dq, nq, k, dk)
-    assert tss.launch_count() - before >= 5 + 1 + 4  # K2 pipeline + compaction + guarded fix-ups
+    assert tss.launch_count() - before >= 5 + 1 + 2  # K2 pipeline + compaction + guarded fix-ups
     ix.sync()
     gr, gs = tss.unpack_keys(dk.download(np.uint64, nq * k).reshape(nq, k))
     assert np.array_equal(gr, want[0]) and np.array_equal(gs.view(np.uint32), want[1].view(np.uint32))
-    # ten hostile queries > four fix-up launches
+    # ten hostile queries > two fix-up launches
     for j in range(10):
         q[20 + j] = rows[7] * (1.0 + 0.01 * j)
     want = orc.cosine_topk(rows, q, k, bf16=True)
     dq.upload(q)
-    for attempt in range(4):
+    for attempt in range(6):
         ix.search_device(dq, nq, k, dk)
         try:
             ix.sync()
@@ -353,7 +353,7 @@ def test_device_resident_batches_fix_up_on_the_device(tss, orc):
             assert e.code == tss.TSS_ERR_STATE
     else:
         raise AssertionError("the fix-up launches never caught up")
-    assert attempt >= 1  # the first try could not cover eleven flagged queries with four launches
+    assert attempt >= 1  # the first try could not cover eleven flagged queries with two launches
     gr, gs = tss.unpack_keys(dk.download(np.uint64, nq * k).reshape(nq, k))
     assert np.array_equal(gr, want[0]) and np.array_equal(gs.view(np.uint32), want[1].view(np.uint32))
     # the host entry covers any number of them in one call

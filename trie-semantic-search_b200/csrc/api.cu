@@ -256,7 +256,8 @@ struct tss_index {
     // the host only where it synchronises anyway
     uint32_t* d_redo = nullptr;
     uint32_t* h_redo = nullptr;
-    uint32_t fixups = 4;               // guarded fix-up scans enqueued behind every batch
+    uint32_t fixups = 2;               // guarded fix-up scans enqueued behind every batch
+                                       // (≈ 5 µs each when idle; doubled on demand up to 64)
     CUtensorMap tmap_q, tmap_e, tmap_e_half, tmap_e_quarter;  // corpus boxes of 256 / 128 (CTA
                                                               // pairs) / 64 rows (quads)
     uint64_t tmap_rows = 0;

@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_topk_kernel(const __grid_c
     for (int s = 0; s < NS; ++s) {
       uint32_t j = 128u * s + 4u * lane;
       const float* qb = q_base + (size_t)b * p.dim;
-      bool live = (uint32_t)b < p.nq_valid;
+      bool live = active && (uint32_t)b < p.nq_valid;  // (an idle guarded launch loads nothing)
       float4 v;
       if (p.use_inline) {  // (b == 0 only: nq_valid == 1)
         v.x = (live && j + 0 < p.dim) ? p.q_inline[(j + 0) % 384] : 0.f;
