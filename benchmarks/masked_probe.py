@@ -58,5 +58,5 @@ for term, ps, sel in zip(terms, posts, a.sel):
     out.append({"selectivity": sel, "live_rows": int(uniq.size), "postings": int(ps.size),
                 "mask_ok": ok, "k4_us": k4, "masked_scan_us": scan,
                 "live_gbs": uniq.size * dim * 4 / (scan * 1e-6) / 1e9,
-                "list_driven": bool(ps.size <= 16384)})
+                "list_driven": bool(ps.size <= 131072)})
 print(json.dumps({"rows": N, "cases": out}))

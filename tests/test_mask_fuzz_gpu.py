@@ -29,7 +29,7 @@ def test_random_mask_op_sequences(tss, orc, seed):
     ix.add_synthetic(0, n, 0x5EED)
     ix.finalize()
     q = orc.gen_rows(0, 16, dim, 0xBEEF)
-    sizes = [1, 5, 300, 5_000, 16_384, 20_000, 1]
+    sizes = [1, 5, 300, 5_000, 16_384, 140_000, 1]
     terms = [b"t%02d" % i for i in range(len(sizes))] + [b"t00 x", b"t01 y z"]
     posts = [[int(r) for r in rng.integers(0, n, size=s)] for s in sizes] + [[7, 8, 9], [n - 1]]
     order = np.argsort(np.array(terms, dtype=object))

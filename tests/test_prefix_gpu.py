@@ -271,7 +271,7 @@ def test_list_driven_scan_and_its_invalidation(tss, orc):
     ix = tss.FlatIndex(dim)
     ix.add_synthetic(0, n, 0x5EED)
     ix.finalize()
-    sizes = [1, 7, 8, 9, 100, 5_000, 16_384, 16_385, 40_000]   # postings; the list holds 16 384
+    sizes = [1, 7, 8, 9, 100, 5_000, 16_385, 40_000, 131_072, 131_073, 150_000]   # postings; the list holds 131 072
     terms = [b"p%02d" % i for i in range(len(sizes))]
     posts = [[int(r) for r in rng.integers(0, n, size=s)] for s in sizes]  # duplicates included
     t = tss.Terms(terms, posts)

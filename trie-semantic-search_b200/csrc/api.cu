@@ -91,7 +91,7 @@ constexpr size_t kStageBytes = 32u << 20;  // one of the two upload staging buff
 constexpr uint32_t kGemmCandCap = 32768;   // K2 survivor keys per query of a FULL workspace batch:
                                            // the pool (kWsQueries x this) is shared out per batch
 constexpr uint32_t kGemmMaxSample = 8192;  // tiles sampled by the K2 threshold pass
-constexpr uint32_t kMaskListCap = 16384;   // rows a prefix scatter may list for the list-driven scan
+constexpr uint32_t kMaskListCap = 131072;  // rows a prefix scatter may list for the list-driven scan
 constexpr uint32_t kPrefilterMaxNq = 2;    // queries per call the shadow prefilter takes (K2 beyond)
 
 typedef CUresult (*TmapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -673,9 +673,9 @@ int enqueue_fixups(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t 
 int enqueue_scan_rounds(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
                         const tss_mask* mask, int mode, uint64_t* d_out);
 
-// K2: nq <= kWsQueries device-resident fp32 queries -> d_out (nq x k local keys).
-// Synchronises the stream once to check the survivor lists for overflow; queries whose list
-// overflowed (adversarially clustered scores) are redone exactly by the K1 scan.
+// K2: nq <= kWsQueries device-resident fp32 queries -> d_out (nq x k local keys).  Queries whose
+// survivor list overflowed (adversarially clustered scores) are redone exactly by the K1 scan:
+// see enqueue_fixups for who does that and when (the host only where it synchronises anyway).
 int enqueue_gemm(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
                  const tss_mask* mask, int mode, uint64_t* d_out) {
   // survivors are re-scored with the scan's arithmetic unless TSS_GEMM_RESCORE=0 (then the

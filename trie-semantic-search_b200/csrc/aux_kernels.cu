@@ -373,31 +373,47 @@ prefix_mask_kernel(const PrefixMaskArgs a, const __grid_constant__ PrefixKeys ke
     a.bounds[4] = total;
     if (a.list_count && !use_list) *a.list_count = 0xFFFFFFFFu;
   }
-  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __shared__ uint32_t s_wcnt[kPrefixThreads / 32];
+  __shared__ uint32_t s_base;
 #pragma unroll
   for (int rng = 0; rng < 2; ++rng) {
-    // whole warps iterate together (the list append uses warp collectives)
-    for (uint64_t i0 = pb[rng] + (gtid - lane); i0 < pe[rng]; i0 += nth) {
-      const uint64_t i = i0 + lane;
+    if (!use_list) {
+      for (uint64_t i = pb[rng] + gtid; i < pe[rng]; i += nth) {
+        const uint64_t r = (uint64_t)a.t.post_rows[i] - a.row_base;
+        if (r < a.nbits) atomicOr(a.words + (r >> 5), 1u << (uint32_t)(r & 31));
+      }
+      continue;
+    }
+    // with a row list: whole CTAs iterate together, and the threads whose atomicOr flipped the
+    // bit (the row is new) reserve their list slots with ONE atomicAdd per CTA per trip
+    for (uint64_t c0 = pb[rng] + (uint64_t)blockIdx.x * blockDim.x; c0 < pe[rng]; c0 += nth) {
+      const uint64_t i = c0 + threadIdx.x;
       const bool in = i < pe[rng];
       const uint64_t r = in ? (uint64_t)a.t.post_rows[i] - a.row_base : ~0ull;
       const bool ok = in && r < a.nbits;
       const uint32_t bit = 1u << (uint32_t)(r & 31);
       uint32_t old = 0xFFFFFFFFu;
       if (ok) old = atomicOr(a.words + (r >> 5), bit);
-      if (use_list) {
-        const bool win = ok && !(old & bit);  // this thread set the bit: the row is new
-        const unsigned m = __ballot_sync(FULL_MASK, win);
-        if (m) {
-          uint32_t base = 0;
-          if (lane == (uint32_t)__ffs(m) - 1u) base = atomicAdd(a.list_count, (uint32_t)__popc(m));
-          base = __shfl_sync(FULL_MASK, base, __ffs(m) - 1);
-          if (win) {
-            const uint32_t pos = base + __popc(m & ((1u << lane) - 1u));
-            if (pos < a.list_cap) a.list[pos] = (uint32_t)r;
-          }
-        }
+      const bool win = ok && !(old & bit);
+      const unsigned m = __ballot_sync(FULL_MASK, win);
+      if (lane == 0) s_wcnt[warp] = __popc(m);
+      __syncthreads();
+      uint32_t before = 0, total_w = 0;
+#pragma unroll
+      for (uint32_t w = 0; w < kPrefixThreads / 32; ++w) {
+        if (w < warp) before += s_wcnt[w];
+        total_w += s_wcnt[w];
       }
+      if (threadIdx.x == 0 && total_w) s_base = atomicAdd(a.list_count, total_w);
+      __syncthreads();
+      if (win) {
+        const uint32_t pos = s_base + before + __popc(m & ((1u << lane) - 1u));
+        if (pos < a.list_cap) a.list[pos] = (uint32_t)r;
+      }
+      // (no third barrier: s_wcnt is rewritten in the next trip only by warps that have passed
+      // the barrier above, after every read of it; s_base only after the next trip's first
+      // barrier, which every thread reaches after reading it here)
     }
   }
 }

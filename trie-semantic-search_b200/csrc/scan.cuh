@@ -361,6 +361,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_topk_kernel(const __grid_c
     pre_word = (MASKED && tc < total_tiles) ? __ldg(p.mask + ((tc * R) >> 5)) : 0u;
     pre_for = m_next;
   };
+  // list-driven: the R list entries starting at entry c0, one per lane, requested ahead of use
+  auto prefetch_list = [&](uint64_t c0) {
+    pre_word = (MASKED && c0 + lane < list_n && lane < R) ? __ldcg(p.row_list + c0 + lane) : 0u;
+    pre_for = c0;
+  };
   auto gather = [&]() -> uint32_t {
     if (list_n != 0xFFFFFFFFu) {
       // list-driven: chunk m_next = rows list[m_next*R .. +R), one bulk copy per row
@@ -370,11 +375,13 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_topk_kernel(const __grid_c
       const uint32_t cnt = list_n - c0 < (uint64_t)R ? (uint32_t)(list_n - c0) : (uint32_t)R;
       if (lane == 0) mbar_arrive_expect_tx(bar, cnt * ROW_BYTES);
       __syncwarp();
+      if (pre_for != c0) prefetch_list(c0);  // (first chunk only: later ones were requested ahead)
       if ((uint32_t)lane < cnt) {
-        const uint32_t r = __ldcg(p.row_list + c0 + lane);
+        const uint32_t r = pre_word;
         bulk_g2s(tile_s + lane * ROW_BYTES, rows_b + (uint64_t)r * ROW_BYTES, ROW_BYTES, bar, policy);
         slot_rows[lane] = r;
       }
+      prefetch_list(m_next * (uint64_t)R);  // the next chunk's entries, in flight during this one
       __syncwarp();
       return cnt;
     }
