@@ -10,6 +10,7 @@
 #include <thread>
 #include <unistd.h>
 #include <unordered_map>
+#include <unordered_set>
 
 #include "../include/tss.h"
 #include "../oracle/oracle.h"
@@ -486,6 +487,128 @@ static void trie_disk_round_trip(bool gpu) {
   CHECK(threw);
 }
 
+
+// S1/S2 end to end, randomized: SearchEngine (trie cascade + device scan + merge + multi-get
+// hydration) against the oracle's literal pieces glued the way execute_hybrid_search glues them
+// (src/search.rs:185-240): orc_trie_search -> exact case ids; orc_cosine_topk (top-50, the
+// seen-case rows excluded first when the policy pushes de-dup onto the device) -> vector hits;
+// orc_hybrid_merge.  Case ids, score bits and match types must agree for every query.
+static uint64_t cid_u64(const CaseId& c) {
+  uint64_t v = 0;
+  for (int i = 0; i < 8; ++i) v |= (uint64_t)c.bytes[15 - i] << (8 * i);
+  return v;
+}
+static void engine_vs_oracle_random() {
+  const uint32_t dim = 128, ncases = 300;
+  std::mt19937 rng(2024);
+  VectorConfig vc;
+  vc.dimension = dim;
+  auto store = std::make_shared<MetadataStore>();
+  SearchEngineConfig sc;
+  sc.enable_query_cache = false;
+  SearchEngine eng(vc, TrieConfig(), sc, store);
+  orc_trie_index* otrie = orc_trie_new();
+  const char* vocab[] = {"state", "v.", "People", "united", "States", "doe", "Roe", "in", "re", "smith"};
+  std::vector<std::string> names;
+  std::vector<float> all;          // every row's embedding, in row order
+  std::vector<uint64_t> row_case;  // row -> case number
+  for (uint32_t c = 0; c < ncases; ++c) {
+    std::string name;
+    int nt = 1 + rng() % 3;
+    for (int j = 0; j < nt; ++j) name += std::string(j ? " " : "") + vocab[rng() % 10];
+    names.push_back(name);  // few tokens from a small vocabulary: many cases share a name
+    CaseMetadata m;
+    m.id = cid(c);
+    m.name = name;
+    m.court = c % 3 ? "scotus" : "ca9";
+    m.decision_date = 1000 + (int)c;
+    if (c % 17 != 5) store->put(m);  // some cases have no metadata: skipped like `if let Ok(Some(..))`
+    eng.trie_index().insert_case_name(name, m.id);
+    orc_trie_insert_case_name(otrie, name.c_str(), m.id.bytes.data());
+    const int paragraphs = 1 + rng() % 3;
+    for (int p = 0; p < paragraphs; ++p) {
+      // clusters: cases c and c+100 are close in embedding space, so vector hits pile up on few cases
+      auto e = synth((c % 100) * 7 + p, dim, 5);
+      auto noise = synth(c * 31 + p, dim, 11);
+      for (uint32_t j = 0; j < dim; ++j) e[j] += 0.05f * noise[j];
+      eng.vector_index().add_embedding(DocRef{m.id, (size_t)p, std::nullopt}, e);
+      all.insert(all.end(), e.begin(), e.end());
+      row_case.push_back(c);
+    }
+  }
+  const uint32_t nrows = (uint32_t)row_case.size();
+  std::unordered_map<std::string, std::vector<float>> embed_of;
+  eng.vector_index().embedding_model().set_encoder(
+      [&](const std::string& text) { return embed_of.at(text); });
+  eng.freeze();
+  std::vector<std::string> queries;
+  for (int i = 0; i < 40; ++i) {
+    std::string q = i % 2 ? names[rng() % ncases] : std::string(vocab[rng() % 10]) + " " + vocab[rng() % 10];
+    if (i % 7 == 0) q = "  " + q + " ";  // whitespace / case noise for the tokeniser
+    if (q.size() < 2) q += "xx";
+    auto e = synth((rng() % 100) * 7 + rng() % 3, dim, 5);
+    auto noise = synth(9000 + i, dim, 13);
+    for (uint32_t j = 0; j < dim; ++j) e[j] += 0.2f * noise[j];
+    embed_of[q] = e;
+    queries.push_back(q);
+  }
+  for (auto policy : {SearchEngine::MaskPolicy::PostHoc, SearchEngine::MaskPolicy::ExcludeOnDevice}) {
+    eng.set_mask_policy(policy);
+    for (size_t qi = 0; qi < queries.size(); ++qi) {
+      SearchQuery q;
+      q.query = queries[qi];
+      q.config.min_similarity = qi % 3 ? 0.5f : 0.2f;
+      if (qi % 5 == 0) q.max_results = 3;
+      auto got = eng.search_with_params(q);
+      // --- the oracle's version ---
+      orc_trie_result* tr = orc_trie_search(otrie, q.query.c_str());
+      std::vector<uint64_t> exact;
+      std::vector<uint32_t> mask_words((nrows + 31) / 32, 0);
+      std::unordered_set<uint64_t> seen;
+      for (uint64_t i = 0; i < tr->n_exact; ++i) {
+        CaseId c;
+        memcpy(c.bytes.data(), tr->exact_matches[i].case_id, 16);
+        if (!store->get_case_metadata(c)) continue;  // :193 skips a case without metadata
+        exact.push_back(cid_u64(c));
+        seen.insert(cid_u64(c));
+      }
+      orc_trie_result_free(tr);
+      int mode = ORC_MASK_NONE;
+      if (policy == SearchEngine::MaskPolicy::ExcludeOnDevice && !seen.empty()) {
+        for (uint32_t r = 0; r < nrows; ++r)
+          if (seen.count(row_case[r])) mask_words[r >> 5] |= 1u << (r & 31);
+        mode = ORC_MASK_EXCLUDE;
+      }
+      const uint32_t k = (uint32_t)SearchEngine::kVectorTopK;
+      std::vector<uint32_t> rows(k), counts(1);
+      std::vector<float> scores(k);
+      orc_cosine_topk(all.data(), nrows, dim, embed_of[q.query].data(), 1, k, mask_words.data(), mode,
+                      0, rows.data(), scores.data(), counts.data(), ORC_ORDER_CANONICAL, 0, 0);
+      std::vector<uint64_t> vcase;
+      std::vector<float> vscore;
+      for (uint32_t i = 0; i < counts[0]; ++i) {
+        if (!store->get_case_metadata(cid(row_case[rows[i]]))) continue;  // :213
+        vcase.push_back(row_case[rows[i]]);
+        vscore.push_back(1.0f - (1.0f - scores[i]));  // VectorIndex::search: 1 - distance, :144
+      }
+      std::vector<orc_hit> want(128);
+      const uint32_t nw = orc_hybrid_merge(exact.data(), (uint32_t)exact.size(), vcase.data(), vscore.data(),
+                                           (uint32_t)vcase.size(), 1, 1, (uint32_t)q.config.max_results,
+                                           q.max_results ? (int64_t)*q.max_results : -1,
+                                           q.config.min_similarity, q.config.exact_match_weight,
+                                           want.data(), 128);
+      CHECK(got.size() == nw);
+      for (size_t i = 0; i < got.size() && i < nw; ++i) {
+        CHECK(cid_u64(got[i].case_metadata.id) == want[i].case_id);
+        CHECK(memcmp(&got[i].score, &want[i].score, 4) == 0);
+        CHECK((got[i].match_type == MatchType::Exact) == (want[i].match_type == 0));
+      }
+    }
+  }
+  eng.set_mask_policy(SearchEngine::MaskPolicy::PostHoc);
+  orc_trie_free(otrie);
+}
+
 int main(int argc, char** argv) {
   std::string mode = argc > 1 ? argv[1] : "cpu";
   try {
@@ -496,6 +619,7 @@ int main(int argc, char** argv) {
       hnsw_vs_oracle();
       stub_embedding_behaviour();
       engine_hybrid();
+      engine_vs_oracle_random();
     } else {
       no_gpu_is_loud();
     }
