@@ -371,3 +371,30 @@ def test_concurrent_searches_on_one_handle(tss, orc):
     for th in threads:
         th.join()
     assert not errors, errors[:5]
+
+
+@pytest.mark.parametrize("storage_bf16", [False, True])
+def test_gpu_scores_equal_exact_rational_arithmetic(tss, storage_bf16):
+    """The kernel against the SPECIFICATION directly (no oracle in between): every score the scan
+    returns equals DESIGN.md section 3 evaluated in exact rational arithmetic with explicit
+    round-to-nearest-even (tests/test_exact_arithmetic.py), bit for bit -- and so does the order."""
+    import test_exact_arithmetic as exact
+    rng = np.random.default_rng(77)
+    for dim in (3, 384, 520):
+        rows = rng.standard_normal((9, dim)).astype(np.float32)
+        rows[1] *= 1e-3
+        rows[2] *= 200.0
+        rows[4] = 0.0
+        rows[7] = rows[0]                       # an exact duplicate: a tie, broken by row id
+        q = rng.standard_normal(dim).astype(np.float32)
+        ix = tss.FlatIndex(dim, tss.TSS_BF16 if storage_bf16 else tss.TSS_F32)
+        ix.add(rows)
+        ix.finalize()
+        gr, gs, gc = ix.search(q, 9)
+        assert gc[0] == 9
+        want = {r: exact._score_bits(rows[r], q, bf16=storage_bf16) for r in range(9)}
+        for r, s in zip(gr[0], gs[0]):
+            assert int(s.view(np.uint32)) == want[int(r)], (dim, int(r))
+        # (score desc, row asc) under the exact scores
+        order = sorted(range(9), key=lambda r: (-np.uint32(want[r]).view(np.float32), r))
+        assert [int(r) for r in gr[0]] == order
