@@ -15,7 +15,9 @@
  * hybrid merge (src/search.rs:185-240,255-274), the result mapping
  * (src/vector.rs:128-150) and the defaults (src/lib.rs:122-145).  The
  * arithmetic (canonical fp32 reduction order, zero-norm rule, tie-break)
- * is defined in DESIGN.md section 3 and restated in oracle.cpp.
+ * is defined in DESIGN.md section 3 and restated in oracle.cpp; that
+ * restatement is itself held, bit for bit, to an evaluation of the
+ * definition in exact rational arithmetic (tests/test_exact_arithmetic.py).
  */
 #ifndef TSS_ORACLE_H
 #define TSS_ORACLE_H
