@@ -418,6 +418,18 @@ def config4_leg(tss, orc, args, ix, device):
             ix.search_into(q[i % 8].ctypes.data, 1, k, out_rows.ctypes.data, out_scores.ctypes.data,
                            out_counts.ctypes.data, mask, tss.TSS_MASK_INCLUDE)
         e2e_us = (time.perf_counter() - t0) / iters * 1e6
+        # ... and as ONE host call (tss_index_search_prefix)
+        two_call = (out_rows.copy(), out_scores.copy(), out_counts.copy())
+        for i in range(3):
+            ix.search_prefix_into(terms, prefix, mask, q[i % 8].ctypes.data, 1, k, out_rows.ctypes.data,
+                                  out_scores.ctypes.data, out_counts.ctypes.data)
+        t0 = time.perf_counter()
+        for i in range(iters):
+            ix.search_prefix_into(terms, prefix, mask, q[i % 8].ctypes.data, 1, k, out_rows.ctypes.data,
+                                  out_scores.ctypes.data, out_counts.ctypes.data)
+        e2e1_us = (time.perf_counter() - t0) / iters * 1e6
+        ok = ok and all(bool(np.array_equal(a.view(np.uint32), b.view(np.uint32)))
+                        for a, b in zip(two_call, (out_rows, out_scores, out_counts)))
         # the last query's result against the oracle: every live row scored on the CPU when the
         # mask is small, else the returned rows' score bits + membership
         qi = (iters - 1) % 8
@@ -446,6 +458,7 @@ def config4_leg(tss, orc, args, ix, device):
             "terms_in_range": int(st.sub_hi - st.sub_lo + st.exact_hi - st.exact_lo),
             "mask_bit_exact_vs_numpy": ok, "prefix_to_mask_us_device": k4_us,
             "query_us_device": dev_us, "query_us_e2e_host_pointers": e2e_us,
+            "query_us_e2e_one_call": e2e1_us,
             "algorithmic_bytes": algo, "dense_scan_bytes": N * dim * 4,
             "did": "row-skipping scan of the live rows (not a dense scan)",
             "masked_scan_gbs_on_live_rows": pc * dim * 4 / (scan_us * 1e-6) / 1e9,
@@ -726,6 +739,40 @@ def main():
     e2e = {"value": args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": args.dim * 4,
            "d2h_bytes_per_step": args.k * 8, "ms_per_step": e2e_s / args.steps * 1e3}
 
+    # the same steps with two searches in flight (tss_index_search_submit / _collect, one host
+    # thread): every step still copies its query from host memory and unpacks its result into host
+    # memory, but the next scan is enqueued while this one runs, so launch and wake-up latency and
+    # the merges' tail hide behind the stream of the corpus.  Reported beside the blocking call's
+    # number, not instead of it.
+    depth = 2
+    p_rows = np.empty((nq_total, args.k), np.uint32)
+    p_scores = np.empty((nq_total, args.k), np.float32)
+    p_counts = np.empty(nq_total, np.uint32)
+    prp, psp, pcp = (a.ctypes.data for a in (p_rows, p_scores, p_counts))
+
+    def pipelined_leg(first, count):
+        tickets = []
+        for i in range(first, first + count):
+            if len(tickets) == depth:
+                j, t = tickets.pop(0)
+                ix.search_collect(t, prp + j * rs, psp + j * rs, pcp + j * 4)
+            tickets.append((i, ix.search_submit(qp + i * qs, 1, args.k)))
+        for j, t in tickets:
+            ix.search_collect(t, prp + j * rs, psp + j * rs, pcp + j * 4)
+
+    pipelined_leg(0, args.warmup)
+    barrier()
+    t0 = time.perf_counter()
+    pipelined_leg(args.warmup, args.steps)
+    pipe_local = time.perf_counter() - t0
+    barrier()
+    pipe_s = max_over_ranks(pipe_local)
+    e2e["pipelined"] = {
+        "value": args.steps / pipe_s, "unit": UNIT, "ms_per_step": pipe_s / args.steps * 1e3,
+        "in_flight": depth, "api": "tss_index_search_submit / tss_index_search_collect, one host thread",
+        "h2d_bytes_per_step": args.dim * 4, "d2h_bytes_per_step": args.k * 8,
+    }
+
     # ---- sanity: the timed work is the real work ----------------------------------------------
     check = "skipped"
     notes = []
@@ -745,10 +792,17 @@ def main():
             for r, s in zip(rows_out[i], scores_out[i]):
                 e = orc.gen_rows(int(r), 1, args.dim, SEED_ROWS)
                 ok &= orc.scores(e, queries[i])[0].view(np.uint32) == s.view(np.uint32)
+        # ... and so did the pipelined leg
+        same_p = bool(np.array_equal(out_rows, p_rows) and
+                      np.array_equal(out_scores.view(np.uint32), p_scores.view(np.uint32)) and
+                      np.array_equal(out_counts, p_counts))
+        e2e["pipelined"]["results_equal_blocking_leg"] = same_p
+        ok &= same_p
         # an end-to-end number above the device-only number is impossible for real work
-        if e2e["value"] > value * 1.03:
-            ok = False
-            notes.append(f"e2e {e2e['value']:.1f} q/s exceeds the device-timed value {value:.1f} q/s")
+        for name, v in (("e2e", e2e["value"]), ("e2e.pipelined", e2e["pipelined"]["value"])):
+            if v > value * 1.03:
+                ok = False
+                notes.append(f"{name} {v:.1f} q/s exceeds the device-timed value {value:.1f} q/s")
         check = "ok" if ok else "FAILED"
 
     # ---- extra (N=1): the same metric for a 1024-query batch on the same index -----------------

@@ -18,12 +18,18 @@
  *
  * Threading: every tss_index entry point takes the handle's own lock, so any
  * number of host threads may call into one index (searches included) with
- * distinct output buffers; the calls are serialised inside the library instead
- * of behind the caller's process-wide write lock (the reference:
- * src/search.rs:249-252).  One scan already saturates HBM, so concurrency is
- * turned into throughput by BATCHING (nq > 1: the corpus is streamed once per
- * 4 queries, or once per batch on the tensor-core path; host/tss_host.hpp
- * QueryBatcher does that for concurrent callers), not by overlapping scans.
+ * distinct output buffers, instead of queueing behind the caller's
+ * process-wide write lock (the reference: src/search.rs:249-252).  A search of
+ * up to TSS_PENDING_MAX_NQ queries holds the lock only while it is ENQUEUED
+ * and waits for its result outside it (each call owns a result slot and an
+ * event), so the scans of concurrent callers run back to back on the device;
+ * tss_index_search_submit / _collect give one thread the same pipelining.
+ * One scan already saturates HBM, so beyond hiding launch and wake-up latency
+ * concurrency is turned into throughput by BATCHING (nq > 1: the corpus is
+ * streamed once per 4 queries, or once per batch on the tensor-core path;
+ * host/tss_host.hpp QueryBatcher does that for concurrent callers).
+ * A sharded index is collective: every rank must issue its searches in the
+ * same order, so drive it from one thread per rank.
  * tss_mask / tss_terms / tss_columns handles: one thread mutates a given
  * handle at a time; concurrent searches may read the same mask.  Distinct
  * handles may always be used from distinct threads.
@@ -69,6 +75,8 @@ enum {
 #define TSS_MAX_K 1024u         /* largest k any search accepts */
 #define TSS_MAX_FUSED_K 128u    /* k <= this runs the fused in-scan top-k */
 #define TSS_ROW_NONE 0xFFFFFFFFu /* row id of an unused output slot */
+#define TSS_MAX_PENDING 4u      /* tss_index_search_submit calls in flight per index */
+#define TSS_PENDING_MAX_NQ 4u   /* queries per submitted search (one scan launch) */
 
 typedef struct tss_index tss_index; /* replaces HnswIndex, src/vector.rs:40-44 */
 typedef struct tss_mask tss_mask;   /* device bitmask over the rows of one shard */
@@ -131,6 +139,25 @@ int tss_index_get_rows(tss_index* ix, uint64_t row_begin, uint64_t nrows, float*
 int tss_index_search(tss_index* ix, const float* queries, uint32_t nq, uint32_t k,
                      const tss_mask* mask, int mask_mode, uint32_t* out_rows,
                      float* out_scores, uint32_t* out_counts);
+
+/* The same search split in two for a caller that pipelines: submit copies the
+ * queries (1..TSS_PENDING_MAX_NQ of them, k <= TSS_MAX_FUSED_K), enqueues the
+ * scan and returns a ticket without waiting; collect waits for that search
+ * alone and unpacks its result.  Up to TSS_MAX_PENDING searches may be in
+ * flight per index (one more submit returns TSS_ERR_STATE); they execute in
+ * submission order, and under programmatic dependent launch the next scan's
+ * prologue overlaps the previous one's merges, so a caller that keeps two in
+ * flight sees the device-resident rate through host pointers.  Always the
+ * exact scan (K1), whatever tss_index_set_batch_policy says.  A ticket is
+ * collected exactly once.  A mask handed to submit may be rewritten right
+ * away: mask writes are stream-ordered behind the searches that read the mask.
+ * The reference's HnswIndex::search
+ * (src/vector.rs:195-202) is an async fn that never awaits; this is the form
+ * an awaiting implementation would take. */
+int tss_index_search_submit(tss_index* ix, const float* queries, uint32_t nq, uint32_t k,
+                            const tss_mask* mask, int mask_mode, uint64_t* out_ticket);
+int tss_index_search_collect(tss_index* ix, uint64_t ticket, uint32_t* out_rows,
+                             float* out_scores, uint32_t* out_counts);
 
 /* Same work with every buffer already in HBM and no host synchronisation:
  * d_queries nq x dim fp32, d_out_keys nq x k packed keys
@@ -284,6 +311,16 @@ int tss_prefix_mask_fresh(tss_terms* t, const char* prefix, uint32_t len, int ki
  * prefix -> mask -> masked search then run back to back on ONE stream with no cross-stream
  * event hop.  The index must outlive the binding. */
 int tss_terms_bind_stream(tss_terms* t, tss_index* ix /* nullable */);
+/* The hybrid query of BASELINE.json config 4 as ONE host call: tss_prefix_mask_fresh(t, prefix,
+ * ..., scratch, row base of ix) followed by tss_index_search(ix, queries, ..., scratch,
+ * TSS_MASK_INCLUDE, ...) -- prefix search + mask + masked top-k are enqueued together and the
+ * host waits once.  scratch is overwritten (a mask of >= tss_index_size(ix) bits on the index's
+ * device); afterwards it holds the prefix's row set.  Replaces the trie walk + vector search
+ * pair of SearchEngine::execute_hybrid_search (src/search.rs:189-190, 210) when the prefix is
+ * used as a filter. */
+int tss_index_search_prefix(tss_index* ix, tss_terms* t, const char* prefix, uint32_t len, int kind,
+                            tss_mask* scratch, const float* queries, uint32_t nq, uint32_t k,
+                            uint32_t* out_rows, float* out_scores, uint32_t* out_counts);
 
 /* ---- plumbing for callers that time or pipeline the device path ------------ */
 void* tss_index_stream(tss_index* ix); /* cudaStream_t the index enqueues on */

@@ -26,6 +26,8 @@ TSS_PREFIX_TOKEN, TSS_PREFIX_CHAR = 0, 1
 TSS_MAX_K = 1024
 TSS_MAX_FUSED_K = 128
 TSS_ROW_NONE = 0xFFFFFFFF
+TSS_MAX_PENDING = 4
+TSS_PENDING_MAX_NQ = 4
 
 # every symbol include/tss.h declares (tests/test_abi.py checks the .so exports all of them)
 ABI_SYMBOLS = [
@@ -45,6 +47,7 @@ ABI_SYMBOLS = [
     "tss_terms_build", "tss_terms_sizes", "tss_terms_export",
     "tss_prefix_mask_fresh", "tss_terms_bind_stream",
     "tss_terms_build_text", "tss_terms_save", "tss_terms_load",
+    "tss_index_search_submit", "tss_index_search_collect", "tss_index_search_prefix",
 ]
 
 
@@ -88,6 +91,9 @@ def lib() -> C.CDLL:
         "tss_index_get_rows": (i32, [vp, u64, u64, vp]),
         "tss_index_search": (i32, [vp, vp, u32, u32, vp, i32, vp, vp, vp]),
         "tss_index_search_device": (i32, [vp, vp, u32, u32, vp, i32, vp]),
+        "tss_index_search_submit": (i32, [vp, vp, u32, u32, vp, i32, pu64]),
+        "tss_index_search_collect": (i32, [vp, u64, vp, vp, vp]),
+        "tss_index_search_prefix": (i32, [vp, vp, C.c_char_p, u32, i32, vp, vp, u32, u32, vp, vp, vp]),
         "tss_unpack_keys": (None, [vp, u64, vp, vp]),
         "tss_comm_unique_id": (i32, [vp]),
         "tss_comm_create": (i32, [C.POINTER(vp), vp, i32, i32, i32]),
@@ -529,6 +535,33 @@ class FlatIndex:
         numpy allocation or conversion): for latency-sensitive callers and bench.py's e2e leg."""
         rc = lib().tss_index_search(self.handle, q_ptr, nq, k, mask.handle if mask else None,
                                     mask_mode, rows_ptr, scores_ptr, counts_ptr)
+        if rc != TSS_OK:
+            _check(rc)
+
+    def search_submit(self, q_ptr: int, nq: int, k: int, mask: Optional[Mask] = None,
+                      mask_mode: int = TSS_MASK_NONE) -> int:
+        """tss_index_search_submit: enqueue a search of 1..4 host queries (raw address), return its
+        ticket without waiting; up to TSS_MAX_PENDING may be in flight."""
+        t = C.c_uint64(0)
+        rc = lib().tss_index_search_submit(self.handle, q_ptr, nq, k, mask.handle if mask else None,
+                                           mask_mode, C.byref(t))
+        if rc != TSS_OK:
+            _check(rc)
+        return t.value
+
+    def search_collect(self, ticket: int, rows_ptr: int, scores_ptr: int, counts_ptr: int) -> None:
+        """tss_index_search_collect: wait for that search alone, unpack into caller-owned buffers."""
+        rc = lib().tss_index_search_collect(self.handle, ticket, rows_ptr, scores_ptr, counts_ptr)
+        if rc != TSS_OK:
+            _check(rc)
+
+    def search_prefix_into(self, terms: "Terms", prefix: bytes, scratch: Mask, q_ptr: int, nq: int,
+                           k: int, rows_ptr: int, scores_ptr: int, counts_ptr: int,
+                           kind: int = TSS_PREFIX_TOKEN) -> None:
+        """tss_index_search_prefix: prefix -> fresh mask -> masked top-k as one host call."""
+        rc = lib().tss_index_search_prefix(self.handle, terms.handle, prefix, len(prefix), kind,
+                                           scratch.handle, q_ptr, nq, k, rows_ptr, scores_ptr,
+                                           counts_ptr)
         if rc != TSS_OK:
             _check(rc)
 

@@ -8,6 +8,7 @@
 #include <dlfcn.h>
 
 #include <atomic>
+#include <condition_variable>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -87,6 +88,8 @@ constexpr int kNcclUint64 = 5;
 constexpr uint32_t kMaxBq = 4;           // queries per scan launch
 constexpr uint32_t kScanSlots = 4;       // scan workspace slots (launches in flight under PDL)
 constexpr uint32_t kWsQueries = 1024;    // device query/result workspace, in queries
+constexpr uint32_t kPending = TSS_MAX_PENDING;  // searches in flight per handle (submit / collect)
+constexpr uint32_t kPendingNq = TSS_PENDING_MAX_NQ;  // queries per pending search
 constexpr size_t kStageBytes = 32u << 20;  // one of the two upload staging buffers
 constexpr uint32_t kGemmCandCap = 32768;   // K2 survivor keys per query of a FULL workspace batch:
                                            // the pool (kWsQueries x this) is shared out per batch
@@ -234,6 +237,22 @@ struct tss_index {
   float* h_queries = nullptr;  // pinned
   uint64_t* h_keys = nullptr;  // pinned + mapped: the scan writes its result straight into it
   unsigned int* h_status = nullptr;  // pinned + mapped exchange status word
+  // Searches in flight (tss_index_search_submit / _collect, and every blocking search of <= 4
+  // queries): each owns a pinned query slot, a device query slot, a pinned + mapped result slot
+  // the scan's last CTA writes straight into, and an event.  The handle's lock is held while a
+  // search is ENQUEUED, not while it is waited for, so the scans of several host threads (or of
+  // one pipelining thread) queue up back to back on the device.
+  struct Pending {
+    cudaEvent_t ev = nullptr;
+    uint32_t nq = 0, k = 0;
+    uint32_t gen = 0;   // bumped by every submit: a stale or repeated ticket is caught
+    int state = 0;      // 0 free, 1 in flight, 2 being collected
+  } pend[kPending];
+  uint32_t pend_next = 0;
+  float* h_pq = nullptr;     // [kPending][kPendingNq][dim] pinned
+  float* d_pq = nullptr;     // [kPending][kPendingNq][dim]
+  uint64_t* h_pk = nullptr;  // [kPending][kPendingNq][TSS_MAX_FUSED_K] pinned + mapped
+  std::condition_variable pend_cv;
   // K2 (tensor-core) workspace, allocated on first large-batch search of a bf16 index
   struct Gemm {
     bool ready = false;
@@ -961,6 +980,95 @@ int check_k_path(const tss_index* ix, uint32_t nq, uint32_t k, int mode) {
   return TSS_OK;
 }
 
+// ---- searches in flight ------------------------------------------------------------------
+// ix->mu held.  Enqueues one scan-path search of nq <= kPendingNq queries, k <= TSS_MAX_FUSED_K,
+// whose result lands in a pending slot; *slot_out = -1 (and TSS_OK) when every slot is taken.
+int pending_submit_locked(tss_index* ix, const float* queries, uint32_t nq, uint32_t k,
+                          const tss_mask* mask, int mask_mode, int* slot_out) {
+  *slot_out = -1;
+  int s = -1;
+  for (uint32_t i = 0; i < kPending; ++i) {
+    uint32_t c = (ix->pend_next + i) % kPending;
+    if (ix->pend[c].state == 0) {
+      s = (int)c;
+      break;
+    }
+  }
+  if (s < 0) return TSS_OK;
+  int rc;
+  if ((rc = ensure_gather_ws(ix))) return rc;
+  MaskReadScope mrs(mask, mask_mode, ix->stream);
+  if (mrs.err != cudaSuccess) return cuda_fail(mrs.err, "mask ordering");
+  const size_t qelems = (size_t)kPendingNq * ix->dim;
+  float* hq = ix->h_pq + (size_t)s * qelems;
+  float* dq = ix->d_pq + (size_t)s * qelems;
+  uint64_t* hk = ix->h_pk + (size_t)s * kPendingNq * TSS_MAX_FUSED_K;
+  // a lone query travels in the kernel parameters; the last CTA writes the result straight into
+  // mapped pinned host memory -- no H2D / D2H copy operations at all
+  const bool inline_q = nq == 1 && ix->dim <= 384;
+  if (!inline_q) {
+    memcpy(hq, queries, (size_t)nq * ix->dim * sizeof(float));
+    CU(cudaMemcpyAsync(dq, hq, (size_t)nq * ix->dim * sizeof(float), cudaMemcpyHostToDevice, ix->stream));
+  }
+  const bool merged = ix->comm && ix->xchg.ready;
+  const bool direct = !ix->comm || merged;
+  rc = enqueue_scan(ix, dq, nq, k, mask, mask_mode, direct ? hk : ix->d_keys,
+                    inline_q ? queries : nullptr);
+  if (rc) return rc;
+  if (!direct) {
+    if ((rc = enqueue_gather_merge(ix, ix->d_keys, nq, k, ix->d_merged))) return rc;
+    CU(cudaMemcpyAsync(hk, ix->d_merged, (size_t)nq * k * sizeof(uint64_t), cudaMemcpyDeviceToHost,
+                       ix->stream));
+  }
+  tss_index::Pending& pd = ix->pend[s];
+  CU(cudaEventRecord(pd.ev, ix->stream));
+  pd.nq = nq;
+  pd.k = k;
+  pd.gen = pd.gen + 1 ? pd.gen + 1 : 1;
+  pd.state = 1;
+  ix->pend_next = ((uint32_t)s + 1) % kPending;
+  *slot_out = s;
+  return TSS_OK;
+}
+
+// slot s is in state 2 (being collected by this thread); ix->mu NOT held while waiting
+int pending_collect(tss_index* ix, int s, uint32_t* out_rows, float* out_scores, uint32_t* out_counts) {
+  tss_index::Pending& pd = ix->pend[s];
+  int rc = TSS_OK;
+  {
+    DeviceGuard g(ix->device);
+    cudaError_t e = cudaEventSynchronize(pd.ev);
+    if (e != cudaSuccess) rc = cuda_fail(e, "waiting for a pending search");
+  }
+  if (!rc && ix->comm && ix->xchg.ready && *ix->h_status) {
+    *ix->h_status = 0;
+    rc = fail(TSS_ERR_NCCL, "a rank of the shard group did not deliver its top-k within 20 s");
+  }
+  if (!rc) {
+    const uint64_t* hk = ix->h_pk + (size_t)s * kPendingNq * TSS_MAX_FUSED_K;
+    tss_unpack_keys(hk, (uint64_t)pd.nq * pd.k, out_rows, out_scores);
+    for (uint32_t qi = 0; qi < pd.nq; ++qi) {
+      uint32_t c = 0;
+      while (c < pd.k && hk[(size_t)qi * pd.k + c] != 0) ++c;
+      out_counts[qi] = c;
+    }
+  }
+  {
+    std::lock_guard<std::mutex> lock(ix->mu);
+    pd.state = 0;
+  }
+  ix->pend_cv.notify_all();
+  return rc;
+}
+
+int validate_host_queries(const tss_index* ix, const float* queries, uint32_t nq) {
+  for (uint64_t i = 0; i < (uint64_t)nq * ix->dim; ++i)
+    if (!std::isfinite(queries[i]))
+      return fail(TSS_ERR_INVALID_ARG, "query %llu contains NaN or Inf",
+                  (unsigned long long)(i / ix->dim));
+  return TSS_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -1028,6 +1136,10 @@ int tss_index_create(tss_index** out, uint32_t dim, int storage, int device) {
   ALLOC(cudaMallocHost(&ix->h_keys, (size_t)kWsQueries * TSS_MAX_K * sizeof(uint64_t)))
   ALLOC(cudaMallocHost(&ix->h_status, 64))
   memset(ix->h_status, 0, 64);
+  ALLOC(cudaMallocHost(&ix->h_pq, (size_t)kPending * kPendingNq * dim * sizeof(float)))
+  ALLOC(cudaMalloc(&ix->d_pq, (size_t)kPending * kPendingNq * dim * sizeof(float)))
+  ALLOC(cudaMallocHost(&ix->h_pk, (size_t)kPending * kPendingNq * TSS_MAX_FUSED_K * sizeof(uint64_t)))
+  for (auto& pd : ix->pend) ALLOC(cudaEventCreateWithFlags(&pd.ev, cudaEventDisableTiming))
   if (const char* sf = getenv("TSS_GEMM_MIN_NQ")) {  // diagnostics: one plain threshold
     ix->gemm_min_nq = (uint32_t)atoi(sf);
     ix->gemm_small_nq = 0xFFFFFFFFu;
@@ -1056,6 +1168,11 @@ void tss_index_destroy(tss_index* ix) {
   if (ix->h_queries) cudaFreeHost(ix->h_queries);
   if (ix->h_keys) cudaFreeHost(ix->h_keys);
   if (ix->h_status) cudaFreeHost(ix->h_status);
+  if (ix->h_pq) cudaFreeHost(ix->h_pq);
+  cudaFree(ix->d_pq);
+  if (ix->h_pk) cudaFreeHost(ix->h_pk);
+  for (auto& pd : ix->pend)
+    if (pd.ev) cudaEventDestroy(pd.ev);
   for (int r = 0; r < 8; ++r)
     if (ix->xchg.peer[r] && ix->xchg.peer[r] != ix->xchg.local) cudaIpcCloseMemHandle(ix->xchg.peer[r]);
   cudaFree(ix->xchg.local);
@@ -1368,7 +1485,7 @@ int tss_index_search(tss_index* ix, const float* queries, uint32_t nq, uint32_t 
                      const tss_mask* mask, int mask_mode, uint32_t* out_rows, float* out_scores,
                      uint32_t* out_counts) {
   if (!ix) return fail(TSS_ERR_INVALID_ARG, "index is NULL");
-  std::lock_guard<std::mutex> lock(ix->mu);
+  std::unique_lock<std::mutex> lock(ix->mu);
   int rc = validate_search(ix, queries, nq, k);
   if (rc) return rc;
   if (!out_rows || !out_scores || !out_counts)
@@ -1376,11 +1493,22 @@ int tss_index_search(tss_index* ix, const float* queries, uint32_t nq, uint32_t 
   if ((rc = check_mask(ix, mask, mask_mode))) return rc;
   if ((rc = check_k_path(ix, nq, k, mask_mode))) return rc;
   if (!nq) return TSS_OK;
-  for (uint64_t i = 0; i < (uint64_t)nq * ix->dim; ++i)
-    if (!std::isfinite(queries[i]))
-      return fail(TSS_ERR_INVALID_ARG, "query %llu contains NaN or Inf",
-                  (unsigned long long)(i / ix->dim));
+  if ((rc = validate_host_queries(ix, queries, nq))) return rc;
   DeviceGuard g(ix->device);
+  if (nq <= kPendingNq && k <= TSS_MAX_FUSED_K && !gemm_route(ix, nq, k, mask_mode)) {
+    // one scan launch: enqueue under the lock, wait outside it, so the searches of several host
+    // threads queue up back to back on the device (the next one's prologue overlaps this one's
+    // merges) instead of each waiting out the other's launch + wake-up latency
+    int s = -1;
+    for (;;) {
+      if ((rc = pending_submit_locked(ix, queries, nq, k, mask, mask_mode, &s))) return rc;
+      if (s >= 0) break;
+      ix->pend_cv.wait(lock);
+    }
+    ix->pend[s].state = 2;
+    lock.unlock();
+    return pending_collect(ix, s, out_rows, out_scores, out_counts);
+  }
   if ((rc = ensure_gather_ws(ix))) return rc;
   MaskReadScope mrs(mask, mask_mode, ix->stream);
   if (mrs.err != cudaSuccess) return cuda_fail(mrs.err, "mask ordering");
@@ -1434,6 +1562,65 @@ int tss_index_search(tss_index* ix, const float* queries, uint32_t nq, uint32_t 
     }
   }
   return TSS_OK;
+}
+
+int tss_index_search_submit(tss_index* ix, const float* queries, uint32_t nq, uint32_t k,
+                            const tss_mask* mask, int mask_mode, uint64_t* out_ticket) {
+  if (!ix) return fail(TSS_ERR_INVALID_ARG, "index is NULL");
+  if (!out_ticket) return fail(TSS_ERR_INVALID_ARG, "out_ticket is NULL");
+  *out_ticket = 0;
+  std::lock_guard<std::mutex> lock(ix->mu);
+  int rc = validate_search(ix, queries, nq, k);
+  if (rc) return rc;
+  if (nq == 0 || nq > kPendingNq || k > TSS_MAX_FUSED_K)
+    return fail(TSS_ERR_INVALID_ARG, "a pending search takes 1..%u queries and k <= %u (got nq=%u k=%u)",
+                kPendingNq, TSS_MAX_FUSED_K, nq, k);
+  if ((rc = check_mask(ix, mask, mask_mode))) return rc;
+  if ((rc = validate_host_queries(ix, queries, nq))) return rc;
+  DeviceGuard g(ix->device);
+  int s = -1;
+  if ((rc = pending_submit_locked(ix, queries, nq, k, mask, mask_mode, &s))) return rc;
+  if (s < 0)
+    return fail(TSS_ERR_STATE, "%u searches are already pending on this index: collect one first", kPending);
+  *out_ticket = ((uint64_t)ix->pend[s].gen << 8) | (uint64_t)(s + 1);
+  return TSS_OK;
+}
+
+int tss_index_search_collect(tss_index* ix, uint64_t ticket, uint32_t* out_rows, float* out_scores,
+                             uint32_t* out_counts) {
+  if (!ix) return fail(TSS_ERR_INVALID_ARG, "index is NULL");
+  if (!out_rows || !out_scores || !out_counts)
+    return fail(TSS_ERR_INVALID_ARG, "output pointer is NULL");
+  const uint32_t slot1 = (uint32_t)(ticket & 0xFF), gen = (uint32_t)(ticket >> 8);
+  if (slot1 == 0 || slot1 > kPending) return fail(TSS_ERR_INVALID_ARG, "not a ticket of tss_index_search_submit");
+  const int s = (int)slot1 - 1;
+  {
+    std::lock_guard<std::mutex> lock(ix->mu);
+    if (ix->pend[s].state != 1 || ix->pend[s].gen != gen)
+      return fail(TSS_ERR_STATE, "ticket was already collected (or never issued by this index)");
+    ix->pend[s].state = 2;
+  }
+  return pending_collect(ix, s, out_rows, out_scores, out_counts);
+}
+
+int tss_index_search_prefix(tss_index* ix, tss_terms* t, const char* prefix, uint32_t len, int kind,
+                            tss_mask* scratch, const float* queries, uint32_t nq, uint32_t k,
+                            uint32_t* out_rows, float* out_scores, uint32_t* out_counts) {
+  if (!ix) return fail(TSS_ERR_INVALID_ARG, "index is NULL");
+  int rc;
+  uint64_t row_base;
+  {  // everything the search would reject is rejected before the scratch mask is touched
+    std::lock_guard<std::mutex> lock(ix->mu);
+    if ((rc = validate_search(ix, queries, nq, k))) return rc;
+    if (!out_rows || !out_scores || !out_counts)
+      return fail(TSS_ERR_INVALID_ARG, "output pointer is NULL");
+    if ((rc = check_mask(ix, scratch, TSS_MASK_INCLUDE))) return rc;
+    if ((rc = check_k_path(ix, nq, k, TSS_MASK_INCLUDE))) return rc;
+    if ((rc = validate_host_queries(ix, queries, nq))) return rc;
+    row_base = ix->row_base;
+  }
+  if ((rc = tss_prefix_mask_fresh(t, prefix, len, kind, scratch, row_base, nullptr))) return rc;
+  return tss_index_search(ix, queries, nq, k, scratch, TSS_MASK_INCLUDE, out_rows, out_scores, out_counts);
 }
 
 // ---- sharding ---------------------------------------------------------------------------
