@@ -76,6 +76,25 @@ def run_checks(tss, orc, comm, rank, world, local, quick=False):
     if not same:
         print(f"rank {rank}: back-to-back sharded scans MISMATCH", flush=True)
     ok &= same
+    # the same from host memory with searches in flight (tss_index_search_submit / _collect, one
+    # thread per rank, every rank in the same order): merged result on every rank
+    qc = np.ascontiguousarray(q)
+    outs = [(np.empty((1, k), np.uint32), np.empty((1, k), np.float32), np.empty(1, np.uint32))
+            for _ in range(60)]
+    tickets = []
+    for i in range(60):
+        if len(tickets) == 3:
+            j, t = tickets.pop(0)
+            ix.search_collect(t, *(a.ctypes.data for a in outs[j]))
+        tickets.append((i, ix.search_submit(qc[i % 4].ctypes.data, 1, k)))
+    for j, t in tickets:
+        ix.search_collect(t, *(a.ctypes.data for a in outs[j]))
+    same = all(np.array_equal(outs[i][0][0], want[0][i % 4]) and
+               np.array_equal(outs[i][1][0].view(np.uint32), want[1][i % 4].view(np.uint32)) and
+               int(outs[i][2][0]) == k for i in range(60))
+    if not same:
+        print(f"rank {rank}: pipelined sharded searches MISMATCH", flush=True)
+    ok &= same
     ix.close()
     # K2 (tensor-core path) on a sharded bf16 index: local GEMM top-k, NCCL all-gather, merge
     # (survivors are re-scored with the scan's arithmetic, so the merged result is bit-identical
