@@ -17,8 +17,10 @@ The same JSON line carries the other BASELINE.json configs as objects of their o
                tensor roofline, recall@100 / @10 against the fp32 exact result
   config4      (N=1) hybrid: ~5M-term flattened trie -> prefix mask (K4) -> masked top-10 (K1) at
                three selectivities; masks checked bit for bit against numpy
-  config5      (N>1) 100M x 384 fp32 row-sharded over the N GPUs: q/s, per-GPU GB/s, result
-               checked against the 10M-row index (the first 10M rows are the same rows)
+  config5      100M x 384 fp32 row-sharded over the N GPUs (N=1: all 153.6 GB in one B200's HBM):
+               q/s, per-GPU GB/s, result checked against the 10M-row index (the first 10M rows
+               are the same rows)
+  top50        batch-1 exact top-50, the call the reference's merge makes (src/search.rs:251)
   selftest     (N>1) sharded == unsharded oracle, bit for bit (tests/dist_worker.py:run_checks)
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
@@ -485,26 +487,37 @@ def config5_leg(tss, orc, args, ix10, comm, rank, world, device, barrier, max_ov
     b = min(rank * per, total)
     n_local = min(per, total - b)
     need = n_local * dim * 4 * 1.02 + (2 << 30)
-    free_b = torch.cuda.mem_get_info()[0]
-    fits = torch.tensor([1 if free_b > need else 0], device="cuda")
-    dist.all_reduce(fits, op=dist.ReduceOp.MIN)
-    if int(fits.item()) == 0:
-        return {"skipped": f"a {n_local}-row shard ({need / 1e9:.1f} GB) does not fit next to the "
-                           f"10M-row index on every GPU ({free_b / 1e9:.1f} GB free on rank {rank})"}
     ix = tss.FlatIndex(dim, tss.TSS_F32, device)
-    ix.reserve(n_local)
+    if world > 1:
+        free_b = torch.cuda.mem_get_info()[0]
+        fits = torch.tensor([1 if free_b > need else 0], device="cuda")
+        dist.all_reduce(fits, op=dist.ReduceOp.MIN)
+        if int(fits.item()) == 0:
+            ix.close()
+            return {"skipped": f"a {n_local}-row shard ({need / 1e9:.1f} GB) does not fit next to the "
+                               f"10M-row index on every GPU ({free_b / 1e9:.1f} GB free on rank {rank})"}
+        ix.reserve(n_local)
+    else:
+        # one GPU: the whole 100M x 384 fp32 matrix (153.6 GB) in one B200's HBM, next to the
+        # 10M-row index it is checked against; the library reports OOM, it does not die of it
+        try:
+            ix.reserve(n_local)
+        except tss.TssError as e:
+            ix.close()
+            return {"skipped": f"{n_local} rows ({need / 1e9:.1f} GB) do not fit on this GPU: {e}"}
     ix.add_synthetic(b, n_local, SEED_ROWS)
     ix.set_shard(b, comm)
     ix.finalize()
-    steps, warm = 60, 5
+    steps, warm = (60, 5) if world > 1 else (30, 3)
     nq = steps + warm
     if rank == 0:
         q, planted = make_queries(orc, nq, dim, total, SEED_Q ^ 0x5555)
     else:
         q, planted = np.empty((nq, dim), np.float32), {}
-    qt = torch.from_numpy(q).cuda()
-    dist.broadcast(qt, 0)
-    q = qt.cpu().numpy()
+    if world > 1:
+        qt = torch.from_numpy(q).cuda()
+        dist.broadcast(qt, 0)
+        q = qt.cpu().numpy()
     d_q = tss.DeviceBuffer(device, q.nbytes).upload(q)
     d_k = tss.DeviceBuffer(device, nq * k * 8)
     ev0, ev1 = tss.Event(device), tss.Event(device)
@@ -523,17 +536,19 @@ def config5_leg(tss, orc, args, ix10, comm, rank, world, device, barrier, max_ov
     ms = max_over_ranks(ev0.elapsed_ms(ev1)) / steps
     barrier()
     # the scan alone (no exchange): per-GPU bandwidth on a 19.2 GB (N=8) shard
-    ix.set_shard(b, None)
-    d_tmp = tss.DeviceBuffer(device, nq * k * 8)
-    leg(ix, 0, warm, d_tmp)
-    ix.sync()
-    barrier()
-    ev0.record(ix)
-    leg(ix, warm, steps, d_tmp)
-    ev1.record(ix)
-    ix.sync()
-    scan_ms = max_over_ranks(ev0.elapsed_ms(ev1)) / steps
-    ix.set_shard(b, comm)
+    scan_ms = ms
+    if world > 1:
+        ix.set_shard(b, None)
+        d_tmp = tss.DeviceBuffer(device, nq * k * 8)
+        leg(ix, 0, warm, d_tmp)
+        ix.sync()
+        barrier()
+        ev0.record(ix)
+        leg(ix, warm, steps, d_tmp)
+        ev1.record(ix)
+        ix.sync()
+        scan_ms = max_over_ranks(ev0.elapsed_ms(ev1)) / steps
+        ix.set_shard(b, comm)
     # the same queries over the 10M-row index (also sharded): rows [0, 10M) are the same rows
     d_k10 = tss.DeviceBuffer(device, nq * k * 8)
     leg(ix10, 0, nq, d_k10)
@@ -563,7 +578,9 @@ def config5_leg(tss, orc, args, ix10, comm, rank, world, device, barrier, max_ov
     return {
         "workload": (f"synthetic {total}x{dim} f32 corpus row-sharded over {world} GPUs "
                      f"({n_local} rows = {algo / 1e9:.2f} GB per GPU), batch-1 exact top-{k}, fused "
-                     "peer-memory exchange + merge"),
+                     "peer-memory exchange + merge") if world > 1 else
+                    (f"synthetic {total}x{dim} f32 corpus ({algo / 1e9:.1f} GB) resident in ONE B200's "
+                     f"HBM, batch-1 exact top-{k}: the N=1 point of config 5's scaling curve"),
         "value": 1e3 / ms, "unit": UNIT, "ms_per_step": ms, "steps": steps, "scaling": "weak-ish: "
         "total rows fixed at 100M, so the shard shrinks with N (SURVEY 8d config 5)",
         "scan_only_ms": scan_ms, "per_gpu_gbs": algo / (scan_ms * 1e-3) / 1e9,
@@ -805,6 +822,30 @@ def main():
                 notes.append(f"{name} {v:.1f} q/s exceeds the device-timed value {value:.1f} q/s")
         check = "ok" if ok else "FAILED"
 
+    # ---- extra: the call the reference's merge actually makes -- top-50 (src/search.rs:251) -------
+    k50 = None
+    if args.k != 50 and n_local >= 50:
+        n50, w50 = min(args.steps, 40), min(args.warmup, 3)
+        d_o50 = tss.DeviceBuffer(device, (n50 + w50) * 50 * 8)
+        for i in range(n50 + w50):
+            if i == w50:
+                barrier()
+                ev0.record(ix)
+            ix.search_device(_Slice(d_q.ptr + i * qstride), 1, 50, _Slice(d_o50.ptr + i * 50 * 8))
+        ev1.record(ix)
+        barrier()
+        ms50 = max_over_ranks(ev0.elapsed_ms(ev1)) / n50
+        same50 = True
+        if rank == 0:   # its first k keys are the top-k leg's keys
+            k50k = d_o50.download(np.uint64, (n50 + w50) * 50).reshape(n50 + w50, 50)
+            same50 = bool(np.array_equal(k50k[:, :args.k], keys_value_leg[:n50 + w50])) if args.k < 50 else True
+            if not same50:
+                check = "FAILED"
+                notes.append("top-50 leg disagrees with the top-k leg")
+        k50 = {"workload": "batch-1, exact top-50: what SearchEngine::search_vector asks of the index "
+                           "(src/search.rs:251)", "value": 1e3 / ms50, "unit": UNIT, "ms_per_step": ms50,
+               "steps": n50, "first_k_keys_equal_topk_leg": same50}
+
     # ---- extra (N=1): the same metric for a 1024-query batch on the same index -----------------
     # K2: tcgen05 GEMM picks candidates (from a bf16 shadow of an fp32 index), survivors are
     # re-scored with the scan's arithmetic -- the keys must equal the batch-1 legs' bit for bit.
@@ -826,13 +867,29 @@ def main():
         ev1.record(ix)
         ix.sync()
         bms = ev0.elapsed_ms(ev1) / iters
+        launches_b = (tss.launch_count() - l0) / iters
         kb = d_kb.download(np.uint64, nb * args.k).reshape(nb, args.k)
         same = bool(np.array_equal(kb[:min(nb, nq_total)], keys_value_leg[:min(nb, nq_total)]))
+        # the same batch end to end: host queries in (1.5 MB H2D), host rows + scores out
+        qb = np.ascontiguousarray(qb)
+        b_rows, b_scores = np.empty((nb, args.k), np.uint32), np.empty((nb, args.k), np.float32)
+        b_counts = np.empty(nb, np.uint32)
+        ix.search_into(qb.ctypes.data, nb, args.k, b_rows.ctypes.data, b_scores.ctypes.data, b_counts.ctypes.data)
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            ix.search_into(qb.ctypes.data, nb, args.k, b_rows.ctypes.data, b_scores.ctypes.data,
+                           b_counts.ctypes.data)
+        be2e_ms = (time.perf_counter() - t0) / iters * 1e3
+        rr, ss = tss.unpack_keys(kb)
+        same = same and bool(np.array_equal(rr, b_rows) and
+                             np.array_equal(ss.view(np.uint32), b_scores.view(np.uint32)))
         tf = 2.0 * nb * args.rows * args.dim / (bms * 1e-3) / 1e12
         batched = {
             "workload": f"{nb}-query batch, same index, exact cosine top-{args.k}", "batch": nb,
             "value": nb / bms * 1e3, "unit": UNIT, "ms_per_batch": bms,
-            "gpu_launches_per_batch": (tss.launch_count() - l0) / iters,
+            "e2e": {"value": nb / be2e_ms * 1e3, "unit": UNIT, "ms_per_batch": be2e_ms,
+                    "h2d_bytes_per_batch": nb * args.dim * 4, "d2h_bytes_per_batch": nb * args.k * 8},
+            "gpu_launches_per_batch": launches_b,
             "keys_equal_batch1_leg": same,
             "roofline": {"bound": "tensor", "kernel": "gemm_topk_kernel", "achieved": tf,
                          "peak": peaks.get("bf16_tflops"), "unit": "TFLOP/s",
@@ -953,6 +1010,15 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline(orc, args, queries)
 
+    # config 5 at N=1: the 100M-row corpus on a single GPU (last: it takes most of the HBM)
+    if (world == 1 and not args.no_extras and args.storage == "f32" and "config4" in extras
+            and args.config5_rows * args.dim * 4 < 170e9):
+        extras["config5"] = config5_leg(tss, orc, args, ix, None, rank, world, device, barrier,
+                                        max_over_ranks, None, None)
+        if extras["config5"].get("check") == "FAILED":
+            extras_ok = False
+            notes.append("config5 check failed")
+
     if not extras_ok and check == "ok":
         check = "FAILED"
     if rank == 0:
@@ -967,6 +1033,8 @@ def main():
         }
         if notes:
             line["check_notes"] = notes
+        if k50 is not None:
+            line["top50"] = k50
         if batched is not None:
             line["batched"] = batched
         if prefiltered is not None:
