@@ -549,6 +549,28 @@ def config5_leg(tss, orc, args, ix10, comm, rank, world, device, barrier, max_ov
         ix.sync()
         scan_ms = max_over_ranks(ev0.elapsed_ms(ev1)) / steps
         ix.set_shard(b, comm)
+    # SURVEY 8(d) config 5 also names B=16: one 16-query call per step.  A sharded fp32 index
+    # answers it with one tensor-core pass over its bf16 shadow (K2, results bit-identical); where
+    # the shadow does not fit (N=1: 153.6 + 76.8 GB) it is four 4-query scans.
+    nb16, it16 = 16, (5 if world > 1 else 3)
+    d_k16 = tss.DeviceBuffer(device, nb16 * k * 8)
+    b16 = None
+    try:
+        ix.search_device(d_q, nb16, k, d_k16)
+        ix.sync()
+        barrier()
+        l0 = tss.launch_count()
+        ev0.record(ix)
+        for _ in range(it16):
+            ix.search_device(d_q, nb16, k, d_k16)
+        ev1.record(ix)
+        ix.sync()
+        ms16 = max_over_ranks(ev0.elapsed_ms(ev1)) / it16
+        b16 = {"batch": nb16, "value": nb16 / ms16 * 1e3, "unit": UNIT, "ms_per_batch": ms16,
+               "gpu_launches_per_batch": (tss.launch_count() - l0) / it16}
+    except tss.TssError as e:   # (a rank without room for its shadow fails the call, loudly)
+        b16 = {"batch": nb16, "skipped": str(e)}
+    barrier()
     # the same queries over the 10M-row index (also sharded): rows [0, 10M) are the same rows
     d_k10 = tss.DeviceBuffer(device, nq * k * 8)
     leg(ix10, 0, nq, d_k10)
@@ -572,6 +594,10 @@ def config5_leg(tss, orc, args, ix10, comm, rank, world, device, barrier, max_ov
             for r, s in zip(r100[i], s100[i]):
                 e = orc.gen_rows(int(r), 1, dim, SEED_ROWS)
                 ok = ok and orc.scores(e, q[i])[0].view(np.uint32) == s.view(np.uint32)
+        if b16 is not None and "value" in b16:
+            k16 = d_k16.download(np.uint64, nb16 * k).reshape(nb16, k)
+            b16["keys_equal_batch1_leg"] = bool(np.array_equal(k16, k100[:nb16]))
+            ok = ok and b16["keys_equal_batch1_leg"]
         check = "ok" if ok else "FAILED"
     ix.close()
     algo = n_local * dim * 4
@@ -585,7 +611,7 @@ def config5_leg(tss, orc, args, ix10, comm, rank, world, device, barrier, max_ov
         "total rows fixed at 100M, so the shard shrinks with N (SURVEY 8d config 5)",
         "scan_only_ms": scan_ms, "per_gpu_gbs": algo / (scan_ms * 1e-3) / 1e9,
         "per_gpu_gbs_incl_exchange": algo / (ms * 1e-3) / 1e9,
-        "ideal_qps_at_8TBs": 1.0 / (algo / 8e12), "check": check,
+        "ideal_qps_at_8TBs": 1.0 / (algo / 8e12), "batch16": b16, "check": check,
         "checks": "planted winners; 100M result vs the 10M-row index on rows < 10M (key for key); "
                   "score bits of 20 winners recomputed by the oracle",
     }

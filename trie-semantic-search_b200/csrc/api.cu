@@ -393,7 +393,7 @@ struct MaskReadScope {
 void staged_copy(void* dst, const void* src, size_t bytes) {
   static const unsigned nthreads = [] {
     unsigned n = std::thread::hardware_concurrency();
-    n = n >= 8 ? 4 : n >= 4 ? 2 : 1;
+    n = n >= 16 ? 8 : n >= 8 ? 4 : n >= 4 ? 2 : 1;
     if (const char* env = getenv("TSS_UPLOAD_THREADS")) n = (unsigned)atoi(env);
     return n < 1 ? 1u : n > 8 ? 8u : n;
   }();
