@@ -885,7 +885,10 @@ __device__ void rescore_keys(uint64_t* sk, uint32_t m, const Rescore& rs, const 
 // One block per query; the kernel is a single wave of latency-bound blocks (8 per SM), so it is
 // written for few dependent memory round trips: lists are walked by warps (no index search),
 // four keys per lane are in flight, and the re-scoring runs 32 rows at a time.
-__global__ void __launch_bounds__(kSelectThreads, 8)
+#ifndef TSS_SELECT_MINB
+#define TSS_SELECT_MINB 8
+#endif
+__global__ void __launch_bounds__(kSelectThreads, TSS_SELECT_MINB)
 select_kernel(const uint64_t* cand, const uint32_t* cand_count, uint32_t nsub, uint32_t cap_s,
               const float* inv_qnorm, const Rescore rs, uint32_t k, uint64_t* out,
               uint32_t* overflow) {
@@ -926,8 +929,28 @@ select_kernel(const uint64_t* cand, const uint32_t* cand_count, uint32_t nsub, u
   __syncthreads();
   const uint32_t cnt = s_tot;
   const uint64_t* base = cand + (size_t)q * nsub * cap_s;
-  // f(key, valid) over all survivors, warp w walking lists w, w + 8, ...: lock-step per warp
+  // f(key, valid) over all survivors, lock-step per warp.  Many short lists (a small batch spread
+  // over every cluster: hundreds of lists of a few keys): a LANE per list, the warp stepping to
+  // its longest one -- a warp per list would pay a memory round trip for two or three keys.
+  // Few long lists (large batches): warp w walks lists w, w + 8, ...
   auto for_each_key = [&](auto f) {
+    if (nsub >= 128) {
+      for (uint32_t sl0 = warp * 32; sl0 < nsub; sl0 += kWarps * 32) {
+        const uint32_t sl = sl0 + lane;
+        const uint32_t c = sl < nsub ? s_cnt[sl] : 0u;
+        const uint32_t cmax = __reduce_max_sync(FULL_MASK, c);
+        const uint64_t* lp = base + (size_t)sl * cap_s;
+        for (uint32_t j0 = 0; j0 < cmax; j0 += 4) {
+          uint64_t key[4];
+#pragma unroll
+          for (uint32_t u = 0; u < 4; ++u) key[u] = j0 + u < c ? lp[j0 + u] : 0ull;
+#pragma unroll
+          for (uint32_t u = 0; u < 4; ++u)
+            if (j0 + u < cmax) f(key[u], j0 + u < c);
+        }
+      }
+      return;
+    }
     for (uint32_t sl = warp; sl < nsub; sl += kWarps) {
       const uint32_t c = s_cnt[sl];
       const uint64_t* lp = base + (size_t)sl * cap_s;
@@ -944,10 +967,27 @@ select_kernel(const uint64_t* cand, const uint32_t* cand_count, uint32_t nsub, u
       }
     }
   };
+  // The survivors are walked in global memory ONCE when they fit the sorter's shared memory (the
+  // ordinary case): they are staged in sk, and the four radix passes and the collection below
+  // read them from there.  Otherwise (crowded scores) every pass walks the lists again.
+  const bool staged = cnt <= kSelectSort;  // (block-uniform)
+  if (staged) {
+    for_each_key([&](uint64_t key, bool valid) {
+      if (valid) sk[atomicAdd(&s_n, 1u)] = key;
+    });
+    __syncthreads();  // s_n == cnt
+  }
+  auto for_each_staged = [&](auto f) {
+    for (uint32_t i0 = 0; i0 < cnt; i0 += kSelectThreads) {
+      const uint32_t i = i0 + threadIdx.x;
+      f(i < cnt ? sk[i] : 0ull, i < cnt);
+    }
+  };
   uint32_t kth = 0;  // orderable score word of the k-th best survivor (0: keep all)
   if (cnt > k) {
     auto for_each_score = [&](auto f) {
-      for_each_key([&](uint64_t key, bool valid) { f((uint32_t)(key >> 32), valid); });
+      if (staged) for_each_staged([&](uint64_t key, bool valid) { f((uint32_t)(key >> 32), valid); });
+      else for_each_key([&](uint64_t key, bool valid) { f((uint32_t)(key >> 32), valid); });
     };
     kth = block_radix_kth(k, for_each_score, hist, s_sel);
   }
@@ -957,7 +997,7 @@ select_kernel(const uint64_t* cand, const uint32_t* cand_count, uint32_t nsub, u
     keep_from = orderable_bits(__float_as_uint(__uint_as_float(u) - rs.margin[q]));
   }
   const float iq = inv_qnorm[q];
-  for_each_key([&](uint64_t key, bool valid) {
+  auto keep = [&](uint64_t key, bool valid) {
     const uint32_t ob = (uint32_t)(key >> 32);
     if (!valid || ob < keep_from) return;
     // (belt and braces: the collect pass never emits a row beyond the shard, and re-scoring
@@ -974,7 +1014,22 @@ select_kernel(const uint64_t* cand, const uint32_t* cand_count, uint32_t nsub, u
       if (sc == 0.f) sc = 0.f;
       sk[pos] = ((uint64_t)orderable_bits(__float_as_uint(sc)) << 32) | (key & 0xFFFFFFFFull);
     }
-  });
+  };
+  if (staged) {
+    // compaction in place, 256 staged keys per round: every thread reads its key, the block
+    // meets, the kept keys are appended from sk[0].  A round writes below 256 * (round + 1) --
+    // no more keys are kept than were read -- i.e. only where every key has been read already.
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    for (uint32_t i0 = 0; i0 < cnt; i0 += kSelectThreads) {
+      const uint32_t i = i0 + threadIdx.x;
+      const uint64_t key = i < cnt ? sk[i] : 0ull;
+      __syncthreads();
+      keep(key, i < cnt);
+    }
+  } else {
+    for_each_key(keep);
+  }
   __syncthreads();
   uint32_t m = s_n;
   if (m > kSelectSort) m = kSelectSort, s_over = 1;  // (benign race: every writer stores 1)
