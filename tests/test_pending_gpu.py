@@ -119,10 +119,14 @@ def test_submit_limits_and_ticket_errors(tss, orc):
     assert t5 != ts[0]
     with pytest.raises(tss.TssError):          # the old ticket of that slot stays dead
         ix.search_collect(ts[0], b[0].ctypes.data, b[1].ctypes.data, b[2].ctypes.data)
-    # a blocking search while four are pending waits for a slot to be freed by another thread:
-    # here there is none, so free one first, then mix blocking and pending searches
+    # a blocking search while this thread's own four tickets hold every slot must not wait for
+    # a slot (nobody else will collect): it takes the serialised path and still answers
     rows = orc.gen_rows(0, n, dim, SEED)
     want = orc.cosine_topk(rows, q, k)
+    got = ix.search(q[7], k)
+    assert _same(got, want, slice(7, 8))
+    got = ix.search(q[4:8], k)
+    assert _same(got, want, slice(4, 8))
     ix.search_collect(ts[1], b[0].ctypes.data, b[1].ctypes.data, b[2].ctypes.data)
     assert _same((b[0][:1], b[1][:1], b[2][:1]), want, slice(1, 2))
     got = ix.search(q[6], k)

@@ -1536,11 +1536,20 @@ int tss_index_search(tss_index* ix, const float* queries, uint32_t nq, uint32_t 
     for (;;) {
       if ((rc = pending_submit_locked(ix, queries, nq, k, mask, mask_mode, &s))) return rc;
       if (s >= 0) break;
+      // every slot is taken.  If some thread is collecting one, it is about to be handed back:
+      // wait for it.  If all of them are submitted-but-uncollected tickets, nobody may ever
+      // collect while this thread waits (they could all be this thread's own): take the
+      // serialised path below instead, which needs no slot.
+      bool collecting = false;
+      for (const auto& pd : ix->pend) collecting |= pd.state == 2;
+      if (!collecting) break;
       ix->pend_cv.wait(lock);
     }
-    ix->pend[s].state = 2;
-    lock.unlock();
-    return pending_collect(ix, s, out_rows, out_scores, out_counts);
+    if (s >= 0) {
+      ix->pend[s].state = 2;
+      lock.unlock();
+      return pending_collect(ix, s, out_rows, out_scores, out_counts);
+    }
   }
   if ((rc = ensure_gather_ws(ix))) return rc;
   MaskReadScope mrs(mask, mask_mode, ix->stream);
