@@ -254,6 +254,45 @@ impl HnswIndex {
             .collect())
     }
 
+    /// The same search split in two (no reference counterpart: `search` above never awaits).
+    /// `submit` enqueues the scan and returns at once; up to `TSS_MAX_PENDING` (4) tickets may be
+    /// outstanding per index, and `collect` waits for that ticket's scan alone -- so a task can
+    /// keep two queries in flight and the device never idles between them.  The index must be
+    /// flushed and finalized (call `search` once, or `flush` + `tss_index_finalize`).
+    pub fn search_submit(&self, query_embedding: &[f32], top_k: usize) -> Result<(u64, usize)> {
+        if query_embedding.len() != self.dim || top_k == 0 || top_k > 128 {
+            return Err(SearchError::HnswSearchError {
+                details: format!("submit: {} dims (index has {}), top_k {}", query_embedding.len(), self.dim, top_k),
+            });
+        }
+        let mut ticket = 0u64;
+        let rc = unsafe {
+            tss_index_search_submit(
+                self.ix, query_embedding.as_ptr(), 1, top_k as u32, std::ptr::null(), TSS_MASK_NONE, &mut ticket,
+            )
+        };
+        if rc != TSS_OK {
+            return Err(SearchError::HnswSearchError { details: last_error() });
+        }
+        Ok((ticket, top_k))
+    }
+
+    pub fn search_collect(&self, ticket: (u64, usize)) -> Result<Vec<(DocRef, f32)>> {
+        let (ticket, top_k) = ticket;
+        let mut rows = vec![0u32; top_k];
+        let mut scores = vec![0f32; top_k];
+        let mut count = 0u32;
+        let rc = unsafe {
+            tss_index_search_collect(self.ix, ticket, rows.as_mut_ptr(), scores.as_mut_ptr(), &mut count)
+        };
+        if rc != TSS_OK {
+            return Err(SearchError::HnswSearchError { details: last_error() });
+        }
+        Ok((0..count as usize)
+            .map(|i| (self.doc_refs[rows[i] as usize].clone(), 1.0 - scores[i]))
+            .collect())
+    }
+
     /// src/vector.rs:204-207
     pub fn size(&self) -> usize {
         self.doc_refs.len()
