@@ -15,11 +15,16 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--rows", type=int, default=10_000_000)
 ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--sel", type=float, nargs="+", default=[1e-5, 1e-3, 1e-2, 0.11])
+ap.add_argument("--contig", type=float, nargs="*", default=[],
+                help="extra cases whose live rows are ONE contiguous range of this fraction of the rows "
+                     "(a date filter over rows added in date order)")
 a = ap.parse_args()
 N, dim, k = a.rows, 384, 10
 rng = np.random.default_rng(9)
-terms = [b"s%02d" % i for i in range(len(a.sel))]
 posts = [rng.integers(0, N, size=max(1, int(N * s)), dtype=np.uint32) for s in a.sel]
+posts += [np.arange(N // 3, N // 3 + max(1, int(N * s)), dtype=np.uint32) for s in a.contig]
+a.sel = list(a.sel) + [-s for s in a.contig]   # (negative: contiguous)
+terms = [b"s%02d" % i for i in range(len(a.sel))]
 poff = np.zeros(len(terms) + 1, dtype=np.uint64); np.cumsum([p.size for p in posts], out=poff[1:])
 toff = np.zeros(len(terms) + 1, dtype=np.uint64); np.cumsum([len(t) for t in terms], out=toff[1:])
 t = tss.Terms.from_arrays(b"".join(terms), toff, poff, np.concatenate(posts))

@@ -233,6 +233,7 @@ struct tss_index {
   // tile at a time (tail balancing)
   float static_frac = 0.0f;
   uint32_t dyn_chunk = 8;
+  uint32_t walk_run_log2 = 5;  // masked scan: a warp walks runs of 32 consecutive tiles (scan.cuh)
   float fine_rounds = 2.0f;
   unsigned long long* d_dbg = nullptr;  // diagnostics (tss_index_debug_phases)
   float* h_queries = nullptr;  // pinned
@@ -525,6 +526,7 @@ int enqueue_scan(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
       const uint64_t gw = (uint64_t)ix->num_sms * 16;
       p.static_rounds = (uint32_t)((double)(tiles / gw) * ix->static_frac);
       p.dyn_chunk = ix->dyn_chunk;
+      p.walk_run_log2 = ix->walk_run_log2;
       const uint64_t fine_tiles = (uint64_t)((double)gw * ix->fine_rounds);
       p.fine_start = tiles > fine_tiles ? tiles - fine_tiles : 0;
     }
@@ -1165,6 +1167,7 @@ int tss_index_create(tss_index** out, uint32_t dim, int storage, int device) {
   if (const char* sf = getenv("TSS_FINE_ROUNDS")) ix->fine_rounds = (float)atof(sf);
   if (const char* sf = getenv("TSS_DYN_CHUNK")) ix->dyn_chunk = (uint32_t)atoi(sf);
   if (ix->dyn_chunk < 1) ix->dyn_chunk = 1;
+  if (const char* sf = getenv("TSS_WALK_RUN")) ix->walk_run_log2 = (uint32_t)atoi(sf) > 5 ? 5u : (uint32_t)atoi(sf);
   ALLOC(cudaMallocHost(&ix->h_queries, (size_t)kWsQueries * dim * sizeof(float)))
   ALLOC(cudaMallocHost(&ix->h_keys, (size_t)kWsQueries * TSS_MAX_K * sizeof(uint64_t)))
   ALLOC(cudaMallocHost(&ix->h_status, 64))
