@@ -1167,7 +1167,10 @@ int tss_index_create(tss_index** out, uint32_t dim, int storage, int device) {
   if (const char* sf = getenv("TSS_FINE_ROUNDS")) ix->fine_rounds = (float)atof(sf);
   if (const char* sf = getenv("TSS_DYN_CHUNK")) ix->dyn_chunk = (uint32_t)atoi(sf);
   if (ix->dyn_chunk < 1) ix->dyn_chunk = 1;
-  if (const char* sf = getenv("TSS_WALK_RUN")) ix->walk_run_log2 = (uint32_t)atoi(sf) > 5 ? 5u : (uint32_t)atoi(sf);
+  if (const char* sf = getenv("TSS_WALK_RUN")) {  // diagnostics: log2 run (0..5), +8 = consecutive runs to different CTAs
+    const uint32_t v = (uint32_t)atoi(sf);
+    ix->walk_run_log2 = ((v & 7u) > 5 ? 5u : (v & 7u)) | (v & 8u);
+  }
   ALLOC(cudaMallocHost(&ix->h_queries, (size_t)kWsQueries * dim * sizeof(float)))
   ALLOC(cudaMallocHost(&ix->h_keys, (size_t)kWsQueries * TSS_MAX_K * sizeof(uint64_t)))
   ALLOC(cudaMallocHost(&ix->h_status, 64))

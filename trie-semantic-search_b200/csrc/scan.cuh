@@ -349,8 +349,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_topk_kernel(const __grid_c
   // a moving front, so an SM's 16 warps work in ~16 pages at a time; the one-tile interleave
   // (wl = 0: tile = g + v * GW) put every lane of every warp 29 MB apart -- 512 different 2 MB
   // pages per SM against a TLB of 128 entries, and no two rows of a fill in one DRAM page.
-  const uint32_t wl = p.walk_run_log2;
-  const uint64_t walk_g = (uint64_t)blockIdx.x * WARPS + warp;
+  const uint32_t wl = p.walk_run_log2 & 7u;
+  // consecutive runs go to the 16 warps of ONE CTA (6 MB = 3 pages per SM at a time).  Bit 3 of
+  // the parameter spreads them over the CTAs instead, which balances a contiguous range of live
+  // rows better (+2 %) and costs a 30 % random mask 3 % (benchmarks/gpu/walk_sweep.sh).
+  const uint64_t walk_g = (p.walk_run_log2 & 8u) ? (uint64_t)warp * gridDim.x + blockIdx.x
+                                                 : (uint64_t)blockIdx.x * WARPS + warp;
   const uint64_t walk_runs = (total_tiles + ((1ull << wl) - 1)) >> wl;
   const uint64_t v_end = walk_g < walk_runs ? ((walk_runs - walk_g + GW - 1) / GW) << wl : 0;
   auto walk_tile = [&](uint64_t v) -> uint64_t {
