@@ -224,6 +224,8 @@ struct tss_index {
   // exchange status word.
   uint64_t* d_partials = nullptr;
   unsigned int* d_counter = nullptr;
+  unsigned int* d_walk_ctr = nullptr;  // [kScanSlots][kWalkCounters] claim counters of the masked
+                                       // scan's walk, one per 128-byte line
   uint32_t launch_no = 0;
   bool no_host_sync = false;  // inside tss_index_search_device: fix-ups must stay on the device
   uint64_t shard_min_rows = 0;  // rows of the smallest shard of the group (tss_index_set_shard)
@@ -234,6 +236,7 @@ struct tss_index {
   float static_frac = 0.0f;
   uint32_t dyn_chunk = 8;
   uint32_t walk_run_log2 = 5;  // masked scan: a warp walks runs of 32 consecutive tiles (scan.cuh)
+  float walk_static_frac = 0.5f;  // ... this share of them assigned statically, the rest claimed
   float fine_rounds = 2.0f;
   unsigned long long* d_dbg = nullptr;  // diagnostics (tss_index_debug_phases)
   float* h_queries = nullptr;  // pinned
@@ -512,6 +515,7 @@ int enqueue_scan(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
     p.done_counter = ix->d_counter + slot * 4;
     p.tile_counter = ix->d_counter + slot * 4 + 1;
     p.slot_gen = ix->d_counter + slot * 4 + 2;
+    p.walk_counters = ix->d_walk_ctr + (size_t)slot * tss::kWalkCounters * 32;
     p.launch_no = no;
     p.expect_gen = no > kScanSlots ? no - kScanSlots : 0;
     p.pdl = ix->pdl ? 1 : 0;
@@ -527,6 +531,11 @@ int enqueue_scan(tss_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
       p.static_rounds = (uint32_t)((double)(tiles / gw) * ix->static_frac);
       p.dyn_chunk = ix->dyn_chunk;
       p.walk_run_log2 = ix->walk_run_log2;
+      {
+        const uint32_t wl = ix->walk_run_log2 & 7u;
+        const uint64_t runs = (tiles + ((1ull << wl) - 1)) >> wl;
+        p.walk_static_rounds = (uint32_t)((double)(runs / gw) * ix->walk_static_frac);
+      }
       const uint64_t fine_tiles = (uint64_t)((double)gw * ix->fine_rounds);
       p.fine_start = tiles > fine_tiles ? tiles - fine_tiles : 0;
     }
@@ -1162,11 +1171,14 @@ int tss_index_create(tss_index** out, uint32_t dim, int storage, int device) {
   ALLOC(cudaMalloc(&ix->d_partials, (size_t)kScanSlots * kMaxBq * ix->num_sms * 128 * sizeof(uint64_t)))
   ALLOC(cudaMalloc(&ix->d_counter, 32 * sizeof(unsigned int)))
   ALLOC(cudaMemset(ix->d_counter, 0, 32 * sizeof(unsigned int)))
+  ALLOC(cudaMalloc(&ix->d_walk_ctr, (size_t)kScanSlots * tss::kWalkCounters * 32 * sizeof(unsigned int)))
+  ALLOC(cudaMemset(ix->d_walk_ctr, 0, (size_t)kScanSlots * tss::kWalkCounters * 32 * sizeof(unsigned int)))
   if (const char* sf = getenv("TSS_PDL")) ix->pdl = atoi(sf) != 0;
   if (const char* sf = getenv("TSS_STATIC_FRAC")) ix->static_frac = (float)atof(sf);
   if (const char* sf = getenv("TSS_FINE_ROUNDS")) ix->fine_rounds = (float)atof(sf);
   if (const char* sf = getenv("TSS_DYN_CHUNK")) ix->dyn_chunk = (uint32_t)atoi(sf);
   if (ix->dyn_chunk < 1) ix->dyn_chunk = 1;
+  if (const char* sf = getenv("TSS_WALK_STATIC")) ix->walk_static_frac = (float)atof(sf);
   if (const char* sf = getenv("TSS_WALK_RUN")) {  // diagnostics: log2 run (0..5), +8 = consecutive runs to different CTAs
     const uint32_t v = (uint32_t)atoi(sf);
     ix->walk_run_log2 = ((v & 7u) > 5 ? 5u : (v & 7u)) | (v & 8u);
@@ -1204,6 +1216,7 @@ void tss_index_destroy(tss_index* ix) {
   cudaFree(ix->d_merged);
   cudaFree(ix->d_partials);
   cudaFree(ix->d_counter);
+  cudaFree(ix->d_walk_ctr);
   if (ix->h_queries) cudaFreeHost(ix->h_queries);
   if (ix->h_keys) cudaFreeHost(ix->h_keys);
   if (ix->h_status) cudaFreeHost(ix->h_status);
