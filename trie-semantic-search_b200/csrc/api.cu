@@ -1181,7 +1181,7 @@ int tss_index_create(tss_index** out, uint32_t dim, int storage, int device) {
   if (const char* sf = getenv("TSS_WALK_STATIC")) ix->walk_static_frac = (float)atof(sf);
   if (const char* sf = getenv("TSS_WALK_RUN")) {  // diagnostics: log2 run (0..5), +8 = consecutive runs to different CTAs
     const uint32_t v = (uint32_t)atoi(sf);
-    ix->walk_run_log2 = ((v & 7u) > 5 ? 5u : (v & 7u)) | (v & 8u);
+    ix->walk_run_log2 = ((v & 7u) > 5 ? 5u : (v & 7u)) | (v & 24u);  // +16: stay on the home counter
   }
   ALLOC(cudaMallocHost(&ix->h_queries, (size_t)kWsQueries * dim * sizeof(float)))
   ALLOC(cudaMallocHost(&ix->h_keys, (size_t)kWsQueries * TSS_MAX_K * sizeof(uint64_t)))

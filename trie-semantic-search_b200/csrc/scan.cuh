@@ -359,7 +359,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_topk_kernel(const __grid_c
   // to kWalkCounters counters (CTA c uses counter c mod 16; counter j hands out runs j, j + 16,
   // ... of the claimed half, so every counter sees an even sample of the matrix and a contiguous
   // range of live rows spreads over all of them): one run per claim whatever the density -- a
-  // single counter would cap an all-dead mask at its atomic rate (39 063 runs at 0.3 G/s).
+  // single counter would cap an all-dead mask at its atomic rate (39 063 runs at 0.3 G/s).  A warp
+  // whose counter has run dry moves on to one that has not (walk_resolve).
   const uint32_t wl = p.walk_run_log2 & 7u;
   // (bit 3 of the parameter spreads consecutive static runs over the CTAs instead)
   // (tile and run indices fit 32 bits: row ids do)
@@ -370,31 +371,71 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_topk_kernel(const __grid_c
   uint32_t c_pos = 0, c_end = 0;       // current run: tiles [c_pos, c_end) still to examine
   uint32_t n_pos = 0, n_end = 0;       // the run after it (resolved)
   const uint32_t walk_nctr = gridDim.x < kWalkCounters ? gridDim.x : kWalkCounters;
-  const uint32_t walk_ctr = blockIdx.x % walk_nctr;
-  uint32_t w_round = 0, w_claim_raw = 0;
+  uint32_t walk_ctr = blockIdx.x % walk_nctr;   // the counter this warp claims from (its home first)
+  // runs of the claimed part (the counters hand out numbers 0, 1, ... of it)
+  const uint32_t walk_dyn_runs = (uint32_t)(((total_tiles + ((1ull << wl) - 1)) >> wl) -
+                                            (walk_static_runs < ((total_tiles + ((1ull << wl) - 1)) >> wl)
+                                                 ? walk_static_runs
+                                                 : ((total_tiles + ((1ull << wl) - 1)) >> wl)));
+  uint32_t w_round = 0, w_claim_raw = 0, w_claim_ctr = 0;
   uint32_t w_claim_run = 0;            // pending claim: its run when it is a static one
-  bool w_claim_dyn = false, w_started = false;
+  // w_claim_kind: 0 static, 1 claimed from counter w_claim_ctr, 2 none (the walk is winding down)
+  uint32_t w_claim_kind = 2;
+  bool w_started = false, w_done = false;
+  uint32_t w_live = 0;                 // live rows found in the current run so far
+  bool w_dense = false;                // ... and whether the last finished run was mostly live
   auto walk_claim = [&]() {            // request the run after the next
     if (w_round < p.walk_static_rounds) {
-      w_claim_dyn = false;
+      w_claim_kind = 0;
       w_claim_run = walk_g + w_round * (uint32_t)GW;
       ++w_round;
-    } else {
-      w_claim_dyn = true;
+    } else if (!w_done) {
+      w_claim_kind = 1;
+      w_claim_ctr = walk_ctr;
       if (lane == 0) w_claim_raw = atomicAdd(p.walk_counters + walk_ctr * 32, 1u);
+    } else {
+      w_claim_kind = 2;
     }
   };
   auto walk_resolve = [&](uint32_t& pos, uint32_t& end) {
-    const uint64_t run =
-        w_claim_dyn ? (uint64_t)walk_static_runs +
-                          (uint64_t)__shfl_sync(FULL_MASK, w_claim_raw, 0) * walk_nctr + walk_ctr
-                    : (uint64_t)w_claim_run;
+    pos = end = tiles32;
+    uint64_t run;
+    if (w_claim_kind == 0) {
+      run = w_claim_run;
+    } else if (w_claim_kind == 1) {
+      const uint64_t c = (uint64_t)__shfl_sync(FULL_MASK, w_claim_raw, 0) * walk_nctr + w_claim_ctr;
+      if (c >= walk_dyn_runs) {
+        // that counter is used up.  148 CTAs over 16 counters is 9 or 10 CTAs each, and SMs differ
+        // in speed: a warp whose counter has run dry looks at all of them once (one load per lane)
+        // and moves to the next one that still has runs, or winds down.
+        // (Only a warp whose runs are mostly live does: over sparser masks the hops cost more than
+        // the balance is worth -- an all-dead mask 18.2 -> 21.0 us -- so there the walk just ends.)
+        if ((p.walk_run_log2 & 16u) || !w_dense) {
+          w_done = true;
+        } else if (w_claim_ctr == walk_ctr && !w_done) {
+          uint32_t v = 0xFFFFFFFFu;
+          if ((uint32_t)lane < walk_nctr)
+            v = *reinterpret_cast<volatile unsigned int*>(p.walk_counters + lane * 32);
+          const bool alive = (uint32_t)lane < walk_nctr && (uint64_t)v * walk_nctr + lane < walk_dyn_runs;
+          const unsigned m = __ballot_sync(FULL_MASK, alive);
+          if (!m) {
+            w_done = true;
+          } else {
+            const unsigned above = m & ~((2u << walk_ctr) - 1u);  // alive counters after this one
+            walk_ctr = (uint32_t)__ffs(above ? above : m) - 1u;
+          }
+        }
+        return;
+      }
+      run = (uint64_t)walk_static_runs + c;
+    } else {
+      return;
+    }
     const uint64_t p0 = run << wl, p1 = (run + 1) << wl;
     pos = p0 < tiles32 ? (uint32_t)p0 : tiles32;
     end = p1 < tiles32 ? (uint32_t)p1 : tiles32;
   };
-  // the current run is used up: move to the next, resolve the one after, claim a further one.
-  // (Runs only grow along a warp's claims, so the first empty one ends the walk.)
+  // the current run is used up: move to the next, resolve the one after, claim a further one
   auto walk_advance = [&]() {
     if (!w_started) {
       w_started = true;
@@ -405,10 +446,21 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_topk_kernel(const __grid_c
       walk_claim();
       return;
     }
+    // How far ahead a warp claims depends on what its runs cost.  Over a sparse mask a run is a
+    // moment's work and two are kept outstanding, so neither the claim's nor the mask words'
+    // latency is ever waited for.  A run with many live rows is ~100 us of this warp's share of the
+    // stream: two of those held back at the end of the scan left CTAs idle for 230 us (dense
+    // EXCLUDE mask: 87 of 148 CTAs done > 50 us before the last).  After such a run only ONE is
+    // kept outstanding: the claim is made when the run is needed and waited for (0.7 us per run).
+    const bool heavy = w_live >= 32u;
+    w_dense = w_live * 2u >= ((uint32_t)R << wl);  // at least half of the run's rows were live
+    w_live = 0;
     c_pos = n_pos;
     c_end = n_end;
+    if (w_claim_kind == 2) walk_claim();  // nothing outstanding: claim now
     walk_resolve(n_pos, n_end);
-    walk_claim();
+    if (heavy) w_claim_kind = 2;
+    else walk_claim();
   };
   uint64_t m_next = 0;  // list-driven: next chunk of the row list
   uint32_t list_n = 0xFFFFFFFFu;  // rows in the list when the scan is list-driven
@@ -445,6 +497,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_topk_kernel(const __grid_c
     const uint32_t tc = c_pos;
     ++c_pos;
     --dense_left;
+    w_live += (uint32_t)R;
     if (lane == 0) {
       mbar_arrive_expect_tx(bar, TILE_BYTES);
       bulk_g2s(tile_s, rows_b + tc * (uint64_t)TILE_BYTES, TILE_BYTES, bar, policy);
@@ -481,7 +534,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_topk_kernel(const __grid_c
     if (!w_started) walk_advance();
     while (filled < (uint32_t)R) {
       if (c_pos >= c_end) {
-        if (c_pos >= tiles32) break;  // an empty chunk: this warp's walk is over
+        // over when no counter has runs left and the claims still outstanding were empty too
+        if (w_done && n_pos >= n_end && w_claim_kind == 2) break;
         walk_advance();
         continue;
       }
@@ -518,6 +572,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_topk_kernel(const __grid_c
       const uint32_t total = __shfl_sync(FULL_MASK, inc, ntake - 1);
       c_pos = c_end - c_pos < (uint32_t)ntake ? c_end : c_pos + (uint32_t)ntake;  // (lanes past
                                                      // the chunk's end examined nothing)
+      w_live += total;
       prefetch_mask();
       if (total == 0) continue;  // nothing live in these tiles
       if (lane == 0) mbar_expect_tx(bar, total * ROW_BYTES);
