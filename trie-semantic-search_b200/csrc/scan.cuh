@@ -368,7 +368,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_topk_kernel(const __grid_c
                                                  : blockIdx.x * WARPS + (uint32_t)warp;
   const uint32_t walk_static_runs = p.walk_static_rounds * (uint32_t)GW;
   const uint32_t tiles32 = (uint32_t)total_tiles;
-  uint32_t c_pos = 0, c_end = 0;       // current run: tiles [c_pos, c_end) still to examine
+  uint32_t c_pos = 0, c_end = 0, c_beg = 0;  // current run [c_beg, c_end): [c_pos, c_end) still to examine
   uint32_t n_pos = 0, n_end = 0;       // the run after it (resolved)
   const uint32_t walk_nctr = gridDim.x < kWalkCounters ? gridDim.x : kWalkCounters;
   uint32_t walk_ctr = blockIdx.x % walk_nctr;   // the counter this warp claims from (its home first)
@@ -383,7 +383,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_topk_kernel(const __grid_c
   uint32_t w_claim_kind = 2;
   bool w_started = false, w_done = false;
   uint32_t w_live = 0;                 // live rows found in the current run so far
-  bool w_dense = false;                // ... and whether the last finished run was mostly live
+  bool w_heavy = false, w_dense = false;  // the last finished run had >= 32 live rows / was mostly live
   auto walk_claim = [&]() {            // request the run after the next
     if (w_round < p.walk_static_rounds) {
       w_claim_kind = 0;
@@ -441,6 +441,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_topk_kernel(const __grid_c
       w_started = true;
       walk_claim();
       walk_resolve(c_pos, c_end);
+      c_beg = c_pos;
       walk_claim();
       walk_resolve(n_pos, n_end);
       walk_claim();
@@ -452,14 +453,16 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_topk_kernel(const __grid_c
     // stream: two of those held back at the end of the scan left CTAs idle for 230 us (dense
     // EXCLUDE mask: 87 of 148 CTAs done > 50 us before the last).  After such a run only ONE is
     // kept outstanding: the claim is made when the run is needed and waited for (0.7 us per run).
-    const bool heavy = w_live >= 32u;
-    w_dense = w_live * 2u >= ((uint32_t)R << wl);  // at least half of the run's rows were live
+    if (c_end != c_beg) {  // (an empty run -- a claim past the end -- says nothing)
+      w_heavy = w_live >= 32u;
+      w_dense = w_live * 2u >= ((uint32_t)R << wl);  // at least half of the run's rows were live
+    }
     w_live = 0;
-    c_pos = n_pos;
+    c_beg = c_pos = n_pos;
     c_end = n_end;
     if (w_claim_kind == 2) walk_claim();  // nothing outstanding: claim now
     walk_resolve(n_pos, n_end);
-    if (heavy) w_claim_kind = 2;
+    if (w_heavy) w_claim_kind = 2;
     else walk_claim();
   };
   uint64_t m_next = 0;  // list-driven: next chunk of the row list
