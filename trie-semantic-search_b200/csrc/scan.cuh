@@ -321,6 +321,17 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_topk_kernel(const __grid_c
   const uint64_t GW = (uint64_t)gridDim.x * WARPS;
   const uint64_t policy = policy_evict_first();
   const uint8_t* rows_b = reinterpret_cast<const uint8_t*>(p.rows);
+  // Every bulk copy of the scan goes through this.  Built with -DTSS_BOUNDS_CHECK (make CHECK=1 ->
+  // libtss_check.so; compute-sanitizer is not available on the pool) it traps when the source
+  // leaves the stored rows or the destination leaves the warp's tile buffer.
+  auto fetch = [&](uint32_t dst_off, const uint8_t* src, uint32_t bytes) {
+#ifdef TSS_BOUNDS_CHECK
+    if (src < rows_b || src + bytes > rows_b + p.n_rows * (uint64_t)ROW_BYTES ||
+        dst_off + bytes > (uint32_t)TILE_BYTES || bytes == 0 || (bytes & 15u))
+      __trap();
+#endif
+    bulk_g2s(tile_s + dst_off, src, bytes, bar, policy);
+  };
 
   // bits of the rows of tile t that must be scored
   auto tile_bits = [&](uint64_t t) -> uint32_t {
@@ -340,7 +351,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_topk_kernel(const __grid_c
     if (lane == 0) {
       const uint32_t bytes = (32 - __clz(bits)) * ROW_BYTES;  // bits = low `valid rows` ones
       mbar_arrive_expect_tx(bar, bytes);
-      bulk_g2s(tile_s, rows_b + t * (uint64_t)TILE_BYTES, bytes, bar, policy);
+      fetch(0, rows_b + t * (uint64_t)TILE_BYTES, bytes);
     }
   };
   // masked: pack the live rows of as many of this warp's next tiles (see "Mask walk order")
@@ -503,7 +514,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_topk_kernel(const __grid_c
     w_live += (uint32_t)R;
     if (lane == 0) {
       mbar_arrive_expect_tx(bar, TILE_BYTES);
-      bulk_g2s(tile_s, rows_b + tc * (uint64_t)TILE_BYTES, TILE_BYTES, bar, policy);
+      fetch(0, rows_b + tc * (uint64_t)TILE_BYTES, TILE_BYTES);
     }
     if (lane < R) slot_rows[lane] = tc * R + lane;
     if (!dense_left) prefetch_mask();  // the next window is examined again
@@ -522,7 +533,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_topk_kernel(const __grid_c
       if (pre_for != c0) prefetch_list(c0);  // (first chunk only: later ones were requested ahead)
       if ((uint32_t)lane < cnt) {
         const uint32_t r = pre_word;
-        bulk_g2s(tile_s + lane * ROW_BYTES, rows_b + (uint64_t)r * ROW_BYTES, ROW_BYTES, bar, policy);
+        fetch(lane * ROW_BYTES, rows_b + (uint64_t)r * ROW_BYTES, ROW_BYTES);
         slot_rows[lane] = r;
       }
       prefetch_list(m_next * (uint64_t)R);  // the next chunk's entries, in flight during this one
@@ -584,12 +595,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_topk_kernel(const __grid_c
         uint32_t slot = filled + inc - pc;
         const uint8_t* src = rows_b + tc * (uint64_t)TILE_BYTES;
         if (b == (1u << pc) - 1u) {  // rows 0..pc-1: contiguous in HBM and in the buffer
-          bulk_g2s(tile_s + slot * ROW_BYTES, src, pc * ROW_BYTES, bar, policy);
+          fetch(slot * ROW_BYTES, src, pc * ROW_BYTES);
           for (uint32_t r = 0; r < pc; ++r) slot_rows[slot + r] = (uint32_t)(tc * R + r);
         } else {
           for (uint32_t bb = b; bb; bb &= bb - 1) {
             const uint32_t r = __ffs(bb) - 1;
-            bulk_g2s(tile_s + slot * ROW_BYTES, src + r * ROW_BYTES, ROW_BYTES, bar, policy);
+            fetch(slot * ROW_BYTES, src + r * ROW_BYTES, ROW_BYTES);
             slot_rows[slot++] = (uint32_t)(tc * R + r);
           }
         }
