@@ -321,6 +321,14 @@ int tss_terms_bind_stream(tss_terms* t, tss_index* ix /* nullable */);
 int tss_index_search_prefix(tss_index* ix, tss_terms* t, const char* prefix, uint32_t len, int kind,
                             tss_mask* scratch, const float* queries, uint32_t nq, uint32_t k,
                             uint32_t* out_rows, float* out_scores, uint32_t* out_counts);
+/* ... and without waiting: the prefix search, the mask and the masked scan are enqueued and a
+ * ticket for tss_index_search_collect comes back (1..TSS_PENDING_MAX_NQ queries, k <=
+ * TSS_MAX_FUSED_K, as tss_index_search_submit).  Each hybrid query in flight needs a scratch mask
+ * of its own until it has been collected; with two in flight the next query's prefix search runs
+ * while this one's rows stream. */
+int tss_index_search_prefix_submit(tss_index* ix, tss_terms* t, const char* prefix, uint32_t len,
+                                   int kind, tss_mask* scratch, const float* queries, uint32_t nq,
+                                   uint32_t k, uint64_t* out_ticket);
 
 /* ---- plumbing for callers that time or pipeline the device path ------------ */
 void* tss_index_stream(tss_index* ix); /* cudaStream_t the index enqueues on */

@@ -204,3 +204,47 @@ def test_search_prefix_is_prefix_mask_then_search(tss, orc):
                               b[1].ctypes.data, b[2].ctypes.data)
     t.close()
     ix.close()
+
+
+def test_hybrid_queries_in_flight(tss, orc):
+    """tss_index_search_prefix_submit: hybrid queries pipelined, one scratch mask per query in
+    flight, every result the oracle's top-k over exactly the prefix's rows."""
+    n, dim, k = 60_000, 384, 10
+    rows = orc.gen_rows(0, n, dim, SEED)
+    ix = tss.FlatIndex(dim)
+    ix.add_synthetic(0, n, SEED)
+    ix.finalize()
+    rng = np.random.default_rng(11)
+    terms = sorted({b"w%03d w%03d" % (a, b) for a, b in rng.integers(0, 30, size=(2500, 2))})
+    postings = [sorted(set(rng.integers(0, n, size=int(rng.integers(1, 12))).tolist())) for _ in terms]
+    t = tss.Terms(terms, postings)
+    t.bind_stream(ix)
+    q = np.ascontiguousarray(orc.gen_rows(0, 24, dim, 0xBEEF))
+    masks = [tss.Mask(n) for _ in range(3)]
+    prefixes = [b"w%03d" % (i % 30) for i in range(24)]
+
+    def want_for(i):
+        live = sorted({r for term, ps in zip(terms, postings) if term.startswith(prefixes[i] + b" ") for r in ps})
+        w = np.zeros((n + 31) // 32, dtype=np.uint32)
+        idx = np.asarray(live, dtype=np.int64)
+        np.bitwise_or.at(w, idx >> 5, np.uint32(1) << (idx & 31).astype(np.uint32))
+        return orc.cosine_topk(rows, q[i:i + 1], k, mask_words=w, mask_mode=orc.MASK_INCLUDE)
+
+    pending = []
+    for i in range(24):
+        if len(pending) == 3:
+            j, tk, b = pending.pop(0)
+            ix.search_collect(tk, b[0].ctypes.data, b[1].ctypes.data, b[2].ctypes.data)
+            assert _same(b, want_for(j), slice(0, 1)), j
+        b = _bufs(1, k)
+        tk = ix.search_prefix_submit(t, prefixes[i], masks[i % 3], q[i].ctypes.data, 1, k)
+        pending.append((i, tk, b))
+    for j, tk, b in pending:
+        ix.search_collect(tk, b[0].ctypes.data, b[1].ctypes.data, b[2].ctypes.data)
+        assert _same(b, want_for(j), slice(0, 1)), j
+    with pytest.raises(tss.TssError) as ei:    # rejected before the scratch mask is touched
+        ix.search_prefix_submit(t, b"w001", masks[0], q.ctypes.data, 5, k)
+    assert ei.value.code == tss.TSS_ERR_INVALID_ARG
+    t.bind_stream(None)
+    t.close()
+    ix.close()

@@ -48,6 +48,7 @@ ABI_SYMBOLS = [
     "tss_prefix_mask_fresh", "tss_terms_bind_stream",
     "tss_terms_build_text", "tss_terms_save", "tss_terms_load",
     "tss_index_search_submit", "tss_index_search_collect", "tss_index_search_prefix",
+    "tss_index_search_prefix_submit",
 ]
 
 
@@ -94,6 +95,7 @@ def lib() -> C.CDLL:
         "tss_index_search_submit": (i32, [vp, vp, u32, u32, vp, i32, pu64]),
         "tss_index_search_collect": (i32, [vp, u64, vp, vp, vp]),
         "tss_index_search_prefix": (i32, [vp, vp, C.c_char_p, u32, i32, vp, vp, u32, u32, vp, vp, vp]),
+        "tss_index_search_prefix_submit": (i32, [vp, vp, C.c_char_p, u32, i32, vp, vp, u32, u32, pu64]),
         "tss_unpack_keys": (None, [vp, u64, vp, vp]),
         "tss_comm_unique_id": (i32, [vp]),
         "tss_comm_create": (i32, [C.POINTER(vp), vp, i32, i32, i32]),
@@ -564,6 +566,16 @@ class FlatIndex:
                                            counts_ptr)
         if rc != TSS_OK:
             _check(rc)
+
+    def search_prefix_submit(self, terms: "Terms", prefix: bytes, scratch: Mask, q_ptr: int, nq: int,
+                             k: int, kind: int = TSS_PREFIX_TOKEN) -> int:
+        """tss_index_search_prefix_submit: the hybrid query enqueued, a ticket for search_collect."""
+        t = C.c_uint64(0)
+        rc = lib().tss_index_search_prefix_submit(self.handle, terms.handle, prefix, len(prefix), kind,
+                                                  scratch.handle, q_ptr, nq, k, C.byref(t))
+        if rc != TSS_OK:
+            _check(rc)
+        return t.value
 
     def search_device(self, d_queries: DeviceBuffer, nq: int, k: int, d_out_keys: DeviceBuffer,
                       mask: Optional[Mask] = None, mask_mode: int = TSS_MASK_NONE) -> None:

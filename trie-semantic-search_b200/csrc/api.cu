@@ -1664,6 +1664,32 @@ int tss_index_search_collect(tss_index* ix, uint64_t ticket, uint32_t* out_rows,
   return pending_collect(ix, s, out_rows, out_scores, out_counts);
 }
 
+int tss_index_search_prefix_submit(tss_index* ix, tss_terms* t, const char* prefix, uint32_t len,
+                                   int kind, tss_mask* scratch, const float* queries, uint32_t nq,
+                                   uint32_t k, uint64_t* out_ticket) {
+  if (!ix) return fail(TSS_ERR_INVALID_ARG, "index is NULL");
+  if (!out_ticket) return fail(TSS_ERR_INVALID_ARG, "out_ticket is NULL");
+  *out_ticket = 0;
+  int rc;
+  uint64_t row_base;
+  {  // everything the search would reject is rejected before the scratch mask is touched
+    std::lock_guard<std::mutex> lock(ix->mu);
+    if ((rc = validate_search(ix, queries, nq, k))) return rc;
+    if (nq == 0 || nq > kPendingNq || k > TSS_MAX_FUSED_K)
+      return fail(TSS_ERR_INVALID_ARG, "a pending search takes 1..%u queries and k <= %u (got nq=%u k=%u)",
+                  kPendingNq, TSS_MAX_FUSED_K, nq, k);
+    if ((rc = check_mask(ix, scratch, TSS_MASK_INCLUDE))) return rc;
+    if ((rc = validate_host_queries(ix, queries, nq))) return rc;
+    bool free_slot = false;
+    for (const auto& pd : ix->pend) free_slot |= pd.state == 0;
+    if (!free_slot)
+      return fail(TSS_ERR_STATE, "%u searches are already pending on this index: collect one first", kPending);
+    row_base = ix->row_base;
+  }
+  if ((rc = tss_prefix_mask_fresh(t, prefix, len, kind, scratch, row_base, nullptr))) return rc;
+  return tss_index_search_submit(ix, queries, nq, k, scratch, TSS_MASK_INCLUDE, out_ticket);
+}
+
 int tss_index_search_prefix(tss_index* ix, tss_terms* t, const char* prefix, uint32_t len, int kind,
                             tss_mask* scratch, const float* queries, uint32_t nq, uint32_t k,
                             uint32_t* out_rows, float* out_scores, uint32_t* out_counts) {

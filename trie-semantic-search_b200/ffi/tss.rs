@@ -82,6 +82,10 @@ extern "C" {
         scratch: *mut tss_mask, queries: *const f32, nq: u32, k: u32, out_rows: *mut u32,
         out_scores: *mut f32, out_counts: *mut u32,
     ) -> c_int;
+    pub fn tss_index_search_prefix_submit(
+        ix: *mut tss_index, t: *mut tss_terms, prefix: *const c_char, len: u32, kind: c_int,
+        scratch: *mut tss_mask, queries: *const f32, nq: u32, k: u32, out_ticket: *mut u64,
+    ) -> c_int;
     pub fn tss_unpack_keys(keys: *const u64, n: u64, out_rows: *mut u32, out_scores: *mut f32);
 
     pub fn tss_comm_unique_id(out_id: *mut u8) -> c_int;
