@@ -447,6 +447,27 @@ def config4_leg(tss, orc, args, ix, device):
         e2e2_us = (time.perf_counter() - t0) / iters * 1e6
         ok = ok and all(bool(np.array_equal(a.view(np.uint32), b.view(np.uint32)))
                         for a, b in zip(two_call, (out_rows, out_scores, out_counts)))
+        # ... and with the prefix searches on the terms' OWN stream (three in flight): query i+1's
+        # prefix search then overlaps query i's scan on the device; the masks' events order them
+        terms.bind_stream(None)
+        mask3 = tss.Mask(N, device)
+        pm3 = (mask, mask2, mask3)
+        tk = []
+        for rep in range(2):   # (first pass warms the cross-stream path)
+            t0 = time.perf_counter()
+            for i in range(iters):
+                if len(tk) == 3:
+                    ix.search_collect(tk.pop(0), out_rows.ctypes.data, out_scores.ctypes.data, out_counts.ctypes.data)
+                tk.append(ix.search_prefix_submit(terms, prefix, pm3[i % 3], q[i % 8].ctypes.data, 1, k))
+            for t_ in tk:
+                ix.search_collect(t_, out_rows.ctypes.data, out_scores.ctypes.data, out_counts.ctypes.data)
+            tk = []
+            e2e3_us = (time.perf_counter() - t0) / iters * 1e6
+        ok = ok and all(bool(np.array_equal(a.view(np.uint32), b.view(np.uint32)))
+                        for a, b in zip(two_call, (out_rows, out_scores, out_counts)))
+        ix.sync()
+        terms.bind_stream(ix)
+        mask3.close()
         mask2.close()
         # the last query's result against the oracle: every live row scored on the CPU when the
         # mask is small, else the returned rows' score bits + membership
@@ -477,6 +498,7 @@ def config4_leg(tss, orc, args, ix, device):
             "mask_bit_exact_vs_numpy": ok, "prefix_to_mask_us_device": k4_us,
             "query_us_device": dev_us, "query_us_e2e_host_pointers": e2e_us,
             "query_us_e2e_one_call": e2e1_us, "query_us_e2e_two_in_flight": e2e2_us,
+            "query_us_e2e_three_in_flight_two_streams": e2e3_us,
             "algorithmic_bytes": algo, "dense_scan_bytes": N * dim * 4,
             "did": "row-skipping scan of the live rows (not a dense scan)",
             "masked_scan_gbs_on_live_rows": pc * dim * 4 / (scan_us * 1e-6) / 1e9,
