@@ -206,9 +206,12 @@ def test_search_prefix_is_prefix_mask_then_search(tss, orc):
     ix.close()
 
 
-def test_hybrid_queries_in_flight(tss, orc):
+@pytest.mark.parametrize("bound", [True, False])
+def test_hybrid_queries_in_flight(tss, orc, bound):
     """tss_index_search_prefix_submit: hybrid queries pipelined, one scratch mask per query in
-    flight, every result the oracle's top-k over exactly the prefix's rows."""
+    flight, every result the oracle's top-k over exactly the prefix's rows.  bound=False leaves the
+    prefix searches on the terms' own stream: query i+1's K4 may then run while query i's scan
+    does, ordered only by the masks' events."""
     n, dim, k = 60_000, 384, 10
     rows = orc.gen_rows(0, n, dim, SEED)
     ix = tss.FlatIndex(dim)
@@ -218,7 +221,8 @@ def test_hybrid_queries_in_flight(tss, orc):
     terms = sorted({b"w%03d w%03d" % (a, b) for a, b in rng.integers(0, 30, size=(2500, 2))})
     postings = [sorted(set(rng.integers(0, n, size=int(rng.integers(1, 12))).tolist())) for _ in terms]
     t = tss.Terms(terms, postings)
-    t.bind_stream(ix)
+    if bound:
+        t.bind_stream(ix)
     q = np.ascontiguousarray(orc.gen_rows(0, 24, dim, 0xBEEF))
     masks = [tss.Mask(n) for _ in range(3)]
     prefixes = [b"w%03d" % (i % 30) for i in range(24)]
