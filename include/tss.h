@@ -300,11 +300,12 @@ uint64_t tss_terms_size(const tss_terms* t);
 void tss_terms_destroy(tss_terms* t);
 int tss_prefix_mask(tss_terms* t, const char* prefix, uint32_t len, int kind, tss_mask* out,
                     uint64_t row_base, tss_prefix_stats* stats /* nullable: no host sync */);
-/* tss_mask_clear + tss_prefix_mask as one enqueue: the search kernel's spare CTAs zero the mask
- * while CTA 0 walks the term array, then the scatter runs -- two launches, no host
- * synchronisation (stats == NULL), what the hybrid path issues per query
- * (SearchEngine::execute_hybrid_search, src/search.rs:185-206 builds its seen-set the same way:
- * from scratch per query). */
+/* tss_mask_clear + tss_prefix_mask as ONE cooperative launch: CTAs 0-3 find the four bounds with
+ * a 256-ary search while every CTA zeroes its share of the mask, a grid barrier, then all CTAs
+ * scatter the posting ranges (and, for <= 131 072 postings, list the unique rows for the
+ * list-driven scan).  No host synchronisation (stats == NULL); what the hybrid path issues per
+ * query (SearchEngine::execute_hybrid_search, src/search.rs:185-206 builds its seen-set the same
+ * way: from scratch per query). */
 int tss_prefix_mask_fresh(tss_terms* t, const char* prefix, uint32_t len, int kind, tss_mask* out,
                           uint64_t row_base, tss_prefix_stats* stats /* nullable: no host sync */);
 /* Enqueue this handle's prefix searches on the index's stream (ix == NULL: back on its own):
