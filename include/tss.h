@@ -195,8 +195,10 @@ void tss_unpack_keys(const uint64_t* keys, uint64_t n, uint32_t* out_rows, float
 
 /* ---- sharding (BASELINE.json config 5; no reference analogue) ---------------
  * One process per GPU.  Rank r owns global rows [row_base, row_base + size).
- * The only exchange on the path is an all-gather of nq*k packed keys per rank
- * followed by a k-way merge kernel. */
+ * The only exchange on the path is nq*k packed keys per rank and a k-way merge on
+ * every rank: fused into the scan's last CTA over NVLink peer memory (batch-1 ..
+ * 4-query scans), or ncclAllGather + a merge kernel (tensor-core batches, > 8
+ * ranks, no IPC). */
 int tss_comm_unique_id(uint8_t out_id[128]);
 int tss_comm_create(tss_comm** out, const uint8_t id[128], int rank, int nranks, int device);
 void tss_comm_destroy(tss_comm* c);
