@@ -33,6 +33,6 @@ for nq in (1, 2, 3, 4, 8, 12):
     e1.record(ix); ix.sync()
     ms = e0.elapsed_ms(e1) / a.iters
     launches = (tss.launch_count() - l0) / a.iters
-    path = "K2" if launches == 5 else "K1"
+    path = "K2" if launches >= 5 else "K1"  # (prep, sample, threshold, main, select, fix-up list + guarded scans)
     print(json.dumps({"storage": a.storage, "shadow": a.shadow, "nq": nq, "ms_per_batch": ms,
                       "queries_per_s": nq / ms * 1e3, "launches": launches, "path": path}))
