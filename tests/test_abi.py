@@ -120,6 +120,15 @@ def test_argument_validation_without_device(tss):
     assert L.tss_index_create(C.byref(p), 384, 7, 0) == tss.TSS_ERR_INVALID_ARG
     assert b"storage" in L.tss_last_error()
     assert L.tss_index_size(None) == 0
+    # the in-flight entries reject a NULL index / ticket before touching anything
+    t = C.c_uint64(7)
+    assert L.tss_index_search_submit(None, None, 1, 10, None, 0, C.byref(t)) == tss.TSS_ERR_INVALID_ARG
+    assert L.tss_index_search_collect(None, 1, None, None, None) == tss.TSS_ERR_INVALID_ARG
+    assert L.tss_index_search_prefix(None, None, b"a", 1, 0, None, None, 1, 10, None, None, None) == \
+        tss.TSS_ERR_INVALID_ARG
+    assert L.tss_index_search_prefix_submit(None, None, b"a", 1, 0, None, None, 1, 10, C.byref(t)) == \
+        tss.TSS_ERR_INVALID_ARG
+    assert b"index is NULL" in L.tss_last_error()
     L.tss_index_destroy(None)  # no-op
     L.tss_mask_destroy(None)
     L.tss_terms_destroy(None)
